@@ -1,0 +1,362 @@
+#!/usr/bin/env python
+"""bench.py -- PD-UNet reconstruction throughput (slices/s) on BASELINE.json configs[1]:
+parallel-beam CT, 256x256, 64 -> 512 views sinogram upsampling, batch 16 per GPU.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A step is one inference pass of the unrolled PD-UNet over one batch of synthetic sparse-view
+sinograms: per unrolled iteration one Radon forward projection (512 views), one dual CNN, one
+ramp-filtered backprojection and one primal UNet, glued by the fused update kernels.  One JSON line
+on rank 0.  `value`: inputs already in HBM, CUDA-event time summed over the K steps (L2 flushed
+between steps outside the events), max over ranks.  `e2e`: the same pass from pinned host memory
+to a host result.  `roofline`: the Radon forward-projection call timed live with CUDA events inside
+those same K steps.  `cpu_baseline` / `--impl reference`: the CPU oracle port of the same model
+on the host cores, on a bounded sample (the reference's own operators, torch_radon, are CUDA-only
+and not mounted: SURVEY.md section 8c/8d).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+N, A_SPARSE, UP, BATCH = 256, 64, 8, 16          # configs[1]
+A_FULL = A_SPARSE * UP
+MODEL_KW = dict(n_iter=4, n_primal=4, n_dual=4, unet_base=32, unet_depth=3, dual_features=32)
+METRIC = "PD-UNet recon slices/sec"
+WORKLOAD = ("configs[1]: parallel-beam CT PD-UNet 256x256, 64->512 views sinogram upsampling, "
+            "batch 16 per GPU (inference pass, 4 unrolled iterations)")
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """Polls SM clock and throttle reasons of one GPU while the timed region runs."""
+    REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+               0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self._nv = None
+
+    def _poll(self):
+        nv = self._nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+                mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self._h))
+                for bit, name in self.REASONS.items():
+                    if mask & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.02)
+
+    def __enter__(self):
+        if self._nv is not None:
+            self._thread = threading.Thread(target=self._poll, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+def build_model(device):
+    import pd_unet_b200 as pdu
+    from pd_unet_b200.model import PrimalDualUNetCT
+    angles = np.linspace(0.0, np.pi, A_FULL, endpoint=False)
+    radon = pdu.Radon(N, angles)
+    torch.manual_seed(1234)                      # random-init weights of the named architecture
+    model = PrimalDualUNetCT(radon, upsample=UP, adjoint="fbp", **MODEL_KW).to(device).eval()
+    return radon, model
+
+
+def synthetic_sparse_sinograms(radon, device, batch, seed):
+    """Sparse-view sinograms of Shepp-Logan-style phantoms, made with the operator itself."""
+    from pd_unet_b200.phantoms import phantom_batch
+    x = phantom_batch(batch, N, seed=seed).to(device)
+    return radon.forward(x)[:, None, ::UP].contiguous()
+
+
+# ============================================================================= our arm
+def run_ours(args):
+    import pd_unet_b200 as pdu
+    from pd_unet_b200 import parallel, radon as radon_mod
+
+    rank, world, local = parallel.init_distributed("nccl")
+    if world != args.gpus:
+        if rank == 0:
+            print(f"bench.py: --gpus {args.gpus} but WORLD_SIZE={world}; launch with torch.distributed.run",
+                  file=sys.stderr)
+        if world == 1 and args.gpus > 1:
+            sys.exit(2)
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    torch.backends.cudnn.benchmark = True
+    radon, model = build_model(dev)
+    sparse = synthetic_sparse_sinograms(radon, dev, BATCH, seed=100 + rank)      # resident in HBM
+    host_in = sparse.cpu().pin_memory()
+    host_out = torch.empty((BATCH, 1, N, N), dtype=torch.float32).pin_memory()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)                # > 126 MB L2
+
+    def step(x):
+        with torch.no_grad():
+            return model(x)
+
+    def e2e_step():
+        x = host_in.to(dev, non_blocking=True)
+        y = step(x)
+        host_out.copy_(y, non_blocking=True)
+
+    for _ in range(max(args.warmup, 3)):
+        step(sparse)
+    e2e_step()
+    torch.cuda.synchronize()
+
+    # ---- device-resident timing, with the forward projector timed live inside the same steps
+    op_events = []
+
+    def hook(kind):
+        if kind != "fwd":
+            return None
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        op_events.append((s, e))
+        return s, e
+
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    parallel.barrier()
+    torch.cuda.synchronize()
+    pdu.launch_count(reset=True)
+    radon_mod.EVENT_HOOK = hook
+    with ClockSampler(local) as clocks:
+        for s, e in ev:
+            flush.zero_()
+            s.record()
+            step(sparse)
+            e.record()
+        torch.cuda.synchronize()
+    radon_mod.EVENT_HOOK = None
+    launches = pdu.launch_count()
+    parallel.barrier()
+    total_ms = sum(s.elapsed_time(e) for s, e in ev)
+    total_ms = parallel.max_over_ranks(total_ms, dev)
+    fwd_ms = [s.elapsed_time(e) for s, e in op_events]
+
+    # ---- end to end from pinned host memory
+    ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    parallel.barrier()
+    torch.cuda.synchronize()
+    for s, e in ev2:
+        flush.zero_()
+        s.record()
+        e2e_step()
+        e.record()
+    torch.cuda.synchronize()
+    parallel.barrier()
+    e2e_ms = parallel.max_over_ranks(sum(s.elapsed_time(e) for s, e in ev2), dev)
+
+    # ---- operator microbenchmarks (each call alone, L2 flushed): GSamples/s and HBM fraction
+    ops = operator_microbench(radon, dev, flush) if rank == 0 else {}
+
+    if rank != 0:
+        return
+    peak, peak_src = peaks()
+    slices = BATCH * world * args.steps
+    alg_bytes = 4.0 * BATCH * (N * N + A_FULL * N)               # 4 B (N^2 + A D) per call
+    fwd_avg_ms = sum(fwd_ms) / len(fwd_ms)
+    achieved = alg_bytes / (fwd_avg_ms * 1e-3) / 1e9
+    line = {
+        "metric": METRIC, "value": slices / (total_ms * 1e-3), "unit": "slices/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "image": N, "views_sparse": A_SPARSE, "views_full": A_FULL,
+                   "batch_per_gpu": BATCH, "model": MODEL_KW, "weights": "random init (seed 1234)",
+                   "parallelism": f"slice-sharded x{world}, no collective",
+                   "l2": "256 MiB write between steps, outside the events; activations (134 MB / feature map) exceed L2"},
+        "e2e": {"value": slices / (e2e_ms * 1e-3), "unit": "slices/s", "h2d_bytes_per_step": host_in.numel() * 4,
+                "d2h_bytes_per_step": host_out.numel() * 4},
+        "gpu_launches": int(launches),
+        "clocks": clocks.summary(),
+        "roofline": {"bound": "hbm", "kernel": "pdu_radon_fwd_f32 (transpose + radon_fwd_strip_kernel), 512 views",
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "peak_source": peak_src, "algorithmic_bytes": alg_bytes, "avg_launch_ms": fwd_avg_ms,
+                     "launches_timed": len(fwd_ms),
+                     "gsamples_per_s": BATCH * A_FULL * N * N / (fwd_avg_ms * 1e-3) / 1e9,
+                     "note": "bound on-chip (FP32 issue + shared-memory bandwidth), not by HBM: DESIGN.md"},
+        "operators": ops,
+    }
+    if not args.no_cpu:
+        line["cpu_baseline"] = cpu_baseline(sample_slices=1)
+    print(json.dumps(line), flush=True)
+
+
+def operator_microbench(radon, dev, flush, reps=10):
+    import pd_unet_b200 as pdu
+    peak, _ = peaks()
+    x = torch.rand(BATCH, N, N, device=dev)
+    s = torch.rand(BATCH, A_FULL, N, device=dev)
+    h = torch.rand(BATCH, 4, A_FULL, N, device=dev)
+
+    def timed(fn):
+        fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(reps):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        return statistics.median(ts)
+
+    rb = 4.0 * BATCH * (N * N + A_FULL * N)
+    out = {}
+    for name, fn, nbytes, samples in (
+            ("radon_fwd", lambda: radon._project(x), rb, BATCH * A_FULL * N * N),
+            ("radon_adj", lambda: radon._backproject(s), rb, BATCH * N * N * A_FULL),
+            ("filter", lambda: radon._filter(s, "ramp"), 4.0 * (2 * BATCH * A_FULL * N + N * N), None),
+            ("residual_slice", lambda: pdu.updates.residual_slice(h, h, 0), 4.0 * h.numel() * 3 + 4.0 * h.numel() / 4,
+             None)):
+        ms = timed(fn)
+        out[name] = {"ms": ms, "GB/s": nbytes / ms / 1e6, "hbm_frac": nbytes / ms / 1e6 / peak}
+        if samples:
+            out[name]["GSamples/s"] = samples / ms / 1e6
+    return out
+
+
+# ============================================================================= CPU oracle port
+def cpu_model_step(model64, sparse, trig, g):
+    """The same unrolled pass on the host: torch CPU convolutions + the oracle's operators."""
+    import oracle
+    from oracle import updates as ou
+    m = model64
+    gg = (ou.angular_upsample(sparse[:, 0], UP, "flip")[:, None] / m.op_scale).float()
+    B = gg.shape[0]
+    h = gg.new_zeros((B, m.n_dual, A_FULL, N))
+    f = gg.new_zeros((B, m.n_primal, N, N))
+    inv = 1.0 / m.op_scale
+    with torch.no_grad():
+        for i in range(m.n_iter):
+            kf = oracle.radon_forward(f[:, 0], trig, g)[:, None].to(gg.dtype) * inv
+            h = h + m.dual[i](torch.cat([h, kf, gg], 1))
+            kth = oracle.fbp(h[:, 0], trig, g)[:, None].to(gg.dtype) * inv
+            f = f + m.primal[i](torch.cat([f, kth], 1))
+    return f[:, :1]
+
+
+def cpu_setup(sample_slices):
+    import oracle
+    from pd_unet_b200.model import PrimalDualUNet
+    from pd_unet_b200.phantoms import phantom_batch
+    angles = np.linspace(0.0, np.pi, A_FULL, endpoint=False)
+    g = oracle.RadonGeom(n=N, n_angles=A_FULL, det_count=N)
+    trig = oracle.trig_table(-angles)
+    torch.manual_seed(1234)
+    model = PrimalDualUNet(None, None, 1, 1, op_scale=float(N), **MODEL_KW).eval()      # same architecture, fp32 CPU
+    gs = oracle.RadonGeom(n=N, n_angles=A_SPARSE, det_count=N)
+    sparse = oracle.radon_forward(phantom_batch(sample_slices, N, seed=100), trig[::UP], gs).float()[:, None]
+    return model, sparse, trig, g
+
+
+def cpu_baseline(sample_slices=1):
+    model, sparse, trig, g = cpu_setup(sample_slices)
+    t0 = time.perf_counter()
+    cpu_model_step(model, sparse, trig, g)
+    dt = time.perf_counter() - t0
+    return {"value": sample_slices / dt, "unit": "slices/s", "cores": torch.get_num_threads(), "kind": "port",
+            "host_cpus": os.cpu_count(), "seconds": dt,
+            "sample": f"{sample_slices} slice(s) of the batch-16 workload, full model (4 iterations, 512 views); "
+                      "own float64 CPU restatement (oracle/), not the reference: torch_radon has no CPU path"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample = 1
+    model, sparse, trig, g = cpu_setup(sample)
+    warm = min(args.warmup, 1)                   # each step is tens of seconds of CPU work
+    for _ in range(warm):
+        cpu_model_step(model, sparse, trig, g)
+    steps = args.steps
+    t0 = time.perf_counter()
+    done = 0
+    for _ in range(steps):
+        cpu_model_step(model, sparse, trig, g)
+        done += 1
+        if time.perf_counter() - t0 > 150.0:     # bounded: a few minutes for the whole run
+            break
+    dt = time.perf_counter() - t0
+    v = sample * done / dt
+    base = {"value": v, "unit": "slices/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{sample} slice per step, {done} step(s) timed (bounded at 150 s); own CPU restatement (oracle/)"}
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "slices/s", "n_gpus": args.gpus, "steps": done,
+        "warmup": warm, "ms_per_step": dt / done * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64 operators / f32 convolutions", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "image": N, "views_sparse": A_SPARSE, "views_full": A_FULL,
+                   "batch_per_step": sample, "model": MODEL_KW},
+        "cpu_baseline": base,
+        "e2e": {"value": v, "unit": "slices/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if int(os.environ.get("RANK", "0")) != 0:
+            args.no_cpu = True
+        run_ours(args)
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,175 @@
+/* pdu.h -- C ABI of libpdu_b200.so: the measurement operators of PD-UNet
+ * (CT: Radon forward / backprojection / sinogram filter; radial MRI: Kaiser-
+ * Bessel NUFFT forward / adjoint; the fused primal-dual elementwise steps) as
+ * hand-written CUDA for sm_100a.
+ *
+ * What each entry point replaces.  The reference mount is a stub
+ * (/root/reference/README.md:1-5: title, paper link, "check out the branches");
+ * the operator code the README points to lives in the third-party libraries
+ * torch_radon and torchkbnufft, neither of which is mounted.  The citations
+ * below are therefore to the library interface each symbol stands in for, as
+ * recalled ([RECALL]), not to files under /root/reference.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless the parameter says "host";
+ *  - tensors are dense, row-major, innermost axis last; complex values are
+ *    interleaved (re, im) float pairs;
+ *  - all work is enqueued on `stream` (a cudaStream_t); nothing synchronises;
+ *  - the caller owns every buffer and workspace; the library allocates only
+ *    inside pdu_nufft_plan_create;
+ *  - every function returns PDU_OK or a negative PDU_E* code and never throws;
+ *    pdu_last_error() gives the thread-local message of the last failure;
+ *  - entry points are re-entrant; one nufft plan may be used by one thread at
+ *    a time (it carries a cuFFT handle whose stream is set per call).
+ */
+#ifndef PDU_H
+#define PDU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define PDU_API __attribute__((visibility("default")))
+#else
+#define PDU_API
+#endif
+
+typedef struct CUstream_st* pdu_stream_t;           /* == cudaStream_t */
+
+enum {
+    PDU_OK = 0,
+    PDU_EINVAL = -1,         /* bad argument (null pointer, size <= 0, unsupported shape) */
+    PDU_ECUDA = -2,          /* a CUDA runtime call or launch failed */
+    PDU_ENOMEM = -3,         /* workspace too small / allocation failed */
+    PDU_EUNSUPPORTED = -4,   /* valid request this build cannot serve */
+    PDU_EFFT = -5            /* cuFFT failure */
+};
+
+PDU_API const char* pdu_last_error(void);
+PDU_API int pdu_version(void);                       /* 10000*major + 100*minor + patch */
+PDU_API int pdu_device_info(int* sm_count, int* cc_major, int* cc_minor);
+/* Kernel-variant switches for A/B measurement ("radon_fwd_variant", "radon_adj_variant",
+ * "filter_variant", "nufft_adj_variant"); value -1 restores the default.  Returns PDU_EINVAL for
+ * an unknown key.  Never changes results beyond floating-point summation order. */
+PDU_API int pdu_set_option(const char* key, int value);
+PDU_API int pdu_get_option(const char* key, int* value);
+/* Number of kernels this library launched (all threads of the process) since the last reset. */
+PDU_API long pdu_launch_count(int reset);
+
+/* ------------------------------------------------------------------ CT ---- */
+enum { PDU_GEOM_PARALLEL = 0, PDU_GEOM_FAN = 1 };
+
+/* [RECALL] torch_radon RaysCfg(width, height, det_count, det_spacing, n_angles,
+ * clip_to_circle, s_dist, d_dist). */
+typedef struct pdu_radon_geom {
+    int32_t geom;            /* PDU_GEOM_* */
+    int32_t n;               /* image is n x n */
+    int32_t n_angles;
+    int32_t det_count;
+    float det_spacing;
+    float s_dist;            /* source -> rotation centre (fan) */
+    float d_dist;            /* rotation centre -> detector (fan) */
+    int32_t clip_to_circle;
+} pdu_radon_geom_t;
+
+/* trig[2a] = cos(angles[a]), trig[2a+1] = sin(angles[a]), evaluated in float64 and rounded
+ * once.  `angles` are the INTERNAL angles (the Python wrapper negates the user's, as
+ * [RECALL] torch_radon BaseRadon.__init__ does). */
+PDU_API int pdu_radon_trig_f32(const float* angles, float* trig, int n_angles, pdu_stream_t stream);
+
+/* Bytes of scratch the projectors want (a transposed copy of the batch for the forward
+ * projector's horizontal-major views).  0 is a valid answer. */
+PDU_API size_t pdu_radon_workspace_bytes(const pdu_radon_geom_t* g, int batch);
+
+/* img [batch, n, n] -> sino [batch, n_angles, det_count].
+ * Replaces [RECALL] torch_radon `Radon.forward` / `RadonFanbeam.forward`
+ * (torch_radon_cuda.forward -> radon_forward_cuda). */
+PDU_API int pdu_radon_fwd_f32(const float* img, float* sino, const float* trig, int batch,
+                              const pdu_radon_geom_t* g, void* workspace, size_t workspace_bytes,
+                              pdu_stream_t stream);
+
+/* sino [batch, n_angles, det_count] -> img [batch, n, n].
+ * Replaces [RECALL] torch_radon `Radon.backprojection` (alias `.backward`)
+ * (torch_radon_cuda.backward -> radon_backward_cuda). */
+PDU_API int pdu_radon_adj_f32(const float* sino, float* img, const float* trig, int batch,
+                              const pdu_radon_geom_t* g, void* workspace, size_t workspace_bytes,
+                              pdu_stream_t stream);
+
+/* out[r, i] = sum_j sino[r, j] * taps[(i - j) + det_count - 1],  r < rows.
+ * taps: 2*det_count - 1 spatial filter taps (already scaled by pi / (2 n_angles)).
+ * Replaces [RECALL] torch_radon `Radon.filter_sinogram` (pad, rfft, multiply, irfft, crop, scale).
+ * The tensor-core variant wants the workspace filled by pdu_filter_prepare_f32. */
+PDU_API size_t pdu_filter_workspace_bytes(int det_count);
+PDU_API int pdu_filter_prepare_f32(const float* taps, void* workspace, size_t workspace_bytes,
+                                   int det_count, pdu_stream_t stream);
+PDU_API int pdu_filter_sinogram_f32(const float* sino, float* out, const float* taps,
+                                    const void* workspace, size_t workspace_bytes, long rows,
+                                    int det_count, pdu_stream_t stream);
+
+/* ----------------------------------------------------------------- MRI ---- */
+typedef struct pdu_nufft_plan pdu_nufft_plan_t;
+
+/* Replaces the buffers [RECALL] torchkbnufft `KbNufft.__init__` registers (tables, scaling_coef,
+ * im_size, grid_size, n_shift, numpoints, table_oversamp).  table0/table1: HOST complex64
+ * [numpoints*table_oversamp + 1]; scal0/scal1: HOST float32 [n0] / [n1]. */
+PDU_API int pdu_nufft_plan_create(pdu_nufft_plan_t** plan, int n0, int n1, int k0, int k1,
+                                  int numpoints, int table_oversamp, int shift0, int shift1,
+                                  const float* table0, const float* table1,
+                                  const float* scal0, const float* scal1);
+PDU_API int pdu_nufft_plan_destroy(pdu_nufft_plan_t* plan);
+/* Scratch for `planes` = batch*coils oversampled grids. */
+PDU_API size_t pdu_nufft_workspace_bytes(const pdu_nufft_plan_t* plan, int planes);
+
+/* image [batch, ci, n0, n1] c64 (ci == coils, or ci == 1 with smaps) -> kdata [batch, coils, m].
+ * omega [2, m] radians.  smaps [smaps_batch (1 or batch), coils, n0, n1] c64 or NULL.
+ * scale multiplies the result (1 or 1/sqrt(k0 k1) for norm="ortho").
+ * Replaces [RECALL] torchkbnufft `KbNufft.forward` (functional.kb_table_nufft). */
+PDU_API int pdu_nufft_fwd_c64(pdu_nufft_plan_t* plan, const float* image, float* kdata,
+                              const float* omega, const float* smaps, int batch, int coils,
+                              int smaps_batch, long m, float scale, void* workspace,
+                              size_t workspace_bytes, pdu_stream_t stream);
+/* kdata [batch, coils, m] -> image [batch, co, n0, n1] (co == coils, or 1 with smaps).
+ * Replaces [RECALL] torchkbnufft `KbNufftAdjoint.forward` (functional.kb_table_nufft_adjoint). */
+PDU_API int pdu_nufft_adj_c64(pdu_nufft_plan_t* plan, const float* kdata, float* image,
+                              const float* omega, const float* smaps, int batch, int coils,
+                              int smaps_batch, long m, float scale, void* workspace,
+                              size_t workspace_bytes, pdu_stream_t stream);
+/* Table interpolation only: grid [planes, k0, k1] <-> kdata [planes, m].
+ * Replace [RECALL] torchkbnufft `KbInterp.forward` / `KbInterpAdjoint.forward`; the adjoint
+ * ACCUMULATES into grid (zero it first). */
+PDU_API int pdu_nufft_interp_fwd_c64(pdu_nufft_plan_t* plan, const float* grid, float* kdata,
+                                     const float* omega, int planes, long m, pdu_stream_t stream);
+PDU_API int pdu_nufft_interp_adj_c64(pdu_nufft_plan_t* plan, const float* kdata, float* grid,
+                                     const float* omega, int planes, long m, pdu_stream_t stream);
+
+/* ------------------------------------------------ primal / dual updates ---- */
+/* out [batch, ca+cb+cc, plane] = cat(a [batch, ca, plane], b [batch, cb, plane], c [batch, cc, plane])
+ * (c may be NULL with cc == 0).  Replaces torch.cat feeding each primal / dual block. */
+PDU_API int pdu_concat_f32(float* out, const float* a, const float* b, const float* c, int batch,
+                           int ca, int cb, int cc, long plane, pdu_stream_t stream);
+/* out = state + delta  ([batch, channels, plane]);  slice [batch, kn, plane] = out[:, k:k+kn]
+ * (slice may be NULL).  out may alias state.  Replaces `h = h + net(...)` followed by
+ * `h[:, k:k+kn]` (kn = 1 for CT, 2 = (re, im) for MRI). */
+PDU_API int pdu_residual_slice_f32(float* out, float* slice, const float* state, const float* delta,
+                                   int batch, int channels, long plane, int k, int kn,
+                                   pdu_stream_t stream);
+/* out = alpha * x + beta * y, n elements. */
+PDU_API int pdu_axpby_f32(float* out, float alpha, const float* x, float beta, const float* y,
+                          long n, pdu_stream_t stream);
+/* Linear interpolation of a_sparse measured views onto a_sparse*factor views and its exact
+ * transpose.  mode: 0 = wrap with detector flip (parallel beam over pi), 1 = periodic (fan beam
+ * over 2 pi), 2 = clamp.  The paper's "sinogram upsampling" input stage. */
+enum { PDU_WRAP_FLIP = 0, PDU_WRAP_PERIODIC = 1, PDU_WRAP_CLAMP = 2 };
+PDU_API int pdu_angular_upsample_f32(const float* sparse, float* full, int batch, int a_sparse,
+                                     int factor, int det_count, int mode, pdu_stream_t stream);
+PDU_API int pdu_angular_upsample_adj_f32(const float* full, float* sparse, int batch, int a_sparse,
+                                         int factor, int det_count, int mode, pdu_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PDU_H */

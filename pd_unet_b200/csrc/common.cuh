@@ -1,0 +1,49 @@
+// Shared plumbing of libpdu_b200: error reporting, launch accounting, option switches.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "pdu.h"
+
+namespace pdu {
+
+void set_error(const char* fmt, ...);
+int option(int which);                 // see enum Opt; -1 == default
+void count_launch(int n = 1);
+int sm_count();                        // cached multiProcessorCount of the current device
+
+enum Opt { OPT_RADON_FWD = 0, OPT_RADON_ADJ = 1, OPT_FILTER = 2, OPT_NUFFT_ADJ = 3, OPT_NUFFT_FWD = 4, OPT_COUNT };
+
+#define PDU_REQUIRE(cond, ...)                         \
+    do {                                               \
+        if (!(cond)) {                                 \
+            pdu::set_error(__VA_ARGS__);               \
+            return PDU_EINVAL;                         \
+        }                                              \
+    } while (0)
+
+#define PDU_CUDA(call)                                                                      \
+    do {                                                                                    \
+        cudaError_t e__ = (call);                                                           \
+        if (e__ != cudaSuccess) {                                                           \
+            pdu::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            return PDU_ECUDA;                                                               \
+        }                                                                                   \
+    } while (0)
+
+// after a <<<>>> launch
+#define PDU_LAUNCHED()                                                                      \
+    do {                                                                                    \
+        pdu::count_launch();                                                                \
+        cudaError_t e__ = cudaPeekAtLastError();                                            \
+        if (e__ != cudaSuccess) {                                                           \
+            (void)cudaGetLastError();                                                       \
+            pdu::set_error("%s:%d launch -> %s", __FILE__, __LINE__, cudaGetErrorString(e__)); \
+            return PDU_ECUDA;                                                               \
+        }                                                                                   \
+    } while (0)
+
+static inline long cdiv(long a, long b) { return (a + b - 1) / b; }
+
+}  // namespace pdu

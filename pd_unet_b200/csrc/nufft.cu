@@ -1,0 +1,423 @@
+// Radial-MRI non-uniform FFT: Kaiser-Bessel table interpolation around an oversampled FFT.
+// Replaces [RECALL] torchkbnufft KbNufft / KbNufftAdjoint / KbInterp / KbInterpAdjoint, which are
+// compositions of ATen ops (complex multiply, pad, torch.fft, index arithmetic, index_add_).
+//
+//   forward :  apod_pad_kernel   image (* smaps) * scaling_coef -> zero-padded grid      (1 pass)
+//              FFT               oversampled grid, in place
+//              interp_fwd_kernel J x J table-weighted gather per k-space sample, * phase
+//   adjoint :  memset grid ; interp_adj_kernel (scatter, float2 atomics) ; inverse FFT ;
+//              crop_apod_kernel  crop * scaling_coef (* conj(smaps), summed over coils)
+//
+// Grid offsets and table indices are computed with explicitly rounded float32 operations, the same
+// sequence oracle/nufft.py::_tap_indices_f32 performs, so both read the same table entries.
+#include <cufft.h>
+
+#include <map>
+#include <mutex>
+
+#include "common.cuh"
+
+struct pdu_nufft_plan {
+    int n0, n1, k0, k1, J, L, shift0, shift1;
+    int device;
+    float2* d_t0;
+    float2* d_t1;
+    float* d_s0;
+    float* d_s1;
+    std::map<int, cufftHandle> fft;   // batched 2-D C2C plans keyed by number of planes
+    std::mutex mu;
+};
+
+namespace pdu {
+
+constexpr int MAXJ = 8;
+
+struct NufftDims {
+    int n0, n1, k0, k1, J, L;
+    float gam0, gam1;       // float32(2 pi / K)
+    double shift0, shift1;
+};
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+    return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
+}
+__device__ __forceinline__ float2 cmul_conj(float2 a, float2 b) {   // a * conj(b)
+    return make_float2(fmaf(a.x, b.x, a.y * b.y), fmaf(a.y, b.x, -a.x * b.y));
+}
+
+// per-axis taps of one sample: wrapped grid index and table coefficient
+__device__ __forceinline__ void axis_taps(float om, float gam, int K, int J, int L, const float2* __restrict__ table,
+                                          int* gi, float2* co) {
+    const float tm = __fdiv_rn(om, gam);
+    const int koff = (int)floorf(__fsub_rn(tm, 0.5f * (float)J));
+    const int half = (J * L) / 2;
+#pragma unroll
+    for (int j = 0; j < MAXJ; ++j) {
+        if (j < J) {
+            const int g = koff + 1 + j;
+            const float dist = __fmul_rn(__fsub_rn(tm, (float)g), (float)L);
+            int q = (int)rintf(dist) + half;
+            q = min(max(q, 0), J * L);
+            co[j] = __ldg(table + q);
+            int gw = g % K;
+            if (gw < 0) gw += K;
+            gi[j] = gw;
+        }
+    }
+}
+
+__device__ __forceinline__ float2 shift_phase(float om0, float om1, double s0, double s1) {
+    double sn, cs;
+    sincos((double)om0 * s0 + (double)om1 * s1, &sn, &cs);
+    return make_float2((float)cs, (float)sn);
+}
+
+// ------------------------------------------------------------------ apodise + zero pad
+__global__ void __launch_bounds__(256)
+    apod_pad_kernel(const float2* __restrict__ image, const float2* __restrict__ smaps, float2* __restrict__ grid,
+                    const float* __restrict__ s0, const float* __restrict__ s1, NufftDims d, int coils, int smaps_batch,
+                    long total) {
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int c1 = (int)(i % d.k1);
+        const long t = i / d.k1;
+        const int c0 = (int)(t % d.k0);
+        const long p = t / d.k0;
+        float2 v = make_float2(0.f, 0.f);
+        if (c0 < d.n0 && c1 < d.n1) {
+            const long b = p / coils, c = p - b * coils;
+            const long pix = (long)c0 * d.n1 + c1;
+            const long plane = (long)d.n0 * d.n1;
+            if (smaps) {
+                const long sb = smaps_batch == 1 ? 0 : b;
+                v = cmul(__ldg(image + b * plane + pix), __ldg(smaps + (sb * coils + c) * plane + pix));
+            } else {
+                v = __ldg(image + p * plane + pix);
+            }
+            const float w = __ldg(s0 + c0) * __ldg(s1 + c1);
+            v.x *= w;
+            v.y *= w;
+        }
+        grid[i] = v;
+    }
+}
+
+// ------------------------------------------------------------------ crop + apodise (+ coil combine)
+__global__ void __launch_bounds__(256)
+    crop_apod_kernel(const float2* __restrict__ grid, const float2* __restrict__ smaps, float2* __restrict__ image,
+                     const float* __restrict__ s0, const float* __restrict__ s1, NufftDims d, int coils, int smaps_batch,
+                     float scale, long total) {
+    const long plane = (long)d.n0 * d.n1;
+    const long gplane = (long)d.k0 * d.k1;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int c1 = (int)(i % d.n1);
+        const long t = i / d.n1;
+        const int c0 = (int)(t % d.n0);
+        const long q = t / d.n0;          // output plane: b (with smaps) or b * coils + c
+        const float w = __ldg(s0 + c0) * __ldg(s1 + c1) * scale;
+        const long gp = (long)c0 * d.k1 + c1;
+        float2 v;
+        if (smaps) {
+            const long sb = smaps_batch == 1 ? 0 : q;
+            float2 acc = make_float2(0.f, 0.f);
+            for (int c = 0; c < coils; ++c) {
+                const float2 z = cmul_conj(__ldg(grid + (q * coils + c) * gplane + gp),
+                                           __ldg(smaps + (sb * coils + c) * plane + (long)c0 * d.n1 + c1));
+                acc.x += z.x;
+                acc.y += z.y;
+            }
+            v = acc;
+        } else {
+            v = __ldg(grid + q * gplane + gp);
+        }
+        image[i] = make_float2(v.x * w, v.y * w);
+    }
+}
+
+// ------------------------------------------------------------------ interpolation (gather)
+// thread = one sample m; loops over the PC planes of its plane chunk (blockIdx.y)
+__global__ void __launch_bounds__(128)
+    interp_fwd_kernel(const float2* __restrict__ grid, float2* __restrict__ kdata, const float* __restrict__ omega,
+                      const float2* __restrict__ t0, const float2* __restrict__ t1, NufftDims d, int planes, int pc,
+                      long M, float scale) {
+    const long m = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    const float om0 = __ldg(omega + m), om1 = __ldg(omega + M + m);
+    int g0[MAXJ], g1[MAXJ];
+    float2 c0[MAXJ], c1[MAXJ];
+    axis_taps(om0, d.gam0, d.k0, d.J, d.L, t0, g0, c0);
+    axis_taps(om1, d.gam1, d.k1, d.J, d.L, t1, g1, c1);
+    float2 ph = shift_phase(om0, om1, d.shift0, d.shift1);
+    ph.x *= scale;
+    ph.y *= scale;
+    const long gplane = (long)d.k0 * d.k1;
+    const int p_end = min(planes, ((int)blockIdx.y + 1) * pc);
+    for (int p = blockIdx.y * pc; p < p_end; ++p) {
+        const float2* gp = grid + p * gplane;
+        float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int a = 0; a < MAXJ; ++a) {
+            if (a < d.J) {
+                const float2* row = gp + (long)g0[a] * d.k1;
+                float2 racc = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int b = 0; b < MAXJ; ++b) {
+                    if (b < d.J) {
+                        const float2 z = cmul(__ldg(row + g1[b]), c1[b]);
+                        racc.x += z.x;
+                        racc.y += z.y;
+                    }
+                }
+                const float2 z = cmul(racc, c0[a]);
+                acc.x += z.x;
+                acc.y += z.y;
+            }
+        }
+        kdata[(long)p * M + m] = cmul(acc, ph);
+    }
+}
+
+// ------------------------------------------------------------------ interpolation adjoint (scatter)
+__global__ void __launch_bounds__(128)
+    interp_adj_kernel(const float2* __restrict__ kdata, float2* __restrict__ grid, const float* __restrict__ omega,
+                      const float2* __restrict__ t0, const float2* __restrict__ t1, NufftDims d, int planes, int pc,
+                      long M) {
+    const long m = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    const float om0 = __ldg(omega + m), om1 = __ldg(omega + M + m);
+    int g0[MAXJ], g1[MAXJ];
+    float2 c0[MAXJ], c1[MAXJ];
+    axis_taps(om0, d.gam0, d.k0, d.J, d.L, t0, g0, c0);
+    axis_taps(om1, d.gam1, d.k1, d.J, d.L, t1, g1, c1);
+    const float2 ph = shift_phase(om0, om1, d.shift0, d.shift1);
+    const long gplane = (long)d.k0 * d.k1;
+    const int p_end = min(planes, ((int)blockIdx.y + 1) * pc);
+    for (int p = blockIdx.y * pc; p < p_end; ++p) {
+        const float2 y = cmul_conj(__ldg(kdata + (long)p * M + m), ph);
+        float2* gp = grid + p * gplane;
+#pragma unroll
+        for (int a = 0; a < MAXJ; ++a) {
+            if (a < d.J) {
+                const float2 ya = cmul_conj(y, c0[a]);
+                float2* row = gp + (long)g0[a] * d.k1;
+#pragma unroll
+                for (int b = 0; b < MAXJ; ++b) {
+                    if (b < d.J) atomicAdd(row + g1[b], cmul_conj(ya, c1[b]));
+                }
+            }
+        }
+    }
+}
+
+static NufftDims dims_of(const pdu_nufft_plan* p) {
+    NufftDims d;
+    d.n0 = p->n0; d.n1 = p->n1; d.k0 = p->k0; d.k1 = p->k1; d.J = p->J; d.L = p->L;
+    d.gam0 = (float)(2.0 * 3.14159265358979323846 / p->k0);
+    d.gam1 = (float)(2.0 * 3.14159265358979323846 / p->k1);
+    d.shift0 = (double)p->shift0;
+    d.shift1 = (double)p->shift1;
+    return d;
+}
+
+static unsigned stream_grid(long items) {
+    const long want = cdiv(items, 256);
+    const long cap = (long)sm_count() * 16;
+    return (unsigned)(want < 1 ? 1 : (want < cap ? want : cap));
+}
+
+static int plane_chunk(int planes, long M) {
+    // enough CTAs for two waves when the problem allows it, otherwise reuse the taps across planes
+    const long ctas_m = cdiv(M, 128);
+    int pc = 1;
+    while (pc < planes && ctas_m * cdiv(planes, pc * 2) >= 2L * sm_count() * 8) pc *= 2;
+    return pc;
+}
+
+static int get_fft(pdu_nufft_plan* p, int planes, cudaStream_t st, cufftHandle* out) {
+    std::lock_guard<std::mutex> lock(p->mu);
+    auto it = p->fft.find(planes);
+    if (it == p->fft.end()) {
+        cufftHandle h;
+        int n[2] = {p->k0, p->k1};
+        cufftResult r = cufftPlanMany(&h, 2, n, nullptr, 1, 0, nullptr, 1, 0, CUFFT_C2C, planes);
+        if (r != CUFFT_SUCCESS) {
+            set_error("cufftPlanMany(%d x %d, batch %d) failed with %d", p->k0, p->k1, planes, (int)r);
+            return PDU_EFFT;
+        }
+        it = p->fft.emplace(planes, h).first;
+    }
+    cufftResult r = cufftSetStream(it->second, st);
+    if (r != CUFFT_SUCCESS) {
+        set_error("cufftSetStream failed with %d", (int)r);
+        return PDU_EFFT;
+    }
+    *out = it->second;
+    return PDU_OK;
+}
+
+static int run_fft(pdu_nufft_plan* p, float2* grid, int planes, int dir, cudaStream_t st) {
+    cufftHandle h;
+    int rc = get_fft(p, planes, st, &h);
+    if (rc) return rc;
+    cufftResult r = cufftExecC2C(h, (cufftComplex*)grid, (cufftComplex*)grid, dir);
+    if (r != CUFFT_SUCCESS) {
+        set_error("cufftExecC2C failed with %d", (int)r);
+        return PDU_EFFT;
+    }
+    count_launch(2);   // a 2-D C2C transform is at least two library kernels
+    return PDU_OK;
+}
+
+static int launch_interp_fwd(pdu_nufft_plan* p, const float2* grid, float2* kdata, const float* omega, int planes,
+                             long M, float scale, cudaStream_t st) {
+    const int pc = plane_chunk(planes, M);
+    dim3 g((unsigned)cdiv(M, 128), (unsigned)cdiv(planes, pc));
+    interp_fwd_kernel<<<g, 128, 0, st>>>(grid, kdata, omega, p->d_t0, p->d_t1, dims_of(p), planes, pc, M, scale);
+    PDU_LAUNCHED();
+    return PDU_OK;
+}
+
+static int launch_interp_adj(pdu_nufft_plan* p, const float2* kdata, float2* grid, const float* omega, int planes,
+                             long M, cudaStream_t st) {
+    const int pc = plane_chunk(planes, M);
+    dim3 g((unsigned)cdiv(M, 128), (unsigned)cdiv(planes, pc));
+    interp_adj_kernel<<<g, 128, 0, st>>>(kdata, grid, omega, p->d_t0, p->d_t1, dims_of(p), planes, pc, M);
+    PDU_LAUNCHED();
+    return PDU_OK;
+}
+
+static int check_call(const pdu_nufft_plan* p, const void* a, const void* b, const void* omega, int batch, int coils,
+                      int smaps_batch, const void* smaps, long m, const char* who) {
+    PDU_REQUIRE(p != nullptr, "%s: plan is null", who);
+    PDU_REQUIRE(a && b && omega, "%s: null pointer", who);
+    PDU_REQUIRE(batch > 0 && coils > 0 && m > 0, "%s: batch, coils and m must be > 0", who);
+    PDU_REQUIRE((long)batch * coils <= 65535L * 64, "%s: too many planes", who);
+    if (smaps) PDU_REQUIRE(smaps_batch == 1 || smaps_batch == batch, "%s: smaps batch must be 1 or batch", who);
+    int dev = -1;
+    PDU_CUDA(cudaGetDevice(&dev));
+    PDU_REQUIRE(dev == p->device, "%s: plan was created on device %d, current device is %d", who, p->device, dev);
+    return PDU_OK;
+}
+
+}  // namespace pdu
+
+using namespace pdu;
+
+extern "C" {
+
+int pdu_nufft_plan_create(pdu_nufft_plan_t** plan, int n0, int n1, int k0, int k1, int numpoints, int table_oversamp,
+                          int shift0, int shift1, const float* table0, const float* table1, const float* scal0,
+                          const float* scal1) {
+    PDU_REQUIRE(plan != nullptr, "pdu_nufft_plan_create: plan is null");
+    *plan = nullptr;
+    PDU_REQUIRE(n0 > 0 && n1 > 0 && k0 >= n0 && k1 >= n1, "pdu_nufft_plan_create: need 0 < n <= k per axis");
+    PDU_REQUIRE(numpoints >= 1 && numpoints <= MAXJ, "pdu_nufft_plan_create: numpoints must be in 1..%d", MAXJ);
+    PDU_REQUIRE(table_oversamp >= 1 && (numpoints * table_oversamp) % 2 == 0,
+                "pdu_nufft_plan_create: numpoints * table_oversamp must be even");
+    PDU_REQUIRE(table0 && table1 && scal0 && scal1, "pdu_nufft_plan_create: null table");
+    pdu_nufft_plan* p = new (std::nothrow) pdu_nufft_plan();
+    if (!p) {
+        set_error("pdu_nufft_plan_create: out of host memory");
+        return PDU_ENOMEM;
+    }
+    p->n0 = n0; p->n1 = n1; p->k0 = k0; p->k1 = k1; p->J = numpoints; p->L = table_oversamp;
+    p->shift0 = shift0; p->shift1 = shift1;
+    p->d_t0 = p->d_t1 = nullptr;
+    p->d_s0 = p->d_s1 = nullptr;
+    const size_t tl = (size_t)numpoints * table_oversamp + 1;
+    cudaError_t e = cudaGetDevice(&p->device);
+    if (e == cudaSuccess) e = cudaMalloc(&p->d_t0, tl * sizeof(float2));
+    if (e == cudaSuccess) e = cudaMalloc(&p->d_t1, tl * sizeof(float2));
+    if (e == cudaSuccess) e = cudaMalloc(&p->d_s0, (size_t)n0 * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&p->d_s1, (size_t)n1 * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemcpy(p->d_t0, table0, tl * sizeof(float2), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(p->d_t1, table1, tl * sizeof(float2), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(p->d_s0, scal0, (size_t)n0 * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(p->d_s1, scal1, (size_t)n1 * sizeof(float), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        set_error("pdu_nufft_plan_create: %s", cudaGetErrorString(e));
+        pdu_nufft_plan_destroy(p);
+        return PDU_ECUDA;
+    }
+    *plan = p;
+    return PDU_OK;
+}
+
+int pdu_nufft_plan_destroy(pdu_nufft_plan_t* p) {
+    if (!p) return PDU_OK;
+    for (auto& kv : p->fft) cufftDestroy(kv.second);
+    cudaFree(p->d_t0);
+    cudaFree(p->d_t1);
+    cudaFree(p->d_s0);
+    cudaFree(p->d_s1);
+    delete p;
+    return PDU_OK;
+}
+
+size_t pdu_nufft_workspace_bytes(const pdu_nufft_plan_t* p, int planes) {
+    if (!p || planes <= 0) return 0;
+    return (size_t)planes * p->k0 * p->k1 * sizeof(float2);
+}
+
+int pdu_nufft_fwd_c64(pdu_nufft_plan_t* p, const float* image, float* kdata, const float* omega, const float* smaps,
+                      int batch, int coils, int smaps_batch, long m, float scale, void* workspace, size_t workspace_bytes,
+                      pdu_stream_t stream) {
+    int rc = check_call(p, image, kdata, omega, batch, coils, smaps_batch, smaps, m, "pdu_nufft_fwd_c64");
+    if (rc) return rc;
+    const int planes = batch * coils;
+    const size_t need = pdu_nufft_workspace_bytes(p, planes);
+    if (!workspace || workspace_bytes < need) {
+        set_error("pdu_nufft_fwd_c64: workspace of %zu bytes required, got %zu", need, workspace ? workspace_bytes : (size_t)0);
+        return PDU_ENOMEM;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    float2* grid = (float2*)workspace;
+    const long total = (long)planes * p->k0 * p->k1;
+    apod_pad_kernel<<<stream_grid(total), 256, 0, st>>>((const float2*)image, (const float2*)smaps, grid, p->d_s0, p->d_s1,
+                                                        dims_of(p), coils, smaps_batch, total);
+    PDU_LAUNCHED();
+    rc = run_fft(p, grid, planes, CUFFT_FORWARD, st);
+    if (rc) return rc;
+    return launch_interp_fwd(p, grid, (float2*)kdata, omega, planes, m, scale, st);
+}
+
+int pdu_nufft_adj_c64(pdu_nufft_plan_t* p, const float* kdata, float* image, const float* omega, const float* smaps,
+                      int batch, int coils, int smaps_batch, long m, float scale, void* workspace, size_t workspace_bytes,
+                      pdu_stream_t stream) {
+    int rc = check_call(p, kdata, image, omega, batch, coils, smaps_batch, smaps, m, "pdu_nufft_adj_c64");
+    if (rc) return rc;
+    const int planes = batch * coils;
+    const size_t need = pdu_nufft_workspace_bytes(p, planes);
+    if (!workspace || workspace_bytes < need) {
+        set_error("pdu_nufft_adj_c64: workspace of %zu bytes required, got %zu", need, workspace ? workspace_bytes : (size_t)0);
+        return PDU_ENOMEM;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    float2* grid = (float2*)workspace;
+    PDU_CUDA(cudaMemsetAsync(grid, 0, need, st));
+    rc = launch_interp_adj(p, (const float2*)kdata, grid, omega, planes, m, st);
+    if (rc) return rc;
+    rc = run_fft(p, grid, planes, CUFFT_INVERSE, st);
+    if (rc) return rc;
+    const int out_planes = smaps ? batch : planes;
+    const long total = (long)out_planes * p->n0 * p->n1;
+    crop_apod_kernel<<<stream_grid(total), 256, 0, st>>>(grid, (const float2*)smaps, (float2*)image, p->d_s0, p->d_s1,
+                                                         dims_of(p), coils, smaps_batch, scale, total);
+    PDU_LAUNCHED();
+    return PDU_OK;
+}
+
+int pdu_nufft_interp_fwd_c64(pdu_nufft_plan_t* p, const float* grid, float* kdata, const float* omega, int planes,
+                             long m, pdu_stream_t stream) {
+    int rc = check_call(p, grid, kdata, omega, planes, 1, 1, nullptr, m, "pdu_nufft_interp_fwd_c64");
+    if (rc) return rc;
+    return launch_interp_fwd(p, (const float2*)grid, (float2*)kdata, omega, planes, m, 1.f, (cudaStream_t)stream);
+}
+
+int pdu_nufft_interp_adj_c64(pdu_nufft_plan_t* p, const float* kdata, float* grid, const float* omega, int planes,
+                             long m, pdu_stream_t stream) {
+    int rc = check_call(p, kdata, grid, omega, planes, 1, 1, nullptr, m, "pdu_nufft_interp_adj_c64");
+    if (rc) return rc;
+    return launch_interp_adj(p, (const float2*)kdata, (float2*)grid, omega, planes, m, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,384 @@
+// Forward projection (ray driven), parallel and fan beam.  Replaces [RECALL] torch_radon
+// radon_forward_kernel, which samples a layered CUDA texture; here the image is staged in shared
+// memory by TMA and interpolated in exact float32.
+//
+// variant 1 (default) -- "strip marching".  A CTA owns DB detectors x AG neighbouring views of
+//   one slice.  Rays are walked in the direction of increasing major coordinate (rows for
+//   mostly-vertical rays; for mostly-horizontal views the CTA reads a transposed copy of the slice
+//   so the same code applies) through horizontal strips of TH rows.  Before marching, every ray
+//   records its column extent in every strip it crosses (shared-memory atomicMin/Max), which fixes
+//   one (TH+1) x W box per strip; thread 0 streams those boxes with cp.async.bulk.tensor
+//   (zero fill outside the image = the texture "border" mode) through an NBUF-deep mbarrier ring
+//   while all threads sample the current box with four LDS per sample.  A strip whose extent does
+//   not fit W columns falls back to global loads for that strip only.
+// variant 0 -- one thread per ray, bilinear taps through L1 (__ldg).  Kept as the A/B baseline
+//   and for shapes TMA cannot describe (n % 4 != 0, unaligned base).
+#include <cuda.h>
+
+#include "radon_common.cuh"
+
+namespace pdu {
+
+// ------------------------------------------------------------------ small kernels
+__global__ void trig_kernel(const float* __restrict__ angles, float* __restrict__ trig, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        double s, c;
+        sincos((double)angles[i], &s, &c);
+        trig[2 * i] = (float)c;
+        trig[2 * i + 1] = (float)s;
+    }
+}
+
+__global__ void transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int n) {
+    __shared__ float t[32][33];
+    const long base = (long)blockIdx.z * n * n;
+    int x = blockIdx.x * 32 + threadIdx.x;
+    for (int r = threadIdx.y; r < 32; r += 8) {
+        int y = blockIdx.y * 32 + r;
+        if (x < n && y < n) t[r][threadIdx.x] = in[base + (long)y * n + x];
+    }
+    __syncthreads();
+    int ox = blockIdx.y * 32 + threadIdx.x;
+    for (int r = threadIdx.y; r < 32; r += 8) {
+        int oy = blockIdx.x * 32 + r;
+        if (ox < n && oy < n) out[base + (long)oy * n + ox] = t[threadIdx.x][r];
+    }
+}
+
+// ------------------------------------------------------------------ variant 0
+__global__ void __launch_bounds__(256) radon_fwd_gather_kernel(const float* __restrict__ img, float* __restrict__ sino,
+                                                               const float* __restrict__ trig, pdu_radon_geom_t g) {
+    const int d = blockIdx.x * blockDim.x + threadIdx.x;
+    const int a = blockIdx.y * blockDim.y + threadIdx.y;
+    const int b = blockIdx.z;
+    if (d >= g.det_count || a >= g.n_angles) return;
+    const float cs = __ldg(trig + 2 * a), sn = __ldg(trig + 2 * a + 1);
+    const Ray r = ray_setup(g, cs, sn, d);
+    float acc = 0.f;
+    const float* src = img + (long)b * g.n * g.n;
+    for (int j = 0; j <= r.n_steps; ++j) {
+        const float jf = (float)j;
+        acc += bilinear_global(src, g.n, fmaf(jf, r.vx, r.xc0), fmaf(jf, r.vy, r.yc0));
+    }
+    sino[((long)b * g.n_angles + a) * g.det_count + d] = acc * r.step;
+}
+
+// ------------------------------------------------------------------ variant 1
+constexpr int MAX_STRIPS = 192;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// Bounded wait: a barrier that never completes must not hang the GPU box.
+__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    for (int spin = 0; spin < (1 << 22); ++spin) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.b32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (ok) return true;
+    }
+    return false;
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, int c0, int c1, int c2, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(smem_u32(dst)), "l"((uint64_t)tm), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+        : "memory");
+}
+
+template <int DB, int AG, int TH, int W, int NBUF>
+struct FwdCfg {
+    static constexpr int THREADS = DB * AG;
+    static constexpr int ROWS = TH + 1;
+    static constexpr int TILE_BYTES = ROWS * W * 4;
+    static constexpr int TILE_STRIDE = (TILE_BYTES + 127) / 128 * 128;
+    static constexpr int SMEM = NBUF * TILE_STRIDE + NBUF * 8 + 2 * MAX_STRIPS * 4 + 128;
+};
+
+template <int DB, int AG, int TH, int W, int NBUF>
+__global__ void __launch_bounds__(DB* AG)
+    radon_fwd_strip_kernel(const __grid_constant__ CUtensorMap tm_img, const __grid_constant__ CUtensorMap tm_imgT,
+                           const float* __restrict__ img, const float* __restrict__ imgT, float* __restrict__ sino,
+                           const float* __restrict__ trig, const pdu_radon_geom_t g, int* __restrict__ err_flag) {
+    using C = FwdCfg<DB, AG, TH, W, NBUF>;
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char* base = (unsigned char*)(((uintptr_t)smem_dyn + 127) & ~(uintptr_t)127);
+    uint64_t* full = (uint64_t*)(base + NBUF * C::TILE_STRIDE);
+    int* s_umin = (int*)(full + NBUF);
+    int* s_umax = s_umin + MAX_STRIPS;
+
+    const int tid = threadIdx.x;
+    const int dl = tid % DB, al = tid / DB;
+    const int d = blockIdx.x * DB + dl;
+    const int a = blockIdx.y * AG + al;
+    const int b = blockIdx.z;
+    const int N = g.n;
+    const int n_strips = (N + 1 + TH - 1) / TH;
+    const bool valid = d < g.det_count && a < g.n_angles;
+
+    for (int k = tid; k < n_strips; k += C::THREADS) {
+        s_umin[k] = INT_MAX;
+        s_umax[k] = INT_MIN;
+    }
+    if (tid == 0) {
+        for (int i = 0; i < NBUF; ++i) mbar_init(full + i, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+
+    // orientation of the whole CTA from its first view: rays run along (sn, -cs)
+    const int a_ref = min(blockIdx.y * AG, g.n_angles - 1);
+    const bool use_t = fabsf(__ldg(trig + 2 * a_ref + 1)) > fabsf(__ldg(trig + 2 * a_ref));
+
+    Ray r;
+    r.n_steps = -1;
+    r.xc0 = r.yc0 = r.vx = r.vy = r.step = 0.f;
+    if (valid) r = ray_setup(g, __ldg(trig + 2 * a), __ldg(trig + 2 * a + 1), d);
+    // (u, w) = (minor, major) coordinates; w indexes the rows of the source the CTA reads
+    float u0 = use_t ? r.yc0 : r.xc0, w0 = use_t ? r.xc0 : r.yc0;
+    float vu = use_t ? r.vy : r.vx, vw = use_t ? r.vx : r.vy;
+    const int n = r.n_steps;
+    // walk in the direction of increasing w: sample s uses j = jf0 + s * dj
+    const bool rev = vw < 0.f;
+    const float dj = rev ? -1.f : 1.f;
+    float jf = rev ? (float)n : 0.f;
+
+    __syncthreads();
+    if (n >= 0) {
+        const float wa = fmaf(jf, vw, w0), ua = fmaf(jf, vu, u0);
+        const float jend = rev ? 0.f : (float)n;
+        const float wb = fmaf(jend, vw, w0), ub = fmaf(jend, vu, u0);
+        const int kA = ((int)floorf(wa) + 1) / TH;
+        const int kB = ((int)floorf(wb) + 1) / TH;
+        const float dw = wb - wa;
+        const float slope = dw > 0.f ? (ub - ua) / dw : 0.f;
+        for (int k = kA; k <= kB; ++k) {
+            const float wlo = fmaxf(wa, (float)(k * TH - 1));
+            const float whi = fminf(wb, (float)((k + 1) * TH - 1));
+            const float ulo = dw > 0.f ? fmaf(wlo - wa, slope, ua) : fminf(ua, ub);
+            const float uhi = dw > 0.f ? fmaf(whi - wa, slope, ua) : fmaxf(ua, ub);
+            atomicMin(&s_umin[k], (int)floorf(fminf(ulo, uhi)) - 1);
+            atomicMax(&s_umax[k], (int)floorf(fmaxf(ulo, uhi)) + 2);
+        }
+    }
+    __syncthreads();
+
+    const CUtensorMap* tm = use_t ? &tm_imgT : &tm_img;
+    const float* src = (use_t ? imgT : img) + (long)b * N * N;
+
+    int k_issue = 0, seq_issue = 0;   // producer state (thread 0)
+    auto issue = [&]() {
+        while (k_issue < n_strips && s_umin[k_issue] > s_umax[k_issue]) ++k_issue;
+        if (k_issue < n_strips) {
+            const int buf = seq_issue % NBUF;
+            const int lo = s_umin[k_issue];
+            if (s_umax[k_issue] - lo + 1 <= W) {
+                mbar_expect_tx(full + buf, C::TILE_BYTES);
+                tma_load_3d(base + buf * C::TILE_STRIDE, tm, lo, k_issue * TH - 1, b, full + buf);
+            } else {
+                mbar_arrive(full + buf);
+            }
+            ++seq_issue;
+            ++k_issue;
+        }
+    };
+    if (tid == 0) {
+#pragma unroll
+        for (int i = 0; i < NBUF - 1; ++i) issue();
+    }
+
+    constexpr float MAGIC = 8388608.f;   // 2^23: x + MAGIC rounded down == floor(x) + MAGIC for 0 <= x < 2^23
+    float acc = 0.f;
+    int s = 0;
+    int seq = 0;
+    bool ok = true;
+    for (int k = 0; k < n_strips; ++k) {
+        const int lo = s_umin[k];
+        const int hi = s_umax[k];
+        if (lo > hi) continue;
+        if (tid == 0) issue();
+        const int buf = seq % NBUF;
+        ok = mbar_wait(full + buf, (seq / NBUF) & 1) && ok;
+        const float wbase = (float)(k * TH - 1);
+        if (hi - lo + 1 <= W) {
+            const float* tile = (const float*)(base + buf * C::TILE_STRIDE);
+            const float u0l = u0 - (float)lo;
+            while (s <= n) {
+                const float wl = fmaf(jf, vw, w0) - wbase;
+                if (wl >= (float)TH) break;
+                const float ul = fmaf(jf, vu, u0l);
+                const float tw = __fadd_rd(wl, MAGIC), tu = __fadd_rd(ul, MAGIC);
+                const int iw = __float_as_int(tw) & 0x7fffff, iu = __float_as_int(tu) & 0x7fffff;
+                const float fw = wl - (tw - MAGIC), fu = ul - (tu - MAGIC);
+                const float* p = tile + iw * W + iu;
+                const float v00 = p[0], v01 = p[1], v10 = p[W], v11 = p[W + 1];
+                const float top = fmaf(fu, v01 - v00, v00);
+                const float bot = fmaf(fu, v11 - v10, v10);
+                acc += fmaf(fw, bot - top, top);
+                ++s;
+                jf += dj;
+            }
+        } else {
+            while (s <= n) {
+                const float w = fmaf(jf, vw, w0);
+                if (w - wbase >= (float)TH) break;
+                acc += bilinear_global(src, N, fmaf(jf, vu, u0), w);
+                ++s;
+                jf += dj;
+            }
+        }
+        __syncthreads();
+        ++seq;
+    }
+    if (!ok && err_flag) atomicExch(err_flag, 1);
+    if (valid) sino[((long)b * g.n_angles + a) * g.det_count + d] = acc * r.step;
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static encode_tiled_fn get_encode_tiled() {
+    static encode_tiled_fn fn = []() -> encode_tiled_fn {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            return nullptr;
+        return (encode_tiled_fn)p;
+    }();
+    return fn;
+}
+
+// [batch, n, n] float32, box (w, rows, 1), zero fill outside.
+static int make_image_map(CUtensorMap* tm, const float* ptr, int batch, int n, int box_w, int box_rows) {
+    encode_tiled_fn enc = get_encode_tiled();
+    if (!enc) {
+        set_error("cuTensorMapEncodeTiled not available from the driver");
+        return PDU_EUNSUPPORTED;
+    }
+    cuuint64_t dims[3] = {(cuuint64_t)n, (cuuint64_t)n, (cuuint64_t)batch};
+    cuuint64_t strides[2] = {(cuuint64_t)n * 4, (cuuint64_t)n * n * 4};
+    cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_rows, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult rc = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)ptr, dims, strides, box, es,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed with CUresult %d (n=%d batch=%d box=%dx%d)", (int)rc, n, batch, box_w,
+                  box_rows);
+        return PDU_ECUDA;
+    }
+    return PDU_OK;
+}
+
+template <int DB, int AG, int TH, int W, int NBUF>
+static int launch_strip(const float* img, const float* imgT, float* sino, const float* trig, int batch,
+                        const pdu_radon_geom_t& g, cudaStream_t st) {
+    using C = FwdCfg<DB, AG, TH, W, NBUF>;
+    CUtensorMap tm, tmT;
+    int rc = make_image_map(&tm, img, batch, g.n, W, C::ROWS);
+    if (rc) return rc;
+    rc = make_image_map(&tmT, imgT, batch, g.n, W, C::ROWS);
+    if (rc) return rc;
+    auto kern = radon_fwd_strip_kernel<DB, AG, TH, W, NBUF>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        PDU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+        attr_set = true;
+    }
+    dim3 grid((unsigned)cdiv(g.det_count, DB), (unsigned)cdiv(g.n_angles, AG), (unsigned)batch);
+    kern<<<grid, C::THREADS, C::SMEM, st>>>(tm, tmT, img, imgT, sino, trig, g, nullptr);
+    PDU_LAUNCHED();
+    return PDU_OK;
+}
+
+}  // namespace pdu
+
+using namespace pdu;
+
+static int check_geom(const pdu_radon_geom_t* g, int batch, const char* who) {
+    PDU_REQUIRE(g != nullptr, "%s: geom is null", who);
+    PDU_REQUIRE(g->geom == PDU_GEOM_PARALLEL || g->geom == PDU_GEOM_FAN, "%s: unknown geom %d", who, g->geom);
+    PDU_REQUIRE(g->n > 0 && g->n_angles > 0 && g->det_count > 0 && batch > 0,
+                "%s: sizes must be positive (n=%d angles=%d det=%d batch=%d)", who, g->n, g->n_angles, g->det_count,
+                batch);
+    PDU_REQUIRE(g->det_spacing > 0.f, "%s: det_spacing must be > 0", who);
+    PDU_REQUIRE(batch <= 65535, "%s: batch %d exceeds 65535 (split the call)", who, batch);
+    if (g->geom == PDU_GEOM_FAN)
+        PDU_REQUIRE(g->s_dist > 0.f && g->d_dist >= 0.f, "%s: fan beam needs s_dist > 0, d_dist >= 0", who);
+    return PDU_OK;
+}
+
+extern "C" {
+
+int pdu_radon_trig_f32(const float* angles, float* trig, int n_angles, pdu_stream_t stream) {
+    PDU_REQUIRE(angles && trig && n_angles > 0, "pdu_radon_trig_f32: null pointer or n_angles <= 0");
+    trig_kernel<<<(unsigned)cdiv(n_angles, 128), 128, 0, (cudaStream_t)stream>>>(angles, trig, n_angles);
+    PDU_LAUNCHED();
+    return PDU_OK;
+}
+
+size_t pdu_radon_workspace_bytes(const pdu_radon_geom_t* g, int batch) {
+    if (!g || g->n <= 0 || batch <= 0) return 0;
+    return (size_t)batch * g->n * g->n * sizeof(float);
+}
+
+int pdu_radon_fwd_f32(const float* img, float* sino, const float* trig, int batch, const pdu_radon_geom_t* g,
+                      void* workspace, size_t workspace_bytes, pdu_stream_t stream) {
+    int rc = check_geom(g, batch, "pdu_radon_fwd_f32");
+    if (rc) return rc;
+    PDU_REQUIRE(img && sino && trig, "pdu_radon_fwd_f32: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    int variant = option(OPT_RADON_FWD);
+    if (variant < 0) variant = 1;
+    const int n_strips32 = (g->n + 1 + 31) / 32;
+    const bool tma_ok = (g->n % 4 == 0) && (((uintptr_t)img & 15) == 0) && n_strips32 <= MAX_STRIPS &&
+                        g->n_angles <= 65535 * 2;
+    if (variant == 1 && !tma_ok) variant = 0;
+    if (variant == 0) {
+        dim3 block(64, 4);
+        dim3 grid((unsigned)cdiv(g->det_count, 64), (unsigned)cdiv(g->n_angles, 4), (unsigned)batch);
+        radon_fwd_gather_kernel<<<grid, block, 0, st>>>(img, sino, trig, *g);
+        PDU_LAUNCHED();
+        return PDU_OK;
+    }
+    const size_t need = (size_t)batch * g->n * g->n * sizeof(float);
+    if (!workspace || workspace_bytes < need || ((uintptr_t)workspace & 15)) {
+        set_error("pdu_radon_fwd_f32: workspace of %zu bytes (16-byte aligned) required, got %zu", need,
+                  workspace ? workspace_bytes : (size_t)0);
+        return PDU_ENOMEM;
+    }
+    float* imgT = (float*)workspace;
+    {
+        dim3 block(32, 8);
+        dim3 grid((unsigned)cdiv(g->n, 32), (unsigned)cdiv(g->n, 32), (unsigned)batch);
+        transpose_kernel<<<grid, block, 0, st>>>(img, imgT, g->n);
+        PDU_LAUNCHED();
+    }
+    // views per CTA: neighbouring views must stay within a few columns of each other across the
+    // slice, otherwise the strip box widens past W (assumes evenly spread views; a wrong guess
+    // costs speed, never correctness -- oversized strips take the global-load path).
+    const float span = g->geom == PDU_GEOM_PARALLEL ? 3.14159265f : 6.2831853f;
+    const float spread4 = 3.f * (span / g->n_angles) * 0.7072f * g->n;
+    if (variant == 2 || (variant == 1 && spread4 > 24.f))
+        return launch_strip<128, 2, 32, 240, 3>(img, imgT, sino, trig, batch, *g, st);
+    return launch_strip<64, 4, 32, 160, 3>(img, imgT, sino, trig, batch, *g, st);
+}
+
+}  // extern "C"

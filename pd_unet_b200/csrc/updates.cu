@@ -1,0 +1,216 @@
+// The elementwise steps of one unrolled primal-dual iteration that are not convolutions:
+//   cat(...) feeding each block, state + delta with the channel slice the next operator consumes,
+//   a x + b y, and PD-UNet's angular sinogram upsampling with its exact transpose.
+// All are HBM streaming kernels: 128-bit accesses when the plane size and pointers allow, grid sized
+// in multiples of the SM count, one pass over the data (the slice is written in the same pass that
+// writes the sum, so the operator input is not re-read from the state).
+#include "common.cuh"
+
+namespace pdu {
+
+static inline bool al16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+
+static inline unsigned stream_grid(long work_items, int threads) {
+    const long want = cdiv(work_items, threads);
+    const long cap = (long)sm_count() * 16;
+    return (unsigned)(want < 1 ? 1 : (want < cap ? want : cap));
+}
+
+// ------------------------------------------------------------------ concat
+template <typename V>
+__global__ void __launch_bounds__(256)
+    concat_kernel(V* __restrict__ out, const V* __restrict__ a, const V* __restrict__ b, const V* __restrict__ c,
+                  long la, long lb, long lc, long total) {
+    // per batch element the output row is [a-row (la) | b-row (lb) | c-row (lc)] in units of V
+    const long lo = la + lb + lc;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const long n = i / lo, r = i - n * lo;
+        V v;
+        if (r < la) v = a[n * la + r];
+        else if (r < la + lb) v = b[n * lb + (r - la)];
+        else v = c[n * lc + (r - la - lb)];
+        out[i] = v;
+    }
+}
+
+// ------------------------------------------------------------------ residual + slice
+template <typename V>
+__device__ __forceinline__ V vadd(V a, V b);
+template <>
+__device__ __forceinline__ float vadd<float>(float a, float b) { return a + b; }
+template <>
+__device__ __forceinline__ float4 vadd<float4>(float4 a, float4 b) {
+    return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+}
+
+template <typename V>
+__global__ void __launch_bounds__(256)
+    residual_slice_kernel(V* out, V* __restrict__ slice, const V* state, const V* delta,
+                          long plane, int channels, int k, int kn, long total) {
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const V v = vadd<V>(state[i], delta[i]);
+        out[i] = v;
+        if (slice) {
+            const long nc = i / plane, p = i - nc * plane;
+            const long n = nc / channels;
+            const int ch = (int)(nc - n * channels) - k;
+            if (ch >= 0 && ch < kn) slice[(n * kn + ch) * plane + p] = v;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ axpby
+template <typename V>
+__device__ __forceinline__ V vaxpby(float a, V x, float b, V y);
+template <>
+__device__ __forceinline__ float vaxpby<float>(float a, float x, float b, float y) { return fmaf(a, x, b * y); }
+template <>
+__device__ __forceinline__ float4 vaxpby<float4>(float a, float4 x, float b, float4 y) {
+    return make_float4(fmaf(a, x.x, b * y.x), fmaf(a, x.y, b * y.y), fmaf(a, x.z, b * y.z), fmaf(a, x.w, b * y.w));
+}
+
+template <typename V>
+__global__ void __launch_bounds__(256)
+    axpby_kernel(V* out, float alpha, const V* x, float beta, const V* y, long total) {
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x)
+        out[i] = vaxpby<V>(alpha, x[i], beta, y[i]);
+}
+
+// ------------------------------------------------------------------ angular upsampling
+// full[b, i*f + r, d] = (1 - r/f) s[b, i, d] + (r/f) s[b, i+1, d];  the row after the last one is
+// s[b, 0, D-1-d] (mode 0), s[b, 0, d] (mode 1) or s[b, As-1, d] (mode 2).
+__global__ void __launch_bounds__(256)
+    upsample_kernel(const float* __restrict__ sparse, float* __restrict__ full, int As, int f, int D, int mode,
+                    long total) {
+    const float inv_f = 1.f / (float)f;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int d = (int)(i % D);
+        const long row = i / D;
+        const int av = (int)(row % ((long)As * f));
+        const long b = row / ((long)As * f);
+        const int ia = av / f, r = av - ia * f;
+        const float* sb = sparse + b * (long)As * D;
+        const float lo = __ldg(sb + (long)ia * D + d);
+        float hi;
+        if (ia + 1 < As) hi = __ldg(sb + (long)(ia + 1) * D + d);
+        else if (mode == PDU_WRAP_FLIP) hi = __ldg(sb + (D - 1 - d));
+        else if (mode == PDU_WRAP_PERIODIC) hi = __ldg(sb + d);
+        else hi = lo;
+        const float w = (float)r * inv_f;
+        full[i] = fmaf(w, hi - lo, lo);
+    }
+}
+
+// Transpose: sparse[b, i, d] = sum_r (1 - r/f) full[b, i f + r, d] + sum_r (r/f) full[b, (i-1) f + r, d]
+// (+ the wrapped contribution of the last group).  Gather form, deterministic, no atomics.
+__global__ void __launch_bounds__(256)
+    upsample_adj_kernel(const float* __restrict__ full, float* __restrict__ sparse, int As, int f, int D, int mode,
+                        long total) {
+    const float inv_f = 1.f / (float)f;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int d = (int)(i % D);
+        const long row = i / D;
+        const int ia = (int)(row % As);
+        const long b = row / As;
+        const float* fb = full + b * (long)As * f * D;
+        float acc = 0.f;
+        for (int r = 0; r < f; ++r) acc = fmaf(1.f - (float)r * inv_f, __ldg(fb + ((long)ia * f + r) * D + d), acc);
+        if (ia > 0)
+            for (int r = 1; r < f; ++r) acc = fmaf((float)r * inv_f, __ldg(fb + ((long)(ia - 1) * f + r) * D + d), acc);
+        // the last group's upper neighbour
+        const long last = (long)(As - 1) * f;
+        if (mode == PDU_WRAP_FLIP && ia == 0) {
+            for (int r = 1; r < f; ++r) acc = fmaf((float)r * inv_f, __ldg(fb + (last + r) * D + (D - 1 - d)), acc);
+        } else if (mode == PDU_WRAP_PERIODIC && ia == 0) {
+            for (int r = 1; r < f; ++r) acc = fmaf((float)r * inv_f, __ldg(fb + (last + r) * D + d), acc);
+        } else if (mode == PDU_WRAP_CLAMP && ia == As - 1) {
+            for (int r = 1; r < f; ++r) acc = fmaf((float)r * inv_f, __ldg(fb + (last + r) * D + d), acc);
+        }
+        sparse[i] = acc;
+    }
+}
+
+}  // namespace pdu
+
+using namespace pdu;
+
+extern "C" {
+
+int pdu_concat_f32(float* out, const float* a, const float* b, const float* c, int batch, int ca, int cb, int cc,
+                   long plane, pdu_stream_t stream) {
+    PDU_REQUIRE(out && a && b, "pdu_concat_f32: null pointer");
+    PDU_REQUIRE(batch > 0 && ca > 0 && cb > 0 && cc >= 0 && plane > 0, "pdu_concat_f32: sizes must be positive");
+    PDU_REQUIRE((c != nullptr) == (cc > 0), "pdu_concat_f32: c must be given exactly when cc > 0");
+    const long la = ca * plane, lb = cb * plane, lc = cc * plane;
+    const long total = (long)batch * (la + lb + lc);
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool vec = plane % 4 == 0 && al16(out) && al16(a) && al16(b) && (c == nullptr || al16(c));
+    if (vec) {
+        concat_kernel<float4><<<stream_grid(total / 4, 256), 256, 0, st>>>((float4*)out, (const float4*)a, (const float4*)b,
+                                                                           (const float4*)c, la / 4, lb / 4, lc / 4, total / 4);
+    } else {
+        concat_kernel<float><<<stream_grid(total, 256), 256, 0, st>>>(out, a, b, c, la, lb, lc, total);
+    }
+    PDU_LAUNCHED();
+    return PDU_OK;
+}
+
+int pdu_residual_slice_f32(float* out, float* slice, const float* state, const float* delta, int batch, int channels,
+                           long plane, int k, int kn, pdu_stream_t stream) {
+    PDU_REQUIRE(out && state && delta, "pdu_residual_slice_f32: null pointer");
+    PDU_REQUIRE(batch > 0 && channels > 0 && plane > 0, "pdu_residual_slice_f32: sizes must be positive");
+    PDU_REQUIRE(slice == nullptr || (k >= 0 && kn >= 1 && k + kn <= channels),
+                "pdu_residual_slice_f32: slice channels [%d, %d) out of range", k, k + kn);
+    const long total = (long)batch * channels * plane;
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool vec = plane % 4 == 0 && al16(out) && al16(state) && al16(delta) && (slice == nullptr || al16(slice));
+    if (vec) {
+        residual_slice_kernel<float4><<<stream_grid(total / 4, 256), 256, 0, st>>>(
+            (float4*)out, (float4*)slice, (const float4*)state, (const float4*)delta, plane / 4, channels, k, kn, total / 4);
+    } else {
+        residual_slice_kernel<float><<<stream_grid(total, 256), 256, 0, st>>>(out, slice, state, delta, plane, channels, k,
+                                                                              kn, total);
+    }
+    PDU_LAUNCHED();
+    return PDU_OK;
+}
+
+int pdu_axpby_f32(float* out, float alpha, const float* x, float beta, const float* y, long n, pdu_stream_t stream) {
+    PDU_REQUIRE(out && x && y && n > 0, "pdu_axpby_f32: null pointer or n <= 0");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n % 4 == 0 && al16(out) && al16(x) && al16(y)) {
+        axpby_kernel<float4><<<stream_grid(n / 4, 256), 256, 0, st>>>((float4*)out, alpha, (const float4*)x, beta,
+                                                                      (const float4*)y, n / 4);
+    } else {
+        axpby_kernel<float><<<stream_grid(n, 256), 256, 0, st>>>(out, alpha, x, beta, y, n);
+    }
+    PDU_LAUNCHED();
+    return PDU_OK;
+}
+
+int pdu_angular_upsample_f32(const float* sparse, float* full, int batch, int a_sparse, int factor, int det_count,
+                             int mode, pdu_stream_t stream) {
+    PDU_REQUIRE(sparse && full, "pdu_angular_upsample_f32: null pointer");
+    PDU_REQUIRE(batch > 0 && a_sparse > 0 && factor > 0 && det_count > 0, "pdu_angular_upsample_f32: sizes must be positive");
+    PDU_REQUIRE(mode >= 0 && mode <= 2, "pdu_angular_upsample_f32: unknown mode %d", mode);
+    const long total = (long)batch * a_sparse * factor * det_count;
+    upsample_kernel<<<stream_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(sparse, full, a_sparse, factor, det_count,
+                                                                               mode, total);
+    PDU_LAUNCHED();
+    return PDU_OK;
+}
+
+int pdu_angular_upsample_adj_f32(const float* full, float* sparse, int batch, int a_sparse, int factor, int det_count,
+                                 int mode, pdu_stream_t stream) {
+    PDU_REQUIRE(sparse && full, "pdu_angular_upsample_adj_f32: null pointer");
+    PDU_REQUIRE(batch > 0 && a_sparse > 0 && factor > 0 && det_count > 0,
+                "pdu_angular_upsample_adj_f32: sizes must be positive");
+    PDU_REQUIRE(mode >= 0 && mode <= 2, "pdu_angular_upsample_adj_f32: unknown mode %d", mode);
+    const long total = (long)batch * a_sparse * det_count;
+    upsample_adj_kernel<<<stream_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(full, sparse, a_sparse, factor,
+                                                                                   det_count, mode, total);
+    PDU_LAUNCHED();
+    return PDU_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,183 @@
+"""Primal-Dual UNet assembled around the B200 operators.
+
+The reference model lives in unmounted branches (/root/reference/README.md:5), so this is a
+[RECALL]/[DESIGN] assembly of what the paper the README cites (arXiv 2112.13443) describes: Adler &
+Oktem's learned primal-dual unrolling in which the image-space (primal) block is a UNet, the
+data-space (dual) block stays a small CNN, and the measured sparse-view sinogram is first upsampled
+to the full angular grid.  Parameter names are this repo's own; they are NOT claimed to match the
+reference checkpoints (unverifiable -- see DESIGN.md).
+
+    h <- h + Dual_i (cat(h, K f[:, :kc] / s, g))       data space
+    f <- f + UNet_i (cat(f, K* h[:, :kc] / s))         image space
+
+K / K* are the operators of pd_unet_b200.radon (CT) or pd_unet_b200.nufft (MRI), kc = 1 real
+channel for CT and 2 (re, im) for MRI; cat and the residual + slice steps are the fused kernels of
+pd_unet_b200.updates.  The convolutions are stock PyTorch / cuDNN as BASELINE.json prescribes.
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional
+
+import torch
+from torch import nn
+
+from . import updates
+from .nufft import KbNufft, KbNufftAdjoint
+from .radon import _BaseRadon
+
+
+def _conv_block(cin: int, cout: int) -> nn.Sequential:
+    return nn.Sequential(nn.Conv2d(cin, cout, 3, padding=1), nn.PReLU(cout),
+                         nn.Conv2d(cout, cout, 3, padding=1), nn.PReLU(cout))
+
+
+class UNet(nn.Module):
+    """Plain 2-D UNet: `depth` poolings, `base` features doubling per level, bilinear up-sampling."""
+
+    def __init__(self, cin: int, cout: int, base: int = 32, depth: int = 3):
+        super().__init__()
+        self.down = nn.ModuleList()
+        ch = cin
+        for d in range(depth + 1):
+            self.down.append(_conv_block(ch, base << d))
+            ch = base << d
+        self.up = nn.ModuleList()
+        for d in reversed(range(depth)):
+            self.up.append(_conv_block(ch + (base << d), base << d))
+            ch = base << d
+        self.head = nn.Conv2d(ch, cout, 1)
+        self.pool = nn.MaxPool2d(2)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        skips = []
+        for i, blk in enumerate(self.down):
+            x = blk(x)
+            if i + 1 < len(self.down):
+                skips.append(x)
+                x = self.pool(x)
+        for blk in self.up:
+            s = skips.pop()
+            x = nn.functional.interpolate(x, size=s.shape[-2:], mode="bilinear", align_corners=False)
+            x = blk(torch.cat([x, s], dim=1))
+        return self.head(x)
+
+
+class DualBlock(nn.Module):
+    """Three 3x3 convolutions with PReLU, as in the learned primal-dual data-space block."""
+
+    def __init__(self, cin: int, cout: int, features: int = 32):
+        super().__init__()
+        self.net = nn.Sequential(nn.Conv2d(cin, features, 3, padding=1), nn.PReLU(features),
+                                 nn.Conv2d(features, features, 3, padding=1), nn.PReLU(features),
+                                 nn.Conv2d(features, cout, 3, padding=1))
+
+    def forward(self, x):
+        return self.net(x)
+
+
+class PrimalDualUNet(nn.Module):
+    """Generic unrolling over a pair of callables.
+
+    op_forward:  [B, kc, *image] float32 -> [B, kc_data, *data] float32
+    op_adjoint:  [B, kc_data, *data]     -> [B, kc, *image]
+    """
+
+    def __init__(self, op_forward: Callable, op_adjoint: Callable, image_channels: int = 1, data_channels: int = 1,
+                 n_iter: int = 4, n_primal: int = 4, n_dual: int = 4, unet_base: int = 32, unet_depth: int = 3,
+                 dual_features: int = 32, op_scale: float = 1.0):
+        super().__init__()
+        if n_primal < image_channels or n_dual < data_channels:
+            raise ValueError("n_primal / n_dual must hold at least one operator-sized slice")
+        self.op_forward, self.op_adjoint = op_forward, op_adjoint
+        self.kc, self.kd = image_channels, data_channels
+        self.n_iter, self.n_primal, self.n_dual = n_iter, n_primal, n_dual
+        self.op_scale = float(op_scale)
+        self.dual = nn.ModuleList(DualBlock(n_dual + 2 * data_channels, n_dual, dual_features) for _ in range(n_iter))
+        self.primal = nn.ModuleList(UNet(n_primal + image_channels, n_primal, unet_base, unet_depth)
+                                    for _ in range(n_iter))
+
+    def forward(self, g: torch.Tensor, image_shape) -> torch.Tensor:
+        """g: measured data on the full grid [B, kd, *data].  Returns the reconstruction [B, kc, *image]."""
+        B = g.shape[0]
+        h = g.new_zeros((B, self.n_dual) + tuple(g.shape[2:]))
+        f = g.new_zeros((B, self.n_primal) + tuple(image_shape))
+        f_op = g.new_zeros((B, self.kc) + tuple(image_shape))
+        inv = 1.0 / self.op_scale
+        for i in range(self.n_iter):
+            kf = self.op_forward(f_op) * inv
+            h, h_op = updates.residual_slice(h, self.dual[i](updates.concat(h, kf, g)), 0, self.kd)
+            kth = self.op_adjoint(h_op) * inv
+            f, f_op = updates.residual_slice(f, self.primal[i](updates.concat(f, kth)), 0, self.kc)
+        return f_op
+
+
+class PrimalDualUNetCT(PrimalDualUNet):
+    """CT flavour: sparse-view sinogram [B, 1, A_sparse, D] -> image [B, 1, N, N].
+
+    radon: a pd_unet_b200.radon.Radon / RadonFanbeam over the FULL view set (A_sparse * upsample views).
+    adjoint: 'fbp' (ramp filter + backprojection) or 'backprojection'."""
+
+    def __init__(self, radon: _BaseRadon, upsample: int = 8, adjoint: str = "fbp", **kw):
+        if adjoint not in ("fbp", "backprojection"):
+            raise ValueError("adjoint must be 'fbp' or 'backprojection'")
+        if radon.n_angles % upsample:
+            raise ValueError("the full view count must be a multiple of the upsampling factor")
+        self_radon = radon
+        back = (lambda s: self_radon.fbp(s)) if adjoint == "fbp" else (lambda s: self_radon.backprojection(s))
+        kw.setdefault("op_scale", float(radon.resolution))
+        super().__init__(lambda x: self_radon.forward(x), back, 1, 1, **kw)
+        self.radon = radon                      # plain object: contributes nothing to state_dict
+        self.upsample = int(upsample)
+        self.wrap = "flip" if radon.geom.geom == 0 else "periodic"
+
+    def forward(self, sparse_sino: torch.Tensor) -> torch.Tensor:
+        g = updates.angular_upsample(sparse_sino, self.upsample, self.wrap) * (1.0 / self.op_scale)
+        n = self.radon.resolution
+        return super().forward(g, (n, n))
+
+
+class PrimalDualUNetMRI(PrimalDualUNet):
+    """Radial-MRI flavour: k-space samples [B, coils, spokes * readout] complex64 (+ trajectory, coil
+    maps, density compensation) -> complex image [B, 1, N, N].  Complex tensors travel through the
+    CNNs as (re, im) channel pairs; data-space tensors are laid out [B, 2 coils, spokes, readout]."""
+
+    def __init__(self, im_size, n_spokes: int, n_readout: int, coils: int = 1, **kw):
+        self.im_size = tuple(im_size)
+        self.n_spokes, self.n_readout, self.coils = n_spokes, n_readout, coils
+        self._omega: Optional[torch.Tensor] = None
+        self._smaps: Optional[torch.Tensor] = None
+        self._dcf: Optional[torch.Tensor] = None
+        kw.setdefault("op_scale", float(im_size[0]))
+        nn.Module.__init__(self)
+        fwd, adj = KbNufft(im_size), KbNufftAdjoint(im_size)
+
+        def op_forward(x):               # [B, 2, N, N] -> [B, 2 coils, spokes, readout]
+            z = torch.view_as_complex(x.permute(0, 2, 3, 1).contiguous())[:, None]
+            y = fwd(z, self._omega, smaps=self._smaps, norm="ortho")
+            y = torch.view_as_real(y).permute(0, 1, 3, 2).reshape(x.shape[0], 2 * self.coils, n_spokes, n_readout)
+            return y
+
+        def op_adjoint(y):               # inverse layout change, density compensated
+            B = y.shape[0]
+            z = y.reshape(B, self.coils, 2, n_spokes * n_readout).permute(0, 1, 3, 2).contiguous()
+            z = torch.view_as_complex(z)
+            if self._dcf is not None:
+                z = z * self._dcf
+            x = adj(z, self._omega, smaps=self._smaps, norm="ortho")
+            return torch.view_as_real(x[:, 0]).permute(0, 3, 1, 2).contiguous()
+
+        PrimalDualUNet.__init__(self, op_forward, op_adjoint, 2, 2 * coils, **kw)
+        self.nufft, self.nufft_adjoint = fwd, adj
+
+    def forward(self, kdata: torch.Tensor, omega: torch.Tensor, smaps: Optional[torch.Tensor] = None,
+                dcf: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if kdata.shape[1] != self.coils:
+            raise ValueError(f"kdata has {kdata.shape[1]} coils, the model was built for {self.coils}")
+        if self.coils > 1 and smaps is None:
+            raise ValueError("multi-coil data needs smaps")
+        self._omega, self._smaps, self._dcf = omega, smaps, dcf
+        B = kdata.shape[0]
+        g = torch.view_as_real(kdata).permute(0, 1, 3, 2).reshape(B, 2 * self.coils, self.n_spokes, self.n_readout)
+        g = (g * (1.0 / self.op_scale)).contiguous()
+        out = PrimalDualUNet.forward(self, g, self.im_size)
+        return torch.view_as_complex(out.permute(0, 2, 3, 1).contiguous())[:, None]

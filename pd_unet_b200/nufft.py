@@ -1,0 +1,302 @@
+"""Radial-MRI operators with the call shapes of torchkbnufft >= 1.0 ([RECALL], SURVEY.md section 8b;
+the reference reaches the library through its unmounted MRI branch, /root/reference/README.md:3-5):
+
+    KbNufft(im_size, grid_size=None, numpoints=6, n_shift=None, table_oversamp=2**10,
+            kbwidth=2.34, order=0.0)(image, omega, interp_mats=None, smaps=None, norm=None)
+    KbNufftAdjoint(...)(data, omega, interp_mats=None, smaps=None, norm=None)
+    KbInterp(...)(image, omega) / KbInterpAdjoint(...)(data, omega)
+    calc_density_compensation_function(ktraj, im_size, num_iterations=10, ...)
+
+image: complex64 [B, C, N0, N1]; omega: float32 [2, M] radians (or [B, 2, M]); data: complex64
+[B, C, M].  With smaps [1 or B, coils, N0, N1] the forward expands a one-channel image to the
+coils and the adjoint combines them.  Both directions are differentiable (each is the other's
+conjugate transpose).  The modules register no parameters and no persistent buffers, so a model
+containing them has the same state_dict as one without.
+
+Everything numeric happens in libpdu_b200.so (pd_unet_b200/csrc/nufft.cu).  No CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Dict, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+from torch import nn
+
+from ._lib import PduError, check, lib, require_cuda, stream_ptr
+
+
+# ----------------------------------------------------------------------------- tables (host, float64)
+def kaiser_bessel_table(n: int, k: int, numpoints: int, table_oversamp: int, kbwidth: float) -> np.ndarray:
+    """complex128 [J L + 1]: kb(u) exp(-i (2 pi / K) ((N - 1) / 2) u) at u = q / L - J / 2
+    (Fessler's NUFFT table, order 0)."""
+    J, L = numpoints, table_oversamp
+    u = np.arange(J * L + 1, dtype=np.float64) / L - J / 2.0
+    inside = np.abs(u) < J / 2.0
+    arg = np.sqrt(np.where(inside, 1.0 - (u / (J / 2.0)) ** 2, 0.0))
+    alpha = kbwidth * J
+    kb = np.where(inside, np.i0(alpha * arg) / np.i0(alpha), 0.0)
+    return kb * np.exp(-1j * (2.0 * np.pi / k) * ((n - 1) / 2.0) * u)
+
+
+def kaiser_bessel_scaling(n: int, k: int, numpoints: int, kbwidth: float) -> np.ndarray:
+    """float64 [N]: reciprocal of the Kaiser-Bessel kernel's Fourier transform (apodisation correction)."""
+    J = numpoints
+    alpha = kbwidth * J
+    om = (np.arange(n, dtype=np.float64) - (n - 1) / 2.0) / k
+    w2 = alpha ** 2 - (np.pi * J * om) ** 2
+    w = np.sqrt(np.abs(w2))
+    with np.errstate(divide="ignore", invalid="ignore"):
+        ratio = np.where(w2 > 0, np.sinh(w) / w, np.sin(w) / w)
+    ratio = np.where(w == 0, 1.0, ratio)
+    return np.i0(alpha) / (J * ratio)
+
+
+class _Plan:
+    """Owns one pdu_nufft_plan_t per device."""
+
+    def __init__(self, im_size, grid_size, numpoints, n_shift, table_oversamp, kbwidth, order):
+        if len(im_size) != 2:
+            raise NotImplementedError("only 2-D transforms are implemented (radial MRI slices)")
+        if float(order) != 0.0:
+            raise NotImplementedError("only order-0 Kaiser-Bessel kernels are implemented")
+        self.im_size = tuple(int(v) for v in im_size)
+        self.grid_size = tuple(int(v) for v in (grid_size or [2 * n for n in self.im_size]))
+        self.n_shift = tuple(int(v) for v in (n_shift or [n // 2 for n in self.im_size]))
+        self.numpoints = int(numpoints if np.isscalar(numpoints) else numpoints[0])
+        self.table_oversamp = int(table_oversamp if np.isscalar(table_oversamp) else table_oversamp[0])
+        self.kbwidth = float(kbwidth)
+        self.tables = [kaiser_bessel_table(n, k, self.numpoints, self.table_oversamp, self.kbwidth).astype(np.complex64)
+                       for n, k in zip(self.im_size, self.grid_size)]
+        self.scaling = [kaiser_bessel_scaling(n, k, self.numpoints, self.kbwidth).astype(np.float32)
+                        for n, k in zip(self.im_size, self.grid_size)]
+        self._handles: Dict[int, C.c_void_p] = {}
+
+    def handle(self, device: torch.device) -> C.c_void_p:
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        h = self._handles.get(idx)
+        if h is None:
+            h = C.c_void_p()
+            t0, t1 = (np.ascontiguousarray(t) for t in self.tables)
+            s0, s1 = (np.ascontiguousarray(s) for s in self.scaling)
+            with torch.cuda.device(idx):
+                check(lib().pdu_nufft_plan_create(C.byref(h), self.im_size[0], self.im_size[1], self.grid_size[0],
+                                                  self.grid_size[1], self.numpoints, self.table_oversamp,
+                                                  self.n_shift[0], self.n_shift[1], t0.ctypes.data, t1.ctypes.data,
+                                                  s0.ctypes.data, s1.ctypes.data), "pdu_nufft_plan_create")
+            self._handles[idx] = h
+        return h
+
+    def __del__(self):
+        try:
+            for h in self._handles.values():
+                lib().pdu_nufft_plan_destroy(h)
+        except Exception:
+            pass
+
+    def scale(self, norm: Optional[str]) -> float:
+        if norm is None:
+            return 1.0
+        if norm == "ortho":
+            return 1.0 / math.sqrt(self.grid_size[0] * self.grid_size[1])
+        raise ValueError("norm must be None or 'ortho'")
+
+    # -------------------------------------------------------------- C-ABI calls (single trajectory)
+    def _omega(self, omega: torch.Tensor) -> torch.Tensor:
+        omega = require_cuda(omega, torch.float32, "omega")
+        if omega.dim() != 2 or omega.shape[0] != 2:
+            raise ValueError(f"omega must be [2, M], got {tuple(omega.shape)}")
+        return omega
+
+    def _smaps(self, smaps, batch):
+        if smaps is None:
+            return None, 0, 1
+        smaps = require_cuda(smaps, torch.complex64, "smaps")
+        if smaps.dim() == 3:
+            smaps = smaps[None]
+        if smaps.dim() != 4 or tuple(smaps.shape[-2:]) != self.im_size or smaps.shape[0] not in (1, batch):
+            raise ValueError(f"smaps must be [1 or {batch}, coils, {self.im_size[0]}, {self.im_size[1]}]")
+        return smaps, smaps.shape[1], smaps.shape[0]
+
+    def forward(self, image, omega, smaps, norm):
+        image = require_cuda(image, torch.complex64, "image")
+        if image.dim() != 4 or tuple(image.shape[-2:]) != self.im_size:
+            raise ValueError(f"image must be [B, C, {self.im_size[0]}, {self.im_size[1]}], got {tuple(image.shape)}")
+        omega = self._omega(omega)
+        B, M = image.shape[0], omega.shape[1]
+        smaps, coils, sb = self._smaps(smaps, B)
+        if smaps is None:
+            coils = image.shape[1]
+        elif image.shape[1] != 1:
+            raise ValueError("with smaps the image must have one channel")
+        out = torch.empty((B, coils, M), dtype=torch.complex64, device=image.device)
+        if B == 0 or M == 0:
+            return out
+        with torch.cuda.device(image.device):
+            L, h = lib(), self.handle(image.device)
+            ws = torch.empty(L.pdu_nufft_workspace_bytes(h, B * coils), dtype=torch.uint8, device=image.device)
+            check(L.pdu_nufft_fwd_c64(h, image.data_ptr(), out.data_ptr(), omega.data_ptr(),
+                                      smaps.data_ptr() if smaps is not None else None, B, coils, sb, M,
+                                      self.scale(norm), ws.data_ptr(), ws.numel(), stream_ptr()), "pdu_nufft_fwd_c64")
+        return out
+
+    def adjoint(self, data, omega, smaps, norm):
+        data = require_cuda(data, torch.complex64, "data")
+        omega = self._omega(omega)
+        if data.dim() != 3 or data.shape[-1] != omega.shape[1]:
+            raise ValueError(f"data must be [B, C, {omega.shape[1]}], got {tuple(data.shape)}")
+        B, coils, M = data.shape
+        smaps, sc, sb = self._smaps(smaps, B)
+        if smaps is not None and sc != coils:
+            raise ValueError(f"data has {coils} coils, smaps {sc}")
+        out = torch.empty((B, 1 if smaps is not None else coils) + self.im_size, dtype=torch.complex64,
+                          device=data.device)
+        if B == 0:
+            return out
+        if M == 0:
+            return out.zero_()
+        with torch.cuda.device(data.device):
+            L, h = lib(), self.handle(data.device)
+            ws = torch.empty(L.pdu_nufft_workspace_bytes(h, B * coils), dtype=torch.uint8, device=data.device)
+            check(L.pdu_nufft_adj_c64(h, data.data_ptr(), out.data_ptr(), omega.data_ptr(),
+                                      smaps.data_ptr() if smaps is not None else None, B, coils, sb, M,
+                                      self.scale(norm), ws.data_ptr(), ws.numel(), stream_ptr()), "pdu_nufft_adj_c64")
+        return out
+
+    def interp(self, grid, omega):
+        grid = require_cuda(grid, torch.complex64, "grid")
+        if grid.dim() != 4 or tuple(grid.shape[-2:]) != self.grid_size:
+            raise ValueError(f"grid must be [B, C, {self.grid_size[0]}, {self.grid_size[1]}]")
+        omega = self._omega(omega)
+        B, Cc, M = grid.shape[0], grid.shape[1], omega.shape[1]
+        out = torch.empty((B, Cc, M), dtype=torch.complex64, device=grid.device)
+        if B * Cc == 0 or M == 0:
+            return out
+        with torch.cuda.device(grid.device):
+            check(lib().pdu_nufft_interp_fwd_c64(self.handle(grid.device), grid.data_ptr(), out.data_ptr(),
+                                                 omega.data_ptr(), B * Cc, M, stream_ptr()), "pdu_nufft_interp_fwd_c64")
+        return out
+
+    def interp_adjoint(self, data, omega):
+        data = require_cuda(data, torch.complex64, "data")
+        omega = self._omega(omega)
+        if data.dim() != 3 or data.shape[-1] != omega.shape[1]:
+            raise ValueError(f"data must be [B, C, {omega.shape[1]}]")
+        B, Cc, M = data.shape
+        out = torch.zeros((B, Cc) + self.grid_size, dtype=torch.complex64, device=data.device)
+        if B * Cc == 0 or M == 0:
+            return out
+        with torch.cuda.device(data.device):
+            check(lib().pdu_nufft_interp_adj_c64(self.handle(data.device), data.data_ptr(), out.data_ptr(),
+                                                 omega.data_ptr(), B * Cc, M, stream_ptr()), "pdu_nufft_interp_adj_c64")
+        return out
+
+
+def _per_trajectory(fn, x, omega, smaps, *rest):
+    """torchkbnufft lets omega carry a batch axis ([B, 2, M]); each trajectory is its own call."""
+    if omega.dim() == 2:
+        return fn(x, omega, smaps, *rest)
+    if omega.dim() != 3 or omega.shape[0] != x.shape[0]:
+        raise ValueError("batched omega must be [B, 2, M] with the batch of the data")
+    outs = []
+    for b in range(x.shape[0]):
+        sm = None if smaps is None else (smaps if smaps.shape[0] == 1 else smaps[b:b + 1])
+        outs.append(fn(x[b:b + 1], omega[b], sm, *rest))
+    return torch.cat(outs, dim=0)
+
+
+class _NufftFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, omega, smaps, plan, norm, adjoint):
+        ctx.plan, ctx.norm, ctx.adjoint = plan, norm, adjoint
+        ctx.save_for_backward(omega, smaps) if smaps is not None else ctx.save_for_backward(omega)
+        fn = plan.adjoint if adjoint else plan.forward
+        return _per_trajectory(fn, x, omega, smaps, norm)
+
+    @staticmethod
+    def backward(ctx, grad):
+        saved = ctx.saved_tensors
+        omega, smaps = saved[0], (saved[1] if len(saved) > 1 else None)
+        fn = ctx.plan.forward if ctx.adjoint else ctx.plan.adjoint
+        return _per_trajectory(fn, grad.contiguous(), omega, smaps, ctx.norm), None, None, None, None, None
+
+
+class _InterpFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, omega, plan, adjoint):
+        ctx.plan, ctx.adjoint = plan, adjoint
+        ctx.save_for_backward(omega)
+        fn = plan.interp_adjoint if adjoint else plan.interp
+        return _per_trajectory(lambda a, o, s: fn(a, o), x, omega, None)
+
+    @staticmethod
+    def backward(ctx, grad):
+        (omega,) = ctx.saved_tensors
+        fn = ctx.plan.interp if ctx.adjoint else ctx.plan.interp_adjoint
+        return _per_trajectory(lambda a, o, s: fn(a, o), grad.contiguous(), omega, None), None, None, None
+
+
+class _KbModule(nn.Module):
+    def __init__(self, im_size: Sequence[int], grid_size: Optional[Sequence[int]] = None, numpoints=6,
+                 n_shift: Optional[Sequence[int]] = None, table_oversamp=2 ** 10, kbwidth: float = 2.34,
+                 order=0.0, dtype=None, device=None):
+        super().__init__()
+        order0 = float(order if np.isscalar(order) else order[0])
+        self._plan = _Plan(im_size, grid_size, numpoints, n_shift, table_oversamp, kbwidth, order0)
+        self.im_size, self.grid_size, self.n_shift = self._plan.im_size, self._plan.grid_size, self._plan.n_shift
+        self.numpoints, self.table_oversamp = self._plan.numpoints, self._plan.table_oversamp
+
+    @staticmethod
+    def _no_interp_mats(interp_mats):
+        if interp_mats is not None:
+            raise NotImplementedError("sparse-matrix interpolation is not implemented; pass interp_mats=None "
+                                      "(table interpolation, torchkbnufft's default)")
+
+
+class KbNufft(_KbModule):
+    """image [B, C, N0, N1] -> k-space samples [B, C (or coils), M].  [RECALL] torchkbnufft.KbNufft."""
+
+    def forward(self, image, omega, interp_mats=None, smaps=None, norm: Optional[str] = None):
+        self._no_interp_mats(interp_mats)
+        return _NufftFn.apply(image, omega, smaps, self._plan, norm, False)
+
+
+class KbNufftAdjoint(_KbModule):
+    """samples [B, C, M] -> image [B, C (or 1), N0, N1].  [RECALL] torchkbnufft.KbNufftAdjoint."""
+
+    def forward(self, data, omega, interp_mats=None, smaps=None, norm: Optional[str] = None):
+        self._no_interp_mats(interp_mats)
+        return _NufftFn.apply(data, omega, smaps, self._plan, norm, True)
+
+
+class KbInterp(_KbModule):
+    """oversampled Cartesian k-space [B, C, K0, K1] -> samples [B, C, M].  [RECALL] torchkbnufft.KbInterp."""
+
+    def forward(self, image, omega, interp_mats=None):
+        self._no_interp_mats(interp_mats)
+        return _InterpFn.apply(image, omega, self._plan, False)
+
+
+class KbInterpAdjoint(_KbModule):
+    """samples [B, C, M] -> gridded k-space [B, C, K0, K1].  [RECALL] torchkbnufft.KbInterpAdjoint."""
+
+    def forward(self, data, omega, interp_mats=None):
+        self._no_interp_mats(interp_mats)
+        return _InterpFn.apply(data, omega, self._plan, True)
+
+
+def calc_density_compensation_function(ktraj: torch.Tensor, im_size: Sequence[int], num_iterations: int = 10,
+                                       grid_size: Optional[Sequence[int]] = None, numpoints=6,
+                                       n_shift: Optional[Sequence[int]] = None, table_oversamp=2 ** 10,
+                                       kbwidth: float = 2.34, order=0.0) -> torch.Tensor:
+    """Pipe & Menon's iteration w <- w / |G G^H w| with the table interpolator only.
+    [RECALL] torchkbnufft.calc_density_compensation_function; returns complex64 [1, 1, M]."""
+    plan = _Plan(im_size, grid_size, numpoints, n_shift, table_oversamp, kbwidth, order)
+    omega = require_cuda(ktraj, torch.float32, "ktraj")
+    w = torch.ones((1, 1, omega.shape[1]), dtype=torch.complex64, device=omega.device)
+    for _ in range(num_iterations):
+        new = plan.interp(plan.interp_adjoint(w, omega), omega)
+        w = w / new.abs()
+    return w

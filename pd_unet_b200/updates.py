@@ -1,0 +1,167 @@
+"""The elementwise steps of the unrolled primal-dual iteration, fused (csrc/updates.cu):
+
+    concat(a, b[, c])                -- torch.cat(..., dim=1) feeding a primal / dual block
+    residual_slice(state, delta, k)  -- state + delta, plus the channel the next operator consumes
+    axpby(alpha, x, beta, y)
+    angular_upsample(sino, factor, mode) -- PD-UNet's sparse-view -> full-view linear interpolation
+
+All are differentiable; float32 CUDA tensors only (no CPU path).
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from ._lib import WRAP_MODES, check, lib, require_cuda, stream_ptr
+
+
+def _plane(t: torch.Tensor) -> int:
+    n = 1
+    for s in t.shape[2:]:
+        n *= s
+    return n
+
+
+class _Concat(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b, c):
+        a = require_cuda(a, torch.float32, "a")
+        b = require_cuda(b, torch.float32, "b")
+        if c is not None:
+            c = require_cuda(c, torch.float32, "c")
+        for t in (b, c):
+            if t is not None and (t.shape[0] != a.shape[0] or t.shape[2:] != a.shape[2:]):
+                raise ValueError("concat: tensors must agree in every axis but the channel axis")
+        ca, cb, cc = a.shape[1], b.shape[1], (c.shape[1] if c is not None else 0)
+        ctx.split = (ca, cb, cc)
+        out = torch.empty((a.shape[0], ca + cb + cc) + tuple(a.shape[2:]), dtype=torch.float32, device=a.device)
+        if out.numel():
+            with torch.cuda.device(a.device):
+                check(lib().pdu_concat_f32(out.data_ptr(), a.data_ptr(), b.data_ptr(),
+                                           c.data_ptr() if c is not None else None, a.shape[0], ca, cb, cc,
+                                           _plane(a), stream_ptr()), "pdu_concat_f32")
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        ca, cb, cc = ctx.split
+        return g[:, :ca], g[:, ca:ca + cb], (g[:, ca + cb:] if cc else None)
+
+
+def concat(a: torch.Tensor, b: torch.Tensor, c: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """cat([a, b(, c)], dim=1) for [B, c_i, ...] tensors in one pass."""
+    return _Concat.apply(a, b, c)
+
+
+class _ResidualSlice(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, state, delta, k, kn):
+        state = require_cuda(state, torch.float32, "state")
+        delta = require_cuda(delta, torch.float32, "delta")
+        if state.shape != delta.shape or state.dim() < 3:
+            raise ValueError("residual_slice: state and delta must be the same [B, C, ...] shape")
+        B, Cn = state.shape[:2]
+        if not (0 <= k and kn >= 1 and k + kn <= Cn):
+            raise ValueError(f"residual_slice: channels [{k}, {k + kn}) out of range for {Cn} channels")
+        ctx.k, ctx.kn = k, kn
+        out = torch.empty_like(state)
+        sl = torch.empty((B, kn) + tuple(state.shape[2:]), dtype=torch.float32, device=state.device)
+        if out.numel():
+            with torch.cuda.device(state.device):
+                check(lib().pdu_residual_slice_f32(out.data_ptr(), sl.data_ptr(), state.data_ptr(), delta.data_ptr(),
+                                                   B, Cn, _plane(state), k, kn, stream_ptr()), "pdu_residual_slice_f32")
+        return out, sl
+
+    @staticmethod
+    def backward(ctx, g_out, g_slice):
+        g = g_out
+        if g_slice is not None:
+            g = g_out.clone()
+            g[:, ctx.k:ctx.k + ctx.kn] += g_slice
+        return g, g, None, None
+
+
+def residual_slice(state: torch.Tensor, delta: torch.Tensor, k: int = 0, kn: int = 1) -> Tuple[torch.Tensor, torch.Tensor]:
+    """-> (state + delta, its channels k:k+kn as a contiguous [B, kn, ...] tensor), one pass over the data."""
+    return _ResidualSlice.apply(state, delta, int(k), int(kn))
+
+
+class _Axpby(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, y, alpha, beta):
+        x = require_cuda(x, torch.float32, "x")
+        y = require_cuda(y, torch.float32, "y")
+        if x.shape != y.shape:
+            raise ValueError("axpby: shapes differ")
+        ctx.ab = (alpha, beta)
+        out = torch.empty_like(x)
+        if out.numel():
+            with torch.cuda.device(x.device):
+                check(lib().pdu_axpby_f32(out.data_ptr(), alpha, x.data_ptr(), beta, y.data_ptr(), x.numel(),
+                                          stream_ptr()), "pdu_axpby_f32")
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b = ctx.ab
+        return g * a, g * b, None, None
+
+
+def axpby(alpha: float, x: torch.Tensor, beta: float, y: torch.Tensor) -> torch.Tensor:
+    return _Axpby.apply(x, y, float(alpha), float(beta))
+
+
+def _upsample_call(fn_name: str, src: torch.Tensor, a_sparse: int, factor: int, mode: str, out_views: int):
+    src = require_cuda(src, torch.float32, "sinogram")
+    lead, D = src.shape[:-2], src.shape[-1]
+    flat = src.reshape(-1, src.shape[-2], D)
+    out = torch.empty((flat.shape[0], out_views, D), dtype=torch.float32, device=src.device)
+    if out.numel():
+        with torch.cuda.device(src.device):
+            check(getattr(lib(), fn_name)(flat.data_ptr(), out.data_ptr(), flat.shape[0], a_sparse, factor, D,
+                                          WRAP_MODES[mode], stream_ptr()), fn_name)
+    return out.reshape(*lead, out_views, D)
+
+
+class _AngularUpsample(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, sino, factor, mode):
+        ctx.cfg = (sino.shape[-2], factor, mode)
+        return _upsample_call("pdu_angular_upsample_f32", sino, sino.shape[-2], factor, mode, sino.shape[-2] * factor)
+
+    @staticmethod
+    def backward(ctx, g):
+        a_sparse, factor, mode = ctx.cfg
+        return _upsample_call("pdu_angular_upsample_adj_f32", g, a_sparse, factor, mode, a_sparse), None, None
+
+
+class _AngularUpsampleAdjoint(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, full, factor, mode):
+        if full.shape[-2] % factor:
+            raise ValueError("angular_upsample_adjoint: view count must be a multiple of the factor")
+        ctx.cfg = (full.shape[-2] // factor, factor, mode)
+        return _upsample_call("pdu_angular_upsample_adj_f32", full, ctx.cfg[0], factor, mode, ctx.cfg[0])
+
+    @staticmethod
+    def backward(ctx, g):
+        a_sparse, factor, mode = ctx.cfg
+        return _upsample_call("pdu_angular_upsample_f32", g, a_sparse, factor, mode, a_sparse * factor), None, None
+
+
+def angular_upsample(sino: torch.Tensor, factor: int, mode: str = "flip") -> torch.Tensor:
+    """[..., A_sparse, D] -> [..., A_sparse * factor, D]; view i f + r = (1 - r/f) s[i] + (r/f) s[i+1].
+    mode: 'flip' (parallel beam over pi: the view after the last is the first, detector reversed),
+    'periodic' (fan beam over 2 pi) or 'clamp'."""
+    if mode not in WRAP_MODES:
+        raise ValueError(f"mode must be one of {tuple(WRAP_MODES)}")
+    if factor < 1:
+        raise ValueError("factor must be >= 1")
+    return _AngularUpsample.apply(sino, int(factor), mode)
+
+
+def angular_upsample_adjoint(full: torch.Tensor, factor: int, mode: str = "flip") -> torch.Tensor:
+    if mode not in WRAP_MODES:
+        raise ValueError(f"mode must be one of {tuple(WRAP_MODES)}")
+    return _AngularUpsampleAdjoint.apply(full, int(factor), mode)

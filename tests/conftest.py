@@ -20,3 +20,20 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+@pytest.fixture(autouse=True)
+def _cuda_context_guard(request):
+    """After every GPU test make sure the CUDA context is still alive.  A faulted context poisons
+    every later test in the process, so leave at once: under `pytest -n 1` xdist reports the test
+    as crashed and carries on in a fresh worker."""
+    yield
+    if "gpu" not in request.keywords:
+        return
+    import torch
+    try:
+        torch.cuda.synchronize()
+    except Exception as e:  # noqa: BLE001
+        sys.stderr.write(f"\nCUDA context lost after {request.node.nodeid}: {e}\n")
+        sys.stderr.flush()
+        os._exit(17)

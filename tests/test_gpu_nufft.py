@@ -1,0 +1,106 @@
+"""Parity of the CUDA NUFFT (through the C ABI, via pd_unet_b200.nufft) with the CPU oracle."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+import pd_unet_b200 as pdu
+from pd_unet_b200.phantoms import coil_maps
+from util import TOL, rel_l2, seeded
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _traj(n_spokes, n_readout):
+    return oracle.radial_trajectory(n_spokes, n_readout)
+
+
+@pytest.mark.parametrize("im,spokes", [((32, 32), 8), ((64, 48), 12), ((256, 256), 32), ((320, 320), 48)])
+def test_forward_and_adjoint_match_oracle(im, spokes):
+    spec = oracle.NufftSpec(im)
+    om = _traj(spokes, 2 * im[0])
+    omd = torch.from_numpy(om).to(DEV)
+    B, C = (2, 3) if im[0] <= 64 else (1, 2)
+    x = seeded((B, C) + im, 1, complex_=True)
+    y = pdu.KbNufft(im)(x.to(DEV), omd)
+    assert y.shape == (B, C, om.shape[1])
+    assert rel_l2(y, oracle.nufft_forward(x, om, spec)) <= TOL
+    k = seeded((B, C, om.shape[1]), 2, complex_=True)
+    xa = pdu.KbNufftAdjoint(im)(k.to(DEV), omd)
+    assert rel_l2(xa, oracle.nufft_adjoint(k, om, spec)) <= TOL
+
+
+def test_ortho_norm_and_smaps():
+    im, coils = (64, 64), 4
+    spec = oracle.NufftSpec(im)
+    om = _traj(16, 128)
+    omd = torch.from_numpy(om).to(DEV)
+    smaps = coil_maps(coils, 64)[None]
+    x = seeded((2, 1) + im, 3, complex_=True)
+    y = pdu.KbNufft(im)(x.to(DEV), omd, smaps=smaps.to(DEV), norm="ortho")
+    assert y.shape == (2, coils, om.shape[1])
+    assert rel_l2(y, oracle.nufft_forward(x, om, spec, smaps=smaps, norm="ortho")) <= TOL
+    k = seeded((2, coils, om.shape[1]), 4, complex_=True)
+    xa = pdu.KbNufftAdjoint(im)(k.to(DEV), omd, smaps=smaps.to(DEV), norm="ortho")
+    assert xa.shape == (2, 1) + im
+    assert rel_l2(xa, oracle.nufft_adjoint(k, om, spec, smaps=smaps, norm="ortho")) <= TOL
+    # per-batch smaps
+    sm2 = torch.cat([smaps, smaps.flip(1)], 0)
+    y2 = pdu.KbNufft(im)(x.to(DEV), omd, smaps=sm2.to(DEV))
+    assert rel_l2(y2, oracle.nufft_forward(x, om, spec, smaps=sm2)) <= TOL
+
+
+def test_against_exact_ndft_small():
+    im = (24, 24)
+    spec = oracle.NufftSpec(im)
+    om = _traj(6, 48)
+    x = seeded((1, 1) + im, 5, complex_=True)
+    y = pdu.KbNufft(im)(x.to(DEV), torch.from_numpy(om).to(DEV))
+    assert rel_l2(y, oracle.ndft_forward(x, om, spec)) < 2e-3     # Kaiser-Bessel J=6 approximation error
+
+
+def test_interp_pair_and_dcf():
+    im = (48, 48)
+    spec = oracle.NufftSpec(im)
+    om = _traj(10, 96)
+    omd = torch.from_numpy(om).to(DEV)
+    grid = seeded((1, 2, 96, 96), 6, complex_=True)
+    y = pdu.KbInterp(im)(grid.to(DEV), omd)
+    assert rel_l2(y, oracle.interp_forward(grid, om, spec)) <= TOL
+    k = seeded((1, 2, om.shape[1]), 7, complex_=True)
+    ga = pdu.KbInterpAdjoint(im)(k.to(DEV), omd)
+    assert rel_l2(ga, oracle.interp_adjoint(k, om, spec)) <= TOL
+    w = pdu.calc_density_compensation_function(omd, im, num_iterations=6)
+    assert w.shape == (1, 1, om.shape[1])
+    assert rel_l2(w.real.reshape(-1), oracle.calc_dcf(om, spec, 6)) <= 5e-5   # six chained divisions
+
+
+def test_adjointness_and_autograd():
+    im = (64, 64)
+    om = torch.from_numpy(_traj(12, 128)).to(DEV)
+    A, AH = pdu.KbNufft(im), pdu.KbNufftAdjoint(im)
+    x = seeded((1, 2) + im, 8, complex_=True).to(DEV)
+    k = seeded((1, 2, om.shape[1]), 9, complex_=True).to(DEV)
+    lhs = torch.vdot(k.reshape(-1).to(torch.complex128), A(x, om).reshape(-1).to(torch.complex128))
+    rhs = torch.vdot(AH(k, om).reshape(-1).to(torch.complex128), x.reshape(-1).to(torch.complex128))
+    assert abs(lhs - rhs) / abs(lhs) < 1e-5
+    xr = x.clone().requires_grad_()
+    (A(xr, om) * k.conj()).real.sum().backward()
+    assert rel_l2(xr.grad, AH(k, om)) <= 1e-6
+
+
+def test_batched_trajectory_empty_and_errors():
+    im = (32, 32)
+    om = torch.from_numpy(_traj(4, 64)).to(DEV)
+    x = seeded((2, 1) + im, 10, complex_=True).to(DEV)
+    A = pdu.KbNufft(im)
+    both = A(x, torch.stack([om, -om]))
+    assert torch.equal(both[0:1], A(x[0:1], om)) and torch.equal(both[1:2], A(x[1:2], -om))
+    assert A(x[:0], om).shape == (0, 1, om.shape[1])
+    with pytest.raises(pdu.PduError):
+        A(x.cpu(), om.cpu())
+    with pytest.raises(TypeError):
+        A(x.real, om)
+    with pytest.raises(NotImplementedError):
+        A(x, om, interp_mats=(None, None))

@@ -1,0 +1,188 @@
+"""Parity of the CUDA CT operators (through the C ABI, via pd_unet_b200.radon) with the CPU oracle."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+import pd_unet_b200 as pdu
+from oracle.radon import FAN, PARALLEL
+from pd_unet_b200.phantoms import phantom_batch
+from util import TOL, rel_l2, seeded, user_angles
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+# name -> (operator kwargs, oracle geometry kwargs)
+def _case(name):
+    if name == "par64":
+        n, A = 64, 24
+        return pdu.Radon(n, user_angles(A)), oracle.RadonGeom(n=n, n_angles=A, det_count=n), -user_angles(A)
+    if name == "par96_wide_det":
+        n, A, D = 96, 40, 140
+        return (pdu.Radon(n, user_angles(A), det_count=D), oracle.RadonGeom(n=n, n_angles=A, det_count=D), -user_angles(A))
+    if name == "par100_spacing":       # n % 4 == 0 but odd-ish sizes, det_spacing != 1
+        n, A, D = 100, 33, 77
+        return (pdu.Radon(n, user_angles(A), det_count=D, det_spacing=1.5),
+                oracle.RadonGeom(n=n, n_angles=A, det_count=D, det_spacing=1.5), -user_angles(A))
+    if name == "par63_no_tma":         # n % 4 != 0: the forward projector must take its gather path
+        n, A = 63, 17
+        return pdu.Radon(n, user_angles(A)), oracle.RadonGeom(n=n, n_angles=A, det_count=n), -user_angles(A)
+    if name == "par128_circle":
+        n, A = 128, 48
+        return (pdu.Radon(n, user_angles(A), clip_to_circle=True),
+                oracle.RadonGeom(n=n, n_angles=A, det_count=n, clip_to_circle=True), -user_angles(A))
+    if name == "par256_sparse":        # BASELINE configs[1] sparse view set
+        n, A = 256, 64
+        return pdu.Radon(n, user_angles(A)), oracle.RadonGeom(n=n, n_angles=A, det_count=n), -user_angles(A)
+    if name == "fan96":
+        n, A = 96, 36
+        ang = user_angles(A, 2 * np.pi)
+        return (pdu.RadonFanbeam(n, ang, 2.0 * n),
+                oracle.RadonGeom(n=n, n_angles=A, det_count=n, det_spacing=2.0, geom=FAN, s_dist=2.0 * n, d_dist=2.0 * n),
+                -ang)
+    if name == "fan128_short":
+        n, A, D = 128, 30, 200
+        ang = user_angles(A, 2 * np.pi)
+        return (pdu.RadonFanbeam(n, ang, 1.2 * n, det_distance=0.8 * n, det_count=D, det_spacing=1.3, clip_to_circle=True),
+                oracle.RadonGeom(n=n, n_angles=A, det_count=D, det_spacing=1.3, geom=FAN, s_dist=1.2 * n, d_dist=0.8 * n,
+                                 clip_to_circle=True), -ang)
+    raise KeyError(name)
+
+
+CASES = ["par64", "par96_wide_det", "par100_spacing", "par63_no_tma", "par128_circle", "par256_sparse", "fan96",
+         "fan128_short"]
+
+
+@pytest.fixture(autouse=True)
+def _reset_variants():
+    yield
+    for k in ("radon_fwd_variant", "radon_adj_variant"):
+        pdu.set_option(k, -1)
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2])
+@pytest.mark.parametrize("name", CASES)
+def test_forward_matches_oracle(name, variant):
+    op, g, internal = _case(name)
+    pdu.set_option("radon_fwd_variant", variant)
+    x = phantom_batch(2, g.n, seed=3) + 0.05 * seeded((2, g.n, g.n), 5)
+    got = op.forward(x.to(DEV))
+    want = oracle.radon_forward(x, oracle.trig_table(internal), g)
+    assert got.shape == want.shape
+    assert rel_l2(got, want) <= TOL
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("name", CASES)
+def test_backprojection_matches_oracle(name, variant):
+    op, g, internal = _case(name)
+    pdu.set_option("radon_adj_variant", variant)
+    s = seeded((2, g.n_angles, g.det_count), 7)
+    got = op.backprojection(s.to(DEV))
+    want = oracle.radon_backprojection(s, oracle.trig_table(internal), g)
+    assert rel_l2(got, want) <= TOL
+
+
+@pytest.mark.parametrize("name", ["par64", "par100_spacing", "fan96"])
+@pytest.mark.parametrize("filt", ["ramp", "hann", "shepp-logan", "cosine", "hamming"])
+def test_filter_matches_oracle(name, filt):
+    op, g, _ = _case(name)
+    s = seeded((3, g.n_angles, g.det_count), 11)
+    got = op.filter_sinogram(s.to(DEV), filt)
+    want = oracle.filter_sinogram(s, filt)
+    assert rel_l2(got, want) <= TOL
+
+
+def test_fbp_reconstructs_phantom_like_the_oracle():
+    n, A = 128, 180
+    op = pdu.Radon(n, user_angles(A), clip_to_circle=True)
+    g = oracle.RadonGeom(n=n, n_angles=A, det_count=n, clip_to_circle=True)
+    trig = oracle.trig_table(-user_angles(A))
+    x = phantom_batch(1, n, noise=0.0)
+    sino = op.forward(x.to(DEV))
+    rec = op.fbp(sino)
+    want = oracle.fbp(oracle.radon_forward(x, trig, g), trig, g)
+    assert rel_l2(rec, want) <= TOL
+    mse_got = float(((rec.cpu().double() - x.double()) ** 2).mean())
+    mse_want = float(((want - x.double()) ** 2).mean())
+    psnr = lambda m: 10 * np.log10(float(x.max()) ** 2 / m)
+    assert abs(psnr(mse_got) - psnr(mse_want)) < 0.01          # north_star: PSNR within 0.01 dB
+
+
+def test_leading_dims_empty_and_errors():
+    op, g, _ = _case("par64")
+    x = seeded((2, 3, 64, 64), 1).to(DEV)
+    y = op.forward(x)
+    assert y.shape == (2, 3, g.n_angles, g.det_count)
+    assert torch.equal(y[1, 2], op.forward(x[1, 2]))
+    assert op.forward(x[:0]).shape == (0, 3, g.n_angles, g.det_count)
+    assert op.backprojection(y[:0]).shape == (0, 3, 64, 64)
+    with pytest.raises(pdu.PduError):
+        op.forward(x.cpu())                       # no CPU fallback
+    with pytest.raises(TypeError):
+        op.forward(x.double())
+    with pytest.raises(ValueError):
+        op.forward(x[..., :32])
+
+
+def test_autograd_pairs_forward_with_backprojection():
+    op, g, _ = _case("par64")
+    x = seeded((2, 64, 64), 2).to(DEV).requires_grad_()
+    w = seeded((2, g.n_angles, g.det_count), 3).to(DEV)
+    (op.forward(x) * w).sum().backward()
+    assert torch.equal(x.grad, op.backprojection(w))
+    s = seeded((2, g.n_angles, g.det_count), 4).to(DEV).requires_grad_()
+    v = seeded((2, 64, 64), 5).to(DEV)
+    (op.backprojection(s) * v).sum().backward()
+    assert torch.equal(s.grad, op.forward(v))
+    s2 = seeded((2, g.n_angles, g.det_count), 6).to(DEV).requires_grad_()
+    (op.filter_sinogram(s2) * w).sum().backward()
+    assert rel_l2(s2.grad, op.filter_sinogram(w)) <= 1e-6
+
+
+# ---------------------------------------------------------------- BASELINE.json full sizes
+def _full_cfg(name):
+    if name == "cfg2":      # parallel 256^2, 512 views, batch 16
+        n, A, B = 256, 512, 16
+        return pdu.Radon(n, user_angles(A)), oracle.RadonGeom(n=n, n_angles=A, det_count=n), -user_angles(A), B
+    n, A, B = 512, 1024, 8   # cfg3 per-GPU share: fan 512^2, 1024 views, batch 8
+    ang = user_angles(A, 2 * np.pi)
+    return (pdu.RadonFanbeam(n, ang, 2.0 * n),
+            oracle.RadonGeom(n=n, n_angles=A, det_count=n, det_spacing=2.0, geom=FAN, s_dist=2.0 * n, d_dist=2.0 * n),
+            -ang, B)
+
+
+@pytest.mark.parametrize("name", ["cfg2", "cfg3"])
+def test_full_size_properties(name):
+    op, g, internal, B = _full_cfg(name)
+    trig = oracle.trig_table(internal)
+    x = (phantom_batch(B, g.n, seed=1)).to(DEV)
+    z = seeded((B, g.n, g.n), 9).to(DEV)
+    y = op.forward(x)
+    # oracle on one slice and a handful of views (the oracle needs seconds per slice at this size)
+    sub = np.arange(3, g.n_angles, 8)
+    gs = oracle.RadonGeom(n=g.n, n_angles=len(sub), det_count=g.det_count, det_spacing=g.det_spacing, geom=g.geom,
+                          s_dist=g.s_dist, d_dist=g.d_dist, clip_to_circle=g.clip_to_circle)
+    want = oracle.radon_forward(x[B - 1:].cpu(), trig[sub], gs)
+    assert rel_l2(y[B - 1:, sub], want) <= TOL
+    # linearity and batch independence
+    assert rel_l2(op.forward(2.0 * x - 0.5 * z), 2.0 * y - 0.5 * op.forward(z)) <= TOL
+    assert torch.equal(op.forward(x[3:5]), y[3:5])
+    # the variants agree
+    pdu.set_option("radon_fwd_variant", 0)
+    assert rel_l2(op.forward(x), y) <= TOL
+    # backprojection: oracle on one slice, linearity, variants
+    s = seeded((B, g.n_angles, g.det_count), 13).to(DEV)
+    img = op.backprojection(s)
+    s_sub = torch.zeros_like(s[:1])
+    s_sub[:, sub] = s[:1, sub]                    # only the sampled views carry data: same sum as the subset geometry
+    want = oracle.radon_backprojection(s[:1, sub].cpu(), trig[sub], gs)
+    assert rel_l2(op.backprojection(s_sub), want) <= TOL
+    pdu.set_option("radon_adj_variant", 0)
+    assert rel_l2(op.backprojection(s), img) <= TOL
+    # the parallel-beam pair is close to adjoint (ray- vs pixel-driven discretisations), as in torch_radon
+    if g.geom == PARALLEL:
+        s2 = op.forward(phantom_batch(B, g.n, seed=21).to(DEV))
+        lhs = float((y.double() * s2.double()).sum())
+        rhs = float((x.double() * op.backprojection(s2).double()).sum())
+        assert abs(lhs - rhs) / abs(lhs) < 2e-2

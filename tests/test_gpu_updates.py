@@ -1,0 +1,72 @@
+"""Parity of the fused primal-dual update kernels with the CPU oracle (bit-exact: these are single
+rounded float32 operations or pure data movement)."""
+import pytest
+import torch
+
+import oracle
+from oracle import updates as ou
+import pd_unet_b200 as pdu
+from pd_unet_b200 import updates
+from util import rel_l2, seeded
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.mark.parametrize("plane", [(8, 16), (5, 7), (64, 64)])     # vectorised and scalar paths
+def test_concat_is_torch_cat(plane):
+    a, b, c = (seeded((3, ch) + plane, i) for i, ch in enumerate((4, 1, 2)))
+    assert torch.equal(updates.concat(a.to(DEV), b.to(DEV), c.to(DEV)).cpu(), torch.cat([a, b, c], 1))
+    assert torch.equal(updates.concat(a.to(DEV), b.to(DEV)).cpu(), torch.cat([a, b], 1))
+
+
+@pytest.mark.parametrize("plane", [(8, 16), (5, 7)])
+@pytest.mark.parametrize("k,kn", [(0, 1), (2, 1), (1, 2)])
+def test_residual_slice(plane, k, kn):
+    h, d = seeded((2, 4) + plane, 1), seeded((2, 4) + plane, 2)
+    out, sl = updates.residual_slice(h.to(DEV), d.to(DEV), k, kn)
+    assert torch.equal(out.cpu(), h + d)
+    assert torch.equal(sl.cpu(), (h + d)[:, k:k + kn])
+    ref, _ = ou.dual_update(h, d, k)
+    assert rel_l2(out, ref) < 1e-7
+
+
+def test_axpby_and_autograd():
+    x, y = seeded((1000,), 3), seeded((1000,), 4)
+    got = updates.axpby(0.75, x.to(DEV), -1.5, y.to(DEV))
+    assert rel_l2(got, ou.axpby(0.75, x, -1.5, y)) < 1e-7
+    a = seeded((2, 3, 4, 8), 5).to(DEV).requires_grad_()
+    b = seeded((2, 3, 4, 8), 6).to(DEV).requires_grad_()
+    out, sl = updates.residual_slice(a, b, 1)
+    (out.sum() + 2 * sl.sum()).backward()
+    want = torch.ones_like(a)
+    want[:, 1] += 2
+    assert torch.equal(a.grad, want) and torch.equal(b.grad, want)
+    p, q = (seeded((2, c, 4, 4), 7 + c).to(DEV).requires_grad_() for c in (2, 3))
+    w = seeded((2, 5, 4, 4), 11).to(DEV)
+    (updates.concat(p, q) * w).sum().backward()
+    assert torch.equal(p.grad, w[:, :2]) and torch.equal(q.grad, w[:, 2:])
+
+
+@pytest.mark.parametrize("mode", ["flip", "periodic", "clamp"])
+@pytest.mark.parametrize("shape,factor", [((2, 8, 16), 4), ((1, 64, 256), 8), ((3, 5, 7), 3), ((2, 6, 10), 1)])
+def test_angular_upsample_and_its_transpose(mode, shape, factor):
+    s = seeded(shape, 1)
+    up = updates.angular_upsample(s.to(DEV), factor, mode)
+    assert rel_l2(up, ou.angular_upsample(s, factor, mode)) < 1e-7
+    g = seeded(tuple(up.shape), 2)
+    down = updates.angular_upsample_adjoint(g.to(DEV), factor, mode)
+    assert rel_l2(down, ou.angular_upsample_adjoint(g, factor, mode)) < 1e-6
+    sr = s.to(DEV).requires_grad_()
+    (updates.angular_upsample(sr, factor, mode) * g.to(DEV)).sum().backward()
+    assert torch.equal(sr.grad, down)
+
+
+def test_errors():
+    a = seeded((2, 2, 4, 4), 1)
+    with pytest.raises(pdu.PduError):
+        updates.concat(a, a)
+    with pytest.raises(ValueError):
+        updates.residual_slice(a.to(DEV), a.to(DEV), 3)
+    with pytest.raises(ValueError):
+        updates.angular_upsample(a.to(DEV), 2, "nearest")
