@@ -222,7 +222,7 @@ def run_ours(args):
         "operators": ops,
     }
     if not args.no_cpu:
-        line["cpu_baseline"] = cpu_baseline(sample_slices=1)
+        line["cpu_baseline"] = cpu_baseline(sample_slices=4)
     print(json.dumps(line), flush=True)
 
 
@@ -265,7 +265,7 @@ def operator_microbench(radon, dev, flush, reps=10):
 # ============================================================================= CPU oracle port
 def cpu_model_step(model64, sparse, trig, g):
     """The same unrolled pass on the host: torch CPU convolutions + the oracle's operators."""
-    import oracle
+    from oracle import c_port as oc          # OpenMP C restatement of oracle/radon.py (all host cores)
     from oracle import updates as ou
     m = model64
     gg = (ou.angular_upsample(sparse[:, 0], UP, "flip")[:, None] / m.op_scale).float()
@@ -275,9 +275,9 @@ def cpu_model_step(model64, sparse, trig, g):
     inv = 1.0 / m.op_scale
     with torch.no_grad():
         for i in range(m.n_iter):
-            kf = oracle.radon_forward(f[:, 0], trig, g)[:, None].to(gg.dtype) * inv
+            kf = oc.radon_forward(f[:, 0], trig, g)[:, None].to(gg.dtype) * inv
             h = h + m.dual[i](torch.cat([h, kf, gg], 1))
-            kth = oracle.fbp(h[:, 0], trig, g)[:, None].to(gg.dtype) * inv
+            kth = oc.fbp(h[:, 0], trig, g)[:, None].to(gg.dtype) * inv
             f = f + m.primal[i](torch.cat([f, kth], 1))
     return f[:, :1]
 
@@ -292,28 +292,38 @@ def cpu_setup(sample_slices):
     torch.manual_seed(1234)
     model = PrimalDualUNet(None, None, 1, 1, op_scale=float(N), **MODEL_KW).eval()      # same architecture, fp32 CPU
     gs = oracle.RadonGeom(n=N, n_angles=A_SPARSE, det_count=N)
-    sparse = oracle.radon_forward(phantom_batch(sample_slices, N, seed=100), trig[::UP], gs).float()[:, None]
+    from oracle import c_port as oc
+    sparse = oc.radon_forward(phantom_batch(sample_slices, N, seed=100), trig[::UP], gs).float()[:, None]
     return model, sparse, trig, g
 
 
-def cpu_baseline(sample_slices=1):
+CPU_NOTE = ("own CPU restatement (oracle/radon_c.c, OpenMP float64 operators + torch CPU fp32 convolutions), "
+            "not the reference: torch_radon has no CPU path and is not mounted")
+
+
+def cpu_cores():
+    from oracle import c_port as oc
+    return max(torch.get_num_threads(), oc.n_threads())
+
+
+def cpu_baseline(sample_slices=4):
     model, sparse, trig, g = cpu_setup(sample_slices)
+    cpu_model_step(model, sparse[:1], trig, g)           # warm the thread pools / page in
     t0 = time.perf_counter()
     cpu_model_step(model, sparse, trig, g)
     dt = time.perf_counter() - t0
-    return {"value": sample_slices / dt, "unit": "slices/s", "cores": torch.get_num_threads(), "kind": "port",
+    return {"value": sample_slices / dt, "unit": "slices/s", "cores": cpu_cores(), "kind": "port",
             "host_cpus": os.cpu_count(), "seconds": dt,
-            "sample": f"{sample_slices} slice(s) of the batch-16 workload, full model (4 iterations, 512 views); "
-                      "own float64 CPU restatement (oracle/), not the reference: torch_radon has no CPU path"}
+            "sample": f"{sample_slices} slices of the batch-16 workload, full model (4 iterations, 512 views); " + CPU_NOTE}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample = 1
+    sample = 2
     model, sparse, trig, g = cpu_setup(sample)
-    warm = min(args.warmup, 1)                   # each step is tens of seconds of CPU work
+    warm = min(args.warmup, 1)                   # each step is seconds of CPU work
     for _ in range(warm):
         cpu_model_step(model, sparse, trig, g)
     steps = args.steps
@@ -326,8 +336,8 @@ def run_reference(args):
             break
     dt = time.perf_counter() - t0
     v = sample * done / dt
-    base = {"value": v, "unit": "slices/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"{sample} slice per step, {done} step(s) timed (bounded at 150 s); own CPU restatement (oracle/)"}
+    base = {"value": v, "unit": "slices/s", "cores": cpu_cores(), "kind": "port", "host_cpus": os.cpu_count(),
+            "sample": f"{sample} slices per step, {done} step(s) timed (bounded at 150 s); " + CPU_NOTE}
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "slices/s", "n_gpus": args.gpus, "steps": done,
         "warmup": warm, "ms_per_step": dt / done * 1e3, "higher_is_better": True, "scaling": "weak",

@@ -185,7 +185,9 @@ __global__ void __launch_bounds__(DB* AG)
         while (k_issue < n_strips && s_umin[k_issue] > s_umax[k_issue]) ++k_issue;
         if (k_issue < n_strips) {
             const int buf = seq_issue % NBUF;
-            const int lo = s_umin[k_issue];
+            // TMA needs the innermost start coordinate on a 16-byte boundary (measured: any c0 % 4 != 0
+            // raises "illegal instruction" on sm_100a, negative values are fine) -> round down to 4 floats
+            const int lo = s_umin[k_issue] & ~3;
             if (s_umax[k_issue] - lo + 1 <= W) {
                 mbar_expect_tx(full + buf, C::TILE_BYTES);
                 tma_load_3d(base + buf * C::TILE_STRIDE, tm, lo, k_issue * TH - 1, b, full + buf);
@@ -207,9 +209,9 @@ __global__ void __launch_bounds__(DB* AG)
     int seq = 0;
     bool ok = true;
     for (int k = 0; k < n_strips; ++k) {
-        const int lo = s_umin[k];
         const int hi = s_umax[k];
-        if (lo > hi) continue;
+        if (s_umin[k] > hi) continue;
+        const int lo = s_umin[k] & ~3;
         if (tid == 0) issue();
         const int buf = seq % NBUF;
         ok = mbar_wait(full + buf, (seq / NBUF) & 1) && ok;
@@ -350,7 +352,7 @@ int pdu_radon_fwd_f32(const float* img, float* sino, const float* trig, int batc
     const int n_strips32 = (g->n + 1 + 31) / 32;
     const bool tma_ok = (g->n % 4 == 0) && (((uintptr_t)img & 15) == 0) && n_strips32 <= MAX_STRIPS &&
                         g->n_angles <= 65535 * 2;
-    if (variant == 1 && !tma_ok) variant = 0;
+    if (variant != 0 && !tma_ok) variant = 0;
     if (variant == 0) {
         dim3 block(64, 4);
         dim3 grid((unsigned)cdiv(g->det_count, 64), (unsigned)cdiv(g->n_angles, 4), (unsigned)batch);

@@ -89,6 +89,13 @@ class _Plan:
             self._handles[idx] = h
         return h
 
+    def __deepcopy__(self, memo):
+        # device handles are per-process resources: a copy starts without any and re-creates them lazily
+        return _Plan(self.im_size, self.grid_size, self.numpoints, self.n_shift, self.table_oversamp, self.kbwidth, 0.0)
+
+    def __getstate__(self):
+        raise TypeError("a NUFFT plan holds device handles and cannot be pickled; rebuild the module instead")
+
     def __del__(self):
         try:
             for h in self._handles.values():
