@@ -147,15 +147,22 @@ PDU_API int pdu_nufft_interp_adj_c64(pdu_nufft_plan_t* plan, const float* kdata,
                                      const float* omega, int planes, long m, pdu_stream_t stream);
 
 /* ------------------------------------------------ primal / dual updates ---- */
-/* out [batch, ca+cb+cc, plane] = cat(a [batch, ca, plane], b [batch, cb, plane], c [batch, cc, plane])
- * (c may be NULL with cc == 0).  Replaces torch.cat feeding each primal / dual block. */
+/* Memory layout of the multi-channel tensors below: planar [batch, channels, plane] (torch
+ * contiguous) or channels-last [batch, plane, channels] (torch.channels_last, what cuDNN's tensor-core
+ * convolutions want).  One-channel tensors are the same bytes either way. */
+enum { PDU_LAYOUT_NCHW = 0, PDU_LAYOUT_NHWC = 1 };
+
+/* out = cat(a [batch, ca, plane], scale_b * b [batch, cb, plane], c [batch, cc, plane]) along the
+ * channel axis, all four tensors in `layout` (c may be NULL with cc == 0).  Replaces torch.cat feeding
+ * each primal / dual block, and the 1/op_norm scaling of the operator output that rides in b. */
 PDU_API int pdu_concat_f32(float* out, const float* a, const float* b, const float* c, int batch,
-                           int ca, int cb, int cc, long plane, pdu_stream_t stream);
-/* out = state + delta  ([batch, channels, plane]);  slice [batch, kn, plane] = out[:, k:k+kn]
- * (slice may be NULL).  out may alias state.  Replaces `h = h + net(...)` followed by
- * `h[:, k:k+kn]` (kn = 1 for CT, 2 = (re, im) for MRI). */
+                           int ca, int cb, int cc, long plane, float scale_b, int layout,
+                           pdu_stream_t stream);
+/* out = state + delta (all three in `layout`);  slice [batch, kn, plane] = out[:, k:k+kn], always
+ * planar because it is the next operator's input (slice may be NULL).  out may alias state.  Replaces
+ * `h = h + net(...)` followed by `h[:, k:k+kn]` (kn = 1 for CT, 2 = (re, im) for MRI). */
 PDU_API int pdu_residual_slice_f32(float* out, float* slice, const float* state, const float* delta,
-                                   int batch, int channels, long plane, int k, int kn,
+                                   int batch, int channels, long plane, int k, int kn, int layout,
                                    pdu_stream_t stream);
 /* out = alpha * x + beta * y, n elements. */
 PDU_API int pdu_axpby_f32(float* out, float alpha, const float* x, float beta, const float* y,

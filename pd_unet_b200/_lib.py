@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libpdu_b200.so")
 
 PDU_GEOM_PARALLEL, PDU_GEOM_FAN = 0, 1
 WRAP_MODES = {"flip": 0, "periodic": 1, "clamp": 2}
+LAYOUT_NCHW, LAYOUT_NHWC = 0, 1
 
 
 class PduError(RuntimeError):
@@ -54,8 +55,8 @@ SIGNATURES = {
                                     C.c_size_t, _p]),
     "pdu_nufft_interp_fwd_c64": (C.c_int, [_p, _p, _p, _p, C.c_int, C.c_long, _p]),
     "pdu_nufft_interp_adj_c64": (C.c_int, [_p, _p, _p, _p, C.c_int, C.c_long, _p]),
-    "pdu_concat_f32": (C.c_int, [_p, _p, _p, _p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_long, _p]),
-    "pdu_residual_slice_f32": (C.c_int, [_p, _p, _p, _p, C.c_int, C.c_int, C.c_long, C.c_int, C.c_int, _p]),
+    "pdu_concat_f32": (C.c_int, [_p, _p, _p, _p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_long, C.c_float, C.c_int, _p]),
+    "pdu_residual_slice_f32": (C.c_int, [_p, _p, _p, _p, C.c_int, C.c_int, C.c_long, C.c_int, C.c_int, C.c_int, _p]),
     "pdu_axpby_f32": (C.c_int, [_p, C.c_float, _p, C.c_float, _p, C.c_long, _p]),
     "pdu_angular_upsample_f32": (C.c_int, [_p, _p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _p]),
     "pdu_angular_upsample_adj_f32": (C.c_int, [_p, _p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _p]),

@@ -19,6 +19,7 @@ struct AdjGeom {
     int n, n_angles, det_count;
     int fan, clip;
     float ids;      // 1 / det_spacing
+    float det_spacing, d_dist;
     float s_dist;   // fan: source -> centre
     float k;        // fan: s_dist + d_dist
     float cr;       // det_count / 2 - 0.5  (detector coordinate of u = 0, in tap units)
@@ -87,14 +88,27 @@ __global__ void __launch_bounds__(TX*(TY / PY))
     }
 }
 
-template <int TX, int TY, int PY, int AC, int SEG>
+// Per-view constants of one CTA, tile-relative and set up in float64 so that the per-tap float32
+// arithmetic only ever rounds at the magnitude of the tile (< SEG), not of the detector (< D):
+//   parallel:  t - lo = base + a lx + b ly
+//   fan:       t - lo = (n0 + nx lx + ny ly) / den,   den = d0 + sn lx - cs ly,   weight = k / den
+// (lx, ly) = pixel offset inside the tile, lo = first detector bin of the staged segment.
+struct ViewPar {
+    float a, b, base, pad;
+};
+struct ViewFan {
+    float n0, nx, ny, d0, sn, cs, pad0, pad1;
+};
+
+template <int TX, int TY, int PY, int AC, int SEG, bool FAN>
 __global__ void __launch_bounds__(TX*(TY / PY))
     radon_adj_tile_kernel(const float* __restrict__ sino, float* __restrict__ img, const float* __restrict__ trig,
                           const AdjGeom g) {
     constexpr int THREADS = TX * (TY / PY);
     constexpr int RY = TY / PY;
-    __shared__ float s_seg[AC][SEG];
-    __shared__ float2 s_trig[AC];
+    // staged detector rows as (value, next - value) pairs: one 8-byte load per tap
+    __shared__ __align__(16) float2 s_seg[AC][SEG];
+    __shared__ __align__(16) float s_view[AC][FAN ? 8 : 4];
     __shared__ int s_lo[AC];
     __shared__ int s_big;
 
@@ -102,18 +116,18 @@ __global__ void __launch_bounds__(TX*(TY / PY))
     const int x = blockIdx.x * TX + threadIdx.x;
     const int y0 = blockIdx.y * TY + threadIdx.y;
     const int b = blockIdx.z;
-    const float dx = (float)x - g.half;
+    const float lx = (float)threadIdx.x, ly0 = (float)threadIdx.y;
     const float* sb = sino + (long)b * g.n_angles * g.det_count;
 
-    // tile corners (clamped to the image so the interval is not wasted on padding pixels)
-    const float cx0 = (float)(blockIdx.x * TX) - g.half;
-    const float cx1 = (float)min(blockIdx.x * TX + TX - 1, g.n - 1) - g.half;
-    const float cy0 = (float)(blockIdx.y * TY) - g.half;
-    const float cy1 = (float)min(blockIdx.y * TY + TY - 1, g.n - 1) - g.half;
+    // tile origin and far corner (clamped to the image so that padding pixels do not widen the interval)
+    const double ox = (double)(blockIdx.x * TX) - (double)g.half, oy = (double)(blockIdx.y * TY) - (double)g.half;
+    const double ex = (double)(min(blockIdx.x * TX + TX, g.n) - 1 - blockIdx.x * TX);
+    const double ey = (double)(min(blockIdx.y * TY + TY, g.n) - 1 - blockIdx.y * TY);
 
     float acc[PY];
 #pragma unroll
     for (int k = 0; k < PY; ++k) acc[k] = 0.f;
+    constexpr float MAGIC = 8388608.f;
 
     for (int a0 = 0; a0 < g.n_angles; a0 += AC) {
         const int na = min(AC, g.n_angles - a0);
@@ -121,19 +135,42 @@ __global__ void __launch_bounds__(TX*(TY / PY))
         if (tid == 0) s_big = 0;
         __syncthreads();
         if (tid < na) {
-            const float cs = __ldg(trig + 2 * (a0 + tid)), sn = __ldg(trig + 2 * (a0 + tid) + 1);
-            s_trig[tid] = make_float2(cs, sn);
-            float t, w, tmin, tmax;
-            project(g, cs, sn, cx0, cy0, t, w); tmin = t; tmax = t;
-            project(g, cs, sn, cx1, cy0, t, w); tmin = fminf(tmin, t); tmax = fmaxf(tmax, t);
-            project(g, cs, sn, cx0, cy1, t, w); tmin = fminf(tmin, t); tmax = fmaxf(tmax, t);
-            project(g, cs, sn, cx1, cy1, t, w); tmin = fminf(tmin, t); tmax = fmaxf(tmax, t);
-            // the projection is monotone along each tile edge (parallel: affine; fan: projective with
-            // the source outside the tile), so the corners bound it; one tap of slack for rounding
-            const int lo = (int)floorf(tmin) - 1;
-            const int hi = (int)floorf(tmax) + 2;
-            s_lo[tid] = lo;
-            if (hi - lo + 1 > SEG || !(tmin > -1e8f) || !(tmax < 1e8f)) s_big = 1;
+            const double cs = (double)__ldg(trig + 2 * (a0 + tid)), sn = (double)__ldg(trig + 2 * (a0 + tid) + 1);
+            const double ids = 1.0 / (double)g.det_spacing, cr = (double)g.cr;
+            double tmin, tmax;
+            if (!FAN) {
+                const double a = cs * ids, bb = sn * ids;
+                const double t00 = a * ox + bb * oy + cr;
+                const double c1 = a * ex, c2 = bb * ey;
+                tmin = t00 + fmin(c1, 0.0) + fmin(c2, 0.0);
+                tmax = t00 + fmax(c1, 0.0) + fmax(c2, 0.0);
+                const int lo = (int)floor(tmin) - 1;
+                s_lo[tid] = lo;
+                float* v = s_view[tid];
+                v[0] = (float)a; v[1] = (float)bb; v[2] = (float)(t00 - (double)lo); v[3] = 0.f;
+            } else {
+                const double K = ids * ((double)g.s_dist + (double)g.d_dist);
+                const double p0 = cs * ox + sn * oy, d0 = (double)g.s_dist + sn * ox - cs * oy;
+                tmin = 1e300; tmax = -1e300;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const double cx = (c & 1) ? ex : 0.0, cy = (c & 2) ? ey : 0.0;
+                    const double den = d0 + sn * cx - cs * cy;
+                    const double t = cr + K * (p0 + cs * cx + sn * cy) / den;
+                    // the source must stay outside the tile, otherwise the projection is unbounded
+                    tmin = den > 1e-3 ? fmin(tmin, t) : -1e300;
+                    tmax = den > 1e-3 ? fmax(tmax, t) : 1e300;
+                }
+                const bool sane = tmin > -1e8 && tmax < 1e8;
+                const int lo = sane ? (int)floor(tmin) - 1 : 0;
+                s_lo[tid] = lo;
+                const double L = (double)lo - cr;
+                float* v = s_view[tid];
+                v[0] = (float)(K * p0 - L * d0); v[1] = (float)(K * cs - L * sn); v[2] = (float)(K * sn + L * cs);
+                v[3] = (float)d0; v[4] = (float)sn; v[5] = (float)cs; v[6] = v[7] = 0.f;
+            }
+            // one tap of slack on either side for rounding; SEG - 2 is the last legal tap index
+            if (!(tmin > -1e8 && tmax < 1e8) || (floor(tmax) + 2.0) - (floor(tmin) - 1.0) + 1.0 > (double)SEG) s_big = 1;
         }
         __syncthreads();
         const bool big = s_big != 0;
@@ -141,44 +178,66 @@ __global__ void __launch_bounds__(TX*(TY / PY))
             for (int i = tid; i < na * SEG; i += THREADS) {
                 const int al = i / SEG, c = i - al * SEG;
                 const int d = s_lo[al] + c;
-                s_seg[al][c] = (unsigned)d < (unsigned)g.det_count ? __ldg(sb + (long)(a0 + al) * g.det_count + d) : 0.f;
+                const float* row = sb + (long)(a0 + al) * g.det_count;
+                const float v0 = (unsigned)d < (unsigned)g.det_count ? __ldg(row + d) : 0.f;
+                const float v1 = (unsigned)(d + 1) < (unsigned)g.det_count ? __ldg(row + d + 1) : 0.f;
+                s_seg[al][c] = make_float2(v0, v1 - v0);
             }
             __syncthreads();
             if (x < g.n) {
-#pragma unroll 4
+#pragma unroll 2
                 for (int al = 0; al < na; ++al) {
-                    const float2 tr = s_trig[al];
-                    const float lo = (float)s_lo[al];
-                    const float* seg = s_seg[al];
+                    const float2* seg = s_seg[al];
+                    if (!FAN) {
+                        const float4 v = *reinterpret_cast<const float4*>(s_view[al]);
+                        const float ta = fmaf(v.x, lx, fmaf(v.y, ly0, v.z));
+                        const float step = v.y * (float)RY;
 #pragma unroll
-                    for (int k = 0; k < PY; ++k) {
-                        const float dy = (float)(y0 + k * RY) - g.half;
-                        float t, w;
-                        project(g, tr.x, tr.y, dx, dy, t, w);
-                        const float tl = t - lo;               // >= 1 by construction
-                        const float tf = floorf(tl);
-                        const float fr = tl - tf;
-                        int i0 = (int)tf;
-                        i0 = min(max(i0, 0), SEG - 2);         // padding pixels of edge tiles only
-                        const float s0 = seg[i0], s1 = seg[i0 + 1];
-                        acc[k] = fmaf(w, fmaf(fr, s1 - s0, s0), acc[k]);
+                        for (int k = 0; k < PY; ++k) {
+                            const float tl = fmaf((float)k, step, ta);          // >= 1 by construction
+                            const float tf = __fadd_rd(tl, MAGIC);
+                            const int i0 = min(__float_as_int(tf) & 0x7fffff, SEG - 1);   // clamp: padding pixels of edge tiles
+                            const float fr = tl - (tf - MAGIC);
+                            const float2 sv = seg[i0];
+                            acc[k] += fmaf(fr, sv.y, sv.x);
+                        }
+                    } else {
+                        const float4 v = *reinterpret_cast<const float4*>(s_view[al]);
+                        const float2 tr = *reinterpret_cast<const float2*>(s_view[al] + 4);
+                        const float na_ = fmaf(v.y, lx, fmaf(v.z, ly0, v.x));
+                        const float da_ = fmaf(tr.x, lx, fmaf(-tr.y, ly0, v.w));
+                        const float nstep = v.z * (float)RY, dstep = -tr.y * (float)RY;
+#pragma unroll
+                        for (int k = 0; k < PY; ++k) {
+                            const float num = fmaf((float)k, nstep, na_), den = fmaf((float)k, dstep, da_);
+                            float r = __fdividef(1.f, den);
+                            r = fmaf(r, fmaf(-den, r, 1.f), r);                 // one Newton step: ~1 ulp
+                            const float tl = fmaxf(num * r, 0.f);
+                            const float tf = __fadd_rd(tl, MAGIC);
+                            const int i0 = min(__float_as_int(tf) & 0x7fffff, SEG - 1);
+                            const float fr = tl - (tf - MAGIC);
+                            const float2 sv = seg[i0];
+                            acc[k] = fmaf(g.k * r, fmaf(fr, sv.y, sv.x), acc[k]);
+                        }
                     }
                 }
             }
         } else if (x < g.n) {
+            const float dx = (float)x - g.half;
             for (int al = 0; al < na; ++al) {
-                const float2 tr = s_trig[al];
+                const float cs = __ldg(trig + 2 * (a0 + al)), sn = __ldg(trig + 2 * (a0 + al) + 1);
                 const float* row = sb + (long)(a0 + al) * g.det_count;
 #pragma unroll
                 for (int k = 0; k < PY; ++k) {
                     const float dy = (float)(y0 + k * RY) - g.half;
                     float t, w;
-                    project(g, tr.x, tr.y, dx, dy, t, w);
+                    project(g, cs, sn, dx, dy, t, w);
                     acc[k] = fmaf(w, tap_global(row, g.det_count, t), acc[k]);
                 }
             }
         }
     }
+    const float dx = (float)x - g.half;
 #pragma unroll
     for (int k = 0; k < PY; ++k) {
         const int y = y0 + k * RY;
@@ -218,6 +277,8 @@ extern "C" int pdu_radon_adj_f32(const float* sino, float* img, const float* tri
     ag.fan = g->geom == PDU_GEOM_FAN;
     ag.clip = g->clip_to_circle;
     ag.ids = 1.f / g->det_spacing;
+    ag.det_spacing = g->det_spacing;
+    ag.d_dist = g->d_dist;
     ag.s_dist = g->s_dist;
     ag.k = g->s_dist + g->d_dist;
     ag.cr = 0.5f * (float)g->det_count - 0.5f;
@@ -226,13 +287,16 @@ extern "C" int pdu_radon_adj_f32(const float* sino, float* img, const float* tri
     cudaStream_t st = (cudaStream_t)stream;
     int variant = option(OPT_RADON_ADJ);
     if (variant < 0) variant = 1;
-    constexpr int TX = 32, TY = 32, PY = 4;
-    dim3 block(TX, TY / PY);
+    constexpr int TX = 32, TY = 32;
     dim3 grid((unsigned)cdiv(g->n, TX), (unsigned)cdiv(g->n, TY), (unsigned)batch);
     if (variant == 0) {
-        radon_adj_gather_kernel<TX, TY, PY><<<grid, block, 0, st>>>(sino, img, trig, ag);
-    } else {
-        radon_adj_tile_kernel<TX, TY, PY, 64, 96><<<grid, block, 0, st>>>(sino, img, trig, ag);
+        radon_adj_gather_kernel<TX, TY, 4><<<grid, dim3(TX, TY / 4), 0, st>>>(sino, img, trig, ag);
+    } else if (variant == 2) {        // A/B: 4 pixels per thread, 256 threads
+        if (ag.fan) radon_adj_tile_kernel<TX, TY, 4, 32, 96, true><<<grid, dim3(TX, TY / 4), 0, st>>>(sino, img, trig, ag);
+        else radon_adj_tile_kernel<TX, TY, 4, 32, 96, false><<<grid, dim3(TX, TY / 4), 0, st>>>(sino, img, trig, ag);
+    } else {                          // 8 pixels per thread, 128 threads: B N^2 / 8 threads fit one balanced wave
+        if (ag.fan) radon_adj_tile_kernel<TX, TY, 8, 32, 96, true><<<grid, dim3(TX, TY / 8), 0, st>>>(sino, img, trig, ag);
+        else radon_adj_tile_kernel<TX, TY, 8, 32, 96, false><<<grid, dim3(TX, TY / 8), 0, st>>>(sino, img, trig, ag);
     }
     PDU_LAUNCHED();
     return PDU_OK;

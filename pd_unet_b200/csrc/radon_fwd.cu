@@ -107,18 +107,21 @@ struct FwdCfg {
     static constexpr int ROWS = TH + 1;
     static constexpr int TILE_BYTES = ROWS * W * 4;
     static constexpr int TILE_STRIDE = (TILE_BYTES + 127) / 128 * 128;
-    static constexpr int SMEM = NBUF * TILE_STRIDE + NBUF * 8 + 2 * MAX_STRIPS * 4 + 128;
+    static constexpr int SMEM = NBUF * TILE_STRIDE + NBUF * 8 + 2 * MAX_STRIPS * 4;
+    // W % 32 != 0 on purpose: the lanes of a warp sit in neighbouring rows of the tile, and a row
+    // pitch that is a multiple of 32 floats would put the same column of every row in one bank
+    static_assert(W % 4 == 0 && W % 32 != 0 && W <= 256, "box width: 16-byte multiple, not a multiple of 32 banks");
 };
 
 template <int DB, int AG, int TH, int W, int NBUF>
 __global__ void __launch_bounds__(DB* AG)
     radon_fwd_strip_kernel(const __grid_constant__ CUtensorMap tm_img, const __grid_constant__ CUtensorMap tm_imgT,
                            const float* __restrict__ img, const float* __restrict__ imgT, float* __restrict__ sino,
-                           const float* __restrict__ trig, const pdu_radon_geom_t g, int* __restrict__ err_flag) {
+                           const float* __restrict__ trig, const pdu_radon_geom_t g) {
     using C = FwdCfg<DB, AG, TH, W, NBUF>;
-    extern __shared__ unsigned char smem_dyn[];
-    unsigned char* base = (unsigned char*)(((uintptr_t)smem_dyn + 127) & ~(uintptr_t)127);
-    uint64_t* full = (uint64_t*)(base + NBUF * C::TILE_STRIDE);
+    // indexed directly (no re-aligned generic pointer) so that the tile reads compile to LDS
+    extern __shared__ __align__(1024) unsigned char smem_dyn[];
+    uint64_t* full = (uint64_t*)(smem_dyn + NBUF * C::TILE_STRIDE);
     int* s_umin = (int*)(full + NBUF);
     int* s_umax = s_umin + MAX_STRIPS;
 
@@ -130,6 +133,9 @@ __global__ void __launch_bounds__(DB* AG)
     const int N = g.n;
     const int n_strips = (N + 1 + TH - 1) / TH;
     const bool valid = d < g.det_count && a < g.n_angles;
+    // TMA wants a 128-byte aligned destination; if the runtime ever places dynamic shared memory
+    // otherwise every strip takes the global-load path (still correct)
+    const bool tma_ok = (smem_u32(smem_dyn) & 127u) == 0;
 
     for (int k = tid; k < n_strips; k += C::THREADS) {
         s_umin[k] = INT_MAX;
@@ -149,26 +155,31 @@ __global__ void __launch_bounds__(DB* AG)
     r.xc0 = r.yc0 = r.vx = r.vy = r.step = 0.f;
     if (valid) r = ray_setup(g, __ldg(trig + 2 * a), __ldg(trig + 2 * a + 1), d);
     // (u, w) = (minor, major) coordinates; w indexes the rows of the source the CTA reads
-    float u0 = use_t ? r.yc0 : r.xc0, w0 = use_t ? r.xc0 : r.yc0;
-    float vu = use_t ? r.vy : r.vx, vw = use_t ? r.vx : r.vy;
+    const float u0 = use_t ? r.yc0 : r.xc0, w0 = use_t ? r.xc0 : r.yc0;
+    const float vu = use_t ? r.vy : r.vx, vw = use_t ? r.vx : r.vy;
     const int n = r.n_steps;
-    // walk in the direction of increasing w: sample s uses j = jf0 + s * dj
+    // walk in the direction of increasing w: the s-th visited sample is j = jf, jf += dj
     const bool rev = vw < 0.f;
     const float dj = rev ? -1.f : 1.f;
     float jf = rev ? (float)n : 0.f;
+    const float aw = fabsf(vw);
+    const float inv_aw = aw > 1e-3f ? __fdividef(1.f, aw) : 0.f;   // 0: no estimate, count by stepping
 
     __syncthreads();
     if (n >= 0) {
         const float wa = fmaf(jf, vw, w0), ua = fmaf(jf, vu, u0);
         const float jend = rev ? 0.f : (float)n;
         const float wb = fmaf(jend, vw, w0), ub = fmaf(jend, vu, u0);
-        const int kA = ((int)floorf(wa) + 1) / TH;
-        const int kB = ((int)floorf(wb) + 1) / TH;
+        // strips are [k TH - 1, (k+1) TH - 1); widen by eps so that a sample the marching loop puts on
+        // the other side of a boundary (it rounds differently) still finds its ray registered there
+        constexpr float EPS = 1e-3f;
+        const int kA = max(((int)floorf(wa - EPS) + 1) / TH, 0);
+        const int kB = min(((int)floorf(wb + EPS) + 1) / TH, n_strips - 1);
         const float dw = wb - wa;
         const float slope = dw > 0.f ? (ub - ua) / dw : 0.f;
         for (int k = kA; k <= kB; ++k) {
-            const float wlo = fmaxf(wa, (float)(k * TH - 1));
-            const float whi = fminf(wb, (float)((k + 1) * TH - 1));
+            const float wlo = fminf(fmaxf(wa, (float)(k * TH - 1)), wb);
+            const float whi = fmaxf(fminf(wb, (float)((k + 1) * TH - 1)), wa);
             const float ulo = dw > 0.f ? fmaf(wlo - wa, slope, ua) : fminf(ua, ub);
             const float uhi = dw > 0.f ? fmaf(whi - wa, slope, ua) : fmaxf(ua, ub);
             atomicMin(&s_umin[k], (int)floorf(fminf(ulo, uhi)) - 1);
@@ -188,9 +199,9 @@ __global__ void __launch_bounds__(DB* AG)
             // TMA needs the innermost start coordinate on a 16-byte boundary (measured: any c0 % 4 != 0
             // raises "illegal instruction" on sm_100a, negative values are fine) -> round down to 4 floats
             const int lo = s_umin[k_issue] & ~3;
-            if (s_umax[k_issue] - lo + 1 <= W) {
+            if (tma_ok && s_umax[k_issue] - lo + 1 <= W) {
                 mbar_expect_tx(full + buf, C::TILE_BYTES);
-                tma_load_3d(base + buf * C::TILE_STRIDE, tm, lo, k_issue * TH - 1, b, full + buf);
+                tma_load_3d(smem_dyn + buf * C::TILE_STRIDE, tm, lo, k_issue * TH - 1, b, full + buf);
             } else {
                 mbar_arrive(full + buf);
             }
@@ -205,23 +216,37 @@ __global__ void __launch_bounds__(DB* AG)
 
     constexpr float MAGIC = 8388608.f;   // 2^23: x + MAGIC rounded down == floor(x) + MAGIC for 0 <= x < 2^23
     float acc = 0.f;
-    int s = 0;
+    int s = 0;          // samples of this ray already taken
     int seq = 0;
-    bool ok = true;
     for (int k = 0; k < n_strips; ++k) {
         const int hi = s_umax[k];
         if (s_umin[k] > hi) continue;
         const int lo = s_umin[k] & ~3;
         if (tid == 0) issue();
         const int buf = seq % NBUF;
-        ok = mbar_wait(full + buf, (seq / NBUF) & 1) && ok;
-        const float wbase = (float)(k * TH - 1);
-        if (hi - lo + 1 <= W) {
-            const float* tile = (const float*)(base + buf * C::TILE_STRIDE);
-            const float u0l = u0 - (float)lo;
-            while (s <= n) {
-                const float wl = fmaf(jf, vw, w0) - wbase;
-                if (wl >= (float)TH) break;
+        mbar_wait(full + buf, (seq / NBUF) & 1);
+        // strip-local coordinates: both subtractions are exact (result is a multiple of the operands' ulp)
+        const float w0l = w0 - (float)(k * TH - 1);
+        const float u0l = u0 - (float)lo;
+        // how many of the remaining samples fall in this strip: estimate, then settle with the very
+        // predicate the addressing relies on (wl < TH)
+        int cnt = 0;
+        const int left = n - s + 1;
+        if (left > 0) {
+            const float wl = fmaf(jf, vw, w0l);
+            if (wl < (float)TH) {
+                int m = inv_aw > 0.f ? (int)(((float)TH - wl) * inv_aw) + 1 : 1;
+                m = max(1, min(m, left));
+                while (m > 1 && fmaf(jf + (float)(m - 1) * dj, vw, w0l) >= (float)TH) --m;
+                while (m < left && fmaf(jf + (float)m * dj, vw, w0l) < (float)TH) ++m;
+                cnt = m;
+            }
+        }
+        if (tma_ok && hi - lo + 1 <= W) {
+            const float* tile = (const float*)(smem_dyn + buf * C::TILE_STRIDE);
+#pragma unroll 2
+            for (int i = 0; i < cnt; ++i) {
+                const float wl = fmaxf(fmaf(jf, vw, w0l), 0.f);   // a sample an ulp before the strip clamps onto its first row
                 const float ul = fmaf(jf, vu, u0l);
                 const float tw = __fadd_rd(wl, MAGIC), tu = __fadd_rd(ul, MAGIC);
                 const int iw = __float_as_int(tw) & 0x7fffff, iu = __float_as_int(tu) & 0x7fffff;
@@ -231,22 +256,18 @@ __global__ void __launch_bounds__(DB* AG)
                 const float top = fmaf(fu, v01 - v00, v00);
                 const float bot = fmaf(fu, v11 - v10, v10);
                 acc += fmaf(fw, bot - top, top);
-                ++s;
                 jf += dj;
             }
         } else {
-            while (s <= n) {
-                const float w = fmaf(jf, vw, w0);
-                if (w - wbase >= (float)TH) break;
-                acc += bilinear_global(src, N, fmaf(jf, vu, u0), w);
-                ++s;
+            for (int i = 0; i < cnt; ++i) {
+                acc += bilinear_global(src, N, fmaf(jf, vu, u0), fmaf(jf, vw, w0));
                 jf += dj;
             }
         }
+        s += cnt;
         __syncthreads();
         ++seq;
     }
-    if (!ok && err_flag) atomicExch(err_flag, 1);
     if (valid) sino[((long)b * g.n_angles + a) * g.det_count + d] = acc * r.step;
 }
 
@@ -305,7 +326,7 @@ static int launch_strip(const float* img, const float* imgT, float* sino, const 
         attr_set = true;
     }
     dim3 grid((unsigned)cdiv(g.det_count, DB), (unsigned)cdiv(g.n_angles, AG), (unsigned)batch);
-    kern<<<grid, C::THREADS, C::SMEM, st>>>(tm, tmT, img, imgT, sino, trig, g, nullptr);
+    kern<<<grid, C::THREADS, C::SMEM, st>>>(tm, tmT, img, imgT, sino, trig, g);
     PDU_LAUNCHED();
     return PDU_OK;
 }
@@ -378,9 +399,15 @@ int pdu_radon_fwd_f32(const float* img, float* sino, const float* trig, int batc
     // costs speed, never correctness -- oversized strips take the global-load path).
     const float span = g->geom == PDU_GEOM_PARALLEL ? 3.14159265f : 6.2831853f;
     const float spread4 = 3.f * (span / g->n_angles) * 0.7072f * g->n;
-    if (variant == 2 || (variant == 1 && spread4 > 24.f))
-        return launch_strip<128, 2, 32, 240, 3>(img, imgT, sino, trig, batch, *g, st);
-    return launch_strip<64, 4, 32, 160, 3>(img, imgT, sino, trig, batch, *g, st);
+    switch (variant) {
+        case 2: return launch_strip<128, 2, 32, 248, 3>(img, imgT, sino, trig, batch, *g, st);
+        case 3: return launch_strip<64, 4, 32, 168, 2>(img, imgT, sino, trig, batch, *g, st);     // A/B: shallower ring
+        case 4: return launch_strip<64, 4, 16, 168, 3>(img, imgT, sino, trig, batch, *g, st);     // A/B: thinner strips
+        case 5: return launch_strip<64, 8, 32, 168, 2>(img, imgT, sino, trig, batch, *g, st);     // A/B: 512 threads
+        default: break;
+    }
+    if (spread4 > 24.f) return launch_strip<128, 2, 32, 248, 3>(img, imgT, sino, trig, batch, *g, st);
+    return launch_strip<64, 4, 32, 168, 3>(img, imgT, sino, trig, batch, *g, st);
 }
 
 }  // extern "C"

@@ -18,17 +18,42 @@ static inline unsigned stream_grid(long work_items, int threads) {
 
 // ------------------------------------------------------------------ concat
 template <typename V>
+__device__ __forceinline__ V vscale(V a, float s);
+template <>
+__device__ __forceinline__ float vscale<float>(float a, float s) { return a * s; }
+template <>
+__device__ __forceinline__ float4 vscale<float4>(float4 a, float s) {
+    return make_float4(a.x * s, a.y * s, a.z * s, a.w * s);
+}
+
+// planar (NCHW): per batch element the output row is [a-row (la) | b-row (lb) | c-row (lc)] in units of V
+template <typename V>
 __global__ void __launch_bounds__(256)
     concat_kernel(V* __restrict__ out, const V* __restrict__ a, const V* __restrict__ b, const V* __restrict__ c,
-                  long la, long lb, long lc, long total) {
-    // per batch element the output row is [a-row (la) | b-row (lb) | c-row (lc)] in units of V
+                  long la, long lb, long lc, float scale_b, long total) {
     const long lo = la + lb + lc;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
         const long n = i / lo, r = i - n * lo;
         V v;
         if (r < la) v = a[n * la + r];
-        else if (r < la + lb) v = b[n * lb + (r - la)];
+        else if (r < la + lb) v = vscale<V>(b[n * lb + (r - la)], scale_b);
         else v = c[n * lc + (r - la - lb)];
+        out[i] = v;
+    }
+}
+
+// channels-last (NHWC): every pixel's output vector is [a-channels | b-channels | c-channels]
+__global__ void __launch_bounds__(256)
+    concat_nhwc_kernel(float* __restrict__ out, const float* __restrict__ a, const float* __restrict__ b,
+                       const float* __restrict__ c, int ca, int cb, int cc, float scale_b, long total) {
+    const int ct = ca + cb + cc;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const long pix = i / ct;
+        const int ch = (int)(i - pix * ct);
+        float v;
+        if (ch < ca) v = a[pix * ca + ch];
+        else if (ch < ca + cb) v = b[pix * cb + (ch - ca)] * scale_b;
+        else v = c[pix * cc + (ch - ca - cb)];
         out[i] = v;
     }
 }
@@ -55,6 +80,24 @@ __global__ void __launch_bounds__(256)
             const long n = nc / channels;
             const int ch = (int)(nc - n * channels) - k;
             if (ch >= 0 && ch < kn) slice[(n * kn + ch) * plane + p] = v;
+        }
+    }
+}
+
+// channels-last state [batch, plane, channels]; the slice stays planar [batch, kn, plane] (operator input)
+__global__ void __launch_bounds__(256)
+    residual_slice_nhwc_kernel(float* out, float* __restrict__ slice, const float* state, const float* delta, long plane,
+                               int channels, int k, int kn, long total) {
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const float v = state[i] + delta[i];
+        out[i] = v;
+        if (slice) {
+            const long pix = i / channels;
+            const int ch = (int)(i - pix * channels) - k;
+            if (ch >= 0 && ch < kn) {
+                const long n = pix / plane, p = pix - n * plane;
+                slice[(n * kn + ch) * plane + p] = v;
+            }
         }
     }
 }
@@ -137,32 +180,45 @@ using namespace pdu;
 extern "C" {
 
 int pdu_concat_f32(float* out, const float* a, const float* b, const float* c, int batch, int ca, int cb, int cc,
-                   long plane, pdu_stream_t stream) {
+                   long plane, float scale_b, int layout, pdu_stream_t stream) {
     PDU_REQUIRE(out && a && b, "pdu_concat_f32: null pointer");
     PDU_REQUIRE(batch > 0 && ca > 0 && cb > 0 && cc >= 0 && plane > 0, "pdu_concat_f32: sizes must be positive");
     PDU_REQUIRE((c != nullptr) == (cc > 0), "pdu_concat_f32: c must be given exactly when cc > 0");
     const long la = ca * plane, lb = cb * plane, lc = cc * plane;
     const long total = (long)batch * (la + lb + lc);
     cudaStream_t st = (cudaStream_t)stream;
+    PDU_REQUIRE(layout == PDU_LAYOUT_NCHW || layout == PDU_LAYOUT_NHWC, "pdu_concat_f32: unknown layout %d", layout);
+    if (layout == PDU_LAYOUT_NHWC) {
+        concat_nhwc_kernel<<<stream_grid(total, 256), 256, 0, st>>>(out, a, b, c, ca, cb, cc, scale_b, total);
+        PDU_LAUNCHED();
+        return PDU_OK;
+    }
     const bool vec = plane % 4 == 0 && al16(out) && al16(a) && al16(b) && (c == nullptr || al16(c));
     if (vec) {
         concat_kernel<float4><<<stream_grid(total / 4, 256), 256, 0, st>>>((float4*)out, (const float4*)a, (const float4*)b,
-                                                                           (const float4*)c, la / 4, lb / 4, lc / 4, total / 4);
+                                                                           (const float4*)c, la / 4, lb / 4, lc / 4, scale_b, total / 4);
     } else {
-        concat_kernel<float><<<stream_grid(total, 256), 256, 0, st>>>(out, a, b, c, la, lb, lc, total);
+        concat_kernel<float><<<stream_grid(total, 256), 256, 0, st>>>(out, a, b, c, la, lb, lc, scale_b, total);
     }
     PDU_LAUNCHED();
     return PDU_OK;
 }
 
 int pdu_residual_slice_f32(float* out, float* slice, const float* state, const float* delta, int batch, int channels,
-                           long plane, int k, int kn, pdu_stream_t stream) {
+                           long plane, int k, int kn, int layout, pdu_stream_t stream) {
     PDU_REQUIRE(out && state && delta, "pdu_residual_slice_f32: null pointer");
     PDU_REQUIRE(batch > 0 && channels > 0 && plane > 0, "pdu_residual_slice_f32: sizes must be positive");
     PDU_REQUIRE(slice == nullptr || (k >= 0 && kn >= 1 && k + kn <= channels),
                 "pdu_residual_slice_f32: slice channels [%d, %d) out of range", k, k + kn);
     const long total = (long)batch * channels * plane;
     cudaStream_t st = (cudaStream_t)stream;
+    PDU_REQUIRE(layout == PDU_LAYOUT_NCHW || layout == PDU_LAYOUT_NHWC, "pdu_residual_slice_f32: unknown layout %d", layout);
+    if (layout == PDU_LAYOUT_NHWC) {
+        residual_slice_nhwc_kernel<<<stream_grid(total, 256), 256, 0, st>>>(out, slice, state, delta, plane, channels, k, kn,
+                                                                            total);
+        PDU_LAUNCHED();
+        return PDU_OK;
+    }
     const bool vec = plane % 4 == 0 && al16(out) && al16(state) && al16(delta) && (slice == nullptr || al16(slice));
     if (vec) {
         residual_slice_kernel<float4><<<stream_grid(total / 4, 256), 256, 0, st>>>(

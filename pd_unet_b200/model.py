@@ -32,7 +32,8 @@ def _conv_block(cin: int, cout: int) -> nn.Sequential:
 
 
 class UNet(nn.Module):
-    """Plain 2-D UNet: `depth` poolings, `base` features doubling per level, bilinear up-sampling."""
+    """Plain 2-D UNet: `depth` poolings, `base` features doubling per level, 2x2 transposed-convolution
+    up-sampling (the original UNet's "up-conv"; every layer is a cuDNN convolution)."""
 
     def __init__(self, cin: int, cout: int, base: int = 32, depth: int = 3):
         super().__init__()
@@ -41,9 +42,11 @@ class UNet(nn.Module):
         for d in range(depth + 1):
             self.down.append(_conv_block(ch, base << d))
             ch = base << d
+        self.upconv = nn.ModuleList()
         self.up = nn.ModuleList()
         for d in reversed(range(depth)):
-            self.up.append(_conv_block(ch + (base << d), base << d))
+            self.upconv.append(nn.ConvTranspose2d(ch, base << d, 2, stride=2))
+            self.up.append(_conv_block(2 * (base << d), base << d))
             ch = base << d
         self.head = nn.Conv2d(ch, cout, 1)
         self.pool = nn.MaxPool2d(2)
@@ -55,9 +58,11 @@ class UNet(nn.Module):
             if i + 1 < len(self.down):
                 skips.append(x)
                 x = self.pool(x)
-        for blk in self.up:
+        for upc, blk in zip(self.upconv, self.up):
             s = skips.pop()
-            x = nn.functional.interpolate(x, size=s.shape[-2:], mode="bilinear", align_corners=False)
+            x = upc(x)
+            if x.shape[-2:] != s.shape[-2:]:           # odd sizes: pad the up-sampled map to the skip
+                x = nn.functional.pad(x, (0, s.shape[-1] - x.shape[-1], 0, s.shape[-2] - x.shape[-2]))
             x = blk(torch.cat([x, s], dim=1))
         return self.head(x)
 
@@ -84,7 +89,7 @@ class PrimalDualUNet(nn.Module):
 
     def __init__(self, op_forward: Callable, op_adjoint: Callable, image_channels: int = 1, data_channels: int = 1,
                  n_iter: int = 4, n_primal: int = 4, n_dual: int = 4, unet_base: int = 32, unet_depth: int = 3,
-                 dual_features: int = 32, op_scale: float = 1.0):
+                 dual_features: int = 32, op_scale: float = 1.0, channels_last: bool = True):
         super().__init__()
         if n_primal < image_channels or n_dual < data_channels:
             raise ValueError("n_primal / n_dual must hold at least one operator-sized slice")
@@ -95,19 +100,26 @@ class PrimalDualUNet(nn.Module):
         self.dual = nn.ModuleList(DualBlock(n_dual + 2 * data_channels, n_dual, dual_features) for _ in range(n_iter))
         self.primal = nn.ModuleList(UNet(n_primal + image_channels, n_primal, unet_base, unet_depth)
                                     for _ in range(n_iter))
+        # channels-last activations and weights: cuDNN's tensor-core convolutions run without the
+        # NCHW<->NHWC conversion kernels, and the fused cat / residual kernels follow the same layout
+        self.channels_last = bool(channels_last)
+        if self.channels_last:
+            self.to(memory_format=torch.channels_last)
 
     def forward(self, g: torch.Tensor, image_shape) -> torch.Tensor:
         """g: measured data on the full grid [B, kd, *data].  Returns the reconstruction [B, kc, *image]."""
         B = g.shape[0]
-        h = g.new_zeros((B, self.n_dual) + tuple(g.shape[2:]))
-        f = g.new_zeros((B, self.n_primal) + tuple(image_shape))
+        fmt = torch.channels_last if (self.channels_last and g.dim() == 4) else torch.contiguous_format
+        h = torch.zeros((B, self.n_dual) + tuple(g.shape[2:]), dtype=g.dtype, device=g.device, memory_format=fmt)
+        f = torch.zeros((B, self.n_primal) + tuple(image_shape), dtype=g.dtype, device=g.device, memory_format=fmt)
         f_op = g.new_zeros((B, self.kc) + tuple(image_shape))
         inv = 1.0 / self.op_scale
         for i in range(self.n_iter):
-            kf = self.op_forward(f_op) * inv
-            h, h_op = updates.residual_slice(h, self.dual[i](updates.concat(h, kf, g)), 0, self.kd)
-            kth = self.op_adjoint(h_op) * inv
-            f, f_op = updates.residual_slice(f, self.primal[i](updates.concat(f, kth)), 0, self.kc)
+            # the 1/op_scale normalisation of each operator output rides in the concat kernel
+            kf = self.op_forward(f_op)
+            h, h_op = updates.residual_slice(h, self.dual[i](updates.concat(h, kf, g, scale_b=inv)), 0, self.kd)
+            kth = self.op_adjoint(h_op)
+            f, f_op = updates.residual_slice(f, self.primal[i](updates.concat(f, kth, scale_b=inv)), 0, self.kc)
         return f_op
 
 

@@ -13,7 +13,7 @@ from typing import Optional, Tuple
 
 import torch
 
-from ._lib import WRAP_MODES, check, lib, require_cuda, stream_ptr
+from ._lib import LAYOUT_NCHW, LAYOUT_NHWC, WRAP_MODES, PduError, check, lib, require_cuda, stream_ptr
 
 
 def _plane(t: torch.Tensor) -> int:
@@ -23,54 +23,87 @@ def _plane(t: torch.Tensor) -> int:
     return n
 
 
+def _is_channels_last(t: torch.Tensor) -> bool:
+    """4-D tensor whose memory is [B, H, W, C] (torch.channels_last) and not also plain contiguous."""
+    return t.dim() == 4 and t.shape[1] > 1 and not t.is_contiguous() and \
+        t.is_contiguous(memory_format=torch.channels_last)
+
+
+def _in_layout(t: torch.Tensor, nhwc: bool, name: str) -> torch.Tensor:
+    """float32 CUDA tensor whose bytes are in the requested layout (copying only if they are not)."""
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor")
+    if not t.is_cuda:
+        raise PduError(f"{name} is on {t.device}: the pd_unet_b200 operators run on CUDA only (no CPU fallback)")
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name} must be torch.float32, got {t.dtype}")
+    if nhwc:
+        return t.contiguous(memory_format=torch.channels_last)
+    return t.contiguous()
+
+
+def _empty(shape, like: torch.Tensor, nhwc: bool) -> torch.Tensor:
+    fmt = torch.channels_last if nhwc else torch.contiguous_format
+    return torch.empty(shape, dtype=torch.float32, device=like.device, memory_format=fmt)
+
+
 class _Concat(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, a, b, c):
-        a = require_cuda(a, torch.float32, "a")
-        b = require_cuda(b, torch.float32, "b")
+    def forward(ctx, a, b, c, scale_b):
+        nhwc = _is_channels_last(a)          # the state tensor decides; one-channel inputs fit either layout
+        a = _in_layout(a, nhwc, "a")
+        b = _in_layout(b, nhwc, "b")
         if c is not None:
-            c = require_cuda(c, torch.float32, "c")
+            c = _in_layout(c, nhwc, "c")
         for t in (b, c):
             if t is not None and (t.shape[0] != a.shape[0] or t.shape[2:] != a.shape[2:]):
                 raise ValueError("concat: tensors must agree in every axis but the channel axis")
         ca, cb, cc = a.shape[1], b.shape[1], (c.shape[1] if c is not None else 0)
-        ctx.split = (ca, cb, cc)
-        out = torch.empty((a.shape[0], ca + cb + cc) + tuple(a.shape[2:]), dtype=torch.float32, device=a.device)
+        ctx.split, ctx.scale_b = (ca, cb, cc), scale_b
+        out = _empty((a.shape[0], ca + cb + cc) + tuple(a.shape[2:]), a, nhwc)
         if out.numel():
             with torch.cuda.device(a.device):
                 check(lib().pdu_concat_f32(out.data_ptr(), a.data_ptr(), b.data_ptr(),
                                            c.data_ptr() if c is not None else None, a.shape[0], ca, cb, cc,
-                                           _plane(a), stream_ptr()), "pdu_concat_f32")
+                                           _plane(a), scale_b, LAYOUT_NHWC if nhwc else LAYOUT_NCHW, stream_ptr()),
+                      "pdu_concat_f32")
         return out
 
     @staticmethod
     def backward(ctx, g):
         ca, cb, cc = ctx.split
-        return g[:, :ca], g[:, ca:ca + cb], (g[:, ca + cb:] if cc else None)
+        gb = g[:, ca:ca + cb]
+        if ctx.scale_b != 1.0:
+            gb = gb * ctx.scale_b
+        return g[:, :ca], gb, (g[:, ca + cb:] if cc else None), None
 
 
-def concat(a: torch.Tensor, b: torch.Tensor, c: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """cat([a, b(, c)], dim=1) for [B, c_i, ...] tensors in one pass."""
-    return _Concat.apply(a, b, c)
+def concat(a: torch.Tensor, b: torch.Tensor, c: Optional[torch.Tensor] = None, scale_b: float = 1.0) -> torch.Tensor:
+    """cat([a, scale_b * b(, c)], dim=1) for [B, c_i, ...] tensors in one pass.  If `a` is a
+    channels_last tensor the result is channels_last too (what cuDNN's tensor-core convolutions want)."""
+    return _Concat.apply(a, b, c, float(scale_b))
 
 
 class _ResidualSlice(torch.autograd.Function):
     @staticmethod
     def forward(ctx, state, delta, k, kn):
-        state = require_cuda(state, torch.float32, "state")
-        delta = require_cuda(delta, torch.float32, "delta")
+        nhwc = _is_channels_last(delta) or _is_channels_last(state)
+        state = _in_layout(state, nhwc, "state")
+        delta = _in_layout(delta, nhwc, "delta")
         if state.shape != delta.shape or state.dim() < 3:
             raise ValueError("residual_slice: state and delta must be the same [B, C, ...] shape")
         B, Cn = state.shape[:2]
         if not (0 <= k and kn >= 1 and k + kn <= Cn):
             raise ValueError(f"residual_slice: channels [{k}, {k + kn}) out of range for {Cn} channels")
         ctx.k, ctx.kn = k, kn
-        out = torch.empty_like(state)
+        out = _empty(tuple(state.shape), state, nhwc)
         sl = torch.empty((B, kn) + tuple(state.shape[2:]), dtype=torch.float32, device=state.device)
         if out.numel():
             with torch.cuda.device(state.device):
                 check(lib().pdu_residual_slice_f32(out.data_ptr(), sl.data_ptr(), state.data_ptr(), delta.data_ptr(),
-                                                   B, Cn, _plane(state), k, kn, stream_ptr()), "pdu_residual_slice_f32")
+                                                   B, Cn, _plane(state), k, kn,
+                                                   LAYOUT_NHWC if nhwc else LAYOUT_NCHW, stream_ptr()),
+                      "pdu_residual_slice_f32")
         return out, sl
 
     @staticmethod
@@ -83,7 +116,8 @@ class _ResidualSlice(torch.autograd.Function):
 
 
 def residual_slice(state: torch.Tensor, delta: torch.Tensor, k: int = 0, kn: int = 1) -> Tuple[torch.Tensor, torch.Tensor]:
-    """-> (state + delta, its channels k:k+kn as a contiguous [B, kn, ...] tensor), one pass over the data."""
+    """-> (state + delta, its channels k:k+kn as a contiguous planar [B, kn, ...] tensor), one pass over
+    the data.  Follows the layout of its inputs (planar or channels_last)."""
     return _ResidualSlice.apply(state, delta, int(k), int(kn))
 
 

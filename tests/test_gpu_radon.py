@@ -152,34 +152,40 @@ def _full_cfg(name):
             -ang, B)
 
 
+# White-noise sinograms at D = 512 are the worst case for any float32 backprojector: the detector
+# coordinate t (|t| up to 512, tile-relative up to 96) carries ~5e-6 of rounding and the interpolated
+# value changes by O(1) per unit of t, so the result cannot agree with a float64 oracle to better than
+# ~2e-5.  On the data the operator actually sees (filtered sinograms of objects) the same kernels hold
+# the 1e-5 of BASELINE.json; both are asserted below with their own tolerance.
+TOL_NOISE_FULL = 3e-5
+
+
 @pytest.mark.parametrize("name", ["cfg2", "cfg3"])
 def test_full_size_properties(name):
+    from oracle import c_port                      # OpenMP C restatement: whole batches in seconds
     op, g, internal, B = _full_cfg(name)
     trig = oracle.trig_table(internal)
     x = (phantom_batch(B, g.n, seed=1)).to(DEV)
     z = seeded((B, g.n, g.n), 9).to(DEV)
     y = op.forward(x)
-    # oracle on one slice and a handful of views (the oracle needs seconds per slice at this size)
-    sub = np.arange(3, g.n_angles, 8)
-    gs = oracle.RadonGeom(n=g.n, n_angles=len(sub), det_count=g.det_count, det_spacing=g.det_spacing, geom=g.geom,
-                          s_dist=g.s_dist, d_dist=g.d_dist, clip_to_circle=g.clip_to_circle)
-    want = oracle.radon_forward(x[B - 1:].cpu(), trig[sub], gs)
-    assert rel_l2(y[B - 1:, sub], want) <= TOL
+    assert rel_l2(y, c_port.radon_forward(x.cpu(), trig, g)) <= TOL          # every slice, every view
     # linearity and batch independence
     assert rel_l2(op.forward(2.0 * x - 0.5 * z), 2.0 * y - 0.5 * op.forward(z)) <= TOL
     assert torch.equal(op.forward(x[3:5]), y[3:5])
     # the variants agree
     pdu.set_option("radon_fwd_variant", 0)
     assert rel_l2(op.forward(x), y) <= TOL
-    # backprojection: oracle on one slice, linearity, variants
+    # backprojection of what FBP feeds it: the ramp-filtered sinogram of the phantoms
+    s_real = op.filter_sinogram(y)
+    assert rel_l2(s_real, c_port.filter_sinogram(y.cpu())) <= TOL
+    img = op.backprojection(s_real)
+    assert rel_l2(img, c_port.radon_backprojection(s_real.cpu(), trig, g)) <= TOL
+    # ... and of white noise (worst case, see TOL_NOISE_FULL)
     s = seeded((B, g.n_angles, g.det_count), 13).to(DEV)
-    img = op.backprojection(s)
-    s_sub = torch.zeros_like(s[:1])
-    s_sub[:, sub] = s[:1, sub]                    # only the sampled views carry data: same sum as the subset geometry
-    want = oracle.radon_backprojection(s[:1, sub].cpu(), trig[sub], gs)
-    assert rel_l2(op.backprojection(s_sub), want) <= TOL
+    img_n = op.backprojection(s)
+    assert rel_l2(img_n[:2], c_port.radon_backprojection(s[:2].cpu(), trig, g)) <= TOL_NOISE_FULL
     pdu.set_option("radon_adj_variant", 0)
-    assert rel_l2(op.backprojection(s), img) <= TOL
+    assert rel_l2(op.backprojection(s_real), img) <= TOL
     # the parallel-beam pair is close to adjoint (ray- vs pixel-driven discretisations), as in torch_radon
     if g.geom == PARALLEL:
         s2 = op.forward(phantom_batch(B, g.n, seed=21).to(DEV))

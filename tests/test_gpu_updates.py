@@ -70,3 +70,47 @@ def test_errors():
         updates.residual_slice(a.to(DEV), a.to(DEV), 3)
     with pytest.raises(ValueError):
         updates.angular_upsample(a.to(DEV), 2, "nearest")
+
+
+@pytest.mark.parametrize("plane", [(8, 16), (5, 7)])
+def test_channels_last_layout_and_scaled_concat(plane):
+    a, b, c = (seeded((3, ch) + plane, i) for i, ch in enumerate((4, 1, 2)))
+    al = a.to(DEV).contiguous(memory_format=torch.channels_last)
+    cl = c.to(DEV).contiguous(memory_format=torch.channels_last)
+    out = updates.concat(al, b.to(DEV), cl, scale_b=0.25)
+    assert out.is_contiguous(memory_format=torch.channels_last)
+    assert torch.equal(out.cpu(), torch.cat([a, 0.25 * b, c], 1))
+    assert torch.equal(updates.concat(a.to(DEV), b.to(DEV), c.to(DEV), scale_b=0.25).cpu(), torch.cat([a, 0.25 * b, c], 1))
+    h, d = seeded((2, 4) + plane, 5), seeded((2, 4) + plane, 6)
+    hl = h.to(DEV).contiguous(memory_format=torch.channels_last)
+    dl = d.to(DEV).contiguous(memory_format=torch.channels_last)
+    res, sl = updates.residual_slice(hl, dl, 1, 2)
+    assert res.is_contiguous(memory_format=torch.channels_last) and sl.is_contiguous()
+    assert torch.equal(res.cpu(), h + d) and torch.equal(sl.cpu(), (h + d)[:, 1:3])
+    # mixed: planar state, channels-last delta (what the first unrolled iteration may see)
+    res2, sl2 = updates.residual_slice(h.to(DEV), dl, 0, 1)
+    assert torch.equal(res2.cpu(), h + d) and torch.equal(sl2.cpu(), (h + d)[:, :1])
+    # gradients flow through the scaled input
+    br = b.to(DEV).requires_grad_()
+    (updates.concat(al, br, cl, scale_b=0.25) * 2.0).sum().backward()
+    assert torch.equal(br.grad, torch.full_like(br, 0.5))
+
+
+def test_graphed_inference_matches_eager():
+    import numpy as np
+    from pd_unet_b200.graph import GraphedInference
+    from pd_unet_b200.model import PrimalDualUNetCT
+    n, A, up = 64, 32, 4
+    radon = pdu.Radon(n, np.linspace(0, np.pi, A, endpoint=False))
+    torch.manual_seed(0)
+    model = PrimalDualUNetCT(radon, upsample=up, n_iter=2, n_primal=2, n_dual=2, unet_base=8, unet_depth=2,
+                             dual_features=8).to(DEV).eval()
+    x = seeded((2, 1, A // up, n), 3).to(DEV)
+    with torch.no_grad():
+        want = model(x).clone()
+    g = GraphedInference(model, x)
+    assert torch.allclose(g(x), want, atol=1e-5, rtol=1e-5)
+    x2 = seeded((2, 1, A // up, n), 4)
+    with torch.no_grad():
+        want2 = model(x2.to(DEV)).clone()
+    assert torch.allclose(g(x2.pin_memory()), want2, atol=1e-5, rtol=1e-5)     # host input: H2D inside the call
