@@ -164,6 +164,12 @@ PDU_API int pdu_concat_f32(float* out, const float* a, const float* b, const flo
 PDU_API int pdu_residual_slice_f32(float* out, float* slice, const float* state, const float* delta,
                                    int batch, int channels, long plane, int k, int kn, int layout,
                                    pdu_stream_t stream);
+/* y <- prelu(y + bias[c], slope[c]) in place: the bias add and activation that follow a cuDNN
+ * convolution, as one pass instead of ATen's two.  y [batch, channels, plane] in `layout`; bias
+ * [channels]; slope NULL (bias only), [1] or [channels] (n_slope says which).  Replaces the epilogue of
+ * nn.Conv2d(bias=True) + nn.PReLU in the primal / dual blocks (inference). */
+PDU_API int pdu_bias_prelu_f32(float* y, const float* bias, const float* slope, int n_slope, int batch,
+                               int channels, long plane, int layout, pdu_stream_t stream);
 /* out = alpha * x + beta * y, n elements. */
 PDU_API int pdu_axpby_f32(float* out, float alpha, const float* x, float beta, const float* y,
                           long n, pdu_stream_t stream);

@@ -12,6 +12,12 @@
 
 namespace pdu {
 
+// filter_tc.cu
+bool filter_tc_supported(int D);
+size_t filter_tc_workspace_bytes(int D);
+int filter_tc_prepare(const float* taps, void* ws, size_t ws_bytes, int D, cudaStream_t st);
+int filter_tc_launch(const float* sino, float* out, const void* ws, long rows, int D, cudaStream_t st);
+
 constexpr int FILT_RB = 16;   // rows per CTA
 
 // dynamic smem: taps[2D+6] (zero padded by 3 in front, 4 behind) | rows[RB][D]
@@ -81,25 +87,27 @@ using namespace pdu;
 
 extern "C" {
 
-size_t pdu_filter_workspace_bytes(int det_count) {
-    (void)det_count;
-    return 0;
-}
+size_t pdu_filter_workspace_bytes(int det_count) { return det_count > 0 ? filter_tc_workspace_bytes(det_count) : 0; }
 
 int pdu_filter_prepare_f32(const float* taps, void* workspace, size_t workspace_bytes, int det_count,
                            pdu_stream_t stream) {
-    (void)taps; (void)workspace; (void)workspace_bytes; (void)stream;
     PDU_REQUIRE(det_count > 0, "pdu_filter_prepare_f32: det_count must be > 0");
-    return PDU_OK;
+    if (!filter_tc_supported(det_count)) return PDU_OK;
+    PDU_REQUIRE(taps != nullptr, "pdu_filter_prepare_f32: taps is null");
+    return filter_tc_prepare(taps, workspace, workspace_bytes, det_count, (cudaStream_t)stream);
 }
 
 int pdu_filter_sinogram_f32(const float* sino, float* out, const float* taps, const void* workspace,
                             size_t workspace_bytes, long rows, int det_count, pdu_stream_t stream) {
-    (void)workspace; (void)workspace_bytes;
     PDU_REQUIRE(sino && out && taps, "pdu_filter_sinogram_f32: null pointer");
     PDU_REQUIRE(rows > 0 && det_count > 0, "pdu_filter_sinogram_f32: rows and det_count must be > 0");
     PDU_REQUIRE(sino != out, "pdu_filter_sinogram_f32: in-place filtering is not supported");
     const int D = det_count;
+    int variant = option(OPT_FILTER);
+    if (variant < 0) variant = 0;      // 1 = tcgen05 3xTF32 GEMM (filter_tc.cu)
+    if (variant == 1 && filter_tc_supported(D) && workspace && workspace_bytes >= filter_tc_workspace_bytes(D) &&
+        (((uintptr_t)sino | (uintptr_t)out | (uintptr_t)workspace) & 15) == 0)
+        return filter_tc_launch(sino, out, workspace, rows, D, (cudaStream_t)stream);
     const size_t smem = ((size_t)(2 * D - 1 + 8 + 3) / 4 * 4 + (size_t)FILT_RB * D) * sizeof(float);
     PDU_REQUIRE(smem <= 200 * 1024, "pdu_filter_sinogram_f32: det_count %d too large for the shared-memory tile", D);
     static bool attr_set = false;

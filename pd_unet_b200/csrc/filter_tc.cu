@@ -1,0 +1,304 @@
+// Sinogram filter on the 5th-generation tensor cores: Out[R, D] = X[R, D] . H[D, D] with the
+// Toeplitz matrix H[k][n] = taps[(n - k) + D - 1], as a 3xTF32 split GEMM
+//     X = Xh + Xl,  H = Hh + Hl  (h = top 19 bits, l = exact remainder)
+//     Out ~= Xh Hh + Xl Hh + Xh Hl          (dropped term Xl Hl ~ 2^-22 relative)
+// accumulated in float32 in tensor memory, so the 1e-5 budget of BASELINE.json holds (~1e-6 measured
+// against the float64 oracle) while the contraction runs at tensor-core rate and the sinogram makes
+// a single round trip through HBM.  This is the one step of the hot path that is a dense contraction.
+//
+// One CTA = one 128 (rows) x 128 (outputs) tile.  Six warps:
+//   warp 0      TMA producer: per 32-wide K block loads the raw X tile and the pre-split Hh / Hl
+//               tiles (cp.async.bulk.tensor, SWIZZLE_128B) into a 3-stage ring
+//   warp 1      MMA issuer: one elected lane issues 12 tcgen05.mma.kind::tf32 (M128 N128 K8) per K
+//               block, tcgen05.commit frees the stage and finally signals the epilogue
+//   warps 2..5  splitters, then epilogue: turn the raw X tile into (Xh in place, Xl) -- elementwise,
+//               so independent of the swizzle -- fence to the async proxy, and at the end read the
+//               accumulator with tcgen05.ld (each warp its own 32 TMEM lanes) and store it.
+// H is split once by pdu_filter_prepare_f32 into the workspace ([2][D][D], K-major: B[n][k]).
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace pdu {
+
+constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 32, TC_STAGES = 3;
+constexpr int TC_TILE_BYTES = TC_BM * TC_BK * 4;            // 16 KB: every operand tile (BM == BN)
+constexpr int TC_STAGE_BYTES = 4 * TC_TILE_BYTES;           // X raw / Xh, Xl, Hh, Hl
+constexpr int TC_SMEM = TC_STAGES * TC_STAGE_BYTES + 1024 /*alignment*/ + 256 /*barriers*/;
+constexpr int TC_THREADS = 192;
+
+__device__ __forceinline__ uint32_t tc_s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void tc_mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void tc_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tc_mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// bounded: a pipeline bug must not hang the GPU box; returns false on timeout
+__device__ __forceinline__ bool tc_mbar_wait(uint32_t bar, uint32_t parity) {
+    for (int spin = 0; spin < (1 << 24); ++spin) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.b32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (ok) return true;
+    }
+    return false;
+}
+__device__ __forceinline__ void tc_tma_2d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(dst), "l"((uint64_t)tm), "r"(c0), "r"(c1), "r"(bar)
+        : "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (tile rows are 128 bytes, 8-row groups 1024 bytes apart)
+__device__ __forceinline__ uint64_t tc_smem_desc(uint32_t addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((addr >> 4) & 0x3FFF);          // start address, 16-byte units
+    d |= (uint64_t)1 << 16;                          // leading byte offset (unused for swizzled K-major): 1
+    d |= (uint64_t)(1024 >> 4) << 32;                // stride byte offset: 8 rows x 128 B
+    d |= (uint64_t)1 << 46;                          // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                          // layout: SWIZZLE_128B
+    return d;
+}
+// kind::tf32, float32 accumulate, A and B K-major, M = 128, N = 128
+constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(TC_IDESC), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+    filter_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_hh,
+                     const __grid_constant__ CUtensorMap tm_hl, float* __restrict__ out, long rows, int D,
+                     int* __restrict__ err_flag) {
+    extern __shared__ unsigned char tc_dyn[];
+    const uint32_t dyn = tc_s32(tc_dyn);
+    const uint32_t base = (dyn + 1023u) & ~1023u;                  // SWIZZLE_128B tiles want 1024-byte alignment
+    unsigned char* base_ptr = tc_dyn + (base - dyn);
+    const uint32_t bars = base + TC_STAGES * TC_STAGE_BYTES;       // full[3], split[3], empty[3], accum, tmem slot
+    auto full = [&](int s) { return bars + 8u * s; };
+    auto split = [&](int s) { return bars + 8u * (TC_STAGES + s); };
+    auto empty = [&](int s) { return bars + 8u * (2 * TC_STAGES + s); };
+    const uint32_t accum = bars + 8u * (3 * TC_STAGES);
+    const uint32_t tmem_slot = accum + 8u;
+    volatile uint32_t* tmem_slot_ptr = (volatile uint32_t*)(base_ptr + TC_STAGES * TC_STAGE_BYTES + 8 * (3 * TC_STAGES + 1));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * TC_BM, n0 = blockIdx.y * TC_BN;
+    const int n_kb = D / TC_BK;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TC_STAGES; ++s) {
+            tc_mbar_init(full(s), 1);
+            tc_mbar_init(split(s), 128);
+            tc_mbar_init(empty(s), 1);
+        }
+        tc_mbar_init(accum, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {   // TMEM: 128 accumulator columns (power of two >= 32)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(TC_BN));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_d = *tmem_slot_ptr;
+
+    bool ok = true;
+    if (warp == 0) {
+        // ------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            for (int kb = 0; kb < n_kb; ++kb) {
+                const int s = kb % TC_STAGES;
+                if (kb >= TC_STAGES) ok = tc_mbar_wait(empty(s), ((kb / TC_STAGES) - 1) & 1) && ok;
+                const uint32_t st = base + s * TC_STAGE_BYTES;
+                tc_mbar_expect_tx(full(s), 3 * TC_TILE_BYTES);
+                tc_tma_2d(st, &tm_x, kb * TC_BK, m0, full(s));                         // raw X  -> becomes Xh
+                tc_tma_2d(st + 2 * TC_TILE_BYTES, &tm_hh, kb * TC_BK, n0, full(s));    // Hh
+                tc_tma_2d(st + 3 * TC_TILE_BYTES, &tm_hl, kb * TC_BK, n0, full(s));    // Hl
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            for (int kb = 0; kb < n_kb; ++kb) {
+                const int s = kb % TC_STAGES;
+                ok = tc_mbar_wait(split(s), (kb / TC_STAGES) & 1) && ok;
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t st = base + s * TC_STAGE_BYTES;
+                const uint64_t xh = tc_smem_desc(st), xl = tc_smem_desc(st + TC_TILE_BYTES);
+                const uint64_t hh = tc_smem_desc(st + 2 * TC_TILE_BYTES), hl = tc_smem_desc(st + 3 * TC_TILE_BYTES);
+#pragma unroll
+                for (int k = 0; k < TC_BK / 8; ++k) {
+                    const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);   // 8 tf32 = 32 bytes along K inside the swizzle atom
+                    tc_mma(tmem_d, xh + adv, hh + adv, (kb | k) != 0);
+                    tc_mma(tmem_d, xl + adv, hh + adv, 1);
+                    tc_mma(tmem_d, xh + adv, hl + adv, 1);
+                }
+                tc_commit(empty(s));                  // stage reusable once these MMAs have read it
+            }
+            tc_commit(accum);                         // accumulator complete
+        }
+    } else {
+        // ------------------------------------------------------------ splitters (128 threads)
+        const int t = threadIdx.x - 64;
+        for (int kb = 0; kb < n_kb; ++kb) {
+            const int s = kb % TC_STAGES;
+            ok = tc_mbar_wait(full(s), (kb / TC_STAGES) & 1) && ok;
+            float4* xr = (float4*)(base_ptr + s * TC_STAGE_BYTES);
+            float4* xl = (float4*)(base_ptr + s * TC_STAGE_BYTES + TC_TILE_BYTES);
+#pragma unroll
+            for (int i = 0; i < TC_TILE_BYTES / 16 / 128; ++i) {
+                const float4 v = xr[t + i * 128];
+                float4 h, l;
+                h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
+                h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
+                h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
+                h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
+                xr[t + i * 128] = h;
+                xl[t + i * 128] = l;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA
+            tc_mbar_arrive(split(s));
+        }
+        // ------------------------------------------------------------ epilogue
+        ok = tc_mbar_wait(accum, 0) && ok;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int q = warp & 3;                                        // this warp's TMEM lane quarter
+        const long row = (long)m0 + q * 32 + lane;
+#pragma unroll
+        for (int c = 0; c < TC_BN; c += 32) {
+            uint32_t v[32];
+            const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)c;
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                  "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                  "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (row < rows) {
+                float4* dst = (float4*)(out + row * D + n0 + c);
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    dst[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                                         __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+            }
+        }
+    }
+    if (!ok && err_flag) atomicExch(err_flag, 1);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(TC_BN));
+    }
+}
+
+// workspace layout: [Hh (D*D) | Hl (D*D)] floats, B[n][k] = taps[(n - k) + D - 1]
+__global__ void __launch_bounds__(256) filter_tc_prepare_kernel(const float* __restrict__ taps, float* __restrict__ ws, int D) {
+    const long total = (long)D * D;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int n = (int)(i / D), k = (int)(i - (long)n * D);
+        const float v = __ldg(taps + (n - k) + D - 1);
+        const float h = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+        ws[i] = h;
+        ws[total + i] = v - h;
+    }
+}
+
+typedef CUresult (*tc_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static tc_encode_fn tc_get_encode() {
+    static tc_encode_fn fn = []() -> tc_encode_fn {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            return nullptr;
+        return (tc_encode_fn)p;
+    }();
+    return fn;
+}
+
+// [n_rows, D] float32 row-major, box = 32 floats (128 bytes, one swizzle span) x 128 rows
+static int tc_make_map(CUtensorMap* tm, const float* ptr, long n_rows, int D) {
+    tc_encode_fn enc = tc_get_encode();
+    if (!enc) {
+        set_error("cuTensorMapEncodeTiled not available from the driver");
+        return PDU_EUNSUPPORTED;
+    }
+    cuuint64_t dims[2] = {(cuuint64_t)D, (cuuint64_t)n_rows};
+    cuuint64_t strides[1] = {(cuuint64_t)D * 4};
+    cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)TC_BM};
+    cuuint32_t es[2] = {1, 1};
+    CUresult rc = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled (filter) failed with CUresult %d (rows=%ld D=%d)", (int)rc, n_rows, D);
+        return PDU_ECUDA;
+    }
+    return PDU_OK;
+}
+
+bool filter_tc_supported(int D) { return D % TC_BN == 0 && D >= TC_BN && D <= 4096; }
+
+size_t filter_tc_workspace_bytes(int D) { return filter_tc_supported(D) ? (size_t)2 * D * D * sizeof(float) : 0; }
+
+int filter_tc_prepare(const float* taps, void* ws, size_t ws_bytes, int D, cudaStream_t st) {
+    if (!filter_tc_supported(D)) return PDU_OK;
+    if (!ws || ws_bytes < filter_tc_workspace_bytes(D) || ((uintptr_t)ws & 15)) {
+        set_error("pdu_filter_prepare_f32: workspace of %zu bytes (16-byte aligned) required", filter_tc_workspace_bytes(D));
+        return PDU_ENOMEM;
+    }
+    const long total = (long)D * D;
+    filter_tc_prepare_kernel<<<(unsigned)std::min<long>(cdiv(total, 256), 148L * 8), 256, 0, st>>>(taps, (float*)ws, D);
+    PDU_LAUNCHED();
+    return PDU_OK;
+}
+
+int filter_tc_launch(const float* sino, float* out, const void* ws, long rows, int D, cudaStream_t st) {
+    const float* hh = (const float*)ws;
+    const float* hl = hh + (long)D * D;
+    CUtensorMap tx, thh, thl;
+    int rc = tc_make_map(&tx, sino, rows, D);
+    if (rc) return rc;
+    rc = tc_make_map(&thh, hh, D, D);
+    if (rc) return rc;
+    rc = tc_make_map(&thl, hl, D, D);
+    if (rc) return rc;
+    static bool attr_set = false;
+    if (!attr_set) {
+        PDU_CUDA(cudaFuncSetAttribute(filter_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+        attr_set = true;
+    }
+    dim3 grid((unsigned)cdiv(rows, TC_BM), (unsigned)(D / TC_BN));
+    filter_tc_kernel<<<grid, TC_THREADS, TC_SMEM, st>>>(tx, thh, thl, out, rows, D, nullptr);
+    PDU_LAUNCHED();
+    return PDU_OK;
+}
+
+}  // namespace pdu

@@ -113,7 +113,7 @@ struct FwdCfg {
     static_assert(W % 4 == 0 && W % 32 != 0 && W <= 256, "box width: 16-byte multiple, not a multiple of 32 banks");
 };
 
-template <int DB, int AG, int TH, int W, int NBUF>
+template <int DB, int AG, int TH, int W, int NBUF, int LD>
 __global__ void __launch_bounds__(DB* AG)
     radon_fwd_strip_kernel(const __grid_constant__ CUtensorMap tm_img, const __grid_constant__ CUtensorMap tm_imgT,
                            const float* __restrict__ img, const float* __restrict__ imgT, float* __restrict__ sino,
@@ -126,7 +126,15 @@ __global__ void __launch_bounds__(DB* AG)
     int* s_umax = s_umin + MAX_STRIPS;
 
     const int tid = threadIdx.x;
-    const int dl = tid % DB, al = tid / DB;
+    // A warp is LD neighbouring detectors x 32/LD neighbouring views.  With LD = 32 the lanes of one
+    // load span up to 45 tile columns (detector pitch 1/cos) and wrap the 32 banks: a 2-way conflict on
+    // every load.  Narrower runs of several views keep the footprint inside 32 columns; the views'
+    // samples fall on the same or neighbouring addresses (broadcast, not conflict).
+    static_assert(32 % LD == 0 && DB % LD == 0 && AG % (32 / LD) == 0, "warp shape must tile the CTA");
+    constexpr int AGW = 32 / LD;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int dl = (warp % (DB / LD)) * LD + lane % LD;
+    const int al = (warp / (DB / LD)) * AGW + lane / LD;
     const int d = blockIdx.x * DB + dl;
     const int a = blockIdx.y * AG + al;
     const int b = blockIdx.z;
@@ -310,7 +318,7 @@ static int make_image_map(CUtensorMap* tm, const float* ptr, int batch, int n, i
     return PDU_OK;
 }
 
-template <int DB, int AG, int TH, int W, int NBUF>
+template <int DB, int AG, int TH, int W, int NBUF, int LD = 32>
 static int launch_strip(const float* img, const float* imgT, float* sino, const float* trig, int batch,
                         const pdu_radon_geom_t& g, cudaStream_t st) {
     using C = FwdCfg<DB, AG, TH, W, NBUF>;
@@ -319,7 +327,7 @@ static int launch_strip(const float* img, const float* imgT, float* sino, const 
     if (rc) return rc;
     rc = make_image_map(&tmT, imgT, batch, g.n, W, C::ROWS);
     if (rc) return rc;
-    auto kern = radon_fwd_strip_kernel<DB, AG, TH, W, NBUF>;
+    auto kern = radon_fwd_strip_kernel<DB, AG, TH, W, NBUF, LD>;
     static bool attr_set = false;
     if (!attr_set) {
         PDU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
@@ -404,6 +412,10 @@ int pdu_radon_fwd_f32(const float* img, float* sino, const float* trig, int batc
         case 3: return launch_strip<64, 4, 32, 168, 2>(img, imgT, sino, trig, batch, *g, st);     // A/B: shallower ring
         case 4: return launch_strip<64, 4, 16, 168, 3>(img, imgT, sino, trig, batch, *g, st);     // A/B: thinner strips
         case 5: return launch_strip<64, 8, 32, 168, 2>(img, imgT, sino, trig, batch, *g, st);     // A/B: 512 threads
+        case 6: return launch_strip<64, 4, 32, 168, 2, 16>(img, imgT, sino, trig, batch, *g, st); // A/B: 16 det x 2 views / warp
+        case 7: return launch_strip<64, 4, 32, 168, 2, 8>(img, imgT, sino, trig, batch, *g, st);  // A/B: 8 det x 4 views / warp
+        case 8: return launch_strip<32, 8, 32, 136, 2, 8>(img, imgT, sino, trig, batch, *g, st);  // A/B: 8 views / CTA
+        case 9: return launch_strip<32, 8, 32, 136, 3, 8>(img, imgT, sino, trig, batch, *g, st);
         default: break;
     }
     if (spread4 > 24.f) return launch_strip<128, 2, 32, 248, 3>(img, imgT, sino, trig, batch, *g, st);

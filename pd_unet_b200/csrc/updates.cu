@@ -270,3 +270,70 @@ int pdu_angular_upsample_adj_f32(const float* full, float* sparse, int batch, in
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------ bias + PReLU epilogue
+// y <- prelu(y + bias[c], slope[c]) in place, one pass (ATen runs the bias add and the activation of a
+// convolution as two full passes over the activation map).  slope may be NULL (bias only) and may hold
+// one value for all channels (n_slope == 1).
+namespace pdu {
+
+__device__ __forceinline__ float prelu1(float v, float s) { return v >= 0.f ? v : v * s; }
+
+template <bool HAS_SLOPE>
+__global__ void __launch_bounds__(256)
+    bias_prelu_nhwc4_kernel(float4* y, const float4* __restrict__ bias, const float4* __restrict__ slope, int c4,
+                            int n_slope, long total4) {
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % c4);
+        const float4 b = __ldg(bias + c);
+        float4 v = y[i];
+        v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+        if (HAS_SLOPE) {
+            float4 s;
+            if (n_slope == 1) { const float s1 = __ldg((const float*)slope); s = make_float4(s1, s1, s1, s1); }
+            else s = __ldg(slope + c);
+            v.x = prelu1(v.x, s.x); v.y = prelu1(v.y, s.y); v.z = prelu1(v.z, s.z); v.w = prelu1(v.w, s.w);
+        }
+        y[i] = v;
+    }
+}
+
+// general: channel = (i / inner) % channels with inner = 1 (NHWC) or plane (NCHW)
+template <bool HAS_SLOPE>
+__global__ void __launch_bounds__(256)
+    bias_prelu_kernel(float* y, const float* __restrict__ bias, const float* __restrict__ slope, int channels, long inner,
+                      int n_slope, long total) {
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int c = (int)((i / inner) % channels);
+        float v = y[i] + __ldg(bias + c);
+        if (HAS_SLOPE) v = prelu1(v, __ldg(slope + (n_slope == 1 ? 0 : c)));
+        y[i] = v;
+    }
+}
+
+}  // namespace pdu
+
+extern "C" int pdu_bias_prelu_f32(float* y, const float* bias, const float* slope, int n_slope, int batch, int channels,
+                                  long plane, int layout, pdu_stream_t stream) {
+    PDU_REQUIRE(y && bias, "pdu_bias_prelu_f32: null pointer");
+    PDU_REQUIRE(batch > 0 && channels > 0 && plane > 0, "pdu_bias_prelu_f32: sizes must be positive");
+    PDU_REQUIRE(slope == nullptr || n_slope == 1 || n_slope == channels, "pdu_bias_prelu_f32: slope must have 1 or %d values",
+                channels);
+    PDU_REQUIRE(layout == PDU_LAYOUT_NCHW || layout == PDU_LAYOUT_NHWC, "pdu_bias_prelu_f32: unknown layout %d", layout);
+    const long total = (long)batch * channels * plane;
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool vec = layout == PDU_LAYOUT_NHWC && channels % 4 == 0 && al16(y) && al16(bias) &&
+                     (slope == nullptr || n_slope == 1 || al16(slope));
+    if (vec) {
+        if (slope) bias_prelu_nhwc4_kernel<true><<<stream_grid(total / 4, 256), 256, 0, st>>>(
+                (float4*)y, (const float4*)bias, (const float4*)slope, channels / 4, n_slope, total / 4);
+        else bias_prelu_nhwc4_kernel<false><<<stream_grid(total / 4, 256), 256, 0, st>>>(
+                (float4*)y, (const float4*)bias, nullptr, channels / 4, 1, total / 4);
+    } else {
+        const long inner = layout == PDU_LAYOUT_NHWC ? 1 : plane;
+        if (slope) bias_prelu_kernel<true><<<stream_grid(total, 256), 256, 0, st>>>(y, bias, slope, channels, inner, n_slope, total);
+        else bias_prelu_kernel<false><<<stream_grid(total, 256), 256, 0, st>>>(y, bias, nullptr, channels, inner, 1, total);
+    }
+    PDU_LAUNCHED();
+    return PDU_OK;
+}

@@ -26,9 +26,44 @@ from .nufft import KbNufft, KbNufftAdjoint
 from .radon import _BaseRadon
 
 
+def _fused_epilogue_ok(x: torch.Tensor) -> bool:
+    return x.is_cuda and x.dtype == torch.float32 and not torch.is_grad_enabled()
+
+
+class ConvAct(nn.Module):
+    """3x3 convolution (cuDNN) + optional PReLU.  In inference the bias add and the activation run as
+    one in-place pass of pdu_bias_prelu_f32 instead of ATen's two; with gradients on, the stock
+    modules are used so autograd sees ordinary ops.  Parameters are those of the wrapped modules."""
+
+    def __init__(self, cin: int, cout: int, act: bool = True, kernel: int = 3):
+        super().__init__()
+        self.conv = nn.Conv2d(cin, cout, kernel, padding=kernel // 2)
+        self.act = nn.PReLU(cout) if act else None
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if _fused_epilogue_ok(x):
+            y = nn.functional.conv2d(x, self.conv.weight, None, self.conv.stride, self.conv.padding)
+            return updates.bias_prelu_(y, self.conv.bias, self.act.weight if self.act is not None else None)
+        y = self.conv(x)
+        return self.act(y) if self.act is not None else y
+
+
+class UpConv(nn.Module):
+    """2x2 stride-2 transposed convolution with the same fused bias epilogue."""
+
+    def __init__(self, cin: int, cout: int):
+        super().__init__()
+        self.conv = nn.ConvTranspose2d(cin, cout, 2, stride=2)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if _fused_epilogue_ok(x):
+            y = nn.functional.conv_transpose2d(x, self.conv.weight, None, 2)
+            return updates.bias_prelu_(y, self.conv.bias, None)
+        return self.conv(x)
+
+
 def _conv_block(cin: int, cout: int) -> nn.Sequential:
-    return nn.Sequential(nn.Conv2d(cin, cout, 3, padding=1), nn.PReLU(cout),
-                         nn.Conv2d(cout, cout, 3, padding=1), nn.PReLU(cout))
+    return nn.Sequential(ConvAct(cin, cout), ConvAct(cout, cout))
 
 
 class UNet(nn.Module):
@@ -45,10 +80,10 @@ class UNet(nn.Module):
         self.upconv = nn.ModuleList()
         self.up = nn.ModuleList()
         for d in reversed(range(depth)):
-            self.upconv.append(nn.ConvTranspose2d(ch, base << d, 2, stride=2))
+            self.upconv.append(UpConv(ch, base << d))
             self.up.append(_conv_block(2 * (base << d), base << d))
             ch = base << d
-        self.head = nn.Conv2d(ch, cout, 1)
+        self.head = ConvAct(ch, cout, act=False, kernel=1)
         self.pool = nn.MaxPool2d(2)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
@@ -72,9 +107,7 @@ class DualBlock(nn.Module):
 
     def __init__(self, cin: int, cout: int, features: int = 32):
         super().__init__()
-        self.net = nn.Sequential(nn.Conv2d(cin, features, 3, padding=1), nn.PReLU(features),
-                                 nn.Conv2d(features, features, 3, padding=1), nn.PReLU(features),
-                                 nn.Conv2d(features, cout, 3, padding=1))
+        self.net = nn.Sequential(ConvAct(cin, features), ConvAct(features, features), ConvAct(features, cout, act=False))
 
     def forward(self, x):
         return self.net(x)
@@ -110,8 +143,8 @@ class PrimalDualUNet(nn.Module):
         """g: measured data on the full grid [B, kd, *data].  Returns the reconstruction [B, kc, *image]."""
         B = g.shape[0]
         fmt = torch.channels_last if (self.channels_last and g.dim() == 4) else torch.contiguous_format
-        h = torch.zeros((B, self.n_dual) + tuple(g.shape[2:]), dtype=g.dtype, device=g.device, memory_format=fmt)
-        f = torch.zeros((B, self.n_primal) + tuple(image_shape), dtype=g.dtype, device=g.device, memory_format=fmt)
+        h = torch.empty((B, self.n_dual) + tuple(g.shape[2:]), dtype=g.dtype, device=g.device, memory_format=fmt).zero_()
+        f = torch.empty((B, self.n_primal) + tuple(image_shape), dtype=g.dtype, device=g.device, memory_format=fmt).zero_()
         f_op = g.new_zeros((B, self.kc) + tuple(image_shape))
         inv = 1.0 / self.op_scale
         for i in range(self.n_iter):

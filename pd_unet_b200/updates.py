@@ -199,3 +199,32 @@ def angular_upsample_adjoint(full: torch.Tensor, factor: int, mode: str = "flip"
     if mode not in WRAP_MODES:
         raise ValueError(f"mode must be one of {tuple(WRAP_MODES)}")
     return _AngularUpsampleAdjoint.apply(full, int(factor), mode)
+
+
+def bias_prelu_(y: torch.Tensor, bias: torch.Tensor, slope: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """In place y <- prelu(y + bias[c], slope[c]) for a [B, C, ...] float32 CUDA tensor in planar or
+    channels_last layout; slope None means bias only.  Inference epilogue of Conv2d + PReLU as one pass.
+    Not differentiable (the modules in pd_unet_b200.model fall back to the ATen ops when gradients are on)."""
+    if not y.is_cuda:
+        raise PduError(f"y is on {y.device}: the pd_unet_b200 operators run on CUDA only (no CPU fallback)")
+    if y.dtype != torch.float32 or y.dim() < 3:
+        raise TypeError("bias_prelu_: y must be a float32 [B, C, ...] tensor")
+    nhwc = _is_channels_last(y)
+    if not nhwc and not y.is_contiguous():
+        raise ValueError("bias_prelu_: y must be contiguous (planar or channels_last) to be updated in place")
+    Cn = y.shape[1]
+    bias = require_cuda(bias.detach(), torch.float32, "bias")
+    if bias.numel() != Cn:
+        raise ValueError(f"bias_prelu_: bias has {bias.numel()} values for {Cn} channels")
+    n_slope = 0
+    if slope is not None:
+        slope = require_cuda(slope.detach(), torch.float32, "slope")
+        n_slope = slope.numel()
+        if n_slope not in (1, Cn):
+            raise ValueError(f"bias_prelu_: slope has {n_slope} values for {Cn} channels")
+    if y.numel():
+        with torch.cuda.device(y.device):
+            check(lib().pdu_bias_prelu_f32(y.data_ptr(), bias.data_ptr(), slope.data_ptr() if slope is not None else None,
+                                           max(n_slope, 1), y.shape[0], Cn, _plane(y),
+                                           LAYOUT_NHWC if nhwc else LAYOUT_NCHW, stream_ptr()), "pdu_bias_prelu_f32")
+    return y

@@ -192,3 +192,28 @@ def test_full_size_properties(name):
         lhs = float((y.double() * s2.double()).sum())
         rhs = float((x.double() * op.backprojection(s2).double()).sum())
         assert abs(lhs - rhs) / abs(lhs) < 2e-2
+
+
+@pytest.mark.parametrize("D,A,B", [(128, 24, 2), (256, 64, 2), (512, 50, 3), (384, 7, 1)])
+def test_filter_tensor_core_variant(D, A, B):
+    """The tcgen05 3xTF32 Toeplitz GEMM (filter_variant 1) against the float64 oracle and the CUDA-core kernel.
+    rows = B*A is deliberately not always a multiple of the 128-row tile."""
+    op = pdu.Radon(D, user_angles(A), det_count=D)
+    s = seeded((B, A, D), 17)
+    try:
+        pdu.set_option("filter_variant", 1)
+        got = op.filter_sinogram(s.to(DEV))
+        torch.cuda.synchronize()
+        pdu.set_option("filter_variant", 0)
+        ref = op.filter_sinogram(s.to(DEV))
+    finally:
+        pdu.set_option("filter_variant", -1)
+    want = oracle.filter_sinogram(s)
+    assert rel_l2(ref, want) <= TOL
+    assert rel_l2(got, want) <= TOL
+    hann = oracle.filter_sinogram(s, "hann")
+    try:
+        pdu.set_option("filter_variant", 1)
+        assert rel_l2(op.filter_sinogram(s.to(DEV), "hann"), hann) <= TOL
+    finally:
+        pdu.set_option("filter_variant", -1)

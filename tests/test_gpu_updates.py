@@ -114,3 +114,36 @@ def test_graphed_inference_matches_eager():
     with torch.no_grad():
         want2 = model(x2.to(DEV)).clone()
     assert torch.allclose(g(x2.pin_memory()), want2, atol=1e-5, rtol=1e-5)     # host input: H2D inside the call
+
+
+@pytest.mark.parametrize("shape", [(2, 8, 6, 10), (3, 5, 7, 9), (1, 32, 16, 16)])
+@pytest.mark.parametrize("channels_last", [True, False])
+@pytest.mark.parametrize("slope_kind", ["per_channel", "single", "none"])
+def test_bias_prelu_epilogue(shape, channels_last, slope_kind):
+    y = seeded(shape, 1)
+    bias = seeded((shape[1],), 2)
+    slope = {"per_channel": seeded((shape[1],), 3).abs(), "single": torch.tensor([0.25]), "none": None}[slope_kind]
+    want = y + bias.view(1, -1, 1, 1)
+    if slope is not None:
+        want = torch.nn.functional.prelu(want, slope)
+    yd = y.to(DEV)
+    if channels_last:
+        yd = yd.contiguous(memory_format=torch.channels_last)
+    out = updates.bias_prelu_(yd, bias.to(DEV), slope.to(DEV) if slope is not None else None)
+    assert out.data_ptr() == yd.data_ptr()
+    assert torch.equal(out.cpu(), want)
+
+
+def test_fused_conv_modules_match_stock_modules():
+    from pd_unet_b200.model import ConvAct, UpConv
+    torch.backends.cudnn.allow_tf32 = False
+    torch.manual_seed(0)
+    for mod, x in ((ConvAct(6, 8).to(DEV), seeded((2, 6, 12, 20), 1)), (ConvAct(8, 4, act=False, kernel=1).to(DEV), seeded((2, 8, 9, 9), 2)),
+                   (UpConv(8, 4).to(DEV), seeded((2, 8, 6, 6), 3))):
+        mod = mod.to(memory_format=torch.channels_last)
+        xd = x.to(DEV).contiguous(memory_format=torch.channels_last)
+        with torch.enable_grad():
+            want = mod(xd.clone().requires_grad_()).detach()      # stock path
+        with torch.no_grad():
+            got = mod(xd)                                         # fused epilogue
+        assert torch.allclose(got, want, atol=1e-5, rtol=1e-5)

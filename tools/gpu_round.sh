@@ -2,13 +2,13 @@
 # tests (isolated workers) -> bench -> op timings -> ncu launch list -> ncu full captures
 mkdir -p gpurun_out
 timeout 1500 python -m pytest tests -m gpu -q -n 1 --max-worker-restart 60 --timeout 600 -rfE > gpurun_out/pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest.log
-tail -12 gpurun_out/pytest.log
-timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?" >> gpurun_out/bench.err
+grep -E "^(FAILED|ERROR)|passed|failed" gpurun_out/pytest.log | tail -12
+timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?" >> gpurun_out/bench.err
 timeout 600 python tools/prof_ops.py 5 > gpurun_out/ops.log 2>&1; cat gpurun_out/ops.log
-export PDU_BENCH_AUTOTUNE=0
+export PDU_BENCH_AUTOTUNE=0 PDU_BENCH_GRAPH=0
 timeout 600 python bench.py --steps 1 --warmup 3 --no-cpu > gpurun_out/plain.log 2>&1 && \
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 3 --no-cpu > gpurun_out/ncu_launches.log 2>&1
 timeout 300 python tools/prof_ops.py 1 > gpurun_out/plain2.log 2>&1 && \
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"radon_fwd_strip|radon_adj_tile|filter_direct" -c 12 -o gpurun_out/prof_ops python tools/prof_ops.py 1 > gpurun_out/ncu_full.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"radon_fwd_strip|radon_adj_tile" -c 16 -o gpurun_out/prof_ops python tools/prof_ops.py 1 > gpurun_out/ncu_full.log 2>&1
 ls -la gpurun_out | tail -20
-cat gpurun_out/bench.json | cut -c1-600
+cat gpurun_out/bench.json | cut -c1-300; tail -3 gpurun_out/bench.err
