@@ -1,31 +1,39 @@
 // Sinogram filter on the 5th-generation tensor cores: Out[R, D] = X[R, D] . H[D, D] with the
-// Toeplitz matrix H[k][n] = taps[(n - k) + D - 1], as a 3xTF32 split GEMM
-//     X = Xh + Xl,  H = Hh + Hl  (h = top 19 bits, l = exact remainder)
-//     Out ~= Xh Hh + Xl Hh + Xh Hl          (dropped term Xl Hl ~ 2^-22 relative)
-// accumulated in float32 in tensor memory, so the 1e-5 budget of BASELINE.json holds (~1e-6 measured
-// against the float64 oracle) while the contraction runs at tensor-core rate and the sinogram makes
-// a single round trip through HBM.  This is the one step of the hot path that is a dense contraction.
+// Toeplitz matrix H[k][n] = taps[(n - k) + D - 1], as a split-TF32 GEMM accumulated in float32 in
+// tensor memory.  Every operand is cut into pieces of 11 significant bits (what kind::tf32 keeps), so
+// each tensor-core product of two pieces is EXACT and only the float32 accumulation rounds:
+//     SPLIT = 3 (default):  X = X1 + X2 + X3, H = H1 + H2 + H3,
+//                           Out = X1H1 + X1H2 + X2H1 + X2H2 + X1H3 + X3H1      (dropped terms < 2^-33)
+//     SPLIT = 2 (A/B only): Out ~= X1H1 + X2H1 + X1H2, ~4e-7 of sum|x||h| -- not enough for ramp-filtered
+//                           object sinograms, whose output is ~50x smaller than sum|x||h| (measured
+//                           1.5e-5 rel-L2 at 512 bins against the 1e-5 budget).
+// The sinogram makes a single round trip through HBM.  This is the one step of the hot path that is a
+// dense contraction.
 //
 // One CTA = one 128 (rows) x 128 (outputs) tile.  Six warps:
-//   warp 0      TMA producer: per 32-wide K block loads the raw X tile and the pre-split Hh / Hl
-//               tiles (cp.async.bulk.tensor, SWIZZLE_128B) into a 3-stage ring
-//   warp 1      MMA issuer: one elected lane issues 12 tcgen05.mma.kind::tf32 (M128 N128 K8) per K
+//   warp 0      TMA producer: per 32-wide K block loads the raw X tile and the pre-split H pieces
+//               (cp.async.bulk.tensor, SWIZZLE_128B) into a 2-stage (SPLIT 3) / 3-stage (SPLIT 2) ring
+//   warp 1      MMA issuer: one elected lane issues 24 (12) tcgen05.mma.kind::tf32 (M128 N128 K8) per K
 //               block, tcgen05.commit frees the stage and finally signals the epilogue
-//   warps 2..5  splitters, then epilogue: turn the raw X tile into (Xh in place, Xl) -- elementwise,
-//               so independent of the swizzle -- fence to the async proxy, and at the end read the
-//               accumulator with tcgen05.ld (each warp its own 32 TMEM lanes) and store it.
-// H is split once by pdu_filter_prepare_f32 into the workspace ([2][D][D], K-major: B[n][k]).
+//   warps 2..5  splitters, then epilogue: cut the raw X tile into its pieces (X1 in place) --
+//               elementwise, so independent of the swizzle -- fence to the async proxy, and at the end
+//               read the accumulator with tcgen05.ld (each warp its own 32 TMEM lanes) and store it.
+// H is split once by pdu_filter_prepare_f32 into the workspace ([3][D][D], K-major: B[n][k]).
 #include <cuda.h>
 
 #include "common.cuh"
 
 namespace pdu {
 
-constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 32, TC_STAGES = 3;
+constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 32;
 constexpr int TC_TILE_BYTES = TC_BM * TC_BK * 4;            // 16 KB: every operand tile (BM == BN)
-constexpr int TC_STAGE_BYTES = 4 * TC_TILE_BYTES;           // X raw / Xh, Xl, Hh, Hl
-constexpr int TC_SMEM = TC_STAGES * TC_STAGE_BYTES + 1024 /*alignment*/ + 256 /*barriers*/;
 constexpr int TC_THREADS = 192;
+template <int SPLIT>
+struct TcCfg {
+    static constexpr int STAGES = SPLIT == 2 ? 3 : 2;
+    static constexpr int STAGE_BYTES = 2 * SPLIT * TC_TILE_BYTES;     // X pieces (piece 0 = raw X, split in place), H pieces
+    static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*alignment*/ + 256 /*barriers*/;
+};
 
 __device__ __forceinline__ uint32_t tc_s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -85,10 +93,14 @@ __device__ __forceinline__ void tc_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
+__device__ __forceinline__ float tf32_head(float v) { return __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
+
+template <int SPLIT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-    filter_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_hh,
-                     const __grid_constant__ CUtensorMap tm_hl, float* __restrict__ out, long rows, int D,
-                     int* __restrict__ err_flag) {
+    filter_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_h,
+                     float* __restrict__ out, long rows, int D, int* __restrict__ err_flag) {
+    constexpr int TC_STAGES = TcCfg<SPLIT>::STAGES;
+    constexpr int TC_STAGE_BYTES = TcCfg<SPLIT>::STAGE_BYTES;
     extern __shared__ unsigned char tc_dyn[];
     const uint32_t dyn = tc_s32(tc_dyn);
     const uint32_t base = (dyn + 1023u) & ~1023u;                  // SWIZZLE_128B tiles want 1024-byte alignment
@@ -131,10 +143,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                 const int s = kb % TC_STAGES;
                 if (kb >= TC_STAGES) ok = tc_mbar_wait(empty(s), ((kb / TC_STAGES) - 1) & 1) && ok;
                 const uint32_t st = base + s * TC_STAGE_BYTES;
-                tc_mbar_expect_tx(full(s), 3 * TC_TILE_BYTES);
-                tc_tma_2d(st, &tm_x, kb * TC_BK, m0, full(s));                         // raw X  -> becomes Xh
-                tc_tma_2d(st + 2 * TC_TILE_BYTES, &tm_hh, kb * TC_BK, n0, full(s));    // Hh
-                tc_tma_2d(st + 3 * TC_TILE_BYTES, &tm_hl, kb * TC_BK, n0, full(s));    // Hl
+                tc_mbar_expect_tx(full(s), (1 + SPLIT) * TC_TILE_BYTES);
+                tc_tma_2d(st, &tm_x, kb * TC_BK, m0, full(s));                         // raw X -> split in place into X1
+#pragma unroll
+                for (int p = 0; p < SPLIT; ++p)                                        // pre-split H pieces, stacked by rows
+                    tc_tma_2d(st + (SPLIT + p) * TC_TILE_BYTES, &tm_h, kb * TC_BK, p * D + n0, full(s));
             }
         }
     } else if (warp == 1) {
@@ -145,14 +158,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                 ok = tc_mbar_wait(split(s), (kb / TC_STAGES) & 1) && ok;
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t st = base + s * TC_STAGE_BYTES;
-                const uint64_t xh = tc_smem_desc(st), xl = tc_smem_desc(st + TC_TILE_BYTES);
-                const uint64_t hh = tc_smem_desc(st + 2 * TC_TILE_BYTES), hl = tc_smem_desc(st + 3 * TC_TILE_BYTES);
+                uint64_t xd[SPLIT], hd[SPLIT];
+#pragma unroll
+                for (int p = 0; p < SPLIT; ++p) {
+                    xd[p] = tc_smem_desc(st + p * TC_TILE_BYTES);
+                    hd[p] = tc_smem_desc(st + (SPLIT + p) * TC_TILE_BYTES);
+                }
 #pragma unroll
                 for (int k = 0; k < TC_BK / 8; ++k) {
                     const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);   // 8 tf32 = 32 bytes along K inside the swizzle atom
-                    tc_mma(tmem_d, xh + adv, hh + adv, (kb | k) != 0);
-                    tc_mma(tmem_d, xl + adv, hh + adv, 1);
-                    tc_mma(tmem_d, xh + adv, hl + adv, 1);
+                    tc_mma(tmem_d, xd[0] + adv, hd[0] + adv, (kb | k) != 0);
+                    tc_mma(tmem_d, xd[1] + adv, hd[0] + adv, 1);
+                    tc_mma(tmem_d, xd[0] + adv, hd[1] + adv, 1);
+                    if (SPLIT == 3) {
+                        tc_mma(tmem_d, xd[1] + adv, hd[1] + adv, 1);
+                        tc_mma(tmem_d, xd[2] + adv, hd[0] + adv, 1);
+                        tc_mma(tmem_d, xd[0] + adv, hd[2] + adv, 1);
+                    }
                 }
                 tc_commit(empty(s));                  // stage reusable once these MMAs have read it
             }
@@ -164,18 +186,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         for (int kb = 0; kb < n_kb; ++kb) {
             const int s = kb % TC_STAGES;
             ok = tc_mbar_wait(full(s), (kb / TC_STAGES) & 1) && ok;
-            float4* xr = (float4*)(base_ptr + s * TC_STAGE_BYTES);
-            float4* xl = (float4*)(base_ptr + s * TC_STAGE_BYTES + TC_TILE_BYTES);
+            float4* x1 = (float4*)(base_ptr + s * TC_STAGE_BYTES);
+            float4* x2 = (float4*)(base_ptr + s * TC_STAGE_BYTES + TC_TILE_BYTES);
+            float4* x3 = (float4*)(base_ptr + s * TC_STAGE_BYTES + 2 * TC_TILE_BYTES);   // SPLIT == 3 only
 #pragma unroll
             for (int i = 0; i < TC_TILE_BYTES / 16 / 128; ++i) {
-                const float4 v = xr[t + i * 128];
-                float4 h, l;
-                h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
-                h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
-                h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
-                h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
-                xr[t + i * 128] = h;
-                xl[t + i * 128] = l;
+                const float4 v = x1[t + i * 128];
+                float4 a, b;
+                a.x = tf32_head(v.x); b.x = v.x - a.x;      // every subtraction here is exact
+                a.y = tf32_head(v.y); b.y = v.y - a.y;
+                a.z = tf32_head(v.z); b.z = v.z - a.z;
+                a.w = tf32_head(v.w); b.w = v.w - a.w;
+                x1[t + i * 128] = a;
+                if (SPLIT == 2) {
+                    x2[t + i * 128] = b;
+                } else {
+                    float4 c, d;
+                    c.x = tf32_head(b.x); d.x = b.x - c.x;
+                    c.y = tf32_head(b.y); d.y = b.y - c.y;
+                    c.z = tf32_head(b.z); d.z = b.z - c.z;
+                    c.w = tf32_head(b.w); d.w = b.w - c.w;
+                    x2[t + i * 128] = c;
+                    x3[t + i * 128] = d;
+                }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA
             tc_mbar_arrive(split(s));
@@ -216,15 +249,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     }
 }
 
-// workspace layout: [Hh (D*D) | Hl (D*D)] floats, B[n][k] = taps[(n - k) + D - 1]
+// workspace layout: [H1 | H2 | H3] each D*D floats (three 11-bit pieces, H1 + H2 + H3 == H exactly),
+// K-major: B[n][k] = taps[(n - k) + D - 1].  The SPLIT = 2 kernel reads H1 and (H2 + H3 rounded by the MMA).
 __global__ void __launch_bounds__(256) filter_tc_prepare_kernel(const float* __restrict__ taps, float* __restrict__ ws, int D) {
     const long total = (long)D * D;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
         const int n = (int)(i / D), k = (int)(i - (long)n * D);
         const float v = __ldg(taps + (n - k) + D - 1);
-        const float h = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
-        ws[i] = h;
-        ws[total + i] = v - h;
+        const float h1 = tf32_head(v), r = v - h1;
+        const float h2 = tf32_head(r);
+        ws[i] = h1;
+        ws[total + i] = h2;
+        ws[2 * total + i] = r - h2;
     }
 }
 
@@ -266,7 +302,7 @@ static int tc_make_map(CUtensorMap* tm, const float* ptr, long n_rows, int D) {
 
 bool filter_tc_supported(int D) { return D % TC_BN == 0 && D >= TC_BN && D <= 4096; }
 
-size_t filter_tc_workspace_bytes(int D) { return filter_tc_supported(D) ? (size_t)2 * D * D * sizeof(float) : 0; }
+size_t filter_tc_workspace_bytes(int D) { return filter_tc_supported(D) ? (size_t)3 * D * D * sizeof(float) : 0; }
 
 int filter_tc_prepare(const float* taps, void* ws, size_t ws_bytes, int D, cudaStream_t st) {
     if (!filter_tc_supported(D)) return PDU_OK;
@@ -280,25 +316,26 @@ int filter_tc_prepare(const float* taps, void* ws, size_t ws_bytes, int D, cudaS
     return PDU_OK;
 }
 
-int filter_tc_launch(const float* sino, float* out, const void* ws, long rows, int D, cudaStream_t st) {
-    const float* hh = (const float*)ws;
-    const float* hl = hh + (long)D * D;
-    CUtensorMap tx, thh, thl;
+template <int SPLIT>
+static int tc_launch(const float* sino, float* out, const void* ws, long rows, int D, cudaStream_t st) {
+    CUtensorMap tx, th;
     int rc = tc_make_map(&tx, sino, rows, D);
     if (rc) return rc;
-    rc = tc_make_map(&thh, hh, D, D);
-    if (rc) return rc;
-    rc = tc_make_map(&thl, hl, D, D);
+    rc = tc_make_map(&th, (const float*)ws, 3L * D, D);     // the three pieces stacked by rows
     if (rc) return rc;
     static bool attr_set = false;
     if (!attr_set) {
-        PDU_CUDA(cudaFuncSetAttribute(filter_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+        PDU_CUDA(cudaFuncSetAttribute(filter_tc_kernel<SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<SPLIT>::SMEM));
         attr_set = true;
     }
     dim3 grid((unsigned)cdiv(rows, TC_BM), (unsigned)(D / TC_BN));
-    filter_tc_kernel<<<grid, TC_THREADS, TC_SMEM, st>>>(tx, thh, thl, out, rows, D, nullptr);
+    filter_tc_kernel<SPLIT><<<grid, TC_THREADS, TcCfg<SPLIT>::SMEM, st>>>(tx, th, out, rows, D, nullptr);
     PDU_LAUNCHED();
     return PDU_OK;
+}
+
+int filter_tc_launch(const float* sino, float* out, const void* ws, long rows, int D, int split, cudaStream_t st) {
+    return split == 2 ? tc_launch<2>(sino, out, ws, rows, D, st) : tc_launch<3>(sino, out, ws, rows, D, st);
 }
 
 }  // namespace pdu

@@ -24,7 +24,7 @@ def timed(name, fn):
     print(f"{name:28s} median {statistics.median(ts)*1e3:9.1f} us  min {min(ts)*1e3:9.1f} us", flush=True)
 
 
-for v in (0, 1, 3, 5, 6, 7, 8, 9):
+for v in (0, 1, 2, 3, 4, 5, 6, 7, 8):
     pdu.set_option("radon_fwd_variant", v)
     timed(f"radon_fwd variant {v}", lambda: op._project(x))
 pdu.set_option("radon_fwd_variant", -1)
@@ -32,14 +32,20 @@ for v in (0, 1, 2):
     pdu.set_option("radon_adj_variant", v)
     timed(f"radon_adj variant {v}", lambda: op._backproject(s))
 pdu.set_option("radon_adj_variant", -1)
-timed("filter", lambda: op._filter(s, "ramp"))
+for v in (0, 1, 2):
+    pdu.set_option("filter_variant", v)
+    timed(f"filter variant {v}", lambda: op._filter(s, "ramp"))
+pdu.set_option("filter_variant", -1)
 # cfg3 share: fan 512^2, 1024 views, batch 8
 fan = pdu.RadonFanbeam(512, np.linspace(0, 2 * np.pi, 1024, endpoint=False), 1024.0)
 xf = torch.rand(8, 512, 512, device=dev)
 sf = torch.rand(8, 1024, 512, device=dev)
 timed("fan512 fwd", lambda: fan._project(xf))
 timed("fan512 adj", lambda: fan._backproject(sf))
-timed("fan512 filter", lambda: fan._filter(sf, "ramp"))
+for v in (0, 1, 2):
+    pdu.set_option("filter_variant", v)
+    timed(f"fan512 filter variant {v}", lambda: fan._filter(sf, "ramp"))
+pdu.set_option("filter_variant", -1)
 # MRI cfg4 share: 320^2, 8 coils, 48 spokes, batch 2
 from pd_unet_b200.phantoms import coil_maps
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
