@@ -122,7 +122,7 @@ struct FwdCfg {
     static constexpr int ROWS = TH + 1;
     static constexpr int TILE_BYTES = ROWS * W * 4;
     static constexpr int TILE_STRIDE = (TILE_BYTES + 127) / 128 * 128;
-    static constexpr int SMEM = NBUF * TILE_STRIDE + NBUF * 8 + 2 * MAX_STRIPS * 4;
+    static constexpr int SMEM = NBUF * TILE_STRIDE + 2 * NBUF * 8 + 2 * MAX_STRIPS * 4;
     // W % 32 != 0 on purpose: the lanes of a warp sit in neighbouring rows of the tile, and a row
     // pitch that is a multiple of 32 floats would put the same column of every row in one bank
     static_assert(W % 4 == 0 && W % 32 != 0 && W <= 256, "box width: 16-byte multiple, not a multiple of 32 banks");
@@ -137,7 +137,8 @@ __global__ void __launch_bounds__(DB* AG)
     // indexed directly (no re-aligned generic pointer) so that the tile reads compile to LDS
     extern __shared__ __align__(1024) unsigned char smem_dyn[];
     uint64_t* full = (uint64_t*)(smem_dyn + NBUF * C::TILE_STRIDE);
-    int* s_umin = (int*)(full + NBUF);
+    uint64_t* empty = full + NBUF;          // one arrival per warp: the buffer may be refilled
+    int* s_umin = (int*)(empty + NBUF);
     int* s_umax = s_umin + MAX_STRIPS;
 
     const int tid = threadIdx.x;
@@ -165,7 +166,10 @@ __global__ void __launch_bounds__(DB* AG)
         s_umax[k] = INT_MIN;
     }
     if (tid == 0) {
-        for (int i = 0; i < NBUF; ++i) mbar_init(full + i, 1);
+        for (int i = 0; i < NBUF; ++i) {
+            mbar_init(full + i, 1);
+            mbar_init(empty + i, C::THREADS / 32);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
 
@@ -219,6 +223,9 @@ __global__ void __launch_bounds__(DB* AG)
         while (k_issue < n_strips && s_umin[k_issue] > s_umax[k_issue]) ++k_issue;
         if (k_issue < n_strips) {
             const int buf = seq_issue % NBUF;
+            // the buffer's previous strip must have been read by every warp (they run ahead of each other
+            // by up to NBUF - 1 strips: there is no block-wide barrier in the marching loop)
+            if (seq_issue >= NBUF) mbar_wait(empty + buf, ((seq_issue / NBUF) - 1) & 1);
             // TMA needs the innermost start coordinate on a 16-byte boundary (measured: any c0 % 4 != 0
             // raises "illegal instruction" on sm_100a, negative values are fine) -> round down to 4 floats
             const int lo = s_umin[k_issue] & ~3;
@@ -325,7 +332,8 @@ __global__ void __launch_bounds__(DB* AG)
             }
         }
         s += cnt;
-        __syncthreads();
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive(empty + buf);     // this warp is done with the buffer
         ++seq;
     }
     if (valid) sino[((long)b * g.n_angles + a) * g.det_count + d] = acc * r.step;

@@ -1,0 +1,48 @@
+"""NUFFT forward / adjoint a few times at the cfg1 / cfg4 shapes (for ncu launch lists and timings)."""
+import sys, os, statistics
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import pd_unet_b200 as pdu
+from pd_unet_b200.phantoms import coil_maps
+
+dev = "cuda:0"
+reps = int(sys.argv[1]) if len(sys.argv) > 1 else 3
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+
+def traj(spokes, readout):
+    phi = np.arange(spokes) * (111.246117975 * np.pi / 180.0)
+    r = (np.arange(readout) - readout / 2) * (2 * np.pi / readout)
+    return torch.from_numpy(np.stack([(r[None] * np.sin(phi)[:, None]).reshape(-1),
+                                      (r[None] * np.cos(phi)[:, None]).reshape(-1)]).astype(np.float32)).to(dev)
+
+
+def timed(name, fn, nbytes):
+    fn(); torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record(); torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    t = statistics.median(ts)
+    print(f"{name:34s} median {t*1e3:8.1f} us   {nbytes / t / 1e6:8.1f} GB/s algorithmic", flush=True)
+
+
+for name, n, coils, B, spokes in (("cfg1 256^2 c1 b1 32sp", 256, 1, 1, 32), ("cfg1 256^2 c1 b1 256sp", 256, 1, 1, 256),
+                                  ("cfg4 320^2 c8 b2 48sp", 320, 8, 2, 48), ("cfg4 320^2 c8 b8 48sp", 320, 8, 8, 48)):
+    im = (n, n)
+    om = traj(spokes, 2 * n)
+    M = om.shape[1]
+    fw, ad = pdu.KbNufft(im), pdu.KbNufftAdjoint(im)
+    if coils > 1:
+        sm = coil_maps(coils, n)[None].to(dev)
+        img = torch.randn(B, 1, n, n, dtype=torch.complex64, device=dev)
+        nb = 8.0 * B * coils * (n * n + M) + 8.0 * M + 8.0 * coils * n * n
+    else:
+        sm = None
+        img = torch.randn(B, 1, n, n, dtype=torch.complex64, device=dev)
+        nb = 8.0 * B * coils * (n * n + M) + 8.0 * M
+    k = fw(img, om, smaps=sm)
+    timed(name + " fwd", lambda: fw(img, om, smaps=sm), nb)
+    timed(name + " adj", lambda: ad(k, om, smaps=sm), nb)
