@@ -236,15 +236,21 @@ def run_ours(args):
                 "d2h_bytes_per_step": host_out.numel() * 4},
         "gpu_launches": int(launches),
         "clocks": clocks.summary(),
-        "roofline": {"bound": "hbm", "kernel": "pdu_radon_fwd_f32 (transpose + radon_fwd_strip_kernel), 512 views",
-                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        "roofline": {"bound": "hbm", "kernel": "pdu_radon_fwd_f32 (transpose_kernel + radon_fwd_strip_kernel<32,8,32,136,2,8>), 512 views",
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     # dram__bytes_read.sum + dram__bytes_write.sum of the strip kernel, one ncu --set full capture
+                     # (profiles/r01_ncu_full_summary_fwd_filter.md): the 8.4 MB sinogram is still in L2 when the kernel ends
+                     "traffic": 8419584,
                      "peak_source": peak_src, "algorithmic_bytes": alg_bytes, "avg_launch_ms": fwd_avg_ms,
                      "launches_timed": len(fwd_ms),
                      "gsamples_per_s": BATCH * A_FULL * N * N / (fwd_avg_ms * 1e-3) / 1e9,
-                     "note": "bound on-chip (FP32 issue + shared-memory bandwidth), not by HBM: DESIGN.md"},
+                     "smem_roof_frac": (BATCH * A_FULL * N * N / (fwd_avg_ms * 1e-3)) / (148 * 8 * 1.965e9),
+                     "note": "bound on-chip, not by HBM (43 samples per algorithmic byte): smem_roof_frac is samples/s "
+                             "against the shared-memory crossbar roof of 8 bilinear samples/clk/SM (16 B/sample at 128 B/clk); "
+                             "ncu: issue 64 %, L1/shared pipe 74 % busy. DESIGN.md section 3"},
         "operators": ops,
     }
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:                 # the CPU leg is reported at N = 1 only
         line["cpu_baseline"] = cpu_baseline(sample_slices=4)
     print(json.dumps(line), flush=True)
 
@@ -324,12 +330,21 @@ CPU_NOTE = ("own CPU restatement (oracle/radon_c.c, OpenMP float64 operators + t
             "not the reference: torch_radon has no CPU path and is not mounted")
 
 
+def use_all_host_cores():
+    """torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU legs are meant to use the whole host."""
+    from oracle import c_port as oc
+    n = os.cpu_count() or 1
+    torch.set_num_threads(n)
+    oc.set_threads(n)
+
+
 def cpu_cores():
     from oracle import c_port as oc
     return max(torch.get_num_threads(), oc.n_threads())
 
 
 def cpu_baseline(sample_slices=4):
+    use_all_host_cores()
     model, sparse, trig, g = cpu_setup(sample_slices)
     cpu_model_step(model, sparse[:1], trig, g)           # warm the thread pools / page in
     t0 = time.perf_counter()
@@ -345,6 +360,7 @@ def run_reference(args):
     if rank != 0:
         return
     sample = 2
+    use_all_host_cores()
     model, sparse, trig, g = cpu_setup(sample)
     warm = min(args.warmup, 1)                   # each step is seconds of CPU work
     for _ in range(warm):

@@ -41,7 +41,12 @@ def _load():
 
 
 def n_threads() -> int:
-    return int(os.environ.get("OMP_NUM_THREADS", os.cpu_count() or 1))
+    return int(_load().pduo_get_threads())
+
+
+def set_threads(n: int) -> None:
+    """Override OMP_NUM_THREADS (torchrun pins it to 1 for its workers)."""
+    _load().pduo_set_threads(C.c_int(int(n)))
 
 
 def _g(g: RadonGeom) -> _Geom:

@@ -183,3 +183,13 @@ void pduo_filter(const double* sino, double* out, const double* taps, long rows,
         }
     }
 }
+
+/* thread control for callers whose launcher pinned OMP_NUM_THREADS (torchrun sets it to 1) */
+#ifdef _OPENMP
+#include <omp.h>
+void pduo_set_threads(int n) { if (n > 0) omp_set_num_threads(n); }
+int pduo_get_threads(void) { return omp_get_max_threads(); }
+#else
+void pduo_set_threads(int n) { (void)n; }
+int pduo_get_threads(void) { return 1; }
+#endif

@@ -65,8 +65,8 @@ WANT = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "la
         "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio"]
 
 
-def full():
-    rep = os.path.join(root, "gpurun_out", "prof_ops.ncu-rep")
+def full(rep_name="prof_ops.ncu-rep", suffix=""):
+    rep = os.path.join(root, "gpurun_out", rep_name)
     if not os.path.exists(rep):
         return
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
@@ -74,15 +74,16 @@ def full():
     hdr, units = rows[0], rows[1]
     idx = [(w, hdr.index(w)) for w in WANT if w in hdr]
     ki = hdr.index("Kernel Name")
-    with open(os.path.join(out_dir, f"{tag}_ncu_full_summary.md"), "w") as f:
+    with open(os.path.join(out_dir, f"{tag}_ncu_full_summary{suffix}.md"), "w") as f:
         f.write(f"# {tag}: ncu --set full, selected counters per captured launch (tools/prof_ops.py)\n\n"
                 "Captured under the profiler (replays, cold caches): use for ratios and stall reasons, not for timing.\n")
         for r in rows[2:]:
             f.write(f"\n## `{r[ki][:120]}`\n\n| metric | value | unit |\n|---|---:|---|\n")
             for w, i in idx:
                 f.write(f"| {w} | {r[i]} | {units[i]} |\n")
-    print("wrote", f"{tag}_ncu_full_summary.md")
+    print("wrote", f"{tag}_ncu_full_summary{suffix}.md")
 
 
 launches()
 full()
+full("prof_fwd2.ncu-rep", "_fwd_filter")
