@@ -128,6 +128,11 @@ __global__ void __launch_bounds__(TX*(TY / PY))
 #pragma unroll
     for (int k = 0; k < PY; ++k) acc[k] = 0.f;
     constexpr float MAGIC = 8388608.f;
+    static_assert(PY % 2 == 0, "pixels are processed in packed pairs");
+    ull ly_pk[PY / 2];      // row offsets inside the tile of this thread's pixel pairs, clamped to the image
+#pragma unroll
+    for (int k = 0; k < PY; k += 2)
+        ly_pk[k / 2] = pk2(fminf(ly0 + (float)(k * RY), (float)ey), fminf(ly0 + (float)((k + 1) * RY), (float)ey));
 
     for (int a0 = 0; a0 < g.n_angles; a0 += AC) {
         const int na = min(AC, g.n_angles - a0);
@@ -185,40 +190,61 @@ __global__ void __launch_bounds__(TX*(TY / PY))
             }
             __syncthreads();
             if (x < g.n) {
+                // Packed FP32 (FFMA2 / FADD2.RM): two of the thread's PY pixels per instruction for the
+                // coordinate, its floor and its fraction.  ly_pk holds the row offsets of the pixel pairs,
+                // clamped to the image so that padding rows of an edge tile stay inside the staged interval
+                // (no per-tap clamp).
+                const ull p_m = pk2(MAGIC, MAGIC);
 #pragma unroll 2
                 for (int al = 0; al < na; ++al) {
                     const float2* seg = s_seg[al];
                     if (!FAN) {
                         const float4 v = *reinterpret_cast<const float4*>(s_view[al]);
-                        const float ta = fmaf(v.x, lx, fmaf(v.y, ly0, v.z));
-                        const float step = v.y * (float)RY;
+                        const float tx = fmaf(v.x, lx, v.z);
+                        const ull p_tx = pk2(tx, tx), p_b = pk2(v.y, v.y);
 #pragma unroll
-                        for (int k = 0; k < PY; ++k) {
-                            const float tl = fmaf((float)k, step, ta);          // >= 1 by construction
-                            const float tf = __fadd_rd(tl, MAGIC);
-                            const int i0 = min(__float_as_int(tf) & 0x7fffff, SEG - 1);   // clamp: padding pixels of edge tiles
-                            const float fr = tl - (tf - MAGIC);
-                            const float2 sv = seg[i0];
-                            acc[k] += fmaf(fr, sv.y, sv.x);
+                        for (int k = 0; k < PY; k += 2) {
+                            const ull p_tl = fma2(p_b, ly_pk[k / 2], p_tx);        // >= 1 by construction
+                            const ull p_t = add2_rm(p_tl, p_m);
+                            const ull p_fr = sub2(p_tl, sub2(p_t, p_m));
+                            float t0, t1, f0, f1;
+                            upk2(p_t, t0, t1);
+                            upk2(p_fr, f0, f1);
+                            const float2 s0 = seg[__float_as_int(t0) & 0x7fffff];
+                            const float2 s1 = seg[__float_as_int(t1) & 0x7fffff];
+                            acc[k] += fmaf(f0, s0.y, s0.x);
+                            acc[k + 1] += fmaf(f1, s1.y, s1.x);
                         }
                     } else {
                         const float4 v = *reinterpret_cast<const float4*>(s_view[al]);
                         const float2 tr = *reinterpret_cast<const float2*>(s_view[al] + 4);
-                        const float na_ = fmaf(v.y, lx, fmaf(v.z, ly0, v.x));
-                        const float da_ = fmaf(tr.x, lx, fmaf(-tr.y, ly0, v.w));
-                        const float nstep = v.z * (float)RY, dstep = -tr.y * (float)RY;
+                        const float nx_ = fmaf(v.y, lx, v.x), dx_ = fmaf(tr.x, lx, v.w);
+                        const ull p_nx = pk2(nx_, nx_), p_dx = pk2(dx_, dx_);
+                        const ull p_ny = pk2(v.z, v.z), p_dy = pk2(-tr.y, -tr.y);
+                        const ull p_one = pk2(1.f, 1.f), p_k = pk2(g.k, g.k), p_zero = pk2(0.f, 0.f);
 #pragma unroll
-                        for (int k = 0; k < PY; ++k) {
-                            const float num = fmaf((float)k, nstep, na_), den = fmaf((float)k, dstep, da_);
-                            float r = __fdividef(1.f, den);
-                            r = fmaf(r, fmaf(-den, r, 1.f), r);                 // one Newton step: ~1 ulp
-                            const float tl = fmaxf(num * r, 0.f);
-                            const float tf = __fadd_rd(tl, MAGIC);
-                            const int i0 = min(__float_as_int(tf) & 0x7fffff, SEG - 1);
-                            const float fr = tl - (tf - MAGIC);
-                            const float2 sv = seg[i0];
-                            acc[k] = fmaf(g.k * r, fmaf(fr, sv.y, sv.x), acc[k]);
+                        for (int k = 0; k < PY; k += 2) {
+                            const ull p_num = fma2(p_ny, ly_pk[k / 2], p_nx);
+                            const ull p_den = fma2(p_dy, ly_pk[k / 2], p_dx);
+                            float d0, d1;
+                            upk2(p_den, d0, d1);
+                            ull p_r = pk2(__fdividef(1.f, d0), __fdividef(1.f, d1));
+                            p_r = fma2(p_r, sub2(p_one, mul2(p_den, p_r)), p_r);   // one Newton step: ~1 ulp
+                            float q0, q1;
+                            upk2(mul2(p_num, p_r), q0, q1);
+                            const ull p_tl = pk2(fmaxf(q0, 0.f), fmaxf(q1, 0.f));
+                            const ull p_t = add2_rm(p_tl, p_m);
+                            const ull p_fr = sub2(p_tl, sub2(p_t, p_m));
+                            float t0, t1, f0, f1, w0, w1;
+                            upk2(p_t, t0, t1);
+                            upk2(p_fr, f0, f1);
+                            upk2(mul2(p_k, p_r), w0, w1);
+                            const float2 s0 = seg[min(__float_as_int(t0) & 0x7fffff, SEG - 1)];
+                            const float2 s1 = seg[min(__float_as_int(t1) & 0x7fffff, SEG - 1)];
+                            acc[k] = fmaf(w0, fmaf(f0, s0.y, s0.x), acc[k]);
+                            acc[k + 1] = fmaf(w1, fmaf(f1, s1.y, s1.x), acc[k + 1]);
                         }
+                        (void)p_zero;
                     }
                 }
             }

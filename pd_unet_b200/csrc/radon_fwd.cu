@@ -101,21 +101,6 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, in
         : "memory");
 }
 
-// packed-FP32 helpers (sm_100 FFMA2 / FADD2): a 64-bit register holds (lo, hi) floats
-typedef unsigned long long ull;
-__device__ __forceinline__ ull pk2(float lo, float hi) { ull r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
-__device__ __forceinline__ void upk2(ull v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
-__device__ __forceinline__ ull fma2(ull a, ull b, ull c) { ull d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
-__device__ __forceinline__ ull add2(ull a, ull b) { ull d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
-__device__ __forceinline__ ull add2_rm(ull a, ull b) { ull d; asm("add.rm.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
-__device__ __forceinline__ ull sub2(ull a, ull b) { ull d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
-template <int OFF>
-__device__ __forceinline__ float lds_f32(uint32_t addr) {
-    float v;
-    asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(addr), "n"(OFF));
-    return v;
-}
-
 template <int DB, int AG, int TH, int W, int NBUF>
 struct FwdCfg {
     static constexpr int THREADS = DB * AG;
