@@ -152,11 +152,13 @@ PDU_API int pdu_nufft_interp_adj_c64(pdu_nufft_plan_t* plan, const float* kdata,
  * convolutions want).  One-channel tensors are the same bytes either way. */
 enum { PDU_LAYOUT_NCHW = 0, PDU_LAYOUT_NHWC = 1 };
 
-/* out = cat(a [batch, ca, plane], scale_b * b [batch, cb, plane], c [batch, cc, plane]) along the
- * channel axis, all four tensors in `layout` (c may be NULL with cc == 0).  Replaces torch.cat feeding
- * each primal / dual block, and the 1/op_norm scaling of the operator output that rides in b. */
+/* out [batch, c_out, plane] = cat(a [batch, ca, plane], scale_b * b [batch, cb, plane],
+ * c [batch, cc, plane], zeros) along the channel axis, all four tensors in `layout` (c may be NULL with
+ * cc == 0; c_out >= ca + cb + cc, the extra channels are zero so that a convolution with zero-padded
+ * weights can run on a tensor-core-friendly channel count).  Replaces torch.cat feeding each primal /
+ * dual block, and the 1/op_norm scaling of the operator output that rides in b. */
 PDU_API int pdu_concat_f32(float* out, const float* a, const float* b, const float* c, int batch,
-                           int ca, int cb, int cc, long plane, float scale_b, int layout,
+                           int ca, int cb, int cc, int c_out, long plane, float scale_b, int layout,
                            pdu_stream_t stream);
 /* out = state + delta (all three in `layout`);  slice [batch, kn, plane] = out[:, k:k+kn], always
  * planar because it is the next operator's input (slice may be NULL).  out may alias state.  Replaces

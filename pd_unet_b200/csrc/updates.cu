@@ -18,6 +18,13 @@ static inline unsigned stream_grid(long work_items, int threads) {
 
 // ------------------------------------------------------------------ concat
 template <typename V>
+__device__ __forceinline__ V vzero();
+template <>
+__device__ __forceinline__ float vzero<float>() { return 0.f; }
+template <>
+__device__ __forceinline__ float4 vzero<float4>() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+
+template <typename V>
 __device__ __forceinline__ V vscale(V a, float s);
 template <>
 __device__ __forceinline__ float vscale<float>(float a, float s) { return a * s; }
@@ -26,34 +33,35 @@ __device__ __forceinline__ float4 vscale<float4>(float4 a, float s) {
     return make_float4(a.x * s, a.y * s, a.z * s, a.w * s);
 }
 
-// planar (NCHW): per batch element the output row is [a-row (la) | b-row (lb) | c-row (lc)] in units of V
+// planar (NCHW): per batch element the output row is [a-row (la) | b-row (lb) | c-row (lc) | zeros (lz)] in units of V
 template <typename V>
 __global__ void __launch_bounds__(256)
     concat_kernel(V* __restrict__ out, const V* __restrict__ a, const V* __restrict__ b, const V* __restrict__ c,
-                  long la, long lb, long lc, float scale_b, long total) {
-    const long lo = la + lb + lc;
+                  long la, long lb, long lc, long lz, float scale_b, long total) {
+    const long lo = la + lb + lc + lz;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
         const long n = i / lo, r = i - n * lo;
         V v;
         if (r < la) v = a[n * la + r];
         else if (r < la + lb) v = vscale<V>(b[n * lb + (r - la)], scale_b);
-        else v = c[n * lc + (r - la - lb)];
+        else if (r < la + lb + lc) v = c[n * lc + (r - la - lb)];
+        else v = vzero<V>();
         out[i] = v;
     }
 }
 
-// channels-last (NHWC): every pixel's output vector is [a-channels | b-channels | c-channels]
+// channels-last (NHWC): every pixel's output vector is [a-channels | b-channels | c-channels | zeros]
 __global__ void __launch_bounds__(256)
     concat_nhwc_kernel(float* __restrict__ out, const float* __restrict__ a, const float* __restrict__ b,
-                       const float* __restrict__ c, int ca, int cb, int cc, float scale_b, long total) {
-    const int ct = ca + cb + cc;
+                       const float* __restrict__ c, int ca, int cb, int cc, int ct, float scale_b, long total) {
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
         const long pix = i / ct;
         const int ch = (int)(i - pix * ct);
         float v;
         if (ch < ca) v = a[pix * ca + ch];
         else if (ch < ca + cb) v = b[pix * cb + (ch - ca)] * scale_b;
-        else v = c[pix * cc + (ch - ca - cb)];
+        else if (ch < ca + cb + cc) v = c[pix * cc + (ch - ca - cb)];
+        else v = 0.f;
         out[i] = v;
     }
 }
@@ -180,25 +188,26 @@ using namespace pdu;
 extern "C" {
 
 int pdu_concat_f32(float* out, const float* a, const float* b, const float* c, int batch, int ca, int cb, int cc,
-                   long plane, float scale_b, int layout, pdu_stream_t stream) {
+                   int c_out, long plane, float scale_b, int layout, pdu_stream_t stream) {
     PDU_REQUIRE(out && a && b, "pdu_concat_f32: null pointer");
     PDU_REQUIRE(batch > 0 && ca > 0 && cb > 0 && cc >= 0 && plane > 0, "pdu_concat_f32: sizes must be positive");
     PDU_REQUIRE((c != nullptr) == (cc > 0), "pdu_concat_f32: c must be given exactly when cc > 0");
-    const long la = ca * plane, lb = cb * plane, lc = cc * plane;
-    const long total = (long)batch * (la + lb + lc);
+    PDU_REQUIRE(c_out >= ca + cb + cc, "pdu_concat_f32: c_out %d is smaller than the %d input channels", c_out, ca + cb + cc);
+    const long la = ca * plane, lb = cb * plane, lc = cc * plane, lz = (long)(c_out - ca - cb - cc) * plane;
+    const long total = (long)batch * (la + lb + lc + lz);
     cudaStream_t st = (cudaStream_t)stream;
     PDU_REQUIRE(layout == PDU_LAYOUT_NCHW || layout == PDU_LAYOUT_NHWC, "pdu_concat_f32: unknown layout %d", layout);
     if (layout == PDU_LAYOUT_NHWC) {
-        concat_nhwc_kernel<<<stream_grid(total, 256), 256, 0, st>>>(out, a, b, c, ca, cb, cc, scale_b, total);
+        concat_nhwc_kernel<<<stream_grid(total, 256), 256, 0, st>>>(out, a, b, c, ca, cb, cc, c_out, scale_b, total);
         PDU_LAUNCHED();
         return PDU_OK;
     }
     const bool vec = plane % 4 == 0 && al16(out) && al16(a) && al16(b) && (c == nullptr || al16(c));
     if (vec) {
         concat_kernel<float4><<<stream_grid(total / 4, 256), 256, 0, st>>>((float4*)out, (const float4*)a, (const float4*)b,
-                                                                           (const float4*)c, la / 4, lb / 4, lc / 4, scale_b, total / 4);
+                                                                           (const float4*)c, la / 4, lb / 4, lc / 4, lz / 4, scale_b, total / 4);
     } else {
-        concat_kernel<float><<<stream_grid(total, 256), 256, 0, st>>>(out, a, b, c, la, lb, lc, scale_b, total);
+        concat_kernel<float><<<stream_grid(total, 256), 256, 0, st>>>(out, a, b, c, la, lb, lc, lz, scale_b, total);
     }
     PDU_LAUNCHED();
     return PDU_OK;

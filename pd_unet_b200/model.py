@@ -39,10 +39,24 @@ class ConvAct(nn.Module):
         super().__init__()
         self.conv = nn.Conv2d(cin, cout, kernel, padding=kernel // 2)
         self.act = nn.PReLU(cout) if act else None
+        self._wpad = None          # (key, weight zero-padded along the input channels); inference-only cache
+
+    def _weight_for(self, cin: int) -> torch.Tensor:
+        """The convolution weight, zero-padded to `cin` input channels when the fused concat delivered a
+        channel count rounded up for the tensor cores (the extra inputs are zeros, so the result is the same)."""
+        w = self.conv.weight
+        if cin == w.shape[1]:
+            return w
+        key = (w.data_ptr(), w._version, cin, w.device)
+        if self._wpad is None or self._wpad[0] != key:
+            wp = torch.zeros((w.shape[0], cin) + tuple(w.shape[2:]), dtype=w.dtype, device=w.device)
+            wp[:, :w.shape[1]] = w.detach()
+            self._wpad = (key, wp.contiguous(memory_format=torch.channels_last))
+        return self._wpad[1]
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         if _fused_epilogue_ok(x):
-            y = nn.functional.conv2d(x, self.conv.weight, None, self.conv.stride, self.conv.padding)
+            y = nn.functional.conv2d(x, self._weight_for(x.shape[1]), None, self.conv.stride, self.conv.padding)
             return updates.bias_prelu_(y, self.conv.bias, self.act.weight if self.act is not None else None)
         y = self.conv(x)
         return self.act(y) if self.act is not None else y
@@ -147,12 +161,15 @@ class PrimalDualUNet(nn.Module):
         f = torch.empty((B, self.n_primal) + tuple(image_shape), dtype=g.dtype, device=g.device, memory_format=fmt).zero_()
         f_op = g.new_zeros((B, self.kc) + tuple(image_shape))
         inv = 1.0 / self.op_scale
+        # inference: round the concatenated channel count up to 8 (zero channels; the first convolution pads
+        # its weights to match) -- with 6 or 5 input channels cuDNN falls back to a CUDA-core kernel
+        pad = 8 if (g.is_cuda and not torch.is_grad_enabled()) else 0
         for i in range(self.n_iter):
             # the 1/op_scale normalisation of each operator output rides in the concat kernel
             kf = self.op_forward(f_op)
-            h, h_op = updates.residual_slice(h, self.dual[i](updates.concat(h, kf, g, scale_b=inv)), 0, self.kd)
+            h, h_op = updates.residual_slice(h, self.dual[i](updates.concat(h, kf, g, scale_b=inv, pad_to=pad)), 0, self.kd)
             kth = self.op_adjoint(h_op)
-            f, f_op = updates.residual_slice(f, self.primal[i](updates.concat(f, kth, scale_b=inv)), 0, self.kc)
+            f, f_op = updates.residual_slice(f, self.primal[i](updates.concat(f, kth, scale_b=inv, pad_to=pad)), 0, self.kc)
         return f_op
 
 

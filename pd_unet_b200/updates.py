@@ -49,7 +49,7 @@ def _empty(shape, like: torch.Tensor, nhwc: bool) -> torch.Tensor:
 
 class _Concat(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, a, b, c, scale_b):
+    def forward(ctx, a, b, c, scale_b, pad_to):
         nhwc = _is_channels_last(a)          # the state tensor decides; one-channel inputs fit either layout
         a = _in_layout(a, nhwc, "a")
         b = _in_layout(b, nhwc, "b")
@@ -60,12 +60,15 @@ class _Concat(torch.autograd.Function):
                 raise ValueError("concat: tensors must agree in every axis but the channel axis")
         ca, cb, cc = a.shape[1], b.shape[1], (c.shape[1] if c is not None else 0)
         ctx.split, ctx.scale_b = (ca, cb, cc), scale_b
-        out = _empty((a.shape[0], ca + cb + cc) + tuple(a.shape[2:]), a, nhwc)
+        c_out = ca + cb + cc
+        if pad_to > 1:
+            c_out = (c_out + pad_to - 1) // pad_to * pad_to
+        out = _empty((a.shape[0], c_out) + tuple(a.shape[2:]), a, nhwc)
         if out.numel():
             with torch.cuda.device(a.device):
                 check(lib().pdu_concat_f32(out.data_ptr(), a.data_ptr(), b.data_ptr(),
                                            c.data_ptr() if c is not None else None, a.shape[0], ca, cb, cc,
-                                           _plane(a), scale_b, LAYOUT_NHWC if nhwc else LAYOUT_NCHW, stream_ptr()),
+                                           c_out, _plane(a), scale_b, LAYOUT_NHWC if nhwc else LAYOUT_NCHW, stream_ptr()),
                       "pdu_concat_f32")
         return out
 
@@ -75,13 +78,16 @@ class _Concat(torch.autograd.Function):
         gb = g[:, ca:ca + cb]
         if ctx.scale_b != 1.0:
             gb = gb * ctx.scale_b
-        return g[:, :ca], gb, (g[:, ca + cb:] if cc else None), None
+        return g[:, :ca], gb, (g[:, ca + cb:ca + cb + cc] if cc else None), None, None
 
 
-def concat(a: torch.Tensor, b: torch.Tensor, c: Optional[torch.Tensor] = None, scale_b: float = 1.0) -> torch.Tensor:
+def concat(a: torch.Tensor, b: torch.Tensor, c: Optional[torch.Tensor] = None, scale_b: float = 1.0,
+           pad_to: int = 0) -> torch.Tensor:
     """cat([a, scale_b * b(, c)], dim=1) for [B, c_i, ...] tensors in one pass.  If `a` is a
-    channels_last tensor the result is channels_last too (what cuDNN's tensor-core convolutions want)."""
-    return _Concat.apply(a, b, c, float(scale_b))
+    channels_last tensor the result is channels_last too (what cuDNN's tensor-core convolutions want).
+    pad_to > 1 appends zero channels up to the next multiple of pad_to (for a convolution whose
+    weights are zero-padded the same way: 6 input channels make cuDNN fall back to a CUDA-core kernel)."""
+    return _Concat.apply(a, b, c, float(scale_b), int(pad_to))
 
 
 class _ResidualSlice(torch.autograd.Function):

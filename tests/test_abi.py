@@ -44,7 +44,7 @@ def test_library_reports_errors_instead_of_crashing(built):
     assert L.pdu_radon_fwd_f32(None, None, None, 1, ctypes.byref(g), None, 0, None) == -1
     assert L.pdu_radon_adj_f32(None, None, None, 1, ctypes.byref(g), None, 0, None) == -1
     assert L.pdu_filter_sinogram_f32(None, None, None, None, 0, 4, 4, None) == -1
-    assert L.pdu_concat_f32(None, None, None, None, 1, 1, 1, 0, 4, 1.0, 0, None) == -1
+    assert L.pdu_concat_f32(None, None, None, None, 1, 1, 1, 0, 2, 4, 1.0, 0, None) == -1
     assert L.pdu_nufft_plan_create(None, 8, 8, 16, 16, 6, 1024, 4, 4, None, None, None, None) == -1
     assert L.pdu_nufft_plan_destroy(None) == 0
     assert L.pdu_radon_workspace_bytes(None, 1) == 0

@@ -147,3 +147,22 @@ def test_fused_conv_modules_match_stock_modules():
         with torch.no_grad():
             got = mod(xd)                                         # fused epilogue
         assert torch.allclose(got, want, atol=1e-5, rtol=1e-5)
+
+
+def test_concat_zero_pads_channels_for_the_tensor_cores():
+    a, b, c = (seeded((2, ch, 6, 10), i) for i, ch in enumerate((4, 1, 1)))
+    want = torch.cat([a, 0.5 * b, c, torch.zeros(2, 2, 6, 10)], 1)
+    al = a.to(DEV).contiguous(memory_format=torch.channels_last)
+    out = updates.concat(al, b.to(DEV), c.to(DEV), scale_b=0.5, pad_to=8)
+    assert out.shape == (2, 8, 6, 10) and torch.equal(out.cpu(), want)
+    assert torch.equal(updates.concat(a.to(DEV), b.to(DEV), c.to(DEV), scale_b=0.5, pad_to=8).cpu(), want)
+    # a convolution fed the padded tensor (fused path pads its weights) equals the stock one on 6 channels
+    from pd_unet_b200.model import ConvAct
+    torch.backends.cudnn.allow_tf32 = False
+    torch.manual_seed(0)
+    conv = ConvAct(6, 8).to(DEV).to(memory_format=torch.channels_last)
+    with torch.enable_grad():
+        ref = conv(want[:, :6].to(DEV).contiguous(memory_format=torch.channels_last).requires_grad_()).detach()
+    with torch.no_grad():
+        got = conv(out)
+    assert torch.allclose(got, ref, atol=1e-5, rtol=1e-5)

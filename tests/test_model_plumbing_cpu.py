@@ -12,7 +12,7 @@ from pd_unet_b200 import model as M, updates
 
 @pytest.fixture
 def cpu_ops(monkeypatch):
-    monkeypatch.setattr(updates, "concat", lambda a, b, c=None, scale_b=1.0:
+    monkeypatch.setattr(updates, "concat", lambda a, b, c=None, scale_b=1.0, pad_to=0:
                         torch.cat([a, scale_b * b] + ([c] if c is not None else []), 1))
 
     def residual_slice(state, delta, k=0, kn=1):
