@@ -33,6 +33,7 @@ import numpy as np
 import torch
 
 N, A_SPARSE, UP, BATCH = 256, 64, 8, 16          # configs[1]
+_STDOUT = None
 A_FULL = A_SPARSE * UP
 MODEL_KW = dict(n_iter=4, n_primal=4, n_dual=4, unet_base=32, unet_depth=3, dual_features=32)
 METRIC = "PD-UNet recon slices/sec"
@@ -252,6 +253,7 @@ def run_ours(args):
     }
     if not args.no_cpu and world == 1:                 # the CPU leg is reported at N = 1 only
         line["cpu_baseline"] = cpu_baseline(sample_slices=4)
+    _STDOUT.restore()
     print(json.dumps(line), flush=True)
 
 
@@ -377,6 +379,7 @@ def run_reference(args):
     v = sample * done / dt
     base = {"value": v, "unit": "slices/s", "cores": cpu_cores(), "kind": "port", "host_cpus": os.cpu_count(),
             "sample": f"{sample} slices per step, {done} step(s) timed (bounded at 150 s); " + CPU_NOTE}
+    _STDOUT.restore()
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "slices/s", "n_gpus": args.gpus, "steps": done,
         "warmup": warm, "ms_per_step": dt / done * 1e3, "higher_is_better": True, "scaling": "weak",
@@ -388,6 +391,21 @@ def run_reference(args):
         "gpu_launches": 0}), flush=True)
 
 
+class StdoutToStderr:
+    """Route file descriptor 1 to stderr while the benchmark runs, so that libraries that print to stdout
+    (NCCL's version banner, cuDNN warnings) cannot get in front of the ONE JSON line; restore() before printing."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self._saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def restore(self):
+        sys.stdout.flush()
+        os.dup2(self._saved, 1)
+        os.close(self._saved)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -396,6 +414,8 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     args = ap.parse_args()
+    global _STDOUT
+    _STDOUT = StdoutToStderr()
     if args.impl == "reference":
         run_reference(args)
     else:
