@@ -152,12 +152,11 @@ def _full_cfg(name):
             -ang, B)
 
 
-# White-noise sinograms at D = 512 are the worst case for any float32 backprojector: the detector
-# coordinate t (|t| up to 512, tile-relative up to 96) carries ~5e-6 of rounding and the interpolated
-# value changes by O(1) per unit of t, so the result cannot agree with a float64 oracle to better than
-# ~2e-5.  On the data the operator actually sees (filtered sinograms of objects) the same kernels hold
-# the 1e-5 of BASELINE.json; both are asserted below with their own tolerance.
-TOL_NOISE_FULL = 3e-5
+# White-noise sinograms are the worst case for a float32 backprojector (the interpolated value changes by
+# O(1) per unit of detector coordinate).  The tile-relative float64 set-up of radon_adj_tile_kernel keeps
+# the coordinate error at the magnitude of the tile, which holds the 1e-5 budget even there
+# (measured 3.4e-6 at 512 bins x 1024 views, profiles/r01_parity.md).
+TOL_NOISE_FULL = TOL
 
 
 @pytest.mark.parametrize("name", ["cfg2", "cfg3"])
