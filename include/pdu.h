@@ -138,6 +138,22 @@ PDU_API int pdu_nufft_adj_c64(pdu_nufft_plan_t* plan, const float* kdata, float*
                               const float* omega, const float* smaps, int batch, int coils,
                               int smaps_batch, long m, float scale, void* workspace,
                               size_t workspace_bytes, pdu_stream_t stream);
+/* The adjoint interpolator of one trajectory as a sparse matrix sorted by grid cell (CSR), built once
+ * and applied as a gather: no atomics, no memset, bit-reproducible sums.  Worth it whenever a trajectory
+ * is used more than once (every unrolled iteration / DCF iteration / training step).  `csr` is a
+ * caller-owned device buffer of pdu_nufft_csr_bytes(plan, m) bytes, 256-byte aligned; it also holds the
+ * build scratch.  pdu_nufft_adj_csr_c64 is pdu_nufft_adj_c64 with the scatter replaced by the gather
+ * (csr == NULL falls back to the atomic scatter).
+ * Replaces [RECALL] torchkbnufft's precomputed `interp_mats` path (calc_tensor_spmatrix + sparse matmul). */
+PDU_API size_t pdu_nufft_csr_bytes(const pdu_nufft_plan_t* plan, long m);
+PDU_API int pdu_nufft_csr_build(pdu_nufft_plan_t* plan, const float* omega, long m, void* csr,
+                                size_t csr_bytes, pdu_stream_t stream);
+PDU_API int pdu_nufft_interp_adj_csr_c64(pdu_nufft_plan_t* plan, const float* kdata, float* grid,
+                                         const void* csr, int planes, long m, pdu_stream_t stream);
+PDU_API int pdu_nufft_adj_csr_c64(pdu_nufft_plan_t* plan, const float* kdata, float* image,
+                                  const float* omega, const float* smaps, int batch, int coils,
+                                  int smaps_batch, long m, float scale, const void* csr, void* workspace,
+                                  size_t workspace_bytes, pdu_stream_t stream);
 /* Table interpolation only: grid [planes, k0, k1] <-> kdata [planes, m].
  * Replace [RECALL] torchkbnufft `KbInterp.forward` / `KbInterpAdjoint.forward`; the adjoint
  * ACCUMULATES into grid (zero it first). */

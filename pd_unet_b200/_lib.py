@@ -53,6 +53,11 @@ SIGNATURES = {
                                     C.c_size_t, _p]),
     "pdu_nufft_adj_c64": (C.c_int, [_p, _p, _p, _p, _p, C.c_int, C.c_int, C.c_int, C.c_long, C.c_float, _p,
                                     C.c_size_t, _p]),
+    "pdu_nufft_csr_bytes": (C.c_size_t, [_p, C.c_long]),
+    "pdu_nufft_csr_build": (C.c_int, [_p, _p, C.c_long, _p, C.c_size_t, _p]),
+    "pdu_nufft_interp_adj_csr_c64": (C.c_int, [_p, _p, _p, _p, C.c_int, C.c_long, _p]),
+    "pdu_nufft_adj_csr_c64": (C.c_int, [_p, _p, _p, _p, _p, C.c_int, C.c_int, C.c_int, C.c_long, C.c_float, _p, _p,
+                                        C.c_size_t, _p]),
     "pdu_nufft_interp_fwd_c64": (C.c_int, [_p, _p, _p, _p, C.c_int, C.c_long, _p]),
     "pdu_nufft_interp_adj_c64": (C.c_int, [_p, _p, _p, _p, C.c_int, C.c_long, _p]),
     "pdu_concat_f32": (C.c_int, [_p, _p, _p, _p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_long, C.c_float, C.c_int, _p]),

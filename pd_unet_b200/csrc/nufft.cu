@@ -12,6 +12,8 @@
 // sequence oracle/nufft.py::_tap_indices_f32 performs, so both read the same table entries.
 #include <cufft.h>
 
+#include <cub/device/device_radix_sort.cuh>
+
 #include <map>
 #include <mutex>
 
@@ -298,6 +300,231 @@ static int launch_interp_adj(pdu_nufft_plan* p, const float2* kdata, float2* gri
     return PDU_OK;
 }
 
+// ------------------------------------------------------------------ adjoint interpolation as a sorted gather
+// The atomic scatter above sits on the L2 atomic unit's rate (measured 0.23 T float2 atomics/s on B200
+// whatever the occupancy), and its summation order changes from run to run.  For a trajectory that is
+// used more than once -- every unrolled iteration, every DCF iteration, every training step -- the
+// adjoint interpolator is built once as a sparse matrix in CSR form (one row per grid cell: the samples
+// that touch it and their conjugated Kaiser-Bessel weights, phase included), sorted by cell with a
+// stable radix sort, and applied as a gather: no atomics, no memset, bit-reproducible.
+//   csr buffer:  row_ptr int32[cells + 1] | samp int32[n] | w float2[n] | build scratch      (n = M J^2)
+constexpr int CSR_LONG = 32;      // rows with more entries than this are summed by a whole warp
+
+struct CsrView {
+    int* row_ptr;
+    int* n_long;       // [1] number of long rows
+    int* long_rows;    // [cells] their cell indices (first n_long valid)
+    int* samp;
+    float2* w;
+    // build scratch
+    unsigned* key_in;
+    unsigned* id_in;
+    unsigned* key_out;
+    unsigned* id_out;
+    float2* w_unsorted;
+    void* cub_tmp;
+    size_t cub_bytes;
+    size_t total;
+};
+
+static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+static CsrView csr_layout(const pdu_nufft_plan* p, long M, void* base, bool with_scratch = true) {
+    const size_t n = (size_t)M * p->J * p->J, cells = (size_t)p->k0 * p->k1;
+    CsrView v;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += align256(bytes); return (char*)base + o; };
+    v.row_ptr = (int*)take((cells + 1) * 4);
+    v.n_long = (int*)take(4);
+    v.long_rows = (int*)take(cells * 4);
+    v.samp = (int*)take(n * 4);
+    v.w = (float2*)take(n * 8);
+    v.key_in = (unsigned*)take(n * 4);
+    v.id_in = (unsigned*)take(n * 4);
+    v.key_out = (unsigned*)take(n * 4);
+    v.id_out = (unsigned*)take(n * 4);
+    v.w_unsorted = (float2*)take(n * 8);
+    v.cub_bytes = 0;
+    v.cub_tmp = nullptr;
+    v.total = off;
+    if (!with_scratch) return v;      // applying the matrix only needs the three arrays above
+    cub::DeviceRadixSort::SortPairs(nullptr, v.cub_bytes, (const unsigned*)nullptr, (unsigned*)nullptr, (const unsigned*)nullptr,
+                                    (unsigned*)nullptr, (int)n);
+    v.cub_tmp = take(v.cub_bytes);
+    v.total = off;
+    return v;
+}
+
+// one thread per sample: its J^2 (cell, weight) entries, weight = conj(phase * c0 * c1)
+__global__ void __launch_bounds__(128)
+    csr_entries_kernel(const float* __restrict__ omega, const float2* __restrict__ t0, const float2* __restrict__ t1,
+                       NufftDims d, long M, unsigned* __restrict__ key, unsigned* __restrict__ id, float2* __restrict__ w) {
+    const long m = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    const float om0 = __ldg(omega + m), om1 = __ldg(omega + M + m);
+    int g0[MAXJ], g1[MAXJ];
+    float2 c0[MAXJ], c1[MAXJ];
+    axis_taps(om0, d.gam0, d.k0, d.J, d.L, t0, g0, c0);
+    axis_taps(om1, d.gam1, d.k1, d.J, d.L, t1, g1, c1);
+    const float2 ph = shift_phase(om0, om1, d.shift0, d.shift1);
+    const float2 one = make_float2(1.f, 0.f);
+    const float2 cph = cmul_conj(one, ph);                       // conj(phase)
+    long e = m * d.J * d.J;
+#pragma unroll
+    for (int a = 0; a < MAXJ; ++a) {
+        if (a < d.J) {
+            const float2 wa = cmul_conj(cph, c0[a]);            // the same association as the scatter: ((y conj ph) conj c0) conj c1
+#pragma unroll
+            for (int b = 0; b < MAXJ; ++b) {
+                if (b < d.J) {
+                    key[e] = (unsigned)(g0[a] * d.k1 + g1[b]);
+                    id[e] = (unsigned)e;
+                    w[e] = cmul_conj(wa, c1[b]);
+                    ++e;
+                }
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+    csr_finish_kernel(const unsigned* __restrict__ key_sorted, const unsigned* __restrict__ id_sorted,
+                      const float2* __restrict__ w_unsorted, int* __restrict__ row_ptr, int* __restrict__ samp,
+                      float2* __restrict__ w, long n, long cells, int taps) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const unsigned e = id_sorted[i];
+        samp[i] = (int)(e / (unsigned)taps);
+        w[i] = w_unsorted[e];
+    }
+    if (i <= cells) {          // row_ptr[c] = first sorted position whose key is >= c
+        long lo = 0, hi = n;
+        while (lo < hi) {
+            const long mid = (lo + hi) >> 1;
+            if ((long)key_sorted[mid] < i) lo = mid + 1; else hi = mid;
+        }
+        row_ptr[i] = (int)lo;
+    }
+}
+
+// rows too long for one thread (the k-space centre of a radial trajectory collects every spoke)
+__global__ void __launch_bounds__(256)
+    csr_long_rows_kernel(const int* __restrict__ row_ptr, int* __restrict__ n_long, int* __restrict__ long_rows, long cells) {
+    const long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cells) return;
+    if (row_ptr[c + 1] - row_ptr[c] > CSR_LONG) long_rows[atomicAdd(n_long, 1)] = (int)c;
+}
+
+// one thread per grid cell, PG planes per thread (an entry is loaded once for all of them)
+template <int PG>
+__global__ void __launch_bounds__(256)
+    interp_adj_csr_kernel(const float2* __restrict__ kdata, float2* __restrict__ grid, const int* __restrict__ row_ptr,
+                          const int* __restrict__ samp, const float2* __restrict__ w, long cells, long M, int planes) {
+    const long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cells) return;
+    const int p0 = blockIdx.y * PG;
+    float2 acc[PG];
+#pragma unroll
+    for (int q = 0; q < PG; ++q) acc[q] = make_float2(0.f, 0.f);
+    const int beg = __ldg(row_ptr + c), end = __ldg(row_ptr + c + 1);
+    if (end - beg > CSR_LONG) return;                     // interp_adj_csr_long_kernel owns this cell
+    for (int i = beg; i < end; ++i) {
+        const long m = __ldg(samp + i);
+        const float2 wi = __ldg(w + i);
+#pragma unroll
+        for (int q = 0; q < PG; ++q) {
+            if (p0 + q < planes) {
+                const float2 z = cmul(__ldg(kdata + (long)(p0 + q) * M + m), wi);
+                acc[q].x += z.x;
+                acc[q].y += z.y;
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < PG; ++q)
+        if (p0 + q < planes) grid[(long)(p0 + q) * cells + c] = acc[q];
+}
+
+// one warp per long row; lanes stride the entries, a fixed-order shuffle tree adds them up (reproducible)
+template <int PG>
+__global__ void __launch_bounds__(256)
+    interp_adj_csr_long_kernel(const float2* __restrict__ kdata, float2* __restrict__ grid, const int* __restrict__ row_ptr,
+                               const int* __restrict__ n_long, const int* __restrict__ long_rows,
+                               const int* __restrict__ samp, const float2* __restrict__ w, long cells, long M, int planes) {
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    const int p0 = blockIdx.y * PG;
+    const int nl = __ldg(n_long);
+    for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < nl; r += warps) {
+        const long c = __ldg(long_rows + r);
+        const int beg = __ldg(row_ptr + c), end = __ldg(row_ptr + c + 1);
+        float2 acc[PG];
+#pragma unroll
+        for (int q = 0; q < PG; ++q) acc[q] = make_float2(0.f, 0.f);
+        for (int i = beg + lane; i < end; i += 32) {
+            const long m = __ldg(samp + i);
+            const float2 wi = __ldg(w + i);
+#pragma unroll
+            for (int q = 0; q < PG; ++q) {
+                if (p0 + q < planes) {
+                    const float2 z = cmul(__ldg(kdata + (long)(p0 + q) * M + m), wi);
+                    acc[q].x += z.x;
+                    acc[q].y += z.y;
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < PG; ++q) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                acc[q].x += __shfl_xor_sync(0xffffffffu, acc[q].x, o);
+                acc[q].y += __shfl_xor_sync(0xffffffffu, acc[q].y, o);
+            }
+            if (lane == 0 && p0 + q < planes) grid[(long)(p0 + q) * cells + c] = acc[q];
+        }
+    }
+}
+
+static int csr_build(pdu_nufft_plan* p, const float* omega, long M, void* buf, size_t bytes, cudaStream_t st) {
+    const long n = M * p->J * p->J, cells = (long)p->k0 * p->k1;
+    PDU_REQUIRE(n < 2147483647L && cells < 2147483647L, "pdu_nufft_csr_build: %ld entries exceed 32-bit indexing", n);
+    CsrView v = csr_layout(p, M, buf);
+    if (!buf || bytes < v.total || ((uintptr_t)buf & 255)) {
+        set_error("pdu_nufft_csr_build: buffer of %zu bytes (256-byte aligned) required, got %zu", v.total, buf ? bytes : (size_t)0);
+        return PDU_ENOMEM;
+    }
+    csr_entries_kernel<<<(unsigned)cdiv(M, 128), 128, 0, st>>>(omega, p->d_t0, p->d_t1, dims_of(p), M, v.key_in, v.id_in,
+                                                              v.w_unsorted);
+    PDU_LAUNCHED();
+    int bits = 1;
+    while ((1L << bits) < cells) ++bits;
+    PDU_CUDA(cub::DeviceRadixSort::SortPairs(v.cub_tmp, v.cub_bytes, v.key_in, v.key_out, v.id_in, v.id_out, (int)n, 0, bits, st));
+    count_launch(4);
+    const long work = n > cells + 1 ? n : cells + 1;
+    csr_finish_kernel<<<(unsigned)cdiv(work, 256), 256, 0, st>>>(v.key_out, v.id_out, v.w_unsorted, v.row_ptr, v.samp, v.w, n,
+                                                                 cells, p->J * p->J);
+    PDU_LAUNCHED();
+    PDU_CUDA(cudaMemsetAsync(v.n_long, 0, 4, st));
+    csr_long_rows_kernel<<<(unsigned)cdiv(cells, 256), 256, 0, st>>>(v.row_ptr, v.n_long, v.long_rows, cells);
+    PDU_LAUNCHED();
+    return PDU_OK;
+}
+
+static int launch_interp_adj_csr(pdu_nufft_plan* p, const float2* kdata, float2* grid, const void* csr, int planes, long M,
+                                 cudaStream_t st) {
+    const CsrView v = csr_layout(p, M, const_cast<void*>(csr), false);
+    const long cells = (long)p->k0 * p->k1;
+    constexpr int PG = 4;
+    dim3 g((unsigned)cdiv(cells, 256), (unsigned)cdiv(planes, PG));
+    interp_adj_csr_kernel<PG><<<g, 256, 0, st>>>(kdata, grid, v.row_ptr, v.samp, v.w, cells, M, planes);
+    PDU_LAUNCHED();
+    dim3 gl((unsigned)(2 * sm_count()), (unsigned)cdiv(planes, PG));      // 8 warps per CTA, grid-stride over the long rows
+    interp_adj_csr_long_kernel<PG><<<gl, 256, 0, st>>>(kdata, grid, v.row_ptr, v.n_long, v.long_rows, v.samp, v.w, cells, M,
+                                                       planes);
+    PDU_LAUNCHED();
+    return PDU_OK;
+}
+
 static int check_call(const pdu_nufft_plan* p, const void* a, const void* b, const void* omega, int batch, int coils,
                       int smaps_batch, const void* smaps, long m, const char* who) {
     PDU_REQUIRE(p != nullptr, "%s: plan is null", who);
@@ -397,10 +624,16 @@ static int nufft_fwd_chunk(pdu_nufft_plan_t* p, const float2* image, float2* kda
 }
 
 static int nufft_adj_chunk(pdu_nufft_plan_t* p, const float2* kdata, float2* image, const float* omega, const float2* smaps,
-                           int batch, int coils, int smaps_batch, long m, float scale, float2* grid, cudaStream_t st) {
+                           int batch, int coils, int smaps_batch, long m, float scale, float2* grid, const void* csr,
+                           cudaStream_t st) {
     const int planes = batch * coils;
-    PDU_CUDA(cudaMemsetAsync(grid, 0, (size_t)planes * p->k0 * p->k1 * sizeof(float2), st));
-    int rc = launch_interp_adj(p, kdata, grid, omega, planes, m, st);
+    int rc;
+    if (csr) {
+        rc = launch_interp_adj_csr(p, kdata, grid, csr, planes, m, st);       // writes every cell: no memset
+    } else {
+        PDU_CUDA(cudaMemsetAsync(grid, 0, (size_t)planes * p->k0 * p->k1 * sizeof(float2), st));
+        rc = launch_interp_adj(p, kdata, grid, omega, planes, m, st);
+    }
     if (rc) return rc;
     rc = run_fft(p, grid, planes, CUFFT_INVERSE, st);
     if (rc) return rc;
@@ -435,9 +668,36 @@ int pdu_nufft_fwd_c64(pdu_nufft_plan_t* p, const float* image, float* kdata, con
     return PDU_OK;
 }
 
+size_t pdu_nufft_csr_bytes(const pdu_nufft_plan_t* p, long m) {
+    if (!p || m <= 0) return 0;
+    return csr_layout(p, m, nullptr).total;
+}
+
+int pdu_nufft_csr_build(pdu_nufft_plan_t* p, const float* omega, long m, void* csr, size_t csr_bytes, pdu_stream_t stream) {
+    PDU_REQUIRE(p && omega && m > 0, "pdu_nufft_csr_build: null pointer or m <= 0");
+    return csr_build(p, omega, m, csr, csr_bytes, (cudaStream_t)stream);
+}
+
+int pdu_nufft_interp_adj_csr_c64(pdu_nufft_plan_t* p, const float* kdata, float* grid, const void* csr, int planes, long m,
+                                 pdu_stream_t stream) {
+    PDU_REQUIRE(p && kdata && grid && csr && planes > 0 && m > 0, "pdu_nufft_interp_adj_csr_c64: null pointer or empty problem");
+    return launch_interp_adj_csr(p, (const float2*)kdata, (float2*)grid, csr, planes, m, (cudaStream_t)stream);
+}
+
+int pdu_nufft_adj_csr_c64(pdu_nufft_plan_t* p, const float* kdata, float* image, const float* omega, const float* smaps,
+                          int batch, int coils, int smaps_batch, long m, float scale, const void* csr, void* workspace,
+                          size_t workspace_bytes, pdu_stream_t stream);
+
 int pdu_nufft_adj_c64(pdu_nufft_plan_t* p, const float* kdata, float* image, const float* omega, const float* smaps,
                       int batch, int coils, int smaps_batch, long m, float scale, void* workspace, size_t workspace_bytes,
                       pdu_stream_t stream) {
+    return pdu_nufft_adj_csr_c64(p, kdata, image, omega, smaps, batch, coils, smaps_batch, m, scale, nullptr, workspace,
+                                 workspace_bytes, stream);
+}
+
+int pdu_nufft_adj_csr_c64(pdu_nufft_plan_t* p, const float* kdata, float* image, const float* omega, const float* smaps,
+                          int batch, int coils, int smaps_batch, long m, float scale, const void* csr, void* workspace,
+                          size_t workspace_bytes, pdu_stream_t stream) {
     int rc = check_call(p, kdata, image, omega, batch, coils, smaps_batch, smaps, m, "pdu_nufft_adj_c64");
     if (rc) return rc;
     const int cb = batch_chunk(p, batch, coils);
@@ -452,7 +712,7 @@ int pdu_nufft_adj_c64(pdu_nufft_plan_t* p, const float* kdata, float* image, con
         const int nb = b0 + cb <= batch ? cb : batch - b0;
         rc = nufft_adj_chunk(p, (const float2*)kdata + (long)b0 * coils * m, (float2*)image + b0 * img_b, omega,
                              smaps ? (const float2*)smaps + b0 * smap_b : nullptr, nb, coils, smaps_batch == 1 ? 1 : nb, m, scale,
-                             (float2*)workspace, (cudaStream_t)stream);
+                             (float2*)workspace, csr, (cudaStream_t)stream);
         if (rc) return rc;
     }
     return PDU_OK;

@@ -104,3 +104,33 @@ def test_batched_trajectory_empty_and_errors():
         A(x.real, om)
     with pytest.raises(NotImplementedError):
         A(x, om, interp_mats=(None, None))
+
+
+def test_sorted_gather_adjoint_matches_scatter_and_is_reproducible():
+    """The CSR (sorted gather) adjoint interpolator: same numbers as the atomic scatter and the oracle,
+    bit-identical from call to call, rebuilt when the trajectory changes."""
+    im = (64, 48)
+    spec = oracle.NufftSpec(im)
+    om = _traj(14, 128)
+    omd = torch.from_numpy(om).to(DEV)
+    k = seeded((2, 3, om.shape[1]), 21, complex_=True)
+    adj = pdu.KbNufftAdjoint(im)
+    adj._plan.use_csr = True                                     # "auto" would pick the scatter for 6 planes
+    a1 = adj(k.to(DEV), omd)
+    a2 = adj(k.to(DEV), omd)
+    assert torch.equal(a1, a2)                                   # no atomics: reproducible
+    assert rel_l2(a1, oracle.nufft_adjoint(k, om, spec)) <= TOL
+    adj._plan.use_csr = False
+    assert rel_l2(adj(k.to(DEV), omd), a1) <= 1e-6               # the scatter agrees
+    adj._plan.use_csr = True
+    # interp-only path and a modified trajectory (in-place change bumps the version -> rebuild)
+    ia = pdu.KbInterpAdjoint(im)
+    ia._plan.use_csr = True
+    g1 = ia(k.to(DEV), omd)
+    assert rel_l2(g1, oracle.interp_adjoint(k, om, spec)) <= TOL
+    omd.mul_(0.5)
+    assert rel_l2(adj(k.to(DEV), omd), oracle.nufft_adjoint(k, 0.5 * om, spec)) <= TOL
+    # smaps + ortho through the same path
+    sm = coil_maps(3, 64)[None][..., :48].contiguous()
+    xa = adj(k.to(DEV), omd, smaps=sm.to(DEV), norm="ortho")
+    assert rel_l2(xa, oracle.nufft_adjoint(k, 0.5 * om, spec, smaps=sm, norm="ortho")) <= TOL

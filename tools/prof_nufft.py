@@ -45,4 +45,8 @@ for name, n, coils, B, spokes in (("cfg1 256^2 c1 b1 32sp", 256, 1, 1, 32), ("cf
         nb = 8.0 * B * coils * (n * n + M) + 8.0 * M
     k = fw(img, om, smaps=sm)
     timed(name + " fwd", lambda: fw(img, om, smaps=sm), nb)
-    timed(name + " adj", lambda: ad(k, om, smaps=sm), nb)
+    ad._plan.use_csr = True
+    timed(name + " adj (sorted gather)", lambda: ad(k, om, smaps=sm), nb)
+    ad._plan.use_csr = False
+    timed(name + " adj (atomic scatter)", lambda: ad(k, om, smaps=sm), nb)
+    ad._plan.use_csr = True
