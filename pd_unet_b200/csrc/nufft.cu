@@ -14,10 +14,15 @@
 
 #include <cub/device/device_radix_sort.cuh>
 
+#include <math.h>
+
+#include <algorithm>
 #include <map>
 #include <mutex>
+#include <vector>
 
 #include "common.cuh"
+#include "pfft.cuh"
 
 struct pdu_nufft_plan {
     int n0, n1, k0, k1, J, L, shift0, shift1;
@@ -28,6 +33,12 @@ struct pdu_nufft_plan {
     float* d_s1;
     std::map<int, cufftHandle> fft;   // batched 2-D C2C plans keyed by number of planes
     std::mutex mu;
+    // own pruned FFT (pfft.cuh): per-axis radix plans and float64-computed twiddle tables; pfft_ok == false
+    // (a grid size with a prime factor above 5) keeps the cuFFT path
+    bool pfft_ok;
+    pdu::PfftPlan pf0, pf1;
+    float2* d_w0;
+    float2* d_w1;
 };
 
 namespace pdu {
@@ -300,6 +311,133 @@ static int launch_interp_adj(pdu_nufft_plan* p, const float2* kdata, float2* gri
     return PDU_OK;
 }
 
+// ------------------------------------------------------------------ pruned FFT passes (pfft.cuh)
+template <typename T>
+__device__ __forceinline__ T* pf_smem() {
+    extern __shared__ __align__(16) unsigned char pf_dyn[];
+    return reinterpret_cast<T*>(pf_dyn);
+}
+
+// forward, along the last axis: SEQ image rows of one plane -> T [planes][n0][k1]
+template <int SEQ>
+__global__ void __launch_bounds__(256)
+    pfft_rows_fwd_kernel(const float2* __restrict__ image, const float2* __restrict__ smaps, float2* __restrict__ T,
+                         const float* __restrict__ s0, const float* __restrict__ s1, const float2* __restrict__ tw_g,
+                         PfftPlan pl, NufftDims d, int coils, int smaps_batch, int pitch) {
+    float2* buf0 = pf_smem<float2>();
+    float2* buf1 = buf0 + SEQ * pitch;
+    float2* tw = buf1 + SEQ * pitch;
+    const int tid = threadIdx.x, K = pl.K;
+    const long p = blockIdx.y;
+    const int r0 = blockIdx.x * SEQ;
+    for (int i = tid; i < K; i += blockDim.x) tw[i] = __ldg(tw_g + i);
+    const long plane = (long)d.n0 * d.n1;
+    const long b = p / coils, c = p - b * coils;
+    const int tps = blockDim.x / SEQ, s = tid / tps, row = r0 + s;      // a fixed row per thread: no run-time division below
+    for (int col = tid - s * tps; col < K; col += tps) {
+        float2 v = make_float2(0.f, 0.f);
+        if (row < d.n0 && col < d.n1) {
+            const long pix = (long)row * d.n1 + col;
+            if (smaps) {
+                const long sb = smaps_batch == 1 ? 0 : b;
+                v = cmul(__ldg(image + b * plane + pix), __ldg(smaps + (sb * coils + c) * plane + pix));
+            } else {
+                v = __ldg(image + p * plane + pix);
+            }
+            const float w = __ldg(s0 + row) * __ldg(s1 + col);
+            v.x *= w;
+            v.y *= w;
+        }
+        buf0[s * pitch + pf_pos(col)] = v;
+    }
+    __syncthreads();
+    const float2* res = pf_transform<false>(buf0, buf1, tw, pl, SEQ, pitch, tid, blockDim.x);
+    if (row < d.n0)
+        for (int col = tid - s * tps; col < K; col += tps) T[(p * d.n0 + row) * K + col] = res[s * pitch + pf_pos(col)];
+}
+
+// forward, along the first axis: SEQ neighbouring columns of T [planes][n0][k1] -> grid [planes][k0][k1]
+template <int SEQ>
+__global__ void __launch_bounds__(256)
+    pfft_cols_fwd_kernel(const float2* __restrict__ T, float2* __restrict__ grid, const float2* __restrict__ tw_g, PfftPlan pl,
+                         NufftDims d, int pitch) {
+    float2* buf0 = pf_smem<float2>();
+    float2* buf1 = buf0 + SEQ * pitch;
+    float2* tw = buf1 + SEQ * pitch;
+    const int tid = threadIdx.x, K = pl.K;           // K == k0
+    const long p = blockIdx.y;
+    const int c0 = blockIdx.x * SEQ;
+    for (int i = tid; i < K; i += blockDim.x) tw[i] = __ldg(tw_g + i);
+    for (int i = tid; i < SEQ * K; i += blockDim.x) {
+        const int row = i / SEQ, s = i - row * SEQ, col = c0 + s;
+        float2 v = make_float2(0.f, 0.f);
+        if (row < d.n0 && col < d.k1) v = __ldg(T + (p * d.n0 + row) * d.k1 + col);
+        buf0[s * pitch + pf_pos(row)] = v;
+    }
+    __syncthreads();
+    const float2* res = pf_transform<false>(buf0, buf1, tw, pl, SEQ, pitch, tid, blockDim.x);
+    for (int i = tid; i < SEQ * K; i += blockDim.x) {
+        const int row = i / SEQ, s = i - row * SEQ, col = c0 + s;
+        if (col < d.k1) grid[(p * K + row) * d.k1 + col] = res[s * pitch + pf_pos(row)];
+    }
+}
+
+// adjoint (unnormalised inverse), along the last axis: SEQ grid rows -> T [planes][k0][n1] (first n1 outputs kept)
+template <int SEQ>
+__global__ void __launch_bounds__(256)
+    pfft_rows_adj_kernel(const float2* __restrict__ grid, float2* __restrict__ T, const float2* __restrict__ tw_g, PfftPlan pl,
+                         NufftDims d, int pitch) {
+    float2* buf0 = pf_smem<float2>();
+    float2* buf1 = buf0 + SEQ * pitch;
+    float2* tw = buf1 + SEQ * pitch;
+    const int tid = threadIdx.x, K = pl.K;           // K == k1
+    const long p = blockIdx.y;
+    const int r0 = blockIdx.x * SEQ;
+    for (int i = tid; i < K; i += blockDim.x) tw[i] = __ldg(tw_g + i);
+    const int tps = blockDim.x / SEQ, s = tid / tps, row = r0 + s;
+    for (int col = tid - s * tps; col < K; col += tps)
+        buf0[s * pitch + pf_pos(col)] = row < d.k0 ? __ldg(grid + (p * d.k0 + row) * K + col) : make_float2(0.f, 0.f);
+    __syncthreads();
+    const float2* res = pf_transform<true>(buf0, buf1, tw, pl, SEQ, pitch, tid, blockDim.x);
+    if (row < d.k0)
+        for (int col = tid - s * tps; col < d.n1; col += tps) T[(p * d.k0 + row) * d.n1 + col] = res[s * pitch + pf_pos(col)];
+}
+
+// adjoint, along the first axis: SEQ neighbouring columns of T [planes][k0][n1] -> U [planes][n0][n1]
+template <int SEQ>
+__global__ void __launch_bounds__(256)
+    pfft_cols_adj_kernel(const float2* __restrict__ T, float2* __restrict__ U, const float2* __restrict__ tw_g, PfftPlan pl,
+                         NufftDims d, int pitch) {
+    float2* buf0 = pf_smem<float2>();
+    float2* buf1 = buf0 + SEQ * pitch;
+    float2* tw = buf1 + SEQ * pitch;
+    const int tid = threadIdx.x, K = pl.K;           // K == k0
+    const long p = blockIdx.y;
+    const int c0 = blockIdx.x * SEQ;
+    for (int i = tid; i < K; i += blockDim.x) tw[i] = __ldg(tw_g + i);
+    for (int i = tid; i < SEQ * K; i += blockDim.x) {
+        const int row = i / SEQ, s = i - row * SEQ, col = c0 + s;
+        buf0[s * pitch + pf_pos(row)] = col < d.n1 ? __ldg(T + (p * K + row) * d.n1 + col) : make_float2(0.f, 0.f);
+    }
+    __syncthreads();
+    const float2* res = pf_transform<true>(buf0, buf1, tw, pl, SEQ, pitch, tid, blockDim.x);
+    for (int i = tid; i < SEQ * d.n0; i += blockDim.x) {
+        const int row = i / SEQ, s = i - row * SEQ, col = c0 + s;
+        if (col < d.n1) U[(p * d.n0 + row) * d.n1 + col] = res[s * pitch + pf_pos(row)];
+    }
+}
+
+constexpr int PF_SEQ_ROWS = 4, PF_SEQ_COLS = 8;
+
+static size_t pf_smem_bytes(int seq, int K) { return ((size_t)2 * seq * pfft_pitch(K) + K) * sizeof(float2); }
+
+template <typename Kern>
+static int pf_set_smem(Kern kern, size_t bytes) {
+    PDU_REQUIRE(bytes <= 200 * 1024, "pruned FFT: %zu bytes of shared memory needed (grid too large)", bytes);
+    PDU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    return PDU_OK;
+}
+
 // ------------------------------------------------------------------ adjoint interpolation as a sorted gather
 // The atomic scatter above sits on the L2 atomic unit's rate (measured 0.23 T float2 atomics/s on B200
 // whatever the occupancy), and its summation order changes from run to run.  For a trajectory that is
@@ -564,6 +702,9 @@ int pdu_nufft_plan_create(pdu_nufft_plan_t** plan, int n0, int n1, int k0, int k
     p->shift0 = shift0; p->shift1 = shift1;
     p->d_t0 = p->d_t1 = nullptr;
     p->d_s0 = p->d_s1 = nullptr;
+    p->d_w0 = p->d_w1 = nullptr;
+    p->pfft_ok = pfft_factor(k0, &p->pf0) && pfft_factor(k1, &p->pf1) &&
+                 pf_smem_bytes(PF_SEQ_ROWS, k1) <= 200 * 1024 && pf_smem_bytes(PF_SEQ_COLS, k0) <= 200 * 1024;
     const size_t tl = (size_t)numpoints * table_oversamp + 1;
     cudaError_t e = cudaGetDevice(&p->device);
     if (e == cudaSuccess) e = cudaMalloc(&p->d_t0, tl * sizeof(float2));
@@ -574,6 +715,19 @@ int pdu_nufft_plan_create(pdu_nufft_plan_t** plan, int n0, int n1, int k0, int k
     if (e == cudaSuccess) e = cudaMemcpy(p->d_t1, table1, tl * sizeof(float2), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(p->d_s0, scal0, (size_t)n0 * sizeof(float), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(p->d_s1, scal1, (size_t)n1 * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && p->pfft_ok) {
+        for (int ax = 0; ax < 2 && e == cudaSuccess; ++ax) {
+            const int K = ax == 0 ? k0 : k1;
+            std::vector<float2> w((size_t)K);
+            for (int i = 0; i < K; ++i) {
+                const double a = -2.0 * 3.14159265358979323846 * (double)i / (double)K;
+                w[i] = make_float2((float)cos(a), (float)sin(a));
+            }
+            float2** dst = ax == 0 ? &p->d_w0 : &p->d_w1;
+            e = cudaMalloc(dst, (size_t)K * sizeof(float2));
+            if (e == cudaSuccess) e = cudaMemcpy(*dst, w.data(), (size_t)K * sizeof(float2), cudaMemcpyHostToDevice);
+        }
+    }
     if (e != cudaSuccess) {
         set_error("pdu_nufft_plan_create: %s", cudaGetErrorString(e));
         pdu_nufft_plan_destroy(p);
@@ -590,13 +744,19 @@ int pdu_nufft_plan_destroy(pdu_nufft_plan_t* p) {
     cudaFree(p->d_t1);
     cudaFree(p->d_s0);
     cudaFree(p->d_s1);
+    cudaFree(p->d_w0);
+    cudaFree(p->d_w1);
     delete p;
     return PDU_OK;
 }
 
 size_t pdu_nufft_workspace_bytes(const pdu_nufft_plan_t* p, int planes) {
     if (!p || planes <= 0) return 0;
-    return (size_t)planes * p->k0 * p->k1 * sizeof(float2);
+    // oversampled grid | intermediate of the pruned FFT (one axis transformed) | cropped adjoint result
+    const size_t grid = (size_t)p->k0 * p->k1;
+    const size_t mid = (size_t)std::max((long)p->n0 * p->k1, (long)p->k0 * p->n1);
+    const size_t crop = (size_t)p->n0 * p->n1;
+    return (size_t)planes * (grid + mid + crop) * sizeof(float2);
 }
 
 // A call is cut into batch chunks so that the scratch grids stay bounded (512 MB).  Measured on B200:
@@ -615,11 +775,35 @@ static int nufft_fwd_chunk(pdu_nufft_plan_t* p, const float2* image, float2* kda
                            int batch, int coils, int smaps_batch, long m, float scale, float2* grid, cudaStream_t st) {
     const int planes = batch * coils;
     const long total = (long)planes * p->k0 * p->k1;
-    apod_pad_kernel<<<stream_grid(total / 2), 256, 0, st>>>(image, smaps, (float4*)grid, p->d_s0, p->d_s1, dims_of(p), coils,
-                                                            smaps_batch, total / 2);
-    PDU_LAUNCHED();
-    int rc = run_fft(p, grid, planes, CUFFT_FORWARD, st);
-    if (rc) return rc;
+    // variant 1 = own pruned shared-memory FFT (pfft.cuh), variant 0 = pad + cuFFT.  Measured on B200 (64 planes of
+    // 640^2): the pruned passes move 2.5x fewer bytes but are still ~1.7x slower than cuFFT's register-resident
+    // radix kernels (row+column 407 us vs 238 us), so cuFFT stays the default until they are.
+    int variant = option(OPT_NUFFT_FWD);
+    if (variant < 0) variant = 0;
+    int rc;
+    if (variant == 1 && p->pfft_ok) {
+        // pruned FFT: apodise + pad + transform the n0 non-zero rows, then every column
+        float2* T = grid + total;
+        const NufftDims d = dims_of(p);
+        const int pitch1 = pfft_pitch(p->k1), pitch0 = pfft_pitch(p->k0);
+        rc = pf_set_smem(pfft_rows_fwd_kernel<PF_SEQ_ROWS>, pf_smem_bytes(PF_SEQ_ROWS, p->k1));
+        if (rc) return rc;
+        rc = pf_set_smem(pfft_cols_fwd_kernel<PF_SEQ_COLS>, pf_smem_bytes(PF_SEQ_COLS, p->k0));
+        if (rc) return rc;
+        pfft_rows_fwd_kernel<PF_SEQ_ROWS><<<dim3((unsigned)cdiv(p->n0, PF_SEQ_ROWS), (unsigned)planes), 256,
+                                            pf_smem_bytes(PF_SEQ_ROWS, p->k1), st>>>(image, smaps, T, p->d_s0, p->d_s1, p->d_w1,
+                                                                                     p->pf1, d, coils, smaps_batch, pitch1);
+        PDU_LAUNCHED();
+        pfft_cols_fwd_kernel<PF_SEQ_COLS><<<dim3((unsigned)cdiv(p->k1, PF_SEQ_COLS), (unsigned)planes), 256,
+                                            pf_smem_bytes(PF_SEQ_COLS, p->k0), st>>>(T, grid, p->d_w0, p->pf0, d, pitch0);
+        PDU_LAUNCHED();
+    } else {
+        apod_pad_kernel<<<stream_grid(total / 2), 256, 0, st>>>(image, smaps, (float4*)grid, p->d_s0, p->d_s1, dims_of(p), coils,
+                                                                smaps_batch, total / 2);
+        PDU_LAUNCHED();
+        rc = run_fft(p, grid, planes, CUFFT_FORWARD, st);
+        if (rc) return rc;
+    }
     return launch_interp_fwd(p, grid, kdata, omega, planes, m, scale, st);
 }
 
@@ -635,10 +819,36 @@ static int nufft_adj_chunk(pdu_nufft_plan_t* p, const float2* kdata, float2* ima
         rc = launch_interp_adj(p, kdata, grid, omega, planes, m, st);
     }
     if (rc) return rc;
-    rc = run_fft(p, grid, planes, CUFFT_INVERSE, st);
-    if (rc) return rc;
     const int out_planes = smaps ? batch : planes;
     const long total = (long)out_planes * p->n0 * p->n1;
+    int variant = option(OPT_NUFFT_ADJ);
+    if (variant < 0) variant = 0;      // see nufft_fwd_chunk
+    if (variant == 1 && p->pfft_ok) {
+        // pruned inverse FFT: every row but only the n1 kept outputs, then the n1 kept columns and n0 kept outputs
+        float2* T = grid + (long)planes * p->k0 * p->k1;
+        float2* U = T + (long)planes * std::max((long)p->n0 * p->k1, (long)p->k0 * p->n1);
+        const NufftDims d = dims_of(p);
+        rc = pf_set_smem(pfft_rows_adj_kernel<PF_SEQ_ROWS>, pf_smem_bytes(PF_SEQ_ROWS, p->k1));
+        if (rc) return rc;
+        rc = pf_set_smem(pfft_cols_adj_kernel<PF_SEQ_COLS>, pf_smem_bytes(PF_SEQ_COLS, p->k0));
+        if (rc) return rc;
+        pfft_rows_adj_kernel<PF_SEQ_ROWS><<<dim3((unsigned)cdiv(p->k0, PF_SEQ_ROWS), (unsigned)planes), 256,
+                                            pf_smem_bytes(PF_SEQ_ROWS, p->k1), st>>>(grid, T, p->d_w1, p->pf1, d,
+                                                                                     pfft_pitch(p->k1));
+        PDU_LAUNCHED();
+        pfft_cols_adj_kernel<PF_SEQ_COLS><<<dim3((unsigned)cdiv(p->n1, PF_SEQ_COLS), (unsigned)planes), 256,
+                                            pf_smem_bytes(PF_SEQ_COLS, p->k0), st>>>(T, U, p->d_w0, p->pf0, d, pfft_pitch(p->k0));
+        PDU_LAUNCHED();
+        NufftDims dc = d;          // the cropped result is a dense [n0][n1] "grid"
+        dc.k0 = d.n0;
+        dc.k1 = d.n1;
+        crop_apod_kernel<<<stream_grid(total), 256, 0, st>>>(U, smaps, image, p->d_s0, p->d_s1, dc, coils, smaps_batch, scale,
+                                                             total);
+        PDU_LAUNCHED();
+        return PDU_OK;
+    }
+    rc = run_fft(p, grid, planes, CUFFT_INVERSE, st);
+    if (rc) return rc;
     crop_apod_kernel<<<stream_grid(total), 256, 0, st>>>(grid, smaps, image, p->d_s0, p->d_s1, dims_of(p), coils, smaps_batch,
                                                          scale, total);
     PDU_LAUNCHED();

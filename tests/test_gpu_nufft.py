@@ -134,3 +134,25 @@ def test_sorted_gather_adjoint_matches_scatter_and_is_reproducible():
     sm = coil_maps(3, 64)[None][..., :48].contiguous()
     xa = adj(k.to(DEV), omd, smaps=sm.to(DEV), norm="ortho")
     assert rel_l2(xa, oracle.nufft_adjoint(k, 0.5 * om, spec, smaps=sm, norm="ortho")) <= TOL
+
+
+@pytest.mark.parametrize("im", [(32, 32), (48, 40), (320, 320), (250, 250)])
+def test_pruned_fft_and_cufft_paths_agree(im):
+    """variant 1: the own pruned shared-memory FFT; variant 0 (default, currently faster): pad + cuFFT.  Same
+    numbers, both within budget of the oracle.  250 -> grid 500 = 4 * 5^3 exercises the radix-5 passes."""
+    spec = oracle.NufftSpec(im)
+    om = _traj(9, 2 * im[0])
+    omd = torch.from_numpy(om).to(DEV)
+    x = seeded((1, 2) + im, 31, complex_=True)
+    k = seeded((1, 2, om.shape[1]), 32, complex_=True)
+    A, AH = pdu.KbNufft(im), pdu.KbNufftAdjoint(im)
+    want_f, want_a = oracle.nufft_forward(x, om, spec), oracle.nufft_adjoint(k, om, spec)
+    try:
+        for v in (1, 0):
+            pdu.set_option("nufft_fwd_variant", v)
+            pdu.set_option("nufft_adj_variant", v)
+            assert rel_l2(A(x.to(DEV), omd), want_f) <= TOL, f"forward variant {v}"
+            assert rel_l2(AH(k.to(DEV), omd), want_a) <= TOL, f"adjoint variant {v}"
+    finally:
+        pdu.set_option("nufft_fwd_variant", -1)
+        pdu.set_option("nufft_adj_variant", -1)
