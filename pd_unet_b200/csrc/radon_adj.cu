@@ -3,14 +3,16 @@
 // linear filtering; here the detector rows are staged in shared memory and interpolated in exact
 // float32.
 //
-// variant 1 (default) -- a CTA owns a TX x TY pixel tile of one slice (each thread PY pixels in a
+// variant 1 (default) -- a CTA owns a TX x TY pixel tile of one slice (each thread PY = 8 pixels in a
 //   column of the tile).  Views are consumed in chunks of AC: for every view of the chunk the CTA
-//   computes the detector interval its tile projects onto (from the four tile corners) and copies
-//   that interval, zero filled outside [0, D) (the texture "border" mode), into a SEG-float shared
-//   row; then every pixel takes its two taps per view from shared memory with no bounds test.
-//   A chunk in which some view's interval does not fit SEG floats is served from global memory.
-// variant 0 -- the same pixel loop with both taps read through L1 (__ldg) and tested against the
-//   detector range.  A/B baseline and the fallback above.
+//   computes, in float64 and relative to the tile, the detector interval the tile projects onto and
+//   copies it -- zero filled outside [0, D) (the texture "border" mode), as (value, next - value)
+//   pairs -- into a SEG-entry shared row; then every pixel takes its tap per view with one 8-byte
+//   load and one FMA, two pixels per packed-FP32 instruction, no bounds test.
+//   A chunk in which some view's interval does not fit SEG entries is served from global memory.
+// variant 2 -- the same with 4 pixels per thread (A/B).
+// variant 0 -- every tap from global memory with float64 coordinates (slow; the reference form of
+//   the fallback above).
 #include "common.cuh"
 
 namespace pdu {
@@ -27,28 +29,28 @@ struct AdjGeom {
 };
 
 // detector coordinate (in tap units: value = (1-fr) s[i0] + fr s[i0+1], i0 = floor(t)) and weight
-__device__ __forceinline__ void project(const AdjGeom& g, float cs, float sn, float dx, float dy, float& t, float& w) {
-    const float p = fmaf(cs, dx, sn * dy);
+// The global-memory path (variant 0, and the chunks of the tile kernel whose detector interval does not
+// fit its shared segment: wide magnification near the source, coarse detectors) evaluates the detector
+// coordinate in float64 and splits it into integer tap and float32 fraction, so it is as accurate as the
+// tile-relative shared-memory path no matter how large the coordinate gets.
+__device__ __noinline__ float tap_global(const AdjGeom& g, const float* __restrict__ row, float cs, float sn, float dx,
+                                            float dy) {
+    const double p = (double)cs * dx + (double)sn * dy;
+    const double ids = 1.0 / (double)g.det_spacing;
+    double t, w = 1.0;
     if (g.fan) {
-        const float den = fmaf(sn, dx, g.s_dist) - cs * dy;
-        const float iden = __fdividef(g.k, den);
-        // one Newton step makes the fast reciprocal exact to ~1 ulp
-        const float iden2 = fmaf(iden, fmaf(-den, iden, g.k) * __fdividef(1.f, g.k), iden);
-        w = iden2;
-        t = fmaf(p * g.ids, iden2, g.cr);
+        w = ((double)g.s_dist + (double)g.d_dist) / ((double)g.s_dist + (double)sn * dx - (double)cs * dy);
+        t = p * ids * w + (double)g.cr;
     } else {
-        w = 1.f;
-        t = fmaf(p, g.ids, g.cr);
+        t = p * ids + (double)g.cr;
     }
-}
-
-__device__ __forceinline__ float tap_global(const float* __restrict__ row, int D, float t) {
-    const float tf = floorf(t);
-    const float fr = t - tf;
-    const int i0 = (int)tf;
+    const double tf = floor(t);
+    if (!(tf > -2.0 && tf < (double)g.det_count)) return 0.f;       // both taps outside the detector (or NaN)
+    const float fr = (float)(t - tf);
+    const int i0 = (int)tf, D = g.det_count;
     const float s0 = (unsigned)i0 < (unsigned)D ? __ldg(row + i0) : 0.f;
     const float s1 = (unsigned)(i0 + 1) < (unsigned)D ? __ldg(row + i0 + 1) : 0.f;
-    return fmaf(fr, s1 - s0, s0);
+    return (float)w * fmaf(fr, s1 - s0, s0);
 }
 
 template <int TX, int TY, int PY>
@@ -70,9 +72,7 @@ __global__ void __launch_bounds__(TX*(TY / PY))
 #pragma unroll
             for (int k = 0; k < PY; ++k) {
                 const float dy = (float)(y0 + k * (TY / PY)) - g.half;
-                float t, w;
-                project(g, cs, sn, dx, dy, t, w);
-                acc[k] = fmaf(w, tap_global(row, g.det_count, t), acc[k]);
+                acc[k] += tap_global(g, row, cs, sn, dx, dy);
             }
         }
     }
@@ -93,15 +93,10 @@ __global__ void __launch_bounds__(TX*(TY / PY))
 //   parallel:  t - lo = base + a lx + b ly
 //   fan:       t - lo = (n0 + nx lx + ny ly) / den,   den = d0 + sn lx - cs ly,   weight = k / den
 // (lx, ly) = pixel offset inside the tile, lo = first detector bin of the staged segment.
-struct ViewPar {
-    float a, b, base, pad;
-};
-struct ViewFan {
-    float n0, nx, ny, d0, sn, cs, pad0, pad1;
-};
-
+// parallel beam: cap the registers so that 7 (PY = 8) / 3 (PY = 4) CTAs fit an SM -- B N^2 / PY threads then
+// make one balanced wave; the rarely taken float64 fallback is what would otherwise raise the count
 template <int TX, int TY, int PY, int AC, int SEG, bool FAN>
-__global__ void __launch_bounds__(TX*(TY / PY))
+__global__ void __launch_bounds__(TX*(TY / PY), FAN ? (PY == 8 ? 5 : 2) : (PY == 8 ? 7 : 3))
     radon_adj_tile_kernel(const float* __restrict__ sino, float* __restrict__ img, const float* __restrict__ trig,
                           const AdjGeom g) {
     constexpr int THREADS = TX * (TY / PY);
@@ -256,9 +251,7 @@ __global__ void __launch_bounds__(TX*(TY / PY))
 #pragma unroll
                 for (int k = 0; k < PY; ++k) {
                     const float dy = (float)(y0 + k * RY) - g.half;
-                    float t, w;
-                    project(g, cs, sn, dx, dy, t, w);
-                    acc[k] = fmaf(w, tap_global(row, g.det_count, t), acc[k]);
+                    acc[k] += tap_global(g, row, cs, sn, dx, dy);
                 }
             }
         }

@@ -460,6 +460,10 @@ int pdu_radon_fwd_f32(const float* img, float* sino, const float* trig, int batc
         case 6: return launch_strip<32, 8, 32, 136, 2, 16>(img, imgT, sino, trig, batch, *g, st);
         case 7: return launch_strip<32, 16, 32, 136, 2, 8>(img, imgT, sino, trig, batch, *g, st);
         case 8: return launch_strip<32, 8, 32, 136, 2, 8, false>(img, imgT, sino, trig, batch, *g, st);   // scalar inner loop
+        case 9: return launch_strip<32, 8, 32, 136, 2, 4>(img, imgT, sino, trig, batch, *g, st);
+        case 10: return launch_strip<16, 16, 32, 104, 2, 4>(img, imgT, sino, trig, batch, *g, st);
+        case 11: return launch_strip<16, 16, 32, 104, 3, 8>(img, imgT, sino, trig, batch, *g, st);
+        case 12: return launch_strip<32, 8, 32, 136, 3, 8>(img, imgT, sino, trig, batch, *g, st);
         default: break;
     }
     // default: as many neighbouring views per CTA as keep the strip box inside W (measured on B200,

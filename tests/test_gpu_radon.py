@@ -60,7 +60,7 @@ def _reset_variants():
         pdu.set_option(k, -1)
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6, 7, 8])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12])
 @pytest.mark.parametrize("name", CASES)
 def test_forward_matches_oracle(name, variant):
     op, g, internal = _case(name)
@@ -219,3 +219,27 @@ def test_filter_tensor_core_variant(D, A, B):
         assert rel_l2(op.filter_sinogram(noise.to(DEV)), oracle.filter_sinogram(noise)) <= TOL
     finally:
         pdu.set_option("filter_variant", -1)
+
+
+def test_unsorted_angles_and_odd_geometries_take_the_fallback_paths_correctly():
+    """Views of a CTA that are NOT neighbours (random angles) blow the strip box past its width, and a
+    coarse detector makes the backprojector's interval overflow its shared segment: both kernels must
+    then serve those strips / chunks from global memory with identical results."""
+    rng = np.random.default_rng(3)
+    n = 96
+    for ang, D, sp in ((rng.uniform(0, 2 * np.pi, 37), 96, 1.0), (rng.uniform(0, np.pi, 16), 300, 0.25),
+                       (np.array([0.0, np.pi / 2, np.pi / 4, 3.0]), 40, 4.0)):
+        op = pdu.Radon(n, ang, det_count=D, det_spacing=sp)
+        g = oracle.RadonGeom(n=n, n_angles=len(ang), det_count=D, det_spacing=sp)
+        trig = oracle.trig_table(-ang)
+        x = phantom_batch(2, n, seed=4) + 0.05 * seeded((2, n, n), 6)
+        assert rel_l2(op.forward(x.to(DEV)), oracle.radon_forward(x, trig, g)) <= TOL
+        s = seeded((2, len(ang), D), 8)
+        assert rel_l2(op.backprojection(s.to(DEV)), oracle.radon_backprojection(s, trig, g)) <= TOL
+    fan = pdu.RadonFanbeam(n, rng.uniform(0, 2 * np.pi, 11), 70.0, det_distance=30.0, det_count=180, det_spacing=0.7)
+    gf = oracle.RadonGeom(n=n, n_angles=11, det_count=180, det_spacing=0.7, geom=FAN, s_dist=70.0, d_dist=30.0)
+    trig = oracle.trig_table(-fan.angles)
+    x = phantom_batch(1, n, seed=9)
+    assert rel_l2(fan.forward(x.to(DEV)), oracle.radon_forward(x, trig, gf)) <= TOL
+    s = seeded((1, 11, 180), 10)
+    assert rel_l2(fan.backprojection(s.to(DEV)), oracle.radon_backprojection(s, trig, gf)) <= TOL
