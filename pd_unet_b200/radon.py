@@ -23,7 +23,6 @@ from typing import Dict, Tuple
 import numpy as np
 import torch
 
-from . import _lib
 from ._lib import PDU_GEOM_FAN, PDU_GEOM_PARALLEL, RadonGeomC, check, lib, require_cuda, stream_ptr
 
 # bench.py sets this to time operator calls with CUDA events inside a larger step:
