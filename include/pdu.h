@@ -188,6 +188,15 @@ PDU_API int pdu_residual_slice_f32(float* out, float* slice, const float* state,
  * nn.Conv2d(bias=True) + nn.PReLU in the primal / dual blocks (inference). */
 PDU_API int pdu_bias_prelu_f32(float* y, const float* bias, const float* slope, int n_slope, int batch,
                                int channels, long plane, int layout, pdu_stream_t stream);
+/* The epilogue of a UNet encoder (or up-convolution) in one pass over the channels-last convolution
+ * output y [batch, height, width, channels]:  v = prelu(y + bias, slope) is written into its slot of the
+ * decoder's concatenation buffer (`skip` already points at the slot's first channel; consecutive pixels are
+ * skip_pixel_stride floats apart) and, if `pooled` is not NULL, the 2x2 max of v into
+ * pooled [batch, height/2, width/2, channels].  Replaces bias add + PReLU + F.max_pool2d + torch.cat
+ * (four ATen passes). */
+PDU_API int pdu_bias_prelu_place_f32(const float* y, const float* bias, const float* slope, int n_slope,
+                                     float* skip, long skip_pixel_stride, float* pooled, int batch,
+                                     int channels, int height, int width, pdu_stream_t stream);
 /* out = alpha * x + beta * y, n elements. */
 PDU_API int pdu_axpby_f32(float* out, float alpha, const float* x, float beta, const float* y,
                           long n, pdu_stream_t stream);

@@ -346,3 +346,85 @@ extern "C" int pdu_bias_prelu_f32(float* y, const float* bias, const float* slop
     PDU_LAUNCHED();
     return PDU_OK;
 }
+
+// ------------------------------------------------------------------ bias + PReLU + skip placement + 2x2 max pool
+// The epilogue of a UNet encoder block in one pass over the convolution output y (channels-last):
+//   v = prelu(y + bias, slope)  ->  written into its slot of the decoder's concatenation buffer
+//                                   (pixel stride skip_pix, channel offset already applied to `skip`)
+//   max over each 2x2 window    ->  pooled [batch, H/2, W/2, C]     (pooled == NULL: no pooling)
+// ATen runs bias add, PReLU, max-pool and torch.cat as four passes.
+namespace pdu {
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ float4 bp4(float4 v, float4 b, float4 s, bool has_slope) {
+    v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+    if (has_slope) { v.x = prelu1(v.x, s.x); v.y = prelu1(v.y, s.y); v.z = prelu1(v.z, s.z); v.w = prelu1(v.w, s.w); }
+    return v;
+}
+__device__ __forceinline__ float4 max4(float4 a, float4 b) {
+    return make_float4(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z), fmaxf(a.w, b.w));
+}
+
+template <bool POOL>
+__global__ void __launch_bounds__(256)
+    bias_prelu_place_kernel(const float* __restrict__ y, const float* __restrict__ bias, const float* __restrict__ slope,
+                            int n_slope, float* __restrict__ skip, long skip_pix, float* __restrict__ pooled, int H, int W,
+                            int C, long total) {
+    const int c4n = C >> 2;
+    const int Ho = POOL ? H >> 1 : H, Wo = POOL ? W >> 1 : W;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % c4n) * 4;
+        long t = i / c4n;
+        const int wo = (int)(t % Wo);
+        t /= Wo;
+        const int ho = (int)(t % Ho);
+        const long b = t / Ho;
+        const float4 bv = ld4(bias + c);
+        float4 sv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (slope) sv = n_slope == 1 ? make_float4(__ldg(slope), __ldg(slope), __ldg(slope), __ldg(slope)) : ld4(slope + c);
+        if (POOL) {
+            float4 m;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const long pix = (b * H + (2 * ho + (q >> 1))) * W + (2 * wo + (q & 1));
+                const float4 v = bp4(ld4(y + pix * C + c), bv, sv, slope != nullptr);
+                st4(skip + pix * skip_pix + c, v);
+                m = q == 0 ? v : max4(m, v);
+            }
+            st4(pooled + ((b * Ho + ho) * Wo + wo) * (long)C + c, m);
+        } else {
+            const long pix = (b * H + ho) * W + wo;
+            st4(skip + pix * skip_pix + c, bp4(ld4(y + pix * C + c), bv, sv, slope != nullptr));
+        }
+    }
+}
+
+}  // namespace pdu
+
+extern "C" int pdu_bias_prelu_place_f32(const float* y, const float* bias, const float* slope, int n_slope, float* skip,
+                                        long skip_pixel_stride, float* pooled, int batch, int channels, int height, int width,
+                                        pdu_stream_t stream) {
+    PDU_REQUIRE(y && bias && skip, "pdu_bias_prelu_place_f32: null pointer");
+    PDU_REQUIRE(batch > 0 && channels > 0 && height > 0 && width > 0, "pdu_bias_prelu_place_f32: sizes must be positive");
+    PDU_REQUIRE(channels % 4 == 0 && skip_pixel_stride % 4 == 0 && skip_pixel_stride >= channels,
+                "pdu_bias_prelu_place_f32: channels (%d) and the destination pixel stride (%ld) must be multiples of 4", channels,
+                skip_pixel_stride);
+    PDU_REQUIRE(al16(y) && al16(bias) && al16(skip) && (!slope || n_slope == 1 || al16(slope)) && (!pooled || al16(pooled)),
+                "pdu_bias_prelu_place_f32: pointers must be 16-byte aligned");
+    PDU_REQUIRE(slope == nullptr || n_slope == 1 || n_slope == channels, "pdu_bias_prelu_place_f32: slope must have 1 or %d values",
+                channels);
+    PDU_REQUIRE(!pooled || (height % 2 == 0 && width % 2 == 0), "pdu_bias_prelu_place_f32: pooling needs even height and width");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (pooled) {
+        const long total = (long)batch * (height / 2) * (width / 2) * (channels / 4);
+        bias_prelu_place_kernel<true><<<stream_grid(total, 256), 256, 0, st>>>(y, bias, slope, n_slope, skip, skip_pixel_stride,
+                                                                               pooled, height, width, channels, total);
+    } else {
+        const long total = (long)batch * height * width * (channels / 4);
+        bias_prelu_place_kernel<false><<<stream_grid(total, 256), 256, 0, st>>>(y, bias, slope, n_slope, skip, skip_pixel_stride,
+                                                                                nullptr, height, width, channels, total);
+    }
+    PDU_LAUNCHED();
+    return PDU_OK;
+}

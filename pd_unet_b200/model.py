@@ -101,6 +101,8 @@ class UNet(nn.Module):
         self.pool = nn.MaxPool2d(2)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if self._fused_ok(x):
+            return self._forward_fused(x)
         skips = []
         for i, blk in enumerate(self.down):
             x = blk(x)
@@ -113,6 +115,37 @@ class UNet(nn.Module):
             if x.shape[-2:] != s.shape[-2:]:           # odd sizes: pad the up-sampled map to the skip
                 x = nn.functional.pad(x, (0, s.shape[-1] - x.shape[-1], 0, s.shape[-2] - x.shape[-2]))
             x = blk(torch.cat([x, s], dim=1))
+        return self.head(x)
+
+    def _fused_ok(self, x: torch.Tensor) -> bool:
+        depth = len(self.upconv)
+        return (_fused_epilogue_ok(x) and x.dim() == 4 and x.is_contiguous(memory_format=torch.channels_last)
+                and x.shape[-1] % (1 << depth) == 0 and x.shape[-2] % (1 << depth) == 0
+                and self.down[0][0].conv.out_channels % 4 == 0)
+
+    def _forward_fused(self, x: torch.Tensor) -> torch.Tensor:
+        """Inference path: every encoder block ends in ONE pass (pdu_bias_prelu_place_f32) that applies bias + PReLU,
+        drops the result into the skip half of the decoder's concatenation buffer and emits the 2x2 max-pooled map;
+        the up-convolution's bias epilogue fills the other half -- no separate max_pool2d or torch.cat passes."""
+        cats = []
+        for i, blk in enumerate(self.down):
+            x = blk[0](x)
+            if i + 1 == len(self.down):
+                x = blk[1](x)
+                break
+            last = blk[1]
+            y = nn.functional.conv2d(x, last._weight_for(x.shape[1]), None, 1, last.conv.padding)
+            B, Cn, H, W = y.shape
+            cat = torch.empty((B, 2 * Cn, H, W), dtype=y.dtype, device=y.device, memory_format=torch.channels_last)
+            x = torch.empty((B, Cn, H // 2, W // 2), dtype=y.dtype, device=y.device, memory_format=torch.channels_last)
+            updates.bias_prelu_place_(y, last.conv.bias, last.act.weight, cat[:, Cn:], x)
+            cats.append(cat)
+        for upc, blk in zip(self.upconv, self.up):
+            cat = cats.pop()
+            Cn = cat.shape[1] // 2
+            y = nn.functional.conv_transpose2d(x, upc.conv.weight, None, 2)
+            updates.bias_prelu_place_(y, upc.conv.bias, None, cat[:, :Cn], None)
+            x = blk(cat)
         return self.head(x)
 
 

@@ -234,3 +234,34 @@ def bias_prelu_(y: torch.Tensor, bias: torch.Tensor, slope: Optional[torch.Tenso
                                            max(n_slope, 1), y.shape[0], Cn, _plane(y),
                                            LAYOUT_NHWC if nhwc else LAYOUT_NCHW, stream_ptr()), "pdu_bias_prelu_f32")
     return y
+
+
+def bias_prelu_place_(y: torch.Tensor, bias: torch.Tensor, slope: Optional[torch.Tensor], dst: torch.Tensor,
+                      pooled: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
+    """One pass over a channels_last convolution output y [B, C, H, W]: v = prelu(y + bias, slope) is written
+    into `dst`, a channel slice (view) of a channels_last buffer -- e.g. the decoder's concatenation buffer
+    -- and, if `pooled` [B, C, H/2, W/2] (channels_last) is given, its 2x2 max into pooled.  Replaces the
+    bias add, PReLU, max_pool2d and torch.cat passes of a UNet encoder block.  Inference only."""
+    if not (y.is_cuda and y.dtype == torch.float32 and y.dim() == 4):
+        raise PduError("bias_prelu_place_: y must be a float32 CUDA [B, C, H, W] tensor (no CPU fallback)")
+    B, Cn, H, W = y.shape
+    if not y.is_contiguous(memory_format=torch.channels_last):
+        raise ValueError("bias_prelu_place_: y must be channels_last")
+    pix = dst.stride(3)
+    if tuple(dst.shape) != (B, Cn, H, W) or dst.dtype != torch.float32 or dst.device != y.device or \
+            dst.stride(1) != 1 or dst.stride(2) != W * pix or dst.stride(0) != H * W * pix:
+        raise ValueError("bias_prelu_place_: dst must be a channel slice of a channels_last buffer shaped like y")
+    bias = require_cuda(bias.detach(), torch.float32, "bias")
+    n_slope = 1
+    if slope is not None:
+        slope = require_cuda(slope.detach(), torch.float32, "slope")
+        n_slope = slope.numel()
+    if pooled is not None and (tuple(pooled.shape) != (B, Cn, H // 2, W // 2) or
+                               not pooled.is_contiguous(memory_format=torch.channels_last) or pooled.dtype != torch.float32):
+        raise ValueError("bias_prelu_place_: pooled must be a channels_last [B, C, H/2, W/2] float32 tensor")
+    if y.numel():
+        with torch.cuda.device(y.device):
+            check(lib().pdu_bias_prelu_place_f32(y.data_ptr(), bias.data_ptr(), slope.data_ptr() if slope is not None else None,
+                                                 n_slope, dst.data_ptr(), pix, pooled.data_ptr() if pooled is not None else None,
+                                                 B, Cn, H, W, stream_ptr()), "pdu_bias_prelu_place_f32")
+    return pooled

@@ -166,3 +166,32 @@ def test_concat_zero_pads_channels_for_the_tensor_cores():
     with torch.no_grad():
         got = conv(out)
     assert torch.allclose(got, ref, atol=1e-5, rtol=1e-5)
+
+
+def test_fused_unet_path_matches_the_plain_modules():
+    """UNet inference path with the one-pass encoder epilogue (bias + PReLU + skip placement + 2x2 max) against
+    the stock-module path on the same weights."""
+    from pd_unet_b200.model import UNet
+    torch.backends.cudnn.allow_tf32 = False
+    torch.manual_seed(0)
+    net = UNet(5, 4, base=8, depth=2).to(DEV).to(memory_format=torch.channels_last).eval()
+    x = seeded((2, 5, 32, 24), 1).to(DEV).contiguous(memory_format=torch.channels_last)
+    with torch.enable_grad():
+        want = net(x.clone().requires_grad_()).detach()       # stock modules (autograd path)
+    with torch.no_grad():
+        assert net._fused_ok(x)
+        got = net(x)
+    assert torch.allclose(got, want, atol=2e-5, rtol=1e-5)
+    # sizes the fused path cannot pool evenly fall back to the stock path
+    x2 = seeded((1, 5, 18, 22), 2).to(DEV).contiguous(memory_format=torch.channels_last)
+    with torch.no_grad():
+        assert not net._fused_ok(x2) and net(x2).shape == (1, 4, 18, 22)
+    # the kernel itself, against ATen
+    y = seeded((2, 8, 6, 10), 3).to(DEV).contiguous(memory_format=torch.channels_last)
+    bias, slope = seeded((8,), 4).to(DEV), seeded((8,), 5).abs().to(DEV)
+    cat = torch.zeros((2, 16, 6, 10), device=DEV).contiguous(memory_format=torch.channels_last)
+    pooled = torch.empty((2, 8, 3, 5), device=DEV).contiguous(memory_format=torch.channels_last)
+    updates.bias_prelu_place_(y, bias, slope, cat[:, 8:], pooled)
+    ref = torch.nn.functional.prelu(y + bias.view(1, -1, 1, 1), slope)
+    assert torch.equal(cat[:, 8:], ref) and torch.equal(cat[:, :8], torch.zeros_like(ref))
+    assert torch.equal(pooled, torch.nn.functional.max_pool2d(ref, 2))
