@@ -185,6 +185,19 @@ __global__ void __launch_bounds__(256)
 
 using namespace pdu;
 
+// channels-last fast path for the shapes the unrolled iteration produces: a has 4 channels, b (and c) one,
+// output padded to 8 -- one thread per pixel, one 16-byte load and two 16-byte stores
+namespace pdu {
+__global__ void __launch_bounds__(256)
+    concat_nhwc_4_1_1_to8_kernel(float4* __restrict__ out, const float4* __restrict__ a, const float* __restrict__ b,
+                                 const float* __restrict__ c, float scale_b, long pixels) {
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < pixels; i += (long)gridDim.x * blockDim.x) {
+        out[2 * i] = a[i];
+        out[2 * i + 1] = make_float4(b[i] * scale_b, c ? c[i] : 0.f, 0.f, 0.f);
+    }
+}
+}  // namespace pdu
+
 extern "C" {
 
 int pdu_concat_f32(float* out, const float* a, const float* b, const float* c, int batch, int ca, int cb, int cc,
@@ -198,6 +211,13 @@ int pdu_concat_f32(float* out, const float* a, const float* b, const float* c, i
     cudaStream_t st = (cudaStream_t)stream;
     PDU_REQUIRE(layout == PDU_LAYOUT_NCHW || layout == PDU_LAYOUT_NHWC, "pdu_concat_f32: unknown layout %d", layout);
     if (layout == PDU_LAYOUT_NHWC) {
+        if (ca == 4 && cb == 1 && cc <= 1 && c_out == 8 && al16(out) && al16(a)) {
+            const long pixels = (long)batch * plane;
+            concat_nhwc_4_1_1_to8_kernel<<<stream_grid(pixels, 256), 256, 0, st>>>((float4*)out, (const float4*)a, b, c, scale_b,
+                                                                                   pixels);
+            PDU_LAUNCHED();
+            return PDU_OK;
+        }
         concat_nhwc_kernel<<<stream_grid(total, 256), 256, 0, st>>>(out, a, b, c, ca, cb, cc, c_out, scale_b, total);
         PDU_LAUNCHED();
         return PDU_OK;

@@ -199,7 +199,8 @@ class PrimalDualUNet(nn.Module):
         pad = 8 if (g.is_cuda and not torch.is_grad_enabled()) else 0
         for i in range(self.n_iter):
             # the 1/op_scale normalisation of each operator output rides in the concat kernel
-            kf = self.op_forward(f_op)
+            # the primal state starts at zero and the operator is linear: K 0 = 0, so the first projection is skipped
+            kf = self.op_forward(f_op) if i > 0 else torch.zeros_like(g[:, :self.kd])
             h, h_op = updates.residual_slice(h, self.dual[i](updates.concat(h, kf, g, scale_b=inv, pad_to=pad)), 0, self.kd)
             kth = self.op_adjoint(h_op)
             f, f_op = updates.residual_slice(f, self.primal[i](updates.concat(f, kth, scale_b=inv, pad_to=pad)), 0, self.kc)

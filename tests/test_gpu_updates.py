@@ -149,6 +149,15 @@ def test_fused_conv_modules_match_stock_modules():
         assert torch.allclose(got, want, atol=1e-5, rtol=1e-5)
 
 
+def test_concat_fast_path_4_1_1_to_8():
+    a, b, c = seeded((2, 4, 6, 10), 1), seeded((2, 1, 6, 10), 2), seeded((2, 1, 6, 10), 3)
+    al = a.to(DEV).contiguous(memory_format=torch.channels_last)
+    out = updates.concat(al, b.to(DEV), c.to(DEV), scale_b=0.5, pad_to=8)
+    assert torch.equal(out.cpu(), torch.cat([a, 0.5 * b, c, torch.zeros(2, 2, 6, 10)], 1))
+    out2 = updates.concat(al, b.to(DEV), scale_b=2.0, pad_to=8)
+    assert torch.equal(out2.cpu(), torch.cat([a, 2.0 * b, torch.zeros(2, 3, 6, 10)], 1))
+
+
 def test_concat_zero_pads_channels_for_the_tensor_cores():
     a, b, c = (seeded((2, ch, 6, 10), i) for i, ch in enumerate((4, 1, 1)))
     want = torch.cat([a, 0.5 * b, c, torch.zeros(2, 2, 6, 10)], 1)
