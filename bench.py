@@ -306,7 +306,8 @@ def cpu_model_step(model64, sparse, trig, g):
     inv = 1.0 / m.op_scale
     with torch.no_grad():
         for i in range(m.n_iter):
-            kf = oc.radon_forward(f[:, 0], trig, g)[:, None].to(gg.dtype) * inv
+            # K 0 = 0: like the CUDA arm, the first (zero) projection is not computed
+            kf = oc.radon_forward(f[:, 0], trig, g)[:, None].to(gg.dtype) * inv if i > 0 else torch.zeros_like(gg)
             h = h + m.dual[i](torch.cat([h, kf, gg], 1))
             kth = oc.fbp(h[:, 0], trig, g)[:, None].to(gg.dtype) * inv
             f = f + m.primal[i](torch.cat([f, kth], 1))

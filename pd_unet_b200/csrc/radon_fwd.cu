@@ -464,6 +464,10 @@ int pdu_radon_fwd_f32(const float* img, float* sino, const float* trig, int batc
         case 10: return launch_strip<16, 16, 32, 104, 2, 4>(img, imgT, sino, trig, batch, *g, st);
         case 11: return launch_strip<16, 16, 32, 104, 3, 8>(img, imgT, sino, trig, batch, *g, st);
         case 12: return launch_strip<32, 8, 32, 136, 3, 8>(img, imgT, sino, trig, batch, *g, st);
+        case 13: return launch_strip<32, 8, 32, 144, 2, 4>(img, imgT, sino, trig, batch, *g, st);   // pitch = 16 (mod 32)
+        case 14: return launch_strip<32, 8, 32, 144, 2, 8>(img, imgT, sino, trig, batch, *g, st);
+        case 15: return launch_strip<32, 8, 32, 132, 2, 4>(img, imgT, sino, trig, batch, *g, st);   // pitch = 4 (mod 32)
+        case 16: return launch_strip<32, 8, 32, 140, 2, 8>(img, imgT, sino, trig, batch, *g, st);   // pitch = 12 (mod 32)
         default: break;
     }
     // default: as many neighbouring views per CTA as keep the strip box inside W (measured on B200,
