@@ -115,3 +115,22 @@ def test_mri_model_matches_cpu_oracle_model():
     want = torch.view_as_complex(want.permute(0, 2, 3, 1).contiguous())[:, None]
     assert got.shape == (1, 1) + im
     assert rel_l2(got, want) < 1e-4
+
+
+def test_on_gpu_data_generation_feeds_both_models():
+    from pd_unet_b200 import data
+    radon = pdu.Radon(64, user_angles(32))
+    ct = data.make_ct_batch(radon, 2, 4, seed=1, device=DEV)
+    assert ct["sino_sparse"].shape == (2, 1, 8, 64) and torch.equal(ct["sino_sparse"], ct["sino_full"][:, :, ::4])
+    torch.manual_seed(0)
+    net = PrimalDualUNetCT(radon, upsample=4, n_iter=1, n_primal=4, n_dual=4, unet_base=8, unet_depth=2, dual_features=8).to(DEV).eval()
+    with torch.no_grad():
+        assert net(ct["sino_sparse"]).shape == ct["image"].shape
+    mri = data.make_mri_batch((32, 32), 8, 2, 1, device=DEV)
+    assert mri["kdata"].shape == (1, 2, 8 * 64) and mri["dcf"].shape == (1, 1, 8 * 64)
+    spec = oracle.NufftSpec((32, 32))
+    want = oracle.nufft_forward(mri["image"].cpu(), mri["omega"].cpu().numpy(), spec, smaps=mri["smaps"].cpu(), norm="ortho")
+    assert rel_l2(mri["kdata"], want) <= 1e-5
+    m = PrimalDualUNetMRI((32, 32), 8, 64, coils=2, n_iter=1, n_primal=4, n_dual=4, unet_base=8, unet_depth=2, dual_features=8).to(DEV).eval()
+    with torch.no_grad():
+        assert m(mri["kdata"], mri["omega"], mri["smaps"], mri["dcf"]).shape == (1, 1, 32, 32)
