@@ -18,7 +18,7 @@ namespace pdu {
 bool filter_tc_supported(int D);
 size_t filter_tc_workspace_bytes(int D);
 int filter_tc_prepare(const float* taps, void* ws, size_t ws_bytes, int D, cudaStream_t st);
-int filter_tc_launch(const float* sino, float* out, const void* ws, long rows, int D, int split, cudaStream_t st);
+int filter_tc_launch(const float* sino, float* out, const void* ws, long rows, int D, int mode, cudaStream_t st);
 
 constexpr int FILT_RB = 16;   // rows per CTA
 
@@ -107,9 +107,9 @@ int pdu_filter_sinogram_f32(const float* sino, float* out, const float* taps, co
     const int D = det_count;
     int variant = option(OPT_FILTER);
     if (variant < 0) variant = 1;      // 1 = tcgen05 split-TF32 GEMM, exact products (filter_tc.cu); 2 = its 3-product A/B form
-    if ((variant == 1 || variant == 2) && filter_tc_supported(D) && workspace && workspace_bytes >= filter_tc_workspace_bytes(D) &&
+    if (variant >= 1 && variant <= 5 && filter_tc_supported(D) && workspace && workspace_bytes >= filter_tc_workspace_bytes(D) &&
         (((uintptr_t)sino | (uintptr_t)out | (uintptr_t)workspace) & 15) == 0)
-        return filter_tc_launch(sino, out, workspace, rows, D, variant == 2 ? 2 : 3, (cudaStream_t)stream);
+        return filter_tc_launch(sino, out, workspace, rows, D, variant, (cudaStream_t)stream);
     const size_t smem = ((size_t)(2 * D - 1 + 8 + 3) / 4 * 4 + (size_t)FILT_RB * D) * sizeof(float);
     PDU_REQUIRE(smem <= 200 * 1024, "pdu_filter_sinogram_f32: det_count %d too large for the shared-memory tile", D);
     static bool attr_set = false;

@@ -25,14 +25,20 @@
 
 namespace pdu {
 
-constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 32;
-constexpr int TC_TILE_BYTES = TC_BM * TC_BK * 4;            // 16 KB: every operand tile (BM == BN)
-constexpr int TC_THREADS = 192;
-template <int SPLIT>
+constexpr int TC_BM = 128, TC_BN = 128;
+constexpr int TC_SPLITTERS = 256;                          // warps 2..9 cut X (and synthesise H); warps 2..5 also run the epilogue
+constexpr int TC_THREADS = 64 + TC_SPLITTERS;
+constexpr int TC_SYNTH_MAX_D = 1024;     // largest detector whose tap pieces fit next to the ring (24 KB)
+// BK = K extent of one pipeline stage: 32 floats (128-byte rows, SWIZZLE_128B) or 16 (64-byte rows,
+// SWIZZLE_64B).  The kernel is latency bound by its ring depth (TMA latency + split + MMA per stage, one wave
+// of CTAs): halving BK doubles the stages that fit in shared memory.
+template <int SPLIT, int BK>
 struct TcCfg {
-    static constexpr int STAGES = SPLIT == 2 ? 3 : 2;
-    static constexpr int STAGE_BYTES = 2 * SPLIT * TC_TILE_BYTES;     // X pieces (piece 0 = raw X, split in place), H pieces
+    static constexpr int TILE_BYTES = TC_BM * BK * 4;                  // every operand tile (BM == BN)
+    static constexpr int STAGE_BYTES = 2 * SPLIT * TILE_BYTES;         // X pieces (piece 0 = raw X, split in place), H pieces
+    static constexpr int STAGES = (192 * 1024) / STAGE_BYTES;          // 2 (SPLIT 3, BK 32) .. 4 (SPLIT 3, BK 16)
     static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*alignment*/ + 256 /*barriers*/;
+    static int smem_synth(int D) { return SMEM + 3 * (2 * D) * 4; }   // + the three pieces of the 2D-1 taps
 };
 
 __device__ __forceinline__ uint32_t tc_s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -69,13 +75,14 @@ __device__ __forceinline__ void tc_tma_2d(uint32_t dst, const CUtensorMap* tm, i
 }
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (tile rows are 128 bytes, 8-row groups 1024 bytes apart)
+template <int BK>
 __device__ __forceinline__ uint64_t tc_smem_desc(uint32_t addr) {
     uint64_t d = 0;
     d |= (uint64_t)((addr >> 4) & 0x3FFF);          // start address, 16-byte units
     d |= (uint64_t)1 << 16;                          // leading byte offset (unused for swizzled K-major): 1
-    d |= (uint64_t)(1024 >> 4) << 32;                // stride byte offset: 8 rows x 128 B
+    d |= (uint64_t)((8 * BK * 4) >> 4) << 32;        // stride byte offset: 8 rows x (BK x 4) bytes
     d |= (uint64_t)1 << 46;                          // descriptor version (Blackwell)
-    d |= (uint64_t)2 << 61;                          // layout: SWIZZLE_128B
+    d |= (uint64_t)(BK == 32 ? 2 : 4) << 61;         // layout: SWIZZLE_128B / SWIZZLE_64B
     return d;
 }
 // kind::tf32, float32 accumulate, A and B K-major, M = 128, N = 128
@@ -95,12 +102,20 @@ __device__ __forceinline__ void tc_commit(uint32_t bar) {
 
 __device__ __forceinline__ float tf32_head(float v) { return __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
 
-template <int SPLIT>
+// SYNTH: the H operand tiles are not loaded at all.  H is Toeplitz -- B[n][k] = taps[n - k + D - 1] -- so
+// every 128 x 32 tile is 128 shifted windows of one 2D-1 vector: the splitter warps write it into shared
+// memory straight in the SWIZZLE_128B layout the MMA descriptor expects, from the three tap pieces kept in
+// shared memory.  That removes 3/4 of the kernel's L2 -> shared traffic (48 of 64 KB per K block).
+template <int SPLIT, bool SYNTH, int BK>
 __global__ void __launch_bounds__(TC_THREADS, 1)
     filter_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_h,
-                     float* __restrict__ out, long rows, int D, int* __restrict__ err_flag) {
-    constexpr int TC_STAGES = TcCfg<SPLIT>::STAGES;
-    constexpr int TC_STAGE_BYTES = TcCfg<SPLIT>::STAGE_BYTES;
+                     const float* __restrict__ tap_pieces, float* __restrict__ out, long rows, int D,
+                     int* __restrict__ err_flag) {
+    constexpr int TC_STAGES = TcCfg<SPLIT, BK>::STAGES;
+    constexpr int TC_STAGE_BYTES = TcCfg<SPLIT, BK>::STAGE_BYTES;
+    constexpr int TC_TILE_BYTES = TcCfg<SPLIT, BK>::TILE_BYTES;
+    constexpr int TC_BK = BK;
+    constexpr int CHUNKS = BK / 4;                   // 16-byte chunks per tile row
     extern __shared__ unsigned char tc_dyn[];
     const uint32_t dyn = tc_s32(tc_dyn);
     const uint32_t base = (dyn + 1023u) & ~1023u;                  // SWIZZLE_128B tiles want 1024-byte alignment
@@ -116,11 +131,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.x * TC_BM, n0 = blockIdx.y * TC_BN;
     const int n_kb = D / TC_BK;
+    float* s_taps = (float*)(base_ptr + TC_STAGES * TC_STAGE_BYTES + 256);      // [3][2 D] (SYNTH only)
+    if (SYNTH) {
+        for (int i = threadIdx.x; i < 3 * 2 * D; i += TC_THREADS) {
+            const int p = i / (2 * D), j = i - p * 2 * D;
+            s_taps[i] = j < 2 * D - 1 ? __ldg(tap_pieces + (long)p * (2 * D - 1) + j) : 0.f;
+        }
+    }
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < TC_STAGES; ++s) {
             tc_mbar_init(full(s), 1);
-            tc_mbar_init(split(s), 128);
+            tc_mbar_init(split(s), TC_SPLITTERS);
             tc_mbar_init(empty(s), 1);
         }
         tc_mbar_init(accum, 1);
@@ -143,11 +165,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                 const int s = kb % TC_STAGES;
                 if (kb >= TC_STAGES) ok = tc_mbar_wait(empty(s), ((kb / TC_STAGES) - 1) & 1) && ok;
                 const uint32_t st = base + s * TC_STAGE_BYTES;
-                tc_mbar_expect_tx(full(s), (1 + SPLIT) * TC_TILE_BYTES);
+                tc_mbar_expect_tx(full(s), (SYNTH ? 1 : 1 + SPLIT) * TC_TILE_BYTES);
                 tc_tma_2d(st, &tm_x, kb * TC_BK, m0, full(s));                         // raw X -> split in place into X1
+                if (!SYNTH) {
 #pragma unroll
-                for (int p = 0; p < SPLIT; ++p)                                        // pre-split H pieces, stacked by rows
-                    tc_tma_2d(st + (SPLIT + p) * TC_TILE_BYTES, &tm_h, kb * TC_BK, p * D + n0, full(s));
+                    for (int p = 0; p < SPLIT; ++p)                                    // pre-split H pieces, stacked by rows
+                        tc_tma_2d(st + (SPLIT + p) * TC_TILE_BYTES, &tm_h, kb * TC_BK, p * D + n0, full(s));
+                }
             }
         }
     } else if (warp == 1) {
@@ -161,8 +185,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                 uint64_t xd[SPLIT], hd[SPLIT];
 #pragma unroll
                 for (int p = 0; p < SPLIT; ++p) {
-                    xd[p] = tc_smem_desc(st + p * TC_TILE_BYTES);
-                    hd[p] = tc_smem_desc(st + (SPLIT + p) * TC_TILE_BYTES);
+                    xd[p] = tc_smem_desc<BK>(st + p * TC_TILE_BYTES);
+                    hd[p] = tc_smem_desc<BK>(st + (SPLIT + p) * TC_TILE_BYTES);
                 }
 #pragma unroll
                 for (int k = 0; k < TC_BK / 8; ++k) {
@@ -190,30 +214,48 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             float4* x2 = (float4*)(base_ptr + s * TC_STAGE_BYTES + TC_TILE_BYTES);
             float4* x3 = (float4*)(base_ptr + s * TC_STAGE_BYTES + 2 * TC_TILE_BYTES);   // SPLIT == 3 only
 #pragma unroll
-            for (int i = 0; i < TC_TILE_BYTES / 16 / 128; ++i) {
-                const float4 v = x1[t + i * 128];
+            for (int i = 0; i < TC_TILE_BYTES / 16 / TC_SPLITTERS; ++i) {
+                const float4 v = x1[t + i * TC_SPLITTERS];
                 float4 a, b;
                 a.x = tf32_head(v.x); b.x = v.x - a.x;      // every subtraction here is exact
                 a.y = tf32_head(v.y); b.y = v.y - a.y;
                 a.z = tf32_head(v.z); b.z = v.z - a.z;
                 a.w = tf32_head(v.w); b.w = v.w - a.w;
-                x1[t + i * 128] = a;
+                x1[t + i * TC_SPLITTERS] = a;
                 if (SPLIT == 2) {
-                    x2[t + i * 128] = b;
+                    x2[t + i * TC_SPLITTERS] = b;
                 } else {
                     float4 c, d;
                     c.x = tf32_head(b.x); d.x = b.x - c.x;
                     c.y = tf32_head(b.y); d.y = b.y - c.y;
                     c.z = tf32_head(b.z); d.z = b.z - c.z;
                     c.w = tf32_head(b.w); d.w = b.w - c.w;
-                    x2[t + i * 128] = c;
-                    x3[t + i * 128] = d;
+                    x2[t + i * TC_SPLITTERS] = c;
+                    x3[t + i * TC_SPLITTERS] = d;
+                }
+            }
+            if (SYNTH) {
+                // H tiles of this K block: element (n, k) = taps[(n0 + n) - (kb BK + k) + D - 1]; a thread writes
+                // float4 = 4 consecutive k of one row into the swizzled 16-byte chunk of that row
+#pragma unroll
+                for (int p = 0; p < SPLIT; ++p) {
+                    float4* h = (float4*)(base_ptr + s * TC_STAGE_BYTES + (SPLIT + p) * TC_TILE_BYTES);
+                    const float* tp = s_taps + p * 2 * D + (n0 - kb * TC_BK + D - 1);
+#pragma unroll
+                    for (int i = 0; i < TC_TILE_BYTES / 16 / TC_SPLITTERS; ++i) {
+                        const int idx = t + i * TC_SPLITTERS, n = idx / CHUNKS, c = idx % CHUNKS;
+                        const float* q = tp + n - 4 * c;
+                        // SWIZZLE_128B: chunk ^= row & 7 ; SWIZZLE_64B: chunk ^= (row >> 1) & 3
+                        const int cs = BK == 32 ? (c ^ (n & 7)) : (c ^ ((n >> 1) & 3));
+                        h[n * CHUNKS + cs] = make_float4(q[0], q[-1], q[-2], q[-3]);
+                    }
                 }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA
             tc_mbar_arrive(split(s));
         }
-        // ------------------------------------------------------------ epilogue
+        // ------------------------------------------------------------ epilogue (warps 2..5: one TMEM lane quarter each)
+        if (warp < 6) {
         ok = tc_mbar_wait(accum, 0) && ok;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int q = warp & 3;                                        // this warp's TMEM lane quarter
@@ -240,6 +282,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                                          __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
             }
         }
+        }
     }
     if (!ok && err_flag) atomicExch(err_flag, 1);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -262,6 +305,17 @@ __global__ void __launch_bounds__(256) filter_tc_prepare_kernel(const float* __r
         ws[total + i] = h2;
         ws[2 * total + i] = r - h2;
     }
+    // the same three pieces of the tap vector itself (for the kernels that synthesise H in shared memory)
+    float* tp = ws + 3 * total;
+    const int TL = 2 * D - 1;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < TL; i += (long)gridDim.x * blockDim.x) {
+        const float v = __ldg(taps + i);
+        const float h1 = tf32_head(v), r = v - h1;
+        const float h2 = tf32_head(r);
+        tp[i] = h1;
+        tp[TL + i] = h2;
+        tp[2 * TL + i] = r - h2;
+    }
 }
 
 typedef CUresult (*tc_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -281,7 +335,7 @@ static tc_encode_fn tc_get_encode() {
 }
 
 // [n_rows, D] float32 row-major, box = 32 floats (128 bytes, one swizzle span) x 128 rows
-static int tc_make_map(CUtensorMap* tm, const float* ptr, long n_rows, int D) {
+static int tc_make_map(CUtensorMap* tm, const float* ptr, long n_rows, int D, int bk) {
     tc_encode_fn enc = tc_get_encode();
     if (!enc) {
         set_error("cuTensorMapEncodeTiled not available from the driver");
@@ -289,10 +343,10 @@ static int tc_make_map(CUtensorMap* tm, const float* ptr, long n_rows, int D) {
     }
     cuuint64_t dims[2] = {(cuuint64_t)D, (cuuint64_t)n_rows};
     cuuint64_t strides[1] = {(cuuint64_t)D * 4};
-    cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)TC_BM};
+    cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)TC_BM};
     cuuint32_t es[2] = {1, 1};
     CUresult rc = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                      bk == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (rc != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled (filter) failed with CUresult %d (rows=%ld D=%d)", (int)rc, n_rows, D);
         return PDU_ECUDA;
@@ -302,7 +356,9 @@ static int tc_make_map(CUtensorMap* tm, const float* ptr, long n_rows, int D) {
 
 bool filter_tc_supported(int D) { return D % TC_BN == 0 && D >= TC_BN && D <= 4096; }
 
-size_t filter_tc_workspace_bytes(int D) { return filter_tc_supported(D) ? (size_t)3 * D * D * sizeof(float) : 0; }
+size_t filter_tc_workspace_bytes(int D) {
+    return filter_tc_supported(D) ? ((size_t)3 * D * D + 3 * (2 * (size_t)D - 1)) * sizeof(float) : 0;
+}
 
 int filter_tc_prepare(const float* taps, void* ws, size_t ws_bytes, int D, cudaStream_t st) {
     if (!filter_tc_supported(D)) return PDU_OK;
@@ -316,26 +372,37 @@ int filter_tc_prepare(const float* taps, void* ws, size_t ws_bytes, int D, cudaS
     return PDU_OK;
 }
 
-template <int SPLIT>
+template <int SPLIT, bool SYNTH, int BK>
 static int tc_launch(const float* sino, float* out, const void* ws, long rows, int D, cudaStream_t st) {
     CUtensorMap tx, th;
-    int rc = tc_make_map(&tx, sino, rows, D);
+    int rc = tc_make_map(&tx, sino, rows, D, BK);
     if (rc) return rc;
-    rc = tc_make_map(&th, (const float*)ws, 3L * D, D);     // the three pieces stacked by rows
+    rc = tc_make_map(&th, (const float*)ws, 3L * D, D, BK);     // the three pieces stacked by rows
     if (rc) return rc;
-    static bool attr_set = false;
-    if (!attr_set) {
-        PDU_CUDA(cudaFuncSetAttribute(filter_tc_kernel<SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<SPLIT>::SMEM));
-        attr_set = true;
+    const int smem = SYNTH ? TcCfg<SPLIT, BK>::smem_synth(D) : TcCfg<SPLIT, BK>::SMEM;
+    static int attr_set = 0;
+    if (attr_set < smem) {
+        PDU_CUDA(cudaFuncSetAttribute(filter_tc_kernel<SPLIT, SYNTH, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_set = smem;
     }
+    const float* tap_pieces = (const float*)ws + 3L * D * D;
     dim3 grid((unsigned)cdiv(rows, TC_BM), (unsigned)(D / TC_BN));
-    filter_tc_kernel<SPLIT><<<grid, TC_THREADS, TcCfg<SPLIT>::SMEM, st>>>(tx, th, out, rows, D, nullptr);
+    filter_tc_kernel<SPLIT, SYNTH, BK><<<grid, TC_THREADS, smem, st>>>(tx, th, tap_pieces, out, rows, D, nullptr);
     PDU_LAUNCHED();
     return PDU_OK;
 }
 
-int filter_tc_launch(const float* sino, float* out, const void* ws, long rows, int D, int split, cudaStream_t st) {
-    return split == 2 ? tc_launch<2>(sino, out, ws, rows, D, st) : tc_launch<3>(sino, out, ws, rows, D, st);
+// mode 1 (default): exact 6-product split, H loaded by TMA, 2 stages of 32; 2: 3-product A/B form; 3: mode 1 with H
+// synthesised in shared memory; 4 / 5: modes 1 / 3 with 4 stages of 16 (deeper ring)
+int filter_tc_launch(const float* sino, float* out, const void* ws, long rows, int D, int mode, cudaStream_t st) {
+    if (D > TC_SYNTH_MAX_D && (mode == 3 || mode == 5)) mode -= 2;
+    switch (mode) {
+        case 2: return tc_launch<2, false, 32>(sino, out, ws, rows, D, st);
+        case 3: return tc_launch<3, true, 32>(sino, out, ws, rows, D, st);
+        case 4: return tc_launch<3, false, 16>(sino, out, ws, rows, D, st);
+        case 5: return tc_launch<3, true, 16>(sino, out, ws, rows, D, st);
+        default: return tc_launch<3, false, 32>(sino, out, ws, rows, D, st);
+    }
 }
 
 }  // namespace pdu

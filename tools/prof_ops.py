@@ -32,7 +32,7 @@ for v in (0, 1, 2):
     pdu.set_option("radon_adj_variant", v)
     timed(f"radon_adj variant {v}", lambda: op._backproject(s))
 pdu.set_option("radon_adj_variant", -1)
-for v in (0, 1, 2):
+for v in (0, 1, 2, 3, 4, 5):
     pdu.set_option("filter_variant", v)
     timed(f"filter variant {v}", lambda: op._filter(s, "ramp"))
 pdu.set_option("filter_variant", -1)
@@ -42,7 +42,7 @@ xf = torch.rand(8, 512, 512, device=dev)
 sf = torch.rand(8, 1024, 512, device=dev)
 timed("fan512 fwd", lambda: fan._project(xf))
 timed("fan512 adj", lambda: fan._backproject(sf))
-for v in (0, 1, 2):
+for v in (0, 1, 2, 3, 4, 5):
     pdu.set_option("filter_variant", v)
     timed(f"fan512 filter variant {v}", lambda: fan._filter(sf, "ramp"))
 pdu.set_option("filter_variant", -1)
