@@ -453,21 +453,13 @@ int pdu_radon_fwd_f32(const float* img, float* sino, const float* trig, int batc
     const float span = g->geom == PDU_GEOM_PARALLEL ? 3.14159265f : 6.2831853f;
     const float drift = (span / g->n_angles) * 0.7072f * g->n;   // columns one view step moves a ray across the slice
     switch (variant) {                                            // explicit shapes for A/B measurement
-        case 2: return launch_strip<128, 2, 32, 248, 3, 32>(img, imgT, sino, trig, batch, *g, st);
-        case 3: return launch_strip<64, 4, 32, 168, 2, 32>(img, imgT, sino, trig, batch, *g, st);
-        case 4: return launch_strip<64, 4, 32, 168, 2, 16>(img, imgT, sino, trig, batch, *g, st);
-        case 5: return launch_strip<32, 8, 32, 136, 2, 8>(img, imgT, sino, trig, batch, *g, st);
-        case 6: return launch_strip<32, 8, 32, 136, 2, 16>(img, imgT, sino, trig, batch, *g, st);
-        case 7: return launch_strip<32, 16, 32, 136, 2, 8>(img, imgT, sino, trig, batch, *g, st);
-        case 8: return launch_strip<32, 8, 32, 136, 2, 8, false>(img, imgT, sino, trig, batch, *g, st);   // scalar inner loop
-        case 9: return launch_strip<32, 8, 32, 136, 2, 4>(img, imgT, sino, trig, batch, *g, st);
-        case 10: return launch_strip<16, 16, 32, 104, 2, 4>(img, imgT, sino, trig, batch, *g, st);
-        case 11: return launch_strip<16, 16, 32, 104, 3, 8>(img, imgT, sino, trig, batch, *g, st);
-        case 12: return launch_strip<32, 8, 32, 136, 3, 8>(img, imgT, sino, trig, batch, *g, st);
-        case 13: return launch_strip<32, 8, 32, 144, 2, 4>(img, imgT, sino, trig, batch, *g, st);   // pitch = 16 (mod 32)
-        case 14: return launch_strip<32, 8, 32, 144, 2, 8>(img, imgT, sino, trig, batch, *g, st);
-        case 15: return launch_strip<32, 8, 32, 132, 2, 4>(img, imgT, sino, trig, batch, *g, st);   // pitch = 4 (mod 32)
-        case 16: return launch_strip<32, 8, 32, 140, 2, 8>(img, imgT, sino, trig, batch, *g, st);   // pitch = 12 (mod 32)
+        case 2: return launch_strip<128, 2, 32, 248, 3, 32>(img, imgT, sino, trig, batch, *g, st);   // widest box (sparse view sets)
+        case 3: return launch_strip<64, 4, 32, 168, 2, 32>(img, imgT, sino, trig, batch, *g, st);    // 32-detector warps
+        case 4: return launch_strip<64, 4, 32, 168, 2, 16>(img, imgT, sino, trig, batch, *g, st);    // 16 det x 2 views / warp
+        case 5: return launch_strip<32, 8, 32, 136, 2, 8>(img, imgT, sino, trig, batch, *g, st);     // 8 det x 4 views / warp
+        case 6: return launch_strip<32, 8, 32, 136, 2, 8, false>(img, imgT, sino, trig, batch, *g, st);   // scalar inner loop
+        // (r01 also measured 4-lane runs, 16 x 16 CTAs, 3-deep rings and row pitches = 4 / 12 / 16 mod 32: all
+        //  within 2 % of shape 5 -- 590..605 us -- so they were dropped)
         default: break;
     }
     // default: as many neighbouring views per CTA as keep the strip box inside W (measured on B200,

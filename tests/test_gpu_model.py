@@ -134,3 +134,27 @@ def test_on_gpu_data_generation_feeds_both_models():
     m = PrimalDualUNetMRI((32, 32), 8, 64, coils=2, n_iter=1, n_primal=4, n_dual=4, unet_base=8, unet_depth=2, dual_features=8).to(DEV).eval()
     with torch.no_grad():
         assert m(mri["kdata"], mri["omega"], mri["smaps"], mri["dcf"]).shape == (1, 1, 32, 32)
+
+
+def test_fan_beam_ct_model_matches_cpu_oracle_model():
+    """BASELINE configs[2] flavour (fan beam, views over 2 pi, periodic angular upsampling) at a small size."""
+    from oracle.radon import FAN
+    torch.backends.cudnn.allow_tf32 = False
+    n, A, up = 64, 32, 4
+    ang = user_angles(A, 2 * np.pi)
+    radon = pdu.RadonFanbeam(n, ang, 2.0 * n)
+    torch.manual_seed(3)
+    model = PrimalDualUNetCT(radon, upsample=up, n_iter=2, n_primal=4, n_dual=4, unet_base=8, unet_depth=2,
+                             dual_features=8).to(DEV).eval()
+    assert model.wrap == "periodic"
+    g = oracle.RadonGeom(n=n, n_angles=A, det_count=n, det_spacing=2.0, geom=FAN, s_dist=2.0 * n, d_dist=2.0 * n)
+    trig = oracle.trig_table(-ang)
+    x = phantom_batch(2, n)
+    sparse = oracle.radon_forward(x, trig, g).float()[:, None, ::up].contiguous()
+    with torch.no_grad():
+        got = model(sparse.to(DEV))
+        gg = ou.angular_upsample(sparse[:, 0].double(), up, "periodic")[:, None] / model.op_scale
+        want = _reference_forward(model, gg, (n, n),
+                                  lambda im: oracle.radon_forward(im[:, 0], trig, g)[:, None],
+                                  lambda s: oracle.fbp(s[:, 0], trig, g)[:, None])
+    assert rel_l2(got, want) < 1e-4
