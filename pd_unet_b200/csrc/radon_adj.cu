@@ -26,6 +26,7 @@ struct AdjGeom {
     float k;        // fan: s_dist + d_dist
     float cr;       // det_count / 2 - 0.5  (detector coordinate of u = 0, in tap units)
     float half;     // n / 2 - 0.5
+    uint32_t koff;  // 0x4B000000 * 8 mod 2^32, passed at run time so that ptxas keeps `base - koff` in one register
 };
 
 // detector coordinate (in tap units: value = (1-fr) s[i0] + fr s[i0+1], i0 = floor(t)) and weight
@@ -95,7 +96,20 @@ __global__ void __launch_bounds__(TX*(TY / PY))
 // (lx, ly) = pixel offset inside the tile, lo = first detector bin of the staged segment.
 // parallel beam: cap the registers so that 7 (PY = 8) / 3 (PY = 4) CTAs fit an SM -- B N^2 / PY threads then
 // make one balanced wave; the rarely taken float64 fallback is what would otherwise raise the count
-template <int TX, int TY, int PY, int AC, int SEG, bool FAN>
+// MODE 0 (r01): the segment holds (value, next - value) and the tap is value + frac * diff: floor, fraction, masked
+//   index -- 7 instructions per tap.
+// MODE 1: the segment holds the line through the two samples in the segment's own coordinate, (A, B) with
+//   tap(t) = A + t B, A = value - c B for entry c.  No fraction is needed, only floor(t) for the index, and the byte
+//   address comes from the magic-number bit pattern with one IMAD (the constant exponent part is folded into the
+//   per-view base, mod 2^32): 4.5 instructions per tap.  A is rounded at the magnitude of c |B| (c < SEG = 96),
+//   i.e. an error of <= 6e-6 |B| per tap, independent from tap to tap.
+__device__ __forceinline__ float2 lds64(uint32_t addr) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+    return v;
+}
+
+template <int TX, int TY, int PY, int AC, int SEG, bool FAN, int MODE = 0>
 __global__ void __launch_bounds__(TX*(TY / PY), FAN ? (PY == 8 ? 5 : 2) : (PY == 8 ? 7 : 3))
     radon_adj_tile_kernel(const float* __restrict__ sino, float* __restrict__ img, const float* __restrict__ trig,
                           const AdjGeom g) {
@@ -122,6 +136,9 @@ __global__ void __launch_bounds__(TX*(TY / PY), FAN ? (PY == 8 ? 5 : 2) : (PY ==
     float acc[PY];
 #pragma unroll
     for (int k = 0; k < PY; ++k) acc[k] = 0.f;
+    ull acc2[PY / 2];        // MODE 1, parallel beam: packed accumulators of the pixel pairs
+#pragma unroll
+    for (int k = 0; k < PY / 2; ++k) acc2[k] = pk2(0.f, 0.f);
     constexpr float MAGIC = 8388608.f;
     static_assert(PY % 2 == 0, "pixels are processed in packed pairs");
     ull ly_pk[PY / 2];      // row offsets inside the tile of this thread's pixel pairs, clamped to the image
@@ -181,7 +198,8 @@ __global__ void __launch_bounds__(TX*(TY / PY), FAN ? (PY == 8 ? 5 : 2) : (PY ==
                 const float* row = sb + (long)(a0 + al) * g.det_count;
                 const float v0 = (unsigned)d < (unsigned)g.det_count ? __ldg(row + d) : 0.f;
                 const float v1 = (unsigned)(d + 1) < (unsigned)g.det_count ? __ldg(row + d + 1) : 0.f;
-                s_seg[al][c] = make_float2(v0, v1 - v0);
+                const float dv = v1 - v0;
+                s_seg[al][c] = MODE ? make_float2(fmaf(-(float)c, dv, v0), dv) : make_float2(v0, dv);
             }
             __syncthreads();
             if (x < g.n) {
@@ -197,6 +215,22 @@ __global__ void __launch_bounds__(TX*(TY / PY), FAN ? (PY == 8 ? 5 : 2) : (PY ==
                         const float4 v = *reinterpret_cast<const float4*>(s_view[al]);
                         const float tx = fmaf(v.x, lx, v.z);
                         const ull p_tx = pk2(tx, tx), p_b = pk2(v.y, v.y);
+                        if (MODE) {
+                            // bits(t + 2^23) = 0x4B000000 + floor(t): fold the constant into the base (mod 2^32)
+                            const uint32_t cbase = (uint32_t)__cvta_generic_to_shared(seg) - g.koff;
+#pragma unroll
+                            for (int k = 0; k < PY; k += 2) {
+                                const ull p_tl = fma2(p_b, ly_pk[k / 2], p_tx);        // >= 1 by construction
+                                const ull p_t = add2_rm(p_tl, p_m);
+                                float t0, t1, c0, c1;
+                                upk2(p_t, t0, t1);
+                                upk2(p_tl, c0, c1);
+                                const float2 s0 = lds64((uint32_t)__float_as_int(t0) * 8u + cbase);
+                                const float2 s1 = lds64((uint32_t)__float_as_int(t1) * 8u + cbase);
+                                acc2[k / 2] = add2(acc2[k / 2], pk2(fmaf(c0, s0.y, s0.x), fmaf(c1, s1.y, s1.x)));
+                            }
+                            continue;
+                        }
 #pragma unroll
                         for (int k = 0; k < PY; k += 2) {
                             const ull p_tl = fma2(p_b, ly_pk[k / 2], p_tx);        // >= 1 by construction
@@ -227,6 +261,18 @@ __global__ void __launch_bounds__(TX*(TY / PY), FAN ? (PY == 8 ? 5 : 2) : (PY ==
                             p_r = fma2(p_r, sub2(p_one, mul2(p_den, p_r)), p_r);   // one Newton step: ~1 ulp
                             float q0, q1;
                             upk2(mul2(p_num, p_r), q0, q1);
+                            if (MODE) {
+                                const float c0 = fminf(fmaxf(q0, 0.f), (float)(SEG - 1)), c1 = fminf(fmaxf(q1, 0.f), (float)(SEG - 1));
+                                float t0, t1, w0, w1;
+                                upk2(add2_rm(pk2(c0, c1), p_m), t0, t1);
+                                upk2(mul2(p_k, p_r), w0, w1);
+                                const uint32_t cbase = (uint32_t)__cvta_generic_to_shared(seg) - g.koff;
+                                const float2 s0 = lds64((uint32_t)__float_as_int(t0) * 8u + cbase);
+                                const float2 s1 = lds64((uint32_t)__float_as_int(t1) * 8u + cbase);
+                                acc[k] = fmaf(w0, fmaf(c0, s0.y, s0.x), acc[k]);
+                                acc[k + 1] = fmaf(w1, fmaf(c1, s1.y, s1.x), acc[k + 1]);
+                                continue;
+                            }
                             const ull p_tl = pk2(fmaxf(q0, 0.f), fmaxf(q1, 0.f));
                             const ull p_t = add2_rm(p_tl, p_m);
                             const ull p_fr = sub2(p_tl, sub2(p_t, p_m));
@@ -257,6 +303,15 @@ __global__ void __launch_bounds__(TX*(TY / PY), FAN ? (PY == 8 ? 5 : 2) : (PY ==
         }
     }
     const float dx = (float)x - g.half;
+    if (MODE && !FAN) {
+#pragma unroll
+        for (int k = 0; k < PY; k += 2) {
+            float a0, a1;
+            upk2(acc2[k / 2], a0, a1);
+            acc[k] += a0;
+            acc[k + 1] += a1;
+        }
+    }
 #pragma unroll
     for (int k = 0; k < PY; ++k) {
         const int y = y0 + k * RY;
@@ -302,6 +357,7 @@ extern "C" int pdu_radon_adj_f32(const float* sino, float* img, const float* tri
     ag.k = g->s_dist + g->d_dist;
     ag.cr = 0.5f * (float)g->det_count - 0.5f;
     ag.half = 0.5f * (float)g->n - 0.5f;
+    ag.koff = 0x4B000000u * 8u;
 
     cudaStream_t st = (cudaStream_t)stream;
     int variant = option(OPT_RADON_ADJ);
@@ -313,6 +369,9 @@ extern "C" int pdu_radon_adj_f32(const float* sino, float* img, const float* tri
     } else if (variant == 2) {        // A/B: 4 pixels per thread, 256 threads
         if (ag.fan) radon_adj_tile_kernel<TX, TY, 4, 32, 96, true><<<grid, dim3(TX, TY / 4), 0, st>>>(sino, img, trig, ag);
         else radon_adj_tile_kernel<TX, TY, 4, 32, 96, false><<<grid, dim3(TX, TY / 4), 0, st>>>(sino, img, trig, ag);
+    } else if (variant == 3) {        // line-form taps (MODE 1), 8 pixels per thread
+        if (ag.fan) radon_adj_tile_kernel<TX, TY, 8, 32, 96, true, 1><<<grid, dim3(TX, TY / 8), 0, st>>>(sino, img, trig, ag);
+        else radon_adj_tile_kernel<TX, TY, 8, 32, 96, false, 1><<<grid, dim3(TX, TY / 8), 0, st>>>(sino, img, trig, ag);
     } else {                          // 8 pixels per thread, 128 threads: B N^2 / 8 threads fit one balanced wave
         if (ag.fan) radon_adj_tile_kernel<TX, TY, 8, 32, 96, true><<<grid, dim3(TX, TY / 8), 0, st>>>(sino, img, trig, ag);
         else radon_adj_tile_kernel<TX, TY, 8, 32, 96, false><<<grid, dim3(TX, TY / 8), 0, st>>>(sino, img, trig, ag);

@@ -178,24 +178,38 @@ __global__ void __launch_bounds__(DB* AG)
     const float inv_aw = aw > 1e-3f ? __fdividef(1.f, aw) : 0.f;   // 0: no estimate, count by stepping
 
     __syncthreads();
-    if (n >= 0) {
+    {
+        // every ray registers its column extent in every strip it crosses.  The lanes of a warp mostly
+        // cross the same strips, so the extents are first reduced across the warp (REDUX) and one lane
+        // updates the shared box: per-lane atomics on one address serialise 32-way (ncu r02: a third of
+        // all shared-memory wavefronts of the kernel)
         const float wa = fmaf(jf, vw, w0), ua = fmaf(jf, vu, u0);
         const float jend = rev ? 0.f : (float)n;
         const float wb = fmaf(jend, vw, w0), ub = fmaf(jend, vu, u0);
         // strips are [k TH - 1, (k+1) TH - 1); widen by eps so that a sample the marching loop puts on
         // the other side of a boundary (it rounds differently) still finds its ray registered there
         constexpr float EPS = 1e-3f;
-        const int kA = max(((int)floorf(wa - EPS) + 1) / TH, 0);
-        const int kB = min(((int)floorf(wb + EPS) + 1) / TH, n_strips - 1);
+        const int kA = n >= 0 ? max(((int)floorf(wa - EPS) + 1) / TH, 0) : INT_MAX;
+        const int kB = n >= 0 ? min(((int)floorf(wb + EPS) + 1) / TH, n_strips - 1) : -1;
         const float dw = wb - wa;
         const float slope = dw > 0.f ? (ub - ua) / dw : 0.f;
-        for (int k = kA; k <= kB; ++k) {
-            const float wlo = fminf(fmaxf(wa, (float)(k * TH - 1)), wb);
-            const float whi = fmaxf(fminf(wb, (float)((k + 1) * TH - 1)), wa);
-            const float ulo = dw > 0.f ? fmaf(wlo - wa, slope, ua) : fminf(ua, ub);
-            const float uhi = dw > 0.f ? fmaf(whi - wa, slope, ua) : fmaxf(ua, ub);
-            atomicMin(&s_umin[k], (int)floorf(fminf(ulo, uhi)) - 1);
-            atomicMax(&s_umax[k], (int)floorf(fmaxf(ulo, uhi)) + 2);
+        const int kA_w = __reduce_min_sync(0xffffffffu, kA), kB_w = __reduce_max_sync(0xffffffffu, kB);
+        for (int k = kA_w; k <= kB_w; ++k) {
+            int lo_k = INT_MAX, hi_k = INT_MIN;
+            if (k >= kA && k <= kB) {
+                const float wlo = fminf(fmaxf(wa, (float)(k * TH - 1)), wb);
+                const float whi = fmaxf(fminf(wb, (float)((k + 1) * TH - 1)), wa);
+                const float ulo = dw > 0.f ? fmaf(wlo - wa, slope, ua) : fminf(ua, ub);
+                const float uhi = dw > 0.f ? fmaf(whi - wa, slope, ua) : fmaxf(ua, ub);
+                lo_k = (int)floorf(fminf(ulo, uhi)) - 1;
+                hi_k = (int)floorf(fmaxf(ulo, uhi)) + 2;
+            }
+            lo_k = __reduce_min_sync(0xffffffffu, lo_k);
+            hi_k = __reduce_max_sync(0xffffffffu, hi_k);
+            if (lane == 0 && lo_k <= hi_k) {
+                atomicMin(&s_umin[k], lo_k);
+                atomicMax(&s_umax[k], hi_k);
+            }
         }
     }
     __syncthreads();
@@ -324,6 +338,265 @@ __global__ void __launch_bounds__(DB* AG)
     if (valid) sino[((long)b * g.n_angles + a) * g.det_count + d] = acc * r.step;
 }
 
+// ------------------------------------------------------------------ variant 7+: "quad" strips
+// Same strip marching, different tile format.  A pre-pass turns the slice (and its transpose) into
+// one float4 per bilinear CELL -- (v00, d_w, d_u, d_uw) with d_w = v10 - v00, d_u = v01 - v00,
+// d_uw = (v11 - v10) - (v01 - v00) -- so a sample is ONE 16-byte shared-memory load and four FMAs,
+//   v00 + fu d_u + fw (d_w + fu d_uw),
+// instead of four 4-byte loads, two subtractions and three FMAs, and the tile address comes straight
+// from the magic-number bit patterns with two integer instructions (no mask: the constant high part
+// is folded into the per-strip base, all arithmetic mod 2^32).  Cell (R, C) has its corners at pixel
+// rows R-1, R and columns C-1, C, so the cell tensor is (n+1) x (n+1) and TMA's zero fill outside
+// it is again the texture "border" mode.  The 16-byte cells also remove the 16-byte start alignment
+// constraint of the float tile (any cell column is a legal TMA start).
+__global__ void __launch_bounds__(256) quad_build_kernel(const float* __restrict__ img, float4* __restrict__ q,
+                                                         float4* __restrict__ qt, int n) {
+    __shared__ float t[33][34];
+    const int n1 = n + 1;
+    const long ibase = (long)blockIdx.z * n * n;
+    const long qbase = (long)blockIdx.z * n1 * n1;
+    const int R0 = blockIdx.y * 32, C0 = blockIdx.x * 32;   // cell tile; pixel rows R0-1 .. R0+31
+    for (int i = threadIdx.y * 32 + threadIdx.x; i < 33 * 33; i += 256) {
+        const int rr = i / 33, cc = i - rr * 33;
+        const int y = R0 - 1 + rr, x = C0 - 1 + cc;
+        t[rr][cc] = ((unsigned)y < (unsigned)n && (unsigned)x < (unsigned)n) ? __ldg(img + ibase + (long)y * n + x) : 0.f;
+    }
+    __syncthreads();
+    for (int rr = threadIdx.y; rr < 32; rr += 8) {
+        const int cc = threadIdx.x;
+        {   // Q(R0 + rr, C0 + cc): rows = image rows
+            const int R = R0 + rr, Cc = C0 + cc;
+            if (R < n1 && Cc < n1) {
+                const float v00 = t[rr][cc], v01 = t[rr][cc + 1], v10 = t[rr + 1][cc], v11 = t[rr + 1][cc + 1];
+                q[qbase + (long)R * n1 + Cc] = make_float4(v00, v10 - v00, v01 - v00, (v11 - v10) - (v01 - v00));
+            }
+        }
+        {   // QT(C0 + rr, R0 + cc): the same cells of the transposed image (rows = image columns)
+            const int R = C0 + rr, Cc = R0 + cc;
+            if (R < n1 && Cc < n1) {
+                const float v00 = t[cc][rr], v01 = t[cc + 1][rr], v10 = t[cc][rr + 1], v11 = t[cc + 1][rr + 1];
+                qt[qbase + (long)R * n1 + Cc] = make_float4(v00, v10 - v00, v01 - v00, (v11 - v10) - (v01 - v00));
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+
+// one cell straight from global memory (oversize strips only); (wc, uc) are cell coordinates
+__device__ __forceinline__ float quad_global(const float4* __restrict__ q, int n1, float wc, float uc) {
+    const float wf = floorf(wc), uf = floorf(uc);
+    const int R = (int)wf, Cc = (int)uf;
+    if ((unsigned)R >= (unsigned)n1 || (unsigned)Cc >= (unsigned)n1) return 0.f;
+    const float4 c = __ldg(q + (long)R * n1 + Cc);
+    const float fw = wc - wf, fu = uc - uf;
+    return fmaf(fu, c.z, c.x) + fw * fmaf(fu, c.w, c.y);
+}
+
+template <int DB, int AG, int TH, int W, int NBUF>
+struct QuadCfg {
+    static constexpr int THREADS = DB * AG;
+    static constexpr int TILE_BYTES = TH * W * 16;
+    static constexpr int SMEM = NBUF * TILE_BYTES + 2 * NBUF * 8 + 2 * MAX_STRIPS * 4;
+    static_assert(W <= 128 && (TH * W) % 8 == 0, "one TMA box of 2 W doubles; 128-byte aligned buffers");
+};
+
+template <int DB, int AG, int TH, int W, int NBUF, int LD>
+__global__ void __launch_bounds__(DB* AG + 32)
+    radon_fwd_quad_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_qt,
+                          const float4* __restrict__ q, const float4* __restrict__ qt, float* __restrict__ sino,
+                          const float* __restrict__ trig, const pdu_radon_geom_t g) {
+    using C = QuadCfg<DB, AG, TH, W, NBUF>;
+    extern __shared__ __align__(1024) unsigned char smem_dyn[];
+    uint64_t* full = (uint64_t*)(smem_dyn + NBUF * C::TILE_BYTES);
+    uint64_t* empty = full + NBUF;
+    int* s_umin = (int*)(empty + NBUF);
+    int* s_umax = s_umin + MAX_STRIPS;
+
+    const int tid = threadIdx.x;
+    static_assert(32 % LD == 0 && DB % LD == 0 && AG % (32 / LD) == 0, "warp shape must tile the CTA");
+    constexpr int AGW = 32 / LD;
+    const int lane = tid & 31, warp = tid >> 5;
+    // warp THREADS/32 is the TMA producer: it owns no rays, so no compute warp ever waits for the other
+    // warps of the CTA (the `empty` barriers) before starting its own strip
+    const bool producer = warp == C::THREADS / 32;
+    const int dl = (warp % (DB / LD)) * LD + lane % LD;
+    const int al = (warp / (DB / LD)) * AGW + lane / LD;
+    const int d = blockIdx.x * DB + dl;
+    const int a = blockIdx.y * AG + al;
+    const int b = blockIdx.z;
+    const int N1 = g.n + 1;
+    const int n_strips = (N1 + TH - 1) / TH;
+    const bool valid = !producer && d < g.det_count && a < g.n_angles;
+    const uint32_t smem_base = smem_u32(smem_dyn);
+    const bool tma_ok = (smem_base & 127u) == 0;
+
+    for (int k = tid; k < n_strips; k += C::THREADS + 32) {
+        s_umin[k] = INT_MAX;
+        s_umax[k] = INT_MIN;
+    }
+    if (tid == 0) {
+        for (int i = 0; i < NBUF; ++i) {
+            mbar_init(full + i, 1);
+            mbar_init(empty + i, C::THREADS / 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+
+    const int a_ref = min(blockIdx.y * AG, g.n_angles - 1);
+    const bool use_t = fabsf(__ldg(trig + 2 * a_ref + 1)) > fabsf(__ldg(trig + 2 * a_ref));
+
+    Ray r;
+    r.n_steps = -1;
+    r.xc0 = r.yc0 = r.vx = r.vy = r.step = 0.f;
+    if (valid) r = ray_setup(g, __ldg(trig + 2 * a), __ldg(trig + 2 * a + 1), d);
+    // cell coordinates (pixel-centre coordinate + 1): (u, w) = (column, row) of the source the CTA reads
+    const float u0 = (use_t ? r.yc0 : r.xc0) + 1.f, w0 = (use_t ? r.xc0 : r.yc0) + 1.f;
+    const float vu = use_t ? r.vy : r.vx, vw = use_t ? r.vx : r.vy;
+    const int n = r.n_steps;
+    const bool rev = vw < 0.f;
+    const float dj = rev ? -1.f : 1.f;
+    float jf = rev ? (float)n : 0.f;
+    const float aw = fabsf(vw);
+    const float inv_aw = aw > 1e-3f ? __fdividef(1.f, aw) : 0.f;
+
+    __syncthreads();
+    {
+        // strip boxes: warp-reduced extents, one lane per warp touches the shared box (see the float-tile kernel)
+        const float wa = fmaf(jf, vw, w0), ua = fmaf(jf, vu, u0);
+        const float jend = rev ? 0.f : (float)n;
+        const float wb = fmaf(jend, vw, w0), ub = fmaf(jend, vu, u0);
+        constexpr float EPS = 1e-3f;
+        const int kA = n >= 0 ? max((int)floorf(wa - EPS), 0) / TH : INT_MAX;
+        const int kB = n >= 0 ? min(max((int)floorf(wb + EPS), 0) / TH, n_strips - 1) : -1;
+        const float dw = wb - wa;
+        const float slope = dw > 0.f ? (ub - ua) / dw : 0.f;
+        const int kA_w = __reduce_min_sync(0xffffffffu, kA), kB_w = __reduce_max_sync(0xffffffffu, kB);
+        for (int k = kA_w; k <= kB_w; ++k) {
+            int lo_k = INT_MAX, hi_k = INT_MIN;
+            if (k >= kA && k <= kB) {
+                const float wlo = fminf(fmaxf(wa, (float)(k * TH)), wb);
+                const float whi = fmaxf(fminf(wb, (float)((k + 1) * TH)), wa);
+                const float ulo = dw > 0.f ? fmaf(wlo - wa, slope, ua) : fminf(ua, ub);
+                const float uhi = dw > 0.f ? fmaf(whi - wa, slope, ua) : fmaxf(ua, ub);
+                lo_k = (int)floorf(fminf(ulo, uhi)) - 1;
+                hi_k = (int)floorf(fmaxf(ulo, uhi)) + 1;
+            }
+            lo_k = __reduce_min_sync(0xffffffffu, lo_k);
+            hi_k = __reduce_max_sync(0xffffffffu, hi_k);
+            if (lane == 0 && lo_k <= hi_k) {
+                atomicMin(&s_umin[k], lo_k);
+                atomicMax(&s_umax[k], hi_k);
+            }
+        }
+    }
+    __syncthreads();
+
+    const CUtensorMap* tm = use_t ? &tm_qt : &tm_q;
+    const float4* src = (use_t ? qt : q) + (long)b * N1 * N1;
+
+    int k_issue = 0, seq_issue = 0;   // producer state
+    auto issue = [&]() {
+        while (k_issue < n_strips && s_umin[k_issue] > s_umax[k_issue]) ++k_issue;
+        if (k_issue < n_strips) {
+            const int buf = seq_issue % NBUF;
+            if (seq_issue >= NBUF) mbar_wait(empty + buf, ((seq_issue / NBUF) - 1) & 1);
+            const int lo = s_umin[k_issue];
+            if (tma_ok && s_umax[k_issue] - lo + 1 <= W) {
+                mbar_expect_tx(full + buf, C::TILE_BYTES);
+                // the map describes the cells as pairs of doubles: start = 2 lo (always 16-byte aligned)
+                tma_load_3d(smem_dyn + buf * C::TILE_BYTES, tm, 2 * lo, k_issue * TH, b, full + buf);
+            } else {
+                mbar_arrive(full + buf);
+            }
+            ++seq_issue;
+            ++k_issue;
+        }
+    };
+    if (producer) {
+        if (lane == 0)
+            while (k_issue < n_strips) issue();
+        return;
+    }
+
+    constexpr float MAGIC = 8388608.f;
+    // bits(x + 2^23) = 0x4B000000 + floor(x):  bits(tw) * 16 W + bits(tu) * 16 = 16 (iw W + iu) + KOFF  (mod 2^32)
+    constexpr uint32_t KOFF = 0x4B000000u * (16u * (uint32_t)W) + 0x4B000000u * 16u;
+    float acc0 = 0.f, acc1 = 0.f;
+    int s = 0;
+    int seq = 0;
+    for (int k = 0; k < n_strips; ++k) {
+        const int hi = s_umax[k];
+        const int lo = s_umin[k];
+        if (lo > hi) continue;
+        const int buf = seq % NBUF;
+        mbar_wait(full + buf, (seq / NBUF) & 1);
+        const float w0l = w0 - (float)(k * TH);
+        const float u0l = u0 - (float)lo;
+        int cnt = 0;
+        const int left = n - s + 1;
+        bool first_low = false;
+        if (left > 0) {
+            const float wl = fmaf(jf, vw, w0l);
+            if (wl < (float)TH) {
+                int m = inv_aw > 0.f ? (int)(((float)TH - wl) * inv_aw) + 1 : 1;
+                m = max(1, min(m, left));
+                while (m > 1 && fmaf(jf + (float)(m - 1) * dj, vw, w0l) >= (float)TH) --m;
+                while (m < left && fmaf(jf + (float)m * dj, vw, w0l) < (float)TH) ++m;
+                cnt = m;
+                first_low = wl < 0.f;
+            }
+        }
+        if (tma_ok && hi - lo + 1 <= W) {
+            const uint32_t cbase = smem_base + (uint32_t)(buf * C::TILE_BYTES) - KOFF;
+            int i = 0;
+            if (first_low && cnt > 0) {
+                // a first sample an ulp before the strip: clamp it onto the strip's first cell row
+                const float ul = fmaf(jf, vu, u0l);
+                const float tu = __fadd_rd(ul, MAGIC);
+                const float fu = ul - (tu - MAGIC);
+                const uint32_t addr = smem_base + (uint32_t)(buf * C::TILE_BYTES) + (((uint32_t)__float_as_int(tu) & 0x7fffffu) << 4);
+                const float4 c = lds128(addr);
+                acc0 += fmaf(fu, c.z, c.x);
+                jf += dj;
+                i = 1;
+            }
+            const ull p_v = pk2(vw, vu), p_0 = pk2(w0l, u0l), p_m = pk2(MAGIC, MAGIC), p_dj = pk2(dj, dj);
+            ull p_j = pk2(jf, jf);
+#pragma unroll 4
+            for (; i < cnt; ++i) {
+                const ull p_c = fma2(p_j, p_v, p_0);            // (wl, ul)
+                const ull p_t = add2_rm(p_c, p_m);              // (floor + 2^23) each
+                const ull p_f = sub2(p_c, sub2(p_t, p_m));      // (fw, fu)
+                float tw, tu, fw, fu;
+                upk2(p_t, tw, tu);
+                upk2(p_f, fw, fu);
+                const uint32_t addr = (uint32_t)__float_as_int(tw) * (16u * (uint32_t)W) + cbase + ((uint32_t)__float_as_int(tu) << 4);
+                const float4 c = lds128(addr);
+                acc0 += fmaf(fu, c.z, c.x);
+                acc1 = fmaf(fw, fmaf(fu, c.w, c.y), acc1);
+                p_j = add2(p_j, p_dj);
+            }
+            float j_hi;
+            upk2(p_j, jf, j_hi);
+        } else {
+            for (int i = 0; i < cnt; ++i) {
+                acc0 += quad_global(src, N1, fmaf(jf, vw, w0), fmaf(jf, vu, u0));
+                jf += dj;
+            }
+        }
+        s += cnt;
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive(empty + buf);
+        ++seq;
+    }
+    if (valid) sino[((long)b * g.n_angles + a) * g.det_count + d] = (acc0 + acc1) * r.step;
+}
+
 // ------------------------------------------------------------------ host side
 typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -384,6 +657,51 @@ static int launch_strip(const float* img, const float* imgT, float* sino, const 
     return PDU_OK;
 }
 
+// cells [batch, n+1, n+1] x 16 bytes, described as pairs of doubles: box (2 w, rows, 1), zero fill outside.
+static int make_quad_map(CUtensorMap* tm, const float4* ptr, int batch, int n1, int box_w, int box_rows) {
+    encode_tiled_fn enc = get_encode_tiled();
+    if (!enc) {
+        set_error("cuTensorMapEncodeTiled not available from the driver");
+        return PDU_EUNSUPPORTED;
+    }
+    cuuint64_t dims[3] = {(cuuint64_t)n1 * 2, (cuuint64_t)n1, (cuuint64_t)batch};
+    cuuint64_t strides[2] = {(cuuint64_t)n1 * 16, (cuuint64_t)n1 * n1 * 16};
+    cuuint32_t box[3] = {(cuuint32_t)box_w * 2, (cuuint32_t)box_rows, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult rc = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void*)ptr, dims, strides, box, es,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled (cells) failed with CUresult %d (n=%d batch=%d box=%dx%d)", (int)rc, n1 - 1,
+                  batch, box_w, box_rows);
+        return PDU_ECUDA;
+    }
+    return PDU_OK;
+}
+
+static size_t quad_bytes(int n, int batch) { return (size_t)2 * batch * (n + 1) * (n + 1) * sizeof(float4); }
+
+template <int DB, int AG, int TH, int W, int NBUF, int LD>
+static int launch_quad(const float4* q, const float4* qt, float* sino, const float* trig, int batch,
+                       const pdu_radon_geom_t& g, cudaStream_t st) {
+    using C = QuadCfg<DB, AG, TH, W, NBUF>;
+    CUtensorMap tm, tmT;
+    int rc = make_quad_map(&tm, q, batch, g.n + 1, W, TH);
+    if (rc) return rc;
+    rc = make_quad_map(&tmT, qt, batch, g.n + 1, W, TH);
+    if (rc) return rc;
+    auto kern = radon_fwd_quad_kernel<DB, AG, TH, W, NBUF, LD>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        PDU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+        attr_set = true;
+    }
+    dim3 grid((unsigned)cdiv(g.det_count, DB), (unsigned)cdiv(g.n_angles, AG), (unsigned)batch);
+    kern<<<grid, C::THREADS + 32, C::SMEM, st>>>(tm, tmT, q, qt, sino, trig, g);
+    PDU_LAUNCHED();
+    return PDU_OK;
+}
+
 }  // namespace pdu
 
 using namespace pdu;
@@ -412,7 +730,9 @@ int pdu_radon_trig_f32(const float* angles, float* trig, int n_angles, pdu_strea
 
 size_t pdu_radon_workspace_bytes(const pdu_radon_geom_t* g, int batch) {
     if (!g || g->n <= 0 || batch <= 0) return 0;
-    return (size_t)batch * g->n * g->n * sizeof(float);
+    // cell tensors of the slice and of its transpose (quad variants); the float-tile variants use the
+    // first batch * n * n floats of the same scratch for the transposed copy
+    return quad_bytes(g->n, batch);
 }
 
 int pdu_radon_fwd_f32(const float* img, float* sino, const float* trig, int batch, const pdu_radon_geom_t* g,
@@ -422,11 +742,7 @@ int pdu_radon_fwd_f32(const float* img, float* sino, const float* trig, int batc
     PDU_REQUIRE(img && sino && trig, "pdu_radon_fwd_f32: null pointer");
     cudaStream_t st = (cudaStream_t)stream;
     int variant = option(OPT_RADON_FWD);
-    if (variant < 0) variant = 1;
-    const int n_strips32 = (g->n + 1 + 31) / 32;
-    const bool tma_ok = (g->n % 4 == 0) && (((uintptr_t)img & 15) == 0) && n_strips32 <= MAX_STRIPS &&
-                        g->n_angles <= 65535 * 2;
-    if (variant != 0 && !tma_ok) variant = 0;
+    if (variant < 0) variant = -1;
     if (variant == 0) {
         dim3 block(64, 4);
         dim3 grid((unsigned)cdiv(g->det_count, 64), (unsigned)cdiv(g->n_angles, 4), (unsigned)batch);
@@ -434,11 +750,58 @@ int pdu_radon_fwd_f32(const float* img, float* sino, const float* trig, int batc
         PDU_LAUNCHED();
         return PDU_OK;
     }
-    const size_t need = (size_t)batch * g->n * g->n * sizeof(float);
+    // columns one view step moves a ray across the slice (assumes evenly spread views; a wrong guess costs
+    // speed, never correctness -- oversized strips take the global-load path)
+    const float span = g->geom == PDU_GEOM_PARALLEL ? 3.14159265f : 6.2831853f;
+    const float drift = (span / g->n_angles) * 0.7072f * g->n;
+    const bool quad_ok = (g->n + 1 + 15) / 16 <= MAX_STRIPS && g->n_angles <= 65535 * 4;
+    const bool tile_ok = (g->n % 4 == 0) && (((uintptr_t)img & 15) == 0) && (g->n + 1 + 31) / 32 <= MAX_STRIPS &&
+                         g->n_angles <= 65535 * 2;
+    // default: cell ("quad") strips while the strip box of the CTA's views fits 128 cells; very sparse view
+    // sets fall back to the float-tile kernel with its 248-column box
+    if (variant < 0) {
+        if (quad_ok && 7.f * drift <= 23.f) variant = 7;
+        else if (quad_ok && 3.f * drift <= 50.f) variant = 9;
+        else if (tile_ok) variant = 2;
+        else if (quad_ok) variant = 9;
+        else variant = 0;
+    }
+    if (variant >= 7 && !quad_ok) variant = tile_ok ? 1 : 0;
+    if (variant >= 1 && variant <= 6 && !tile_ok) variant = quad_ok ? 9 : 0;
+    if (variant == 0) {
+        dim3 block(64, 4);
+        dim3 grid((unsigned)cdiv(g->det_count, 64), (unsigned)cdiv(g->n_angles, 4), (unsigned)batch);
+        radon_fwd_gather_kernel<<<grid, block, 0, st>>>(img, sino, trig, *g);
+        PDU_LAUNCHED();
+        return PDU_OK;
+    }
+    const size_t need = variant >= 7 ? quad_bytes(g->n, batch) : (size_t)batch * g->n * g->n * sizeof(float);
     if (!workspace || workspace_bytes < need || ((uintptr_t)workspace & 15)) {
         set_error("pdu_radon_fwd_f32: workspace of %zu bytes (16-byte aligned) required, got %zu", need,
                   workspace ? workspace_bytes : (size_t)0);
         return PDU_ENOMEM;
+    }
+    if (variant >= 7) {
+        const int n1 = g->n + 1;
+        float4* q = (float4*)workspace;
+        float4* qt = q + (size_t)batch * n1 * n1;
+        {
+            dim3 block(32, 8);
+            dim3 grid((unsigned)cdiv(n1, 32), (unsigned)cdiv(n1, 32), (unsigned)batch);
+            quad_build_kernel<<<grid, block, 0, st>>>(img, q, qt, g->n);
+            PDU_LAUNCHED();
+        }
+        switch (variant) {                                        // explicit shapes for A/B measurement
+            case 8: return launch_quad<32, 8, 32, 104, 2, 8>(q, qt, sino, trig, batch, *g, st);    // 32-row strips
+            case 9: return launch_quad<32, 4, 16, 120, 2, 8>(q, qt, sino, trig, batch, *g, st);    // 4 views / CTA (sparser views)
+            case 10: return launch_quad<32, 8, 16, 84, 3, 8>(q, qt, sino, trig, batch, *g, st);    // 3-deep ring, odd-multiple-of-4 pitch
+            case 11: return launch_quad<64, 4, 16, 128, 2, 16>(q, qt, sino, trig, batch, *g, st);  // 16 det x 2 views / warp
+            case 12: return launch_quad<32, 16, 16, 88, 3, 8>(q, qt, sino, trig, batch, *g, st);   // 512 threads: 16 views share a box
+            case 13: return launch_quad<32, 8, 16, 76, 3, 8>(q, qt, sino, trig, batch, *g, st);    // narrow box, 3-deep ring
+            case 14: return launch_quad<32, 8, 16, 89, 2, 8>(q, qt, sino, trig, batch, *g, st);    // odd row pitch
+            case 15: return launch_quad<32, 16, 16, 92, 2, 8>(q, qt, sino, trig, batch, *g, st);   // 512 threads, 2-deep
+            default: return launch_quad<32, 8, 16, 88, 2, 8>(q, qt, sino, trig, batch, *g, st);    // 7
+        }
     }
     float* imgT = (float*)workspace;
     {
@@ -447,23 +810,15 @@ int pdu_radon_fwd_f32(const float* img, float* sino, const float* trig, int batc
         transpose_kernel<<<grid, block, 0, st>>>(img, imgT, g->n);
         PDU_LAUNCHED();
     }
-    // views per CTA: neighbouring views must stay within a few columns of each other across the
-    // slice, otherwise the strip box widens past W (assumes evenly spread views; a wrong guess
-    // costs speed, never correctness -- oversized strips take the global-load path).
-    const float span = g->geom == PDU_GEOM_PARALLEL ? 3.14159265f : 6.2831853f;
-    const float drift = (span / g->n_angles) * 0.7072f * g->n;   // columns one view step moves a ray across the slice
-    switch (variant) {                                            // explicit shapes for A/B measurement
+    switch (variant) {                                            // float-tile shapes (r01 A/B)
         case 2: return launch_strip<128, 2, 32, 248, 3, 32>(img, imgT, sino, trig, batch, *g, st);   // widest box (sparse view sets)
         case 3: return launch_strip<64, 4, 32, 168, 2, 32>(img, imgT, sino, trig, batch, *g, st);    // 32-detector warps
         case 4: return launch_strip<64, 4, 32, 168, 2, 16>(img, imgT, sino, trig, batch, *g, st);    // 16 det x 2 views / warp
         case 5: return launch_strip<32, 8, 32, 136, 2, 8>(img, imgT, sino, trig, batch, *g, st);     // 8 det x 4 views / warp
         case 6: return launch_strip<32, 8, 32, 136, 2, 8, false>(img, imgT, sino, trig, batch, *g, st);   // scalar inner loop
-        // (r01 also measured 4-lane runs, 16 x 16 CTAs, 3-deep rings and row pitches = 4 / 12 / 16 mod 32: all
-        //  within 2 % of shape 5 -- 590..605 us -- so they were dropped)
         default: break;
     }
-    // default: as many neighbouring views per CTA as keep the strip box inside W (measured on B200,
-    // 256^2 x 512 views x 16 slices: 32 det x 8 views, 8-lane detector runs 620 us; 64 x 4 / 32-lane 716 us)
+    // variant 1: the r01 default -- as many neighbouring views per CTA as keep the strip box inside W
     if (7.f * drift <= 40.f) return launch_strip<32, 8, 32, 136, 2, 8>(img, imgT, sino, trig, batch, *g, st);
     if (3.f * drift <= 28.f) return launch_strip<64, 4, 32, 168, 2, 16>(img, imgT, sino, trig, batch, *g, st);
     return launch_strip<128, 2, 32, 248, 3, 32>(img, imgT, sino, trig, batch, *g, st);

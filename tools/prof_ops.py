@@ -24,11 +24,11 @@ def timed(name, fn):
     print(f"{name:28s} median {statistics.median(ts)*1e3:9.1f} us  min {min(ts)*1e3:9.1f} us", flush=True)
 
 
-for v in (0, 1, 2, 3, 4, 6):
+for v in (1, 7, 15):
     pdu.set_option("radon_fwd_variant", v)
     timed(f"radon_fwd variant {v}", lambda: op._project(x))
 pdu.set_option("radon_fwd_variant", -1)
-for v in (0, 1, 2):
+for v in (1, 2, 3):
     pdu.set_option("radon_adj_variant", v)
     timed(f"radon_adj variant {v}", lambda: op._backproject(s))
 pdu.set_option("radon_adj_variant", -1)
@@ -40,8 +40,15 @@ pdu.set_option("filter_variant", -1)
 fan = pdu.RadonFanbeam(512, np.linspace(0, 2 * np.pi, 1024, endpoint=False), 1024.0)
 xf = torch.rand(8, 512, 512, device=dev)
 sf = torch.rand(8, 1024, 512, device=dev)
+for v in (1, 7):
+    pdu.set_option("radon_fwd_variant", v)
+    timed(f"fan512 fwd variant {v}", lambda: fan._project(xf))
+pdu.set_option("radon_fwd_variant", -1)
 timed("fan512 fwd", lambda: fan._project(xf))
-timed("fan512 adj", lambda: fan._backproject(sf))
+for v in (1, 3):
+    pdu.set_option("radon_adj_variant", v)
+    timed(f"fan512 adj variant {v}", lambda: fan._backproject(sf))
+pdu.set_option("radon_adj_variant", -1)
 for v in (0, 1, 2, 3, 4, 5):
     pdu.set_option("filter_variant", v)
     timed(f"fan512 filter variant {v}", lambda: fan._filter(sf, "ramp"))
