@@ -109,6 +109,46 @@ __device__ __forceinline__ float2 lds64(uint32_t addr) {
     return v;
 }
 
+// Fan-beam taps in line form (MODE 1) for the PY pixels of one thread and one view.
+// SAFE: every corner of the tile is at least 8 pixels in front of the source (checked per chunk in float64), so
+// MUFU.RCP's 1 ulp is enough (t < 96: < 1.2e-5 bins) and the quotient cannot leave the staged interval -- no
+// Newton step, no clamps.  Otherwise one Newton step and a clamp onto the segment, as in MODE 0.
+template <int PY, int SEG, bool SAFE>
+__device__ __forceinline__ void fan_taps_line(const float* __restrict__ view, uint32_t cbase, float lx,
+                                              const ull* __restrict__ ly_pk, float kk, float* __restrict__ acc) {
+    constexpr float MAGIC = 8388608.f;
+    const float4 v = *reinterpret_cast<const float4*>(view);
+    const float2 tr = *reinterpret_cast<const float2*>(view + 4);
+    const float nx_ = fmaf(v.y, lx, v.x), dx_ = fmaf(tr.x, lx, v.w);
+    const ull p_nx = pk2(nx_, nx_), p_dx = pk2(dx_, dx_);
+    const ull p_ny = pk2(v.z, v.z), p_dy = pk2(-tr.y, -tr.y);
+    const ull p_one = pk2(1.f, 1.f), p_k = pk2(kk, kk), p_m = pk2(MAGIC, MAGIC);
+#pragma unroll
+    for (int k = 0; k < PY; k += 2) {
+        const ull p_num = fma2(p_ny, ly_pk[k / 2], p_nx);
+        const ull p_den = fma2(p_dy, ly_pk[k / 2], p_dx);
+        float d0, d1;
+        upk2(p_den, d0, d1);
+        ull p_r = pk2(__fdividef(1.f, d0), __fdividef(1.f, d1));
+        if (!SAFE) p_r = fma2(p_r, sub2(p_one, mul2(p_den, p_r)), p_r);
+        ull p_c = mul2(p_num, p_r);
+        float c0, c1;
+        upk2(p_c, c0, c1);
+        if (!SAFE) {
+            c0 = fminf(fmaxf(c0, 0.f), (float)(SEG - 1));
+            c1 = fminf(fmaxf(c1, 0.f), (float)(SEG - 1));
+            p_c = pk2(c0, c1);
+        }
+        float t0, t1, w0, w1;
+        upk2(add2_rm(p_c, p_m), t0, t1);
+        upk2(mul2(p_k, p_r), w0, w1);
+        const float2 s0 = lds64((uint32_t)__float_as_int(t0) * 8u + cbase);
+        const float2 s1 = lds64((uint32_t)__float_as_int(t1) * 8u + cbase);
+        acc[k] = fmaf(w0, fmaf(c0, s0.y, s0.x), acc[k]);
+        acc[k + 1] = fmaf(w1, fmaf(c1, s1.y, s1.x), acc[k + 1]);
+    }
+}
+
 template <int TX, int TY, int PY, int AC, int SEG, bool FAN, int MODE = 0>
 __global__ void __launch_bounds__(TX*(TY / PY), FAN ? (PY == 8 ? 5 : 2) : (PY == 8 ? 7 : 3))
     radon_adj_tile_kernel(const float* __restrict__ sino, float* __restrict__ img, const float* __restrict__ trig,
@@ -120,6 +160,7 @@ __global__ void __launch_bounds__(TX*(TY / PY), FAN ? (PY == 8 ? 5 : 2) : (PY ==
     __shared__ __align__(16) float s_view[AC][FAN ? 8 : 4];
     __shared__ int s_lo[AC];
     __shared__ int s_big;
+    __shared__ int s_close;   // fan: some view of the chunk has the source within 8 pixels of the tile
 
     const int tid = threadIdx.y * TX + threadIdx.x;
     const int x = blockIdx.x * TX + threadIdx.x;
@@ -149,7 +190,7 @@ __global__ void __launch_bounds__(TX*(TY / PY), FAN ? (PY == 8 ? 5 : 2) : (PY ==
     for (int a0 = 0; a0 < g.n_angles; a0 += AC) {
         const int na = min(AC, g.n_angles - a0);
         __syncthreads();   // previous chunk fully consumed
-        if (tid == 0) s_big = 0;
+        if (tid == 0) { s_big = 0; s_close = 0; }
         __syncthreads();
         if (tid < na) {
             const double cs = (double)__ldg(trig + 2 * (a0 + tid)), sn = (double)__ldg(trig + 2 * (a0 + tid) + 1);
@@ -177,6 +218,7 @@ __global__ void __launch_bounds__(TX*(TY / PY), FAN ? (PY == 8 ? 5 : 2) : (PY ==
                     // the source must stay outside the tile, otherwise the projection is unbounded
                     tmin = den > 1e-3 ? fmin(tmin, t) : -1e300;
                     tmax = den > 1e-3 ? fmax(tmax, t) : 1e300;
+                    if (!(den >= 8.0)) s_close = 1;
                 }
                 const bool sane = tmin > -1e8 && tmax < 1e8;
                 const int lo = sane ? (int)floor(tmin) - 1 : 0;
@@ -191,7 +233,33 @@ __global__ void __launch_bounds__(TX*(TY / PY), FAN ? (PY == 8 ? 5 : 2) : (PY ==
         }
         __syncthreads();
         const bool big = s_big != 0;
+        const bool close = s_close != 0;
         if (!big) {
+            if (MODE) {
+                // one warp per view, lanes along the segment: each bin is loaded once and its right neighbour comes
+                // from the next lane (SHFL) -- half the loads and none of the index arithmetic of the generic loop
+                static_assert(SEG % 32 == 0, "segment = whole warps of bins");
+                constexpr int NB = SEG / 32;
+                const int lane = tid & 31;
+                for (int al = tid >> 5; al < na; al += THREADS / 32) {
+                    const int lo = s_lo[al];
+                    const float* row = sb + (long)(a0 + al) * g.det_count;
+                    float v[NB + 1];
+#pragma unroll
+                    for (int i = 0; i <= NB; ++i) {
+                        const int d = lo + i * 32 + lane;
+                        v[i] = ((unsigned)d < (unsigned)g.det_count && (i < NB || lane == 0)) ? __ldg(row + d) : 0.f;
+                    }
+#pragma unroll
+                    for (int i = 0; i < NB; ++i) {
+                        const float nxt = __shfl_sync(0xffffffffu, v[i + 1], 0);
+                        const float dn = __shfl_down_sync(0xffffffffu, v[i], 1);
+                        const float dv = (lane == 31 ? nxt : dn) - v[i];
+                        const int c = i * 32 + lane;
+                        s_seg[al][c] = make_float2(fmaf(-(float)c, dv, v[i]), dv);
+                    }
+                }
+            } else {
             for (int i = tid; i < na * SEG; i += THREADS) {
                 const int al = i / SEG, c = i - al * SEG;
                 const int d = s_lo[al] + c;
@@ -200,6 +268,7 @@ __global__ void __launch_bounds__(TX*(TY / PY), FAN ? (PY == 8 ? 5 : 2) : (PY ==
                 const float v1 = (unsigned)(d + 1) < (unsigned)g.det_count ? __ldg(row + d + 1) : 0.f;
                 const float dv = v1 - v0;
                 s_seg[al][c] = MODE ? make_float2(fmaf(-(float)c, dv, v0), dv) : make_float2(v0, dv);
+            }
             }
             __syncthreads();
             if (x < g.n) {
@@ -229,8 +298,7 @@ __global__ void __launch_bounds__(TX*(TY / PY), FAN ? (PY == 8 ? 5 : 2) : (PY ==
                                 const float2 s1 = lds64((uint32_t)__float_as_int(t1) * 8u + cbase);
                                 acc2[k / 2] = add2(acc2[k / 2], pk2(fmaf(c0, s0.y, s0.x), fmaf(c1, s1.y, s1.x)));
                             }
-                            continue;
-                        }
+                        } else {
 #pragma unroll
                         for (int k = 0; k < PY; k += 2) {
                             const ull p_tl = fma2(p_b, ly_pk[k / 2], p_tx);        // >= 1 by construction
@@ -244,6 +312,11 @@ __global__ void __launch_bounds__(TX*(TY / PY), FAN ? (PY == 8 ? 5 : 2) : (PY ==
                             acc[k] += fmaf(f0, s0.y, s0.x);
                             acc[k + 1] += fmaf(f1, s1.y, s1.x);
                         }
+                        }
+                    } else if (MODE) {
+                        const uint32_t cbase = (uint32_t)__cvta_generic_to_shared(seg) - g.koff;
+                        if (close) fan_taps_line<PY, SEG, false>(s_view[al], cbase, lx, ly_pk, g.k, acc);
+                        else fan_taps_line<PY, SEG, true>(s_view[al], cbase, lx, ly_pk, g.k, acc);
                     } else {
                         const float4 v = *reinterpret_cast<const float4*>(s_view[al]);
                         const float2 tr = *reinterpret_cast<const float2*>(s_view[al] + 4);
@@ -261,18 +334,6 @@ __global__ void __launch_bounds__(TX*(TY / PY), FAN ? (PY == 8 ? 5 : 2) : (PY ==
                             p_r = fma2(p_r, sub2(p_one, mul2(p_den, p_r)), p_r);   // one Newton step: ~1 ulp
                             float q0, q1;
                             upk2(mul2(p_num, p_r), q0, q1);
-                            if (MODE) {
-                                const float c0 = fminf(fmaxf(q0, 0.f), (float)(SEG - 1)), c1 = fminf(fmaxf(q1, 0.f), (float)(SEG - 1));
-                                float t0, t1, w0, w1;
-                                upk2(add2_rm(pk2(c0, c1), p_m), t0, t1);
-                                upk2(mul2(p_k, p_r), w0, w1);
-                                const uint32_t cbase = (uint32_t)__cvta_generic_to_shared(seg) - g.koff;
-                                const float2 s0 = lds64((uint32_t)__float_as_int(t0) * 8u + cbase);
-                                const float2 s1 = lds64((uint32_t)__float_as_int(t1) * 8u + cbase);
-                                acc[k] = fmaf(w0, fmaf(c0, s0.y, s0.x), acc[k]);
-                                acc[k + 1] = fmaf(w1, fmaf(c1, s1.y, s1.x), acc[k + 1]);
-                                continue;
-                            }
                             const ull p_tl = pk2(fmaxf(q0, 0.f), fmaxf(q1, 0.f));
                             const ull p_t = add2_rm(p_tl, p_m);
                             const ull p_fr = sub2(p_tl, sub2(p_t, p_m));
@@ -361,7 +422,7 @@ extern "C" int pdu_radon_adj_f32(const float* sino, float* img, const float* tri
 
     cudaStream_t st = (cudaStream_t)stream;
     int variant = option(OPT_RADON_ADJ);
-    if (variant < 0) variant = 1;
+    if (variant < 0) variant = 3;
     constexpr int TX = 32, TY = 32;
     dim3 grid((unsigned)cdiv(g->n, TX), (unsigned)cdiv(g->n, TY), (unsigned)batch);
     if (variant == 0) {
@@ -369,8 +430,12 @@ extern "C" int pdu_radon_adj_f32(const float* sino, float* img, const float* tri
     } else if (variant == 2) {        // A/B: 4 pixels per thread, 256 threads
         if (ag.fan) radon_adj_tile_kernel<TX, TY, 4, 32, 96, true><<<grid, dim3(TX, TY / 4), 0, st>>>(sino, img, trig, ag);
         else radon_adj_tile_kernel<TX, TY, 4, 32, 96, false><<<grid, dim3(TX, TY / 4), 0, st>>>(sino, img, trig, ag);
-    } else if (variant == 3) {        // line-form taps (MODE 1), 8 pixels per thread
+    } else if (variant == 3 || variant == 4) {   // line-form taps (MODE 1), 8 pixels per thread: the default
+        // a 32 x 32 tile projects onto at most 32 sqrt(2) / det_spacing bins: a 64-entry segment is enough for
+        // parallel beams with det_spacing >= 0.8 (a third less staging work); variant 4 forces 96 for A/B
+        const bool seg64 = variant == 3 && !ag.fan && 46.f * ag.ids + 5.f <= 64.f;
         if (ag.fan) radon_adj_tile_kernel<TX, TY, 8, 32, 96, true, 1><<<grid, dim3(TX, TY / 8), 0, st>>>(sino, img, trig, ag);
+        else if (seg64) radon_adj_tile_kernel<TX, TY, 8, 32, 64, false, 1><<<grid, dim3(TX, TY / 8), 0, st>>>(sino, img, trig, ag);
         else radon_adj_tile_kernel<TX, TY, 8, 32, 96, false, 1><<<grid, dim3(TX, TY / 8), 0, st>>>(sino, img, trig, ag);
     } else {                          // 8 pixels per thread, 128 threads: B N^2 / 8 threads fit one balanced wave
         if (ag.fan) radon_adj_tile_kernel<TX, TY, 8, 32, 96, true><<<grid, dim3(TX, TY / 8), 0, st>>>(sino, img, trig, ag);

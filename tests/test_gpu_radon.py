@@ -72,7 +72,7 @@ def test_forward_matches_oracle(name, variant):
     assert rel_l2(got, want) <= TOL
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+@pytest.mark.parametrize("variant", [-1, 0, 1, 2, 3, 4])
 @pytest.mark.parametrize("name", CASES)
 def test_backprojection_matches_oracle(name, variant):
     op, g, internal = _case(name)
