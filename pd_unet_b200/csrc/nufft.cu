@@ -23,6 +23,7 @@
 
 #include "common.cuh"
 #include "pfft.cuh"
+#include "pfft_fast.cuh"
 
 struct pdu_nufft_plan {
     int n0, n1, k0, k1, J, L, shift0, shift1;
@@ -427,6 +428,151 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// ------------------------------------------------------------------ register-resident pruned FFT (pfft_fast.cuh)
+// Same four passes as above for K = 512 / 640 (grid = 2 x image).  Row kernels: thread = (row s, butterfly t),
+// consecutive threads along the row; column kernels: consecutive threads across the SEQ neighbouring columns so
+// that a warp touches whole 64-byte runs of every grid row.
+template <int K, int SEQ>
+__global__ void __launch_bounds__(SEQ* FastFft<K>::TPS)
+    ff_rows_fwd_kernel(const float2* __restrict__ image, const float2* __restrict__ smaps, float2* __restrict__ T,
+                       const float* __restrict__ s0, const float* __restrict__ s1, const float2* __restrict__ tw_g, NufftDims d,
+                       int coils, int smaps_batch) {
+    using F = FastFft<K>;
+    float2* buf = pf_smem<float2>();
+    float2* tw = buf + SEQ * F::PITCH;
+    const int tid = threadIdx.x, s = tid / F::TPS, t = tid - s * F::TPS;
+    const long p = blockIdx.y;
+    const int row = blockIdx.x * SEQ + s;
+    for (int i = tid; i < K; i += SEQ * F::TPS) tw[i] = __ldg(tw_g + i);
+    const long plane = (long)d.n0 * d.n1;
+    const long b = p / coils, c = p - b * coils;
+    const bool live = row < d.n0;
+    const float w0 = live ? __ldg(s0 + row) : 0.f;
+    const float2* src = image + (smaps ? b : p) * plane + (long)row * d.n1;
+    const float2* sm = smaps ? smaps + ((smaps_batch == 1 ? 0 : b) * coils + c) * plane + (long)row * d.n1 : nullptr;
+    auto ld = [&](int e) {
+        if (!live) return make_float2(0.f, 0.f);
+        float2 v = __ldg(src + e);
+        if (sm) v = cmul(v, __ldg(sm + e));
+        const float w = w0 * __ldg(s1 + e);
+        return make_float2(v.x * w, v.y * w);
+    };
+    float2* dst = T + (p * d.n0 + row) * K;
+    auto st = [&](int e, float2 v) {
+        if (live) dst[e] = v;
+    };
+    ff_transform<K, false, true, false>(buf + s * F::PITCH, tw, t, ld, st);
+}
+
+template <int K, int SEQ>
+__global__ void __launch_bounds__(SEQ* FastFft<K>::TPS)
+    ff_cols_fwd_kernel(const float2* __restrict__ T, float2* __restrict__ grid, const float2* __restrict__ tw_g, NufftDims d) {
+    using F = FastFft<K>;
+    float2* buf = pf_smem<float2>();
+    float2* tw = buf + SEQ * F::PITCH;
+    const int tid = threadIdx.x, t = tid / SEQ, s = tid - t * SEQ;
+    const long p = blockIdx.y;
+    const int col = blockIdx.x * SEQ + s;
+    for (int i = tid; i < K; i += SEQ * F::TPS) tw[i] = __ldg(tw_g + i);
+    const bool live = col < d.k1;
+    const float2* src = T + p * d.n0 * d.k1 + col;
+    float2* dst = grid + p * K * d.k1 + col;
+    auto ld = [&](int e) { return live ? __ldg(src + (long)e * d.k1) : make_float2(0.f, 0.f); };
+    auto st = [&](int e, float2 v) {
+        if (live) dst[(long)e * d.k1] = v;
+    };
+    ff_transform<K, false, true, false>(buf + s * F::PITCH, tw, t, ld, st);
+}
+
+template <int K, int SEQ>
+__global__ void __launch_bounds__(SEQ* FastFft<K>::TPS)
+    ff_rows_adj_kernel(const float2* __restrict__ grid, float2* __restrict__ T, const float2* __restrict__ tw_g, NufftDims d) {
+    using F = FastFft<K>;
+    float2* buf = pf_smem<float2>();
+    float2* tw = buf + SEQ * F::PITCH;
+    const int tid = threadIdx.x, s = tid / F::TPS, t = tid - s * F::TPS;
+    const long p = blockIdx.y;
+    const int row = blockIdx.x * SEQ + s;
+    for (int i = tid; i < K; i += SEQ * F::TPS) tw[i] = __ldg(tw_g + i);
+    const bool live = row < d.k0;
+    const float2* src = grid + (p * d.k0 + row) * K;
+    float2* dst = T + (p * d.k0 + row) * d.n1;
+    auto ld = [&](int e) { return live ? __ldg(src + e) : make_float2(0.f, 0.f); };
+    auto st = [&](int e, float2 v) {
+        if (live) dst[e] = v;
+    };
+    ff_transform<K, true, false, true>(buf + s * F::PITCH, tw, t, ld, st);
+}
+
+template <int K, int SEQ>
+__global__ void __launch_bounds__(SEQ* FastFft<K>::TPS)
+    ff_cols_adj_kernel(const float2* __restrict__ T, float2* __restrict__ U, const float2* __restrict__ tw_g, NufftDims d) {
+    using F = FastFft<K>;
+    float2* buf = pf_smem<float2>();
+    float2* tw = buf + SEQ * F::PITCH;
+    const int tid = threadIdx.x, t = tid / SEQ, s = tid - t * SEQ;
+    const long p = blockIdx.y;
+    const int col = blockIdx.x * SEQ + s;
+    for (int i = tid; i < K; i += SEQ * F::TPS) tw[i] = __ldg(tw_g + i);
+    const bool live = col < d.n1;
+    const float2* src = T + p * K * d.n1 + col;
+    float2* dst = U + p * d.n0 * d.n1 + col;
+    auto ld = [&](int e) { return live ? __ldg(src + (long)e * d.n1) : make_float2(0.f, 0.f); };
+    auto st = [&](int e, float2 v) {
+        if (live) dst[(long)e * d.n1] = v;
+    };
+    ff_transform<K, true, false, true>(buf + s * F::PITCH, tw, t, ld, st);
+}
+
+constexpr int FF_SEQ_ROWS = 4, FF_SEQ_COLS = 8;
+template <int K>
+static constexpr size_t ff_smem_bytes(int seq) { return ((size_t)seq * FastFft<K>::PITCH + K) * sizeof(float2); }
+
+static bool ff_supported(const pdu_nufft_plan* p) {
+    return p->k0 == p->k1 && p->k0 == 2 * p->n0 && p->k1 == 2 * p->n1 && (p->k0 == 512 || p->k0 == 640) && p->pfft_ok;
+}
+
+template <int K>
+static int ff_forward(pdu_nufft_plan* p, const float2* image, const float2* smaps, float2* T, float2* grid, int planes,
+                      int coils, int smaps_batch, cudaStream_t st) {
+    const NufftDims d = dims_of(p);
+    auto rows = ff_rows_fwd_kernel<K, FF_SEQ_ROWS>;
+    auto cols = ff_cols_fwd_kernel<K, FF_SEQ_COLS>;
+    static bool attr = false;
+    if (!attr) {
+        PDU_CUDA(cudaFuncSetAttribute(rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ff_smem_bytes<K>(FF_SEQ_ROWS)));
+        PDU_CUDA(cudaFuncSetAttribute(cols, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ff_smem_bytes<K>(FF_SEQ_COLS)));
+        attr = true;
+    }
+    rows<<<dim3((unsigned)cdiv(p->n0, FF_SEQ_ROWS), (unsigned)planes), FF_SEQ_ROWS * FastFft<K>::TPS, ff_smem_bytes<K>(FF_SEQ_ROWS), st>>>(
+        image, smaps, T, p->d_s0, p->d_s1, p->d_w1, d, coils, smaps_batch);
+    PDU_LAUNCHED();
+    cols<<<dim3((unsigned)cdiv(p->k1, FF_SEQ_COLS), (unsigned)planes), FF_SEQ_COLS * FastFft<K>::TPS, ff_smem_bytes<K>(FF_SEQ_COLS), st>>>(
+        T, grid, p->d_w0, d);
+    PDU_LAUNCHED();
+    return PDU_OK;
+}
+
+template <int K>
+static int ff_adjoint(pdu_nufft_plan* p, const float2* grid, float2* T, float2* U, int planes, cudaStream_t st) {
+    const NufftDims d = dims_of(p);
+    auto rows = ff_rows_adj_kernel<K, FF_SEQ_ROWS>;
+    auto cols = ff_cols_adj_kernel<K, FF_SEQ_COLS>;
+    static bool attr = false;
+    if (!attr) {
+        PDU_CUDA(cudaFuncSetAttribute(rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ff_smem_bytes<K>(FF_SEQ_ROWS)));
+        PDU_CUDA(cudaFuncSetAttribute(cols, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ff_smem_bytes<K>(FF_SEQ_COLS)));
+        attr = true;
+    }
+    rows<<<dim3((unsigned)cdiv(p->k0, FF_SEQ_ROWS), (unsigned)planes), FF_SEQ_ROWS * FastFft<K>::TPS, ff_smem_bytes<K>(FF_SEQ_ROWS), st>>>(
+        grid, T, p->d_w1, d);
+    PDU_LAUNCHED();
+    cols<<<dim3((unsigned)cdiv(p->n1, FF_SEQ_COLS), (unsigned)planes), FF_SEQ_COLS * FastFft<K>::TPS, ff_smem_bytes<K>(FF_SEQ_COLS), st>>>(
+        T, U, p->d_w0, d);
+    PDU_LAUNCHED();
+    return PDU_OK;
+}
+
 constexpr int PF_SEQ_ROWS = 4, PF_SEQ_COLS = 8;
 
 static size_t pf_smem_bytes(int seq, int K) { return ((size_t)2 * seq * pfft_pitch(K) + K) * sizeof(float2); }
@@ -781,7 +927,13 @@ static int nufft_fwd_chunk(pdu_nufft_plan_t* p, const float2* image, float2* kda
     int variant = option(OPT_NUFFT_FWD);
     if (variant < 0) variant = 0;
     int rc;
-    if (variant == 1 && p->pfft_ok) {
+    if (variant == 2 && !ff_supported(p)) variant = 0;
+    if (variant == 2) {
+        float2* T = grid + total;
+        rc = p->k0 == 512 ? ff_forward<512>(p, image, smaps, T, grid, planes, coils, smaps_batch, st)
+                          : ff_forward<640>(p, image, smaps, T, grid, planes, coils, smaps_batch, st);
+        if (rc) return rc;
+    } else if (variant == 1 && p->pfft_ok) {
         // pruned FFT: apodise + pad + transform the n0 non-zero rows, then every column
         float2* T = grid + total;
         const NufftDims d = dims_of(p);
@@ -823,6 +975,20 @@ static int nufft_adj_chunk(pdu_nufft_plan_t* p, const float2* kdata, float2* ima
     const long total = (long)out_planes * p->n0 * p->n1;
     int variant = option(OPT_NUFFT_ADJ);
     if (variant < 0) variant = 0;      // see nufft_fwd_chunk
+    if (variant == 2 && !ff_supported(p)) variant = 0;
+    if (variant == 2) {
+        float2* T = grid + (long)planes * p->k0 * p->k1;
+        float2* U = T + (long)planes * std::max((long)p->n0 * p->k1, (long)p->k0 * p->n1);
+        rc = p->k0 == 512 ? ff_adjoint<512>(p, grid, T, U, planes, st) : ff_adjoint<640>(p, grid, T, U, planes, st);
+        if (rc) return rc;
+        NufftDims dc = dims_of(p);          // the cropped result is a dense [n0][n1] "grid"
+        dc.k0 = dc.n0;
+        dc.k1 = dc.n1;
+        crop_apod_kernel<<<stream_grid(total), 256, 0, st>>>(U, smaps, image, p->d_s0, p->d_s1, dc, coils, smaps_batch, scale,
+                                                             total);
+        PDU_LAUNCHED();
+        return PDU_OK;
+    }
     if (variant == 1 && p->pfft_ok) {
         // pruned inverse FFT: every row but only the n1 kept outputs, then the n1 kept columns and n0 kept outputs
         float2* T = grid + (long)planes * p->k0 * p->k1;

@@ -85,10 +85,10 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
         uint32_t ok;
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
             "selp.b32 %0, 1, 0, p;\n\t}"
             : "=r"(ok)
-            : "r"(addr), "r"(parity)
+            : "r"(addr), "r"(parity), "r"(0x989680u)     // suspend-time hint: sleep in hardware instead of spinning
             : "memory");
         if (ok) return true;
     }
@@ -794,12 +794,9 @@ int pdu_radon_fwd_f32(const float* img, float* sino, const float* trig, int batc
         switch (variant) {                                        // explicit shapes for A/B measurement
             case 8: return launch_quad<32, 8, 32, 104, 2, 8>(q, qt, sino, trig, batch, *g, st);    // 32-row strips
             case 9: return launch_quad<32, 4, 16, 120, 2, 8>(q, qt, sino, trig, batch, *g, st);    // 4 views / CTA (sparser views)
-            case 10: return launch_quad<32, 8, 16, 84, 3, 8>(q, qt, sino, trig, batch, *g, st);    // 3-deep ring, odd-multiple-of-4 pitch
-            case 11: return launch_quad<64, 4, 16, 128, 2, 16>(q, qt, sino, trig, batch, *g, st);  // 16 det x 2 views / warp
-            case 12: return launch_quad<32, 16, 16, 88, 3, 8>(q, qt, sino, trig, batch, *g, st);   // 512 threads: 16 views share a box
-            case 13: return launch_quad<32, 8, 16, 76, 3, 8>(q, qt, sino, trig, batch, *g, st);    // narrow box, 3-deep ring
-            case 14: return launch_quad<32, 8, 16, 89, 2, 8>(q, qt, sino, trig, batch, *g, st);    // odd row pitch
-            case 15: return launch_quad<32, 16, 16, 92, 2, 8>(q, qt, sino, trig, batch, *g, st);   // 512 threads, 2-deep
+            case 10: return launch_quad<32, 16, 16, 92, 2, 8>(q, qt, sino, trig, batch, *g, st);   // 512 threads: 16 views share a box
+            // (r02 also measured 3-deep rings, 84/76/89-cell pitches, 16-detector warps and 8-row strips:
+            //  520..600 us against 513 for shape 7 -- dropped)
             default: return launch_quad<32, 8, 16, 88, 2, 8>(q, qt, sino, trig, batch, *g, st);    // 7
         }
     }

@@ -136,7 +136,7 @@ def test_sorted_gather_adjoint_matches_scatter_and_is_reproducible():
     assert rel_l2(xa, oracle.nufft_adjoint(k, 0.5 * om, spec, smaps=sm, norm="ortho")) <= TOL
 
 
-@pytest.mark.parametrize("im", [(32, 32), (48, 40), (320, 320), (250, 250)])
+@pytest.mark.parametrize("im", [(32, 32), (48, 40), (320, 320), (256, 256), (250, 250)])
 def test_pruned_fft_and_cufft_paths_agree(im):
     """variant 1: the own pruned shared-memory FFT; variant 0 (default, currently faster): pad + cuFFT.  Same
     numbers, both within budget of the oracle.  250 -> grid 500 = 4 * 5^3 exercises the radix-5 passes."""
@@ -148,7 +148,7 @@ def test_pruned_fft_and_cufft_paths_agree(im):
     A, AH = pdu.KbNufft(im), pdu.KbNufftAdjoint(im)
     want_f, want_a = oracle.nufft_forward(x, om, spec), oracle.nufft_adjoint(k, om, spec)
     try:
-        for v in (1, 0):
+        for v in (2, 1, 0):      # 2: register-resident pruned FFT (grids 512 / 640; other sizes fall back to 0)
             pdu.set_option("nufft_fwd_variant", v)
             pdu.set_option("nufft_adj_variant", v)
             assert rel_l2(A(x.to(DEV), omd), want_f) <= TOL, f"forward variant {v}"

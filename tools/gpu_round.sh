@@ -9,6 +9,9 @@ export PDU_BENCH_AUTOTUNE=0 PDU_BENCH_GRAPH=0
 timeout 600 python bench.py --steps 1 --warmup 3 --no-cpu > gpurun_out/plain.log 2>&1 && \
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 3 --no-cpu > gpurun_out/ncu_launches.log 2>&1
 timeout 300 python tools/prof_ops.py 1 > gpurun_out/plain2.log 2>&1 && \
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"radon_fwd_strip|radon_adj_tile" -c 16 -o gpurun_out/prof_ops python tools/prof_ops.py 1 > gpurun_out/ncu_full.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"radon_fwd_quad|quad_build|radon_adj_tile" -c 12 -f -o gpurun_out/prof_ops python tools/prof_fwd.py -1 > gpurun_out/ncu_full.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"radon_adj_tile" -c 4 -f -o gpurun_out/prof_adj python tools/prof_adj.py -1 > gpurun_out/ncu_full_adj.log 2>&1
+# DRAM traffic as it is inside a step (caches not flushed between kernels): the cell tensors come from L2
+timeout 600 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --cache-control none --clock-control none -k regex:"radon_fwd_quad|quad_build|radon_adj_tile" --csv --log-file gpurun_out/traffic_warm.csv python tools/prof_fwd.py -1 > gpurun_out/ncu_traffic.log 2>&1
 ls -la gpurun_out | tail -20
 cat gpurun_out/bench.json | cut -c1-300; tail -3 gpurun_out/bench.err

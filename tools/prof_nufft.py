@@ -49,6 +49,9 @@ for name, n, coils, B, spokes in (("cfg1 256^2 c1 b1 32sp", 256, 1, 1, 32), ("cf
     pdu.set_option("nufft_fwd_variant", 1); pdu.set_option("nufft_adj_variant", 1)
     timed(name + " fwd (pruned own FFT)", lambda: fw(img, om, smaps=sm), nb)
     timed(name + " adj (pruned own FFT, auto interp)", lambda: ad(k, om, smaps=sm), nb)
+    pdu.set_option("nufft_fwd_variant", 2); pdu.set_option("nufft_adj_variant", 2)
+    timed(name + " fwd (register pruned FFT)", lambda: fw(img, om, smaps=sm), nb)
+    timed(name + " adj (register pruned FFT, auto interp)", lambda: ad(k, om, smaps=sm), nb)
     pdu.set_option("nufft_fwd_variant", -1); pdu.set_option("nufft_adj_variant", -1)
     ad._plan.use_csr = True
     timed(name + " adj (sorted gather)", lambda: ad(k, om, smaps=sm), nb)
