@@ -143,10 +143,28 @@ __global__ void __launch_bounds__(256)
         float2 v;
         if (smaps) {
             const long sb = smaps_batch == 1 ? 0 : q;
+            // coils in groups of four: eight independent loads in flight per thread (the serial loop was
+            // latency bound: ncu long-scoreboard 19 cycles per issue)
             float2 acc = make_float2(0.f, 0.f);
-            for (int c = 0; c < coils; ++c) {
-                const float2 z = cmul_conj(__ldg(grid + (q * coils + c) * gplane + gp),
-                                           __ldg(smaps + (sb * coils + c) * plane + (long)c0 * d.n1 + c1));
+            const float2* gq = grid + q * coils * gplane + gp;
+            const float2* sq = smaps + sb * coils * plane + (long)c0 * d.n1 + c1;
+            int c = 0;
+            for (; c + 4 <= coils; c += 4) {
+                float2 gv[4], sv[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    gv[u] = __ldg(gq + (c + u) * gplane);
+                    sv[u] = __ldg(sq + (c + u) * plane);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const float2 z = cmul_conj(gv[u], sv[u]);
+                    acc.x += z.x;
+                    acc.y += z.y;
+                }
+            }
+            for (; c < coils; ++c) {
+                const float2 z = cmul_conj(__ldg(gq + c * gplane), __ldg(sq + c * plane));
                 acc.x += z.x;
                 acc.y += z.y;
             }
@@ -160,7 +178,7 @@ __global__ void __launch_bounds__(256)
 
 // ------------------------------------------------------------------ interpolation (gather)
 // thread = one sample m; loops over the PC planes of its plane chunk (blockIdx.y)
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128)    // (r02: capping at 64 registers for 32 warps / SM spills and is not faster)
     interp_fwd_kernel(const float2* __restrict__ grid, float2* __restrict__ kdata, const float* __restrict__ omega,
                       const float2* __restrict__ t0, const float2* __restrict__ t1, NufftDims d, int planes, int pc,
                       long M, float scale) {
@@ -439,7 +457,7 @@ __global__ void __launch_bounds__(SEQ* FastFft<K>::TPS)
                        int coils, int smaps_batch) {
     using F = FastFft<K>;
     float2* buf = pf_smem<float2>();
-    float2* tw = buf + SEQ * F::PITCH;
+    float2* tw = buf + SEQ * F::template pitch<4>();
     const int tid = threadIdx.x, s = tid / F::TPS, t = tid - s * F::TPS;
     const long p = blockIdx.y;
     const int row = blockIdx.x * SEQ + s;
@@ -461,7 +479,7 @@ __global__ void __launch_bounds__(SEQ* FastFft<K>::TPS)
     auto st = [&](int e, float2 v) {
         if (live) dst[e] = v;
     };
-    ff_transform<K, false, true, false>(buf + s * F::PITCH, tw, t, ld, st);
+    ff_transform<K, 4, false, true, false>(buf + s * F::template pitch<4>(), tw, t, ld, st);
 }
 
 template <int K, int SEQ>
@@ -469,7 +487,7 @@ __global__ void __launch_bounds__(SEQ* FastFft<K>::TPS)
     ff_cols_fwd_kernel(const float2* __restrict__ T, float2* __restrict__ grid, const float2* __restrict__ tw_g, NufftDims d) {
     using F = FastFft<K>;
     float2* buf = pf_smem<float2>();
-    float2* tw = buf + SEQ * F::PITCH;
+    float2* tw = buf + SEQ * F::template pitch<3>();
     const int tid = threadIdx.x, t = tid / SEQ, s = tid - t * SEQ;
     const long p = blockIdx.y;
     const int col = blockIdx.x * SEQ + s;
@@ -481,7 +499,7 @@ __global__ void __launch_bounds__(SEQ* FastFft<K>::TPS)
     auto st = [&](int e, float2 v) {
         if (live) dst[(long)e * d.k1] = v;
     };
-    ff_transform<K, false, true, false>(buf + s * F::PITCH, tw, t, ld, st);
+    ff_transform<K, 3, false, true, false>(buf + s * F::template pitch<3>(), tw, t, ld, st);
 }
 
 template <int K, int SEQ>
@@ -489,7 +507,7 @@ __global__ void __launch_bounds__(SEQ* FastFft<K>::TPS)
     ff_rows_adj_kernel(const float2* __restrict__ grid, float2* __restrict__ T, const float2* __restrict__ tw_g, NufftDims d) {
     using F = FastFft<K>;
     float2* buf = pf_smem<float2>();
-    float2* tw = buf + SEQ * F::PITCH;
+    float2* tw = buf + SEQ * F::template pitch<4>();
     const int tid = threadIdx.x, s = tid / F::TPS, t = tid - s * F::TPS;
     const long p = blockIdx.y;
     const int row = blockIdx.x * SEQ + s;
@@ -501,7 +519,7 @@ __global__ void __launch_bounds__(SEQ* FastFft<K>::TPS)
     auto st = [&](int e, float2 v) {
         if (live) dst[e] = v;
     };
-    ff_transform<K, true, false, true>(buf + s * F::PITCH, tw, t, ld, st);
+    ff_transform<K, 4, true, false, true>(buf + s * F::template pitch<4>(), tw, t, ld, st);
 }
 
 template <int K, int SEQ>
@@ -509,7 +527,7 @@ __global__ void __launch_bounds__(SEQ* FastFft<K>::TPS)
     ff_cols_adj_kernel(const float2* __restrict__ T, float2* __restrict__ U, const float2* __restrict__ tw_g, NufftDims d) {
     using F = FastFft<K>;
     float2* buf = pf_smem<float2>();
-    float2* tw = buf + SEQ * F::PITCH;
+    float2* tw = buf + SEQ * F::template pitch<3>();
     const int tid = threadIdx.x, t = tid / SEQ, s = tid - t * SEQ;
     const long p = blockIdx.y;
     const int col = blockIdx.x * SEQ + s;
@@ -521,12 +539,12 @@ __global__ void __launch_bounds__(SEQ* FastFft<K>::TPS)
     auto st = [&](int e, float2 v) {
         if (live) dst[(long)e * d.n1] = v;
     };
-    ff_transform<K, true, false, true>(buf + s * F::PITCH, tw, t, ld, st);
+    ff_transform<K, 3, true, false, true>(buf + s * F::template pitch<3>(), tw, t, ld, st);
 }
 
 constexpr int FF_SEQ_ROWS = 4, FF_SEQ_COLS = 8;
 template <int K>
-static constexpr size_t ff_smem_bytes(int seq) { return ((size_t)seq * FastFft<K>::PITCH + K) * sizeof(float2); }
+static constexpr size_t ff_smem_bytes(int seq) { return ((size_t)seq * FastFft<K>::template pitch<3>() + K) * sizeof(float2); }   // PS = 3 is the larger pitch
 
 static bool ff_supported(const pdu_nufft_plan* p) {
     return p->k0 == p->k1 && p->k0 == 2 * p->n0 && p->k1 == 2 * p->n1 && (p->k0 == 512 || p->k0 == 640) && p->pfft_ok;
@@ -925,7 +943,7 @@ static int nufft_fwd_chunk(pdu_nufft_plan_t* p, const float2* image, float2* kda
     // 640^2): the pruned passes move 2.5x fewer bytes but are still ~1.7x slower than cuFFT's register-resident
     // radix kernels (row+column 407 us vs 238 us), so cuFFT stays the default until they are.
     int variant = option(OPT_NUFFT_FWD);
-    if (variant < 0) variant = 0;
+    if (variant < 0) variant = ff_supported(p) ? 2 : 0;      // register-resident pruned FFT where it exists (r02)
     int rc;
     if (variant == 2 && !ff_supported(p)) variant = 0;
     if (variant == 2) {
@@ -974,7 +992,7 @@ static int nufft_adj_chunk(pdu_nufft_plan_t* p, const float2* kdata, float2* ima
     const int out_planes = smaps ? batch : planes;
     const long total = (long)out_planes * p->n0 * p->n1;
     int variant = option(OPT_NUFFT_ADJ);
-    if (variant < 0) variant = 0;      // see nufft_fwd_chunk
+    if (variant < 0) variant = ff_supported(p) ? 2 : 0;      // see nufft_fwd_chunk
     if (variant == 2 && !ff_supported(p)) variant = 0;
     if (variant == 2) {
         float2* T = grid + (long)planes * p->k0 * p->k1;

@@ -20,12 +20,17 @@ struct FastFft {
     static constexpr bool ok = (K == 512 || K == 640);
     static constexpr int TPS = K / 8;     // threads per sequence (radix-8 butterflies per pass)
     static constexpr int R3 = K / 64;     // radix of the last pass: 8 or 10
-    // one padding slot every 8 and every 64 elements: the stride-8 / stride-64 float2 stores of the first two
-    // passes then spread over the banks; the pitch == 2 (mod 16) float2 keeps neighbouring sequences apart
-    static constexpr int BASE = K + K / 8 + K / 64;
-    static constexpr int PITCH = (BASE + 13) / 16 * 16 + 2;
+    // Padding: one slot every 2^PS elements, chosen per thread layout (measured, ncu r02):
+    //  PS = 3 (column kernels: a half-warp is 8 neighbouring sequences x 2 butterflies) -- element 8 t + r sits at
+    //    9 t + r; with the pitch == 2 (mod 16) float2 every access of the three passes is conflict free;
+    //  PS = 4 (row kernels: a half-warp is 16 consecutive butterflies of one sequence) -- the unit-stride loads of
+    //    passes 2 and 3 then never straddle a padding slot (PS = 3 made 16 lanes span 18 slots: a 2-way conflict on
+    //    every load), the stride-8 stores of pass 1 stay conflict free, only the pass-2 stores keep a 2-way conflict.
+    template <int PS>
+    __host__ __device__ static constexpr int pitch() { return (K + (K >> PS) + 13) / 16 * 16 + 2; }
 };
-__device__ __forceinline__ int ff_pos(int e) { return e + (e >> 3) + (e >> 6); }
+template <int PS>
+__device__ __forceinline__ int ff_pos(int e) { return e + (e >> PS); }
 
 template <bool INV>
 __device__ __forceinline__ float2 ff_tw(const float2* __restrict__ tw, int i) {
@@ -69,9 +74,9 @@ __device__ __forceinline__ void ff_r10(float2* v) {
 }
 
 // One sequence of length K held by the TPS threads t = 0 .. TPS-1 of a CTA (every thread of the CTA must call
-// this: it synchronises).  buf = this sequence's PITCH float2 of shared memory, tw = the K-entry table
+// this: it synchronises).  buf = this sequence's pitch<PS>() float2 of shared memory, tw = the K-entry table
 // exp(-2 pi i m / K) in shared memory.  ld(e) returns input element e, st(e, v) consumes output element e.
-template <int K, bool INV, bool HALF_IN, bool HALF_OUT, class LD, class ST>
+template <int K, int PS, bool INV, bool HALF_IN, bool HALF_OUT, class LD, class ST>
 __device__ __forceinline__ void ff_transform(float2* __restrict__ buf, const float2* __restrict__ tw, int t, LD ld, ST st) {
     using F = FastFft<K>;
     constexpr int TPS = F::TPS, R3 = F::R3;
@@ -81,11 +86,11 @@ __device__ __forceinline__ void ff_transform(float2* __restrict__ buf, const flo
     for (int r = 0; r < 8; ++r) v[r] = (HALF_IN && r >= 4) ? make_float2(0.f, 0.f) : ld(t + r * TPS);
     pf_r8<INV>(v);
 #pragma unroll
-    for (int r = 0; r < 8; ++r) buf[ff_pos(t * 8 + r)] = v[r];
+    for (int r = 0; r < 8; ++r) buf[ff_pos<PS>(t * 8 + r)] = v[r];
     __syncthreads();
     // pass 2: radix 8, Ns = 8
 #pragma unroll
-    for (int r = 0; r < 8; ++r) v[r] = buf[ff_pos(t + r * TPS)];
+    for (int r = 0; r < 8; ++r) v[r] = buf[ff_pos<PS>(t + r * TPS)];
     __syncthreads();
     {
         const int k = t & 7;
@@ -94,14 +99,14 @@ __device__ __forceinline__ void ff_transform(float2* __restrict__ buf, const flo
         pf_r8<INV>(v);
         const int o0 = (t >> 3) * 64 + k;
 #pragma unroll
-        for (int r = 0; r < 8; ++r) buf[ff_pos(o0 + r * 8)] = v[r];
+        for (int r = 0; r < 8; ++r) buf[ff_pos<PS>(o0 + r * 8)] = v[r];
     }
     __syncthreads();
     // pass 3: radix K / 64, Ns = 64; 64 butterflies
     if (t < 64) {
         float2 u[R3];
 #pragma unroll
-        for (int r = 0; r < R3; ++r) u[r] = buf[ff_pos(t + r * 64)];
+        for (int r = 0; r < R3; ++r) u[r] = buf[ff_pos<PS>(t + r * 64)];
 #pragma unroll
         for (int r = 1; r < R3; ++r) u[r] = pf_mul(u[r], ff_tw<INV>(tw, r * t));
         if constexpr (R3 == 8) pf_r8<INV>(u);

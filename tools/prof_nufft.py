@@ -44,11 +44,14 @@ for name, n, coils, B, spokes in (("cfg1 256^2 c1 b1 32sp", 256, 1, 1, 32), ("cf
         img = torch.randn(B, 1, n, n, dtype=torch.complex64, device=dev)
         nb = 8.0 * B * coils * (n * n + M) + 8.0 * M
     k = fw(img, om, smaps=sm)
-    timed(name + " fwd (cuFFT, default)", lambda: fw(img, om, smaps=sm), nb)
-    timed(name + " adj (cuFFT, auto interp; default)", lambda: ad(k, om, smaps=sm), nb)
+    timed(name + " fwd (default)", lambda: fw(img, om, smaps=sm), nb)
+    timed(name + " adj (default, auto interp)", lambda: ad(k, om, smaps=sm), nb)
+    pdu.set_option("nufft_fwd_variant", 0); pdu.set_option("nufft_adj_variant", 0)
+    timed(name + " fwd (pad + cuFFT)", lambda: fw(img, om, smaps=sm), nb)
+    timed(name + " adj (cuFFT, auto interp)", lambda: ad(k, om, smaps=sm), nb)
     pdu.set_option("nufft_fwd_variant", 1); pdu.set_option("nufft_adj_variant", 1)
-    timed(name + " fwd (pruned own FFT)", lambda: fw(img, om, smaps=sm), nb)
-    timed(name + " adj (pruned own FFT, auto interp)", lambda: ad(k, om, smaps=sm), nb)
+    timed(name + " fwd (generic pruned FFT)", lambda: fw(img, om, smaps=sm), nb)
+    timed(name + " adj (generic pruned FFT, auto interp)", lambda: ad(k, om, smaps=sm), nb)
     pdu.set_option("nufft_fwd_variant", 2); pdu.set_option("nufft_adj_variant", 2)
     timed(name + " fwd (register pruned FFT)", lambda: fw(img, om, smaps=sm), nb)
     timed(name + " adj (register pruned FFT, auto interp)", lambda: ad(k, om, smaps=sm), nb)
