@@ -747,6 +747,61 @@ __global__ void __launch_bounds__(256)
         if (p0 + q < planes) grid[(long)(p0 + q) * cells + c] = acc[q];
 }
 
+// kdata [planes][M] -> kT [M][planes4] (planes4 = planes rounded up to 4, padding zeroed): an entry of the sparse
+// matrix then finds the samples of PG neighbouring planes in PG * 8 contiguous bytes (one or two 16-byte loads
+// from one sector) instead of PG sectors M * 8 bytes apart
+__global__ void __launch_bounds__(256)
+    transpose_kdata_kernel(const float2* __restrict__ kdata, float2* __restrict__ kT, long M, int planes, int planes4) {
+    __shared__ float2 t[32][33];
+    const long m0 = (long)blockIdx.x * 32;
+    const int p0 = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += 8) {
+        const int pl = p0 + r;
+        const long m = m0 + threadIdx.x;
+        t[r][threadIdx.x] = (pl < planes && m < M) ? __ldg(kdata + (long)pl * M + m) : make_float2(0.f, 0.f);
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += 8) {
+        const long m = m0 + r;
+        const int pl = p0 + threadIdx.x;
+        if (m < M && pl < planes4) kT[m * planes4 + pl] = t[threadIdx.x][r];
+    }
+}
+
+template <int PG>
+__global__ void __launch_bounds__(256)
+    interp_adj_csrT_kernel(const float2* __restrict__ kT, float2* __restrict__ grid, const int* __restrict__ row_ptr,
+                           const int* __restrict__ samp, const float2* __restrict__ w, long cells, int planes, int planes4) {
+    static_assert(PG % 2 == 0, "planes are read in pairs");
+    const long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cells) return;
+    const int p0 = blockIdx.y * PG;
+    float2 acc[PG];
+#pragma unroll
+    for (int q = 0; q < PG; ++q) acc[q] = make_float2(0.f, 0.f);
+    const int beg = __ldg(row_ptr + c), end = __ldg(row_ptr + c + 1);
+    if (end - beg > CSR_LONG) return;                     // interp_adj_csr_long_kernel owns this cell
+    for (int i = beg; i < end; ++i) {
+        const long m = __ldg(samp + i);
+        const float2 wi = __ldg(w + i);
+        const float4* src = reinterpret_cast<const float4*>(kT + m * planes4 + p0);
+#pragma unroll
+        for (int q = 0; q < PG; q += 2) {
+            if (p0 + q < planes4) {
+                const float4 v = __ldg(src + q / 2);
+                const float2 z0 = cmul(make_float2(v.x, v.y), wi), z1 = cmul(make_float2(v.z, v.w), wi);
+                acc[q].x += z0.x;
+                acc[q].y += z0.y;
+                acc[q + 1].x += z1.x;
+                acc[q + 1].y += z1.y;
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < PG; ++q)
+        if (p0 + q < planes) grid[(long)(p0 + q) * cells + c] = acc[q];
+}
+
 // one warp per long row; lanes stride the entries, a fixed-order shuffle tree adds them up (reproducible)
 template <int PG>
 __global__ void __launch_bounds__(256)
@@ -812,13 +867,24 @@ static int csr_build(pdu_nufft_plan* p, const float* omega, long M, void* buf, s
     return PDU_OK;
 }
 
+// kT_scratch (optional): room for M * round_up(planes, 4) float2 -- the plane-interleaved copy of kdata
 static int launch_interp_adj_csr(pdu_nufft_plan* p, const float2* kdata, float2* grid, const void* csr, int planes, long M,
-                                 cudaStream_t st) {
+                                 cudaStream_t st, float2* kT_scratch = nullptr) {
     const CsrView v = csr_layout(p, M, const_cast<void*>(csr), false);
     const long cells = (long)p->k0 * p->k1;
     constexpr int PG = 4;
     dim3 g((unsigned)cdiv(cells, 256), (unsigned)cdiv(planes, PG));
-    interp_adj_csr_kernel<PG><<<g, 256, 0, st>>>(kdata, grid, v.row_ptr, v.samp, v.w, cells, M, planes);
+    if (kT_scratch && planes >= 4) {
+        const int planes4 = (planes + 3) & ~3;
+        transpose_kdata_kernel<<<dim3((unsigned)cdiv(M, 32), (unsigned)cdiv(planes4, 32)), dim3(32, 8), 0, st>>>(
+            kdata, kT_scratch, M, planes, planes4);
+        PDU_LAUNCHED();
+        constexpr int PGT = 8;
+        dim3 gt((unsigned)cdiv(cells, 256), (unsigned)cdiv(planes, PGT));
+        interp_adj_csrT_kernel<PGT><<<gt, 256, 0, st>>>(kT_scratch, grid, v.row_ptr, v.samp, v.w, cells, planes, planes4);
+    } else {
+        interp_adj_csr_kernel<PG><<<g, 256, 0, st>>>(kdata, grid, v.row_ptr, v.samp, v.w, cells, M, planes);
+    }
     PDU_LAUNCHED();
     dim3 gl((unsigned)(2 * sm_count()), (unsigned)cdiv(planes, PG));      // 8 warps per CTA, grid-stride over the long rows
     interp_adj_csr_long_kernel<PG><<<gl, 256, 0, st>>>(kdata, grid, v.row_ptr, v.n_long, v.long_rows, v.samp, v.w, cells, M,
@@ -983,7 +1049,11 @@ static int nufft_adj_chunk(pdu_nufft_plan_t* p, const float2* kdata, float2* ima
     const int planes = batch * coils;
     int rc;
     if (csr) {
-        rc = launch_interp_adj_csr(p, kdata, grid, csr, planes, m, st);       // writes every cell: no memset
+        // the FFT's intermediate buffer is free until the transform starts: it holds the plane-interleaved kdata
+        float2* mid = grid + (long)planes * p->k0 * p->k1;
+        const long mid_elems = (long)planes * std::max((long)p->n0 * p->k1, (long)p->k0 * p->n1);
+        const bool fits = m * (long)((planes + 3) & ~3) <= mid_elems;
+        rc = launch_interp_adj_csr(p, kdata, grid, csr, planes, m, st, fits ? mid : nullptr);   // writes every cell: no memset
     } else {
         PDU_CUDA(cudaMemsetAsync(grid, 0, (size_t)planes * p->k0 * p->k1 * sizeof(float2), st));
         rc = launch_interp_adj(p, kdata, grid, omega, planes, m, st);
