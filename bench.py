@@ -237,18 +237,22 @@ def run_ours(args):
                 "d2h_bytes_per_step": host_out.numel() * 4},
         "gpu_launches": int(launches),
         "clocks": clocks.summary(),
-        "roofline": {"bound": "hbm", "kernel": "pdu_radon_fwd_f32 (transpose_kernel + radon_fwd_strip_kernel<32,8,32,136,2,8>), 512 views",
+        "roofline": {"bound": "hbm", "kernel": "pdu_radon_fwd_f32 (quad_build_kernel + radon_fwd_quad_kernel<32,8,16,88,2,8>), 512 views",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     # dram__bytes_read.sum + dram__bytes_write.sum of the strip kernel, one ncu --set full capture
-                     # (profiles/r01_ncu_full_summary_fwd_filter.md): the 8.4 MB sinogram is still in L2 when the kernel ends
-                     "traffic": 8419584,
+                     # dram__bytes_read.sum + dram__bytes_write.sum of the quad kernel in one ncu --set full capture
+                     # (profiles/r01_ncu_full_summary.md).  ncu flushes the caches before every kernel, so this is the
+                     # cold figure: the two 16.9 MB cell tensors quad_build_kernel has just written.  Inside a step they
+                     # are still in L2 (traffic_in_step: the same counters with --cache-control none,
+                     # profiles/r01_traffic_in_step.csv).
+                     "traffic": 33847040 + 378368, "traffic_in_step": 512 + 105984,
                      "peak_source": peak_src, "algorithmic_bytes": alg_bytes, "avg_launch_ms": fwd_avg_ms,
                      "launches_timed": len(fwd_ms),
                      "gsamples_per_s": BATCH * A_FULL * N * N / (fwd_avg_ms * 1e-3) / 1e9,
                      "smem_roof_frac": (BATCH * A_FULL * N * N / (fwd_avg_ms * 1e-3)) / (148 * 8 * 1.965e9),
                      "note": "bound on-chip, not by HBM (43 samples per algorithmic byte): smem_roof_frac is samples/s "
-                             "against the shared-memory crossbar roof of 8 bilinear samples/clk/SM (16 B/sample at 128 B/clk); "
-                             "ncu: issue 64 %, L1/shared pipe 74 % busy. DESIGN.md section 3"},
+                             "against the shared-memory roof of 8 bilinear samples/clk/SM (16 B/sample at 128 B/clk); "
+                             "ncu: L1/shared pipe 74 % busy (1.56 wavefronts per ideal one: bank conflicts of the 16-byte "
+                             "cell loads), issue 72 %. DESIGN.md section 3"},
         "operators": ops,
     }
     if not args.no_cpu and world == 1:                 # the CPU leg is reported at N = 1 only

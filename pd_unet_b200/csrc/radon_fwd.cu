@@ -757,13 +757,14 @@ int pdu_radon_fwd_f32(const float* img, float* sino, const float* trig, int batc
     const bool quad_ok = (g->n + 1 + 15) / 16 <= MAX_STRIPS && g->n_angles <= 65535 * 4;
     const bool tile_ok = (g->n % 4 == 0) && (((uintptr_t)img & 15) == 0) && (g->n + 1 + 31) / 32 <= MAX_STRIPS &&
                          g->n_angles <= 65535 * 2;
-    // default: cell ("quad") strips while the strip box of the CTA's views fits 128 cells; very sparse view
-    // sets fall back to the float-tile kernel with its 248-column box
+    // default: cell ("quad") strips for dense view sets (8 neighbouring views share an 88-cell box); sparser view
+    // sets go to the float-tile kernel, whose wider boxes (136 .. 248 columns) keep several views per CTA --
+    // measured on the sweep's sparse shapes (tools/prof_fwd_shapes.py): tile kernel 1.2 - 1.4x faster there,
+    // cell kernel 1.03 - 1.15x faster at drift <= 3.3
     if (variant < 0) {
         if (quad_ok && 7.f * drift <= 23.f) variant = 7;
-        else if (quad_ok && 3.f * drift <= 50.f) variant = 9;
-        else if (tile_ok) variant = 2;
-        else if (quad_ok) variant = 9;
+        else if (tile_ok) variant = 1;
+        else if (quad_ok) variant = 7.f * drift <= 63.f ? 11 : 9;
         else variant = 0;
     }
     if (variant >= 7 && !quad_ok) variant = tile_ok ? 1 : 0;
@@ -795,6 +796,7 @@ int pdu_radon_fwd_f32(const float* img, float* sino, const float* trig, int batc
             case 8: return launch_quad<32, 8, 32, 104, 2, 8>(q, qt, sino, trig, batch, *g, st);    // 32-row strips
             case 9: return launch_quad<32, 4, 16, 120, 2, 8>(q, qt, sino, trig, batch, *g, st);    // 4 views / CTA (sparser views)
             case 10: return launch_quad<32, 16, 16, 92, 2, 8>(q, qt, sino, trig, batch, *g, st);   // 512 threads: 16 views share a box
+            case 11: return launch_quad<32, 8, 16, 128, 2, 8>(q, qt, sino, trig, batch, *g, st);   // widest cell box (sparser views)
             // (r02 also measured 3-deep rings, 84/76/89-cell pitches, 16-detector warps and 8-row strips:
             //  520..600 us against 513 for shape 7 -- dropped)
             default: return launch_quad<32, 8, 16, 88, 2, 8>(q, qt, sino, trig, batch, *g, st);    // 7

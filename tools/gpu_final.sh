@@ -11,5 +11,6 @@ timeout 900 python tools/sweep.py gpurun_out/r01_sweep.md > gpurun_out/sweep.log
 timeout 600 python tools/parity_report.py gpurun_out/r01_parity.md > gpurun_out/parity.log 2>&1
 bash tools/gpu_launches.sh > /dev/null 2>&1
 timeout 300 python tools/prof_ops.py 1 > gpurun_out/plain2.log 2>&1 && \
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"radon_fwd_strip|radon_adj_tile|filter_tc_kernel" -c 8 -o gpurun_out/prof_ops python tools/prof_ops.py 1 > gpurun_out/ncu_full.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"radon_fwd_quad|quad_build|radon_adj_tile|filter_tc_kernel" -c 10 -f -o gpurun_out/prof_ops python tools/prof_ops.py 1 > gpurun_out/ncu_full.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"ff_|interp_|crop_apod|transpose_kdata" -c 10 -f -o gpurun_out/prof_nufft python tools/prof_nufft_one.py -1 > gpurun_out/ncu_full_nufft.log 2>&1
 ls -la gpurun_out | tail -30
