@@ -113,6 +113,14 @@ __device__ __forceinline__ float2 lds64(uint32_t addr) {
 // SAFE: every corner of the tile is at least 8 pixels in front of the source (checked per chunk in float64), so
 // MUFU.RCP's 1 ulp is enough (t < 96: < 1.2e-5 bins) and the quotient cannot leave the staged interval -- no
 // Newton step, no clamps.  Otherwise one Newton step and a clamp onto the segment, as in MODE 0.
+// MUFU.RCP alone: __fdividef(1, d) wraps it in range scaling (FSETP + 2 FSEL + 2 FMUL per call) that the
+// denominators here (distance from the source, 1e-3 .. 1e5) never need
+__device__ __forceinline__ float rcp_approx(float d) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
+    return r;
+}
+
 template <int PY, int SEG, bool SAFE>
 __device__ __forceinline__ void fan_taps_line(const float* __restrict__ view, uint32_t cbase, float lx,
                                               const ull* __restrict__ ly_pk, float kk, float* __restrict__ acc) {
@@ -129,7 +137,7 @@ __device__ __forceinline__ void fan_taps_line(const float* __restrict__ view, ui
         const ull p_den = fma2(p_dy, ly_pk[k / 2], p_dx);
         float d0, d1;
         upk2(p_den, d0, d1);
-        ull p_r = pk2(__fdividef(1.f, d0), __fdividef(1.f, d1));
+        ull p_r = pk2(rcp_approx(d0), rcp_approx(d1));
         if (!SAFE) p_r = fma2(p_r, sub2(p_one, mul2(p_den, p_r)), p_r);
         ull p_c = mul2(p_num, p_r);
         float c0, c1;
