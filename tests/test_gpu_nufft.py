@@ -156,3 +156,38 @@ def test_pruned_fft_and_cufft_paths_agree(im):
     finally:
         pdu.set_option("nufft_fwd_variant", -1)
         pdu.set_option("nufft_adj_variant", -1)
+
+
+@pytest.mark.parametrize("n,coils,batch,spokes", [(320, 8, 8, 48), (256, 1, 1, 32)])
+def test_full_size_adjointness_and_linearity(n, coils, batch, spokes):
+    """BASELINE configs[3] / configs[0] shapes (the register-resident pruned FFT and the sorted gather are the
+    default paths there), checked through size-independent properties: <A x, y> = <x, A^H y> with coil maps and
+    ortho norm, and A(a x1 + x2) = a A x1 + A x2."""
+    im = (n, n)
+    om = torch.from_numpy(_traj(spokes, 2 * n)).to(DEV)
+    A, AH = pdu.KbNufft(im), pdu.KbNufftAdjoint(im)
+    sm = coil_maps(coils, n)[None].to(DEV) if coils > 1 else None
+    ci = 1 if coils > 1 else coils
+    x = seeded((batch, ci) + im, 41, complex_=True).to(DEV)
+    x2 = seeded((batch, ci) + im, 42, complex_=True).to(DEV)
+    k = seeded((batch, coils, om.shape[1]), 43, complex_=True).to(DEV)
+    Ax = A(x, om, smaps=sm, norm="ortho")
+    AHk = AH(k, om, smaps=sm, norm="ortho")
+    assert Ax.shape == k.shape and AHk.shape == x.shape
+    c128 = torch.complex128
+    lhs = torch.vdot(k.reshape(-1).to(c128), Ax.reshape(-1).to(c128))
+    rhs = torch.vdot(AHk.reshape(-1).to(c128), x.reshape(-1).to(c128))
+    assert abs(lhs - rhs) / abs(lhs) < 1e-5
+    a = 0.37 - 1.2j
+    assert rel_l2(A(a * x + x2, om, smaps=sm, norm="ortho"), a * Ax + A(x2, om, smaps=sm, norm="ortho")) <= 1e-6
+    # the three FFT paths agree at full size
+    try:
+        outs = []
+        for v in (2, 0):
+            pdu.set_option("nufft_fwd_variant", v)
+            pdu.set_option("nufft_adj_variant", v)
+            outs.append((A(x, om, smaps=sm, norm="ortho"), AH(k, om, smaps=sm, norm="ortho")))
+        assert rel_l2(outs[0][0], outs[1][0]) <= 2e-6 and rel_l2(outs[0][1], outs[1][1]) <= 2e-6
+    finally:
+        pdu.set_option("nufft_fwd_variant", -1)
+        pdu.set_option("nufft_adj_variant", -1)
