@@ -237,7 +237,7 @@ def run_ours(args):
                 "d2h_bytes_per_step": host_out.numel() * 4},
         "gpu_launches": int(launches),
         "clocks": clocks.summary(),
-        "roofline": {"bound": "hbm", "kernel": "pdu_radon_fwd_f32 (quad_build_kernel + radon_fwd_quad_kernel<32,8,16,88,2,8>), 512 views",
+        "roofline": {"bound": "hbm", "kernel": "pdu_radon_fwd_f32 (quad_build_kernel + radon_fwd_quad_kernel<32,8,16,92,2,4>), 512 views",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      # dram__bytes_read.sum + dram__bytes_write.sum of the quad kernel in one ncu --set full capture
                      # (profiles/r01_ncu_full_summary.md).  ncu flushes the caches before every kernel, so this is the

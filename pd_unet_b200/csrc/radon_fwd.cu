@@ -760,9 +760,10 @@ int pdu_radon_fwd_f32(const float* img, float* sino, const float* trig, int batc
     // default: cell ("quad") strips for dense view sets (8 neighbouring views share an 88-cell box); sparser view
     // sets go to the float-tile kernel, whose wider boxes (136 .. 248 columns) keep several views per CTA --
     // measured on the sweep's sparse shapes (tools/prof_fwd_shapes.py): tile kernel 1.2 - 1.4x faster there,
-    // cell kernel 1.03 - 1.15x faster at drift <= 3.3
+    // cell kernel 1.03 - 1.15x faster at drift <= 3.3.  Shape 13 (a quarter-warp = 4 detectors x 2 neighbouring views:
+    // the 8 lanes of one LDS.128 phase then span < 8 cell columns) is 2-3 % faster than shape 7 (8 detectors of one view)
     if (variant < 0) {
-        if (quad_ok && 7.f * drift <= 23.f) variant = 7;
+        if (quad_ok && 7.f * drift <= 27.f) variant = 13;
         else if (tile_ok) variant = 1;
         else if (quad_ok) variant = 7.f * drift <= 63.f ? 11 : 9;
         else variant = 0;
@@ -797,9 +798,12 @@ int pdu_radon_fwd_f32(const float* img, float* sino, const float* trig, int batc
             case 9: return launch_quad<32, 4, 16, 120, 2, 8>(q, qt, sino, trig, batch, *g, st);    // 4 views / CTA (sparser views)
             case 10: return launch_quad<32, 16, 16, 92, 2, 8>(q, qt, sino, trig, batch, *g, st);   // 512 threads: 16 views share a box
             case 11: return launch_quad<32, 8, 16, 128, 2, 8>(q, qt, sino, trig, batch, *g, st);   // widest cell box (sparser views)
+            case 12: return launch_quad<32, 8, 16, 88, 2, 4>(q, qt, sino, trig, batch, *g, st);    // quarter-warp = 4 detectors x 2 views
+            case 13: return launch_quad<32, 8, 16, 92, 2, 4>(q, qt, sino, trig, batch, *g, st);    // same, rows 4 bank groups apart
+            case 14: return launch_quad<32, 16, 16, 92, 2, 2>(q, qt, sino, trig, batch, *g, st);   // quarter-warp = 2 detectors x 4 views (16 views / CTA)
             // (r02 also measured 3-deep rings, 84/76/89-cell pitches, 16-detector warps and 8-row strips:
             //  520..600 us against 513 for shape 7 -- dropped)
-            default: return launch_quad<32, 8, 16, 88, 2, 8>(q, qt, sino, trig, batch, *g, st);    // 7
+            default: return launch_quad<32, 8, 16, 88, 2, 8>(q, qt, sino, trig, batch, *g, st);    // 7: quarter-warp = 8 detectors of one view
         }
     }
     float* imgT = (float*)workspace;

@@ -60,7 +60,7 @@ def _reset_variants():
         pdu.set_option(k, -1)
 
 
-@pytest.mark.parametrize("variant", [-1, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11])
+@pytest.mark.parametrize("variant", [-1, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14])
 @pytest.mark.parametrize("name", CASES)
 def test_forward_matches_oracle(name, variant):
     op, g, internal = _case(name)
