@@ -59,14 +59,18 @@ __device__ __forceinline__ float2 cmul_conj(float2 a, float2 b) {   // a * conj(
     return make_float2(fmaf(a.x, b.x, a.y * b.y), fmaf(a.y, b.x, -a.x * b.y));
 }
 
-// per-axis taps of one sample: wrapped grid index and table coefficient
-__device__ __forceinline__ void axis_taps(float om, float gam, int K, int J, int L, const float2* __restrict__ table,
+// per-axis taps of one sample: wrapped grid index and table coefficient.  JT > 0: compile-time tap count (the
+// default J = 6 gets straight-line code, 6-entry register arrays and no per-tap branches); JT == 0: run-time J <= MAXJ
+template <int JT = 0>
+__device__ __forceinline__ void axis_taps(float om, float gam, int K, int Jrt, int L, const float2* __restrict__ table,
                                           int* gi, float2* co) {
+    const int J = JT > 0 ? JT : Jrt;
+    constexpr int N = JT > 0 ? JT : MAXJ;
     const float tm = __fdiv_rn(om, gam);
     const int koff = (int)floorf(__fsub_rn(tm, 0.5f * (float)J));
     const int half = (J * L) / 2;
 #pragma unroll
-    for (int j = 0; j < MAXJ; ++j) {
+    for (int j = 0; j < N; ++j) {
         if (j < J) {
             const int g = koff + 1 + j;
             const float dist = __fmul_rn(__fsub_rn(tm, (float)g), (float)L);
@@ -178,17 +182,20 @@ __global__ void __launch_bounds__(256)
 
 // ------------------------------------------------------------------ interpolation (gather)
 // thread = one sample m; loops over the PC planes of its plane chunk (blockIdx.y)
+template <int JT>
 __global__ void __launch_bounds__(128)    // (r02: capping at 64 registers for 32 warps / SM spills and is not faster)
     interp_fwd_kernel(const float2* __restrict__ grid, float2* __restrict__ kdata, const float* __restrict__ omega,
                       const float2* __restrict__ t0, const float2* __restrict__ t1, NufftDims d, int planes, int pc,
                       long M, float scale) {
     const long m = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= M) return;
+    const int J = JT > 0 ? JT : d.J;
+    constexpr int N = JT > 0 ? JT : MAXJ;
     const float om0 = __ldg(omega + m), om1 = __ldg(omega + M + m);
-    int g0[MAXJ], g1[MAXJ];
-    float2 c0[MAXJ], c1[MAXJ];
-    axis_taps(om0, d.gam0, d.k0, d.J, d.L, t0, g0, c0);
-    axis_taps(om1, d.gam1, d.k1, d.J, d.L, t1, g1, c1);
+    int g0[N], g1[N];
+    float2 c0[N], c1[N];
+    axis_taps<JT>(om0, d.gam0, d.k0, d.J, d.L, t0, g0, c0);
+    axis_taps<JT>(om1, d.gam1, d.k1, d.J, d.L, t1, g1, c1);
     float2 ph = shift_phase(om0, om1, d.shift0, d.shift1);
     ph.x *= scale;
     ph.y *= scale;
@@ -198,13 +205,13 @@ __global__ void __launch_bounds__(128)    // (r02: capping at 64 registers for 3
         const float2* gp = grid + p * gplane;
         float2 acc = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int a = 0; a < MAXJ; ++a) {
-            if (a < d.J) {
+        for (int a = 0; a < N; ++a) {
+            if (a < J) {
                 const float2* row = gp + (long)g0[a] * d.k1;
                 float2 racc = make_float2(0.f, 0.f);
 #pragma unroll
-                for (int b = 0; b < MAXJ; ++b) {
-                    if (b < d.J) {
+                for (int b = 0; b < N; ++b) {
+                    if (b < J) {
                         const float2 z = cmul(__ldg(row + g1[b]), c1[b]);
                         racc.x += z.x;
                         racc.y += z.y;
@@ -220,17 +227,20 @@ __global__ void __launch_bounds__(128)    // (r02: capping at 64 registers for 3
 }
 
 // ------------------------------------------------------------------ interpolation adjoint (scatter)
+template <int JT>
 __global__ void __launch_bounds__(128)
     interp_adj_kernel(const float2* __restrict__ kdata, float2* __restrict__ grid, const float* __restrict__ omega,
                       const float2* __restrict__ t0, const float2* __restrict__ t1, NufftDims d, int planes, int pc,
                       long M) {
     const long m = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= M) return;
+    const int J = JT > 0 ? JT : d.J;
+    constexpr int N = JT > 0 ? JT : MAXJ;
     const float om0 = __ldg(omega + m), om1 = __ldg(omega + M + m);
-    int g0[MAXJ], g1[MAXJ];
-    float2 c0[MAXJ], c1[MAXJ];
-    axis_taps(om0, d.gam0, d.k0, d.J, d.L, t0, g0, c0);
-    axis_taps(om1, d.gam1, d.k1, d.J, d.L, t1, g1, c1);
+    int g0[N], g1[N];
+    float2 c0[N], c1[N];
+    axis_taps<JT>(om0, d.gam0, d.k0, d.J, d.L, t0, g0, c0);
+    axis_taps<JT>(om1, d.gam1, d.k1, d.J, d.L, t1, g1, c1);
     const float2 ph = shift_phase(om0, om1, d.shift0, d.shift1);
     const long gplane = (long)d.k0 * d.k1;
     const int p_end = min(planes, ((int)blockIdx.y + 1) * pc);
@@ -238,13 +248,13 @@ __global__ void __launch_bounds__(128)
         const float2 y = cmul_conj(__ldg(kdata + (long)p * M + m), ph);
         float2* gp = grid + p * gplane;
 #pragma unroll
-        for (int a = 0; a < MAXJ; ++a) {
-            if (a < d.J) {
+        for (int a = 0; a < N; ++a) {
+            if (a < J) {
                 const float2 ya = cmul_conj(y, c0[a]);
                 float2* row = gp + (long)g0[a] * d.k1;
 #pragma unroll
-                for (int b = 0; b < MAXJ; ++b) {
-                    if (b < d.J) atomicAdd(row + g1[b], cmul_conj(ya, c1[b]));
+                for (int b = 0; b < N; ++b) {
+                    if (b < J) atomicAdd(row + g1[b], cmul_conj(ya, c1[b]));
                 }
             }
         }
@@ -316,7 +326,8 @@ static int launch_interp_fwd(pdu_nufft_plan* p, const float2* grid, float2* kdat
                              long M, float scale, cudaStream_t st) {
     const int pc = plane_chunk(planes, M);
     dim3 g((unsigned)cdiv(M, 128), (unsigned)cdiv(planes, pc));
-    interp_fwd_kernel<<<g, 128, 0, st>>>(grid, kdata, omega, p->d_t0, p->d_t1, dims_of(p), planes, pc, M, scale);
+    if (p->J == 6) interp_fwd_kernel<6><<<g, 128, 0, st>>>(grid, kdata, omega, p->d_t0, p->d_t1, dims_of(p), planes, pc, M, scale);
+    else interp_fwd_kernel<0><<<g, 128, 0, st>>>(grid, kdata, omega, p->d_t0, p->d_t1, dims_of(p), planes, pc, M, scale);
     PDU_LAUNCHED();
     return PDU_OK;
 }
@@ -325,7 +336,8 @@ static int launch_interp_adj(pdu_nufft_plan* p, const float2* kdata, float2* gri
                              long M, cudaStream_t st) {
     const int pc = plane_chunk(planes, M);
     dim3 g((unsigned)cdiv(M, 128), (unsigned)cdiv(planes, pc));
-    interp_adj_kernel<<<g, 128, 0, st>>>(kdata, grid, omega, p->d_t0, p->d_t1, dims_of(p), planes, pc, M);
+    if (p->J == 6) interp_adj_kernel<6><<<g, 128, 0, st>>>(kdata, grid, omega, p->d_t0, p->d_t1, dims_of(p), planes, pc, M);
+    else interp_adj_kernel<0><<<g, 128, 0, st>>>(kdata, grid, omega, p->d_t0, p->d_t1, dims_of(p), planes, pc, M);
     PDU_LAUNCHED();
     return PDU_OK;
 }

@@ -191,3 +191,17 @@ def test_full_size_adjointness_and_linearity(n, coils, batch, spokes):
     finally:
         pdu.set_option("nufft_fwd_variant", -1)
         pdu.set_option("nufft_adj_variant", -1)
+
+
+@pytest.mark.parametrize("numpoints", [4, 5, 8])
+def test_non_default_numpoints(numpoints):
+    """J != 6 takes the run-time-J instantiation of the gather / scatter kernels (J = 6 is compiled straight-line)."""
+    im = (48, 40)
+    spec = oracle.NufftSpec(im, numpoints=numpoints)
+    om = _traj(10, 96)
+    omd = torch.from_numpy(om).to(DEV)
+    x = seeded((2, 2) + im, 51, complex_=True)
+    k = seeded((2, 2, om.shape[1]), 52, complex_=True)
+    A, AH = pdu.KbNufft(im, numpoints=numpoints), pdu.KbNufftAdjoint(im, numpoints=numpoints)
+    assert rel_l2(A(x.to(DEV), omd), oracle.nufft_forward(x, om, spec)) <= TOL
+    assert rel_l2(AH(k.to(DEV), omd), oracle.nufft_adjoint(k, om, spec)) <= TOL
