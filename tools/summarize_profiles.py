@@ -75,7 +75,7 @@ def full(rep_name="prof_ops.ncu-rep", suffix=""):
     idx = [(w, hdr.index(w)) for w in WANT if w in hdr]
     ki = hdr.index("Kernel Name")
     with open(os.path.join(out_dir, f"{tag}_ncu_full_summary{suffix}.md"), "w") as f:
-        f.write(f"# {tag}: ncu --set full, selected counters per captured launch (tools/prof_ops.py)\n\n"
+        f.write(f"# {tag}: ncu --set full, selected counters per captured launch (tools/gpu_final.sh)\n\n"
                 "Captured under the profiler (replays, cold caches): use for ratios and stall reasons, not for timing.\n")
         seen = collections.Counter()
         for r in rows[2:]:
@@ -89,5 +89,8 @@ def full(rep_name="prof_ops.ncu-rep", suffix=""):
 
 
 launches()
-full()
+full()                                         # forward projector (cell build + strip kernel)
+full("prof_adj.ncu-rep", "_adj")
+full("prof_fan.ncu-rep", "_fan")
+full("prof_filter.ncu-rep", "_filter")
 full("prof_nufft.ncu-rep", "_nufft")
