@@ -188,6 +188,19 @@ PDU_API int pdu_residual_slice_f32(float* out, float* slice, const float* state,
  * nn.Conv2d(bias=True) + nn.PReLU in the primal / dual blocks (inference). */
 PDU_API int pdu_bias_prelu_f32(float* y, const float* bias, const float* slope, int n_slope, int batch,
                                int channels, long plane, int layout, pdu_stream_t stream);
+/* Training forms of the same epilogue (channels-last, channels in {4, 8, ..., 256}, 16-byte aligned; anything else
+ * returns PDU_EUNSUPPORTED and the caller keeps the ATen ops).
+ *   fwd: out = prelu(y + bias, slope), y kept for the backward.
+ *   bwd: one pass over (g, y): gz = g * (z > 0 ? 1 : slope), gbias[c] = sum gz, gslope[c] = sum g * min(z, 0)
+ *        (gslope has n_slope entries); per-block partial sums go through `workspace` and are added in a fixed
+ *        order (bit-reproducible, no atomics).
+ * Replaces nn.Conv2d's bias add + nn.PReLU forward, and PReLU backward + the bias / slope gradient reductions. */
+PDU_API int pdu_bias_prelu_fwd_f32(const float* y, float* out, const float* bias, const float* slope, int n_slope,
+                                   int batch, int channels, long plane, int layout, pdu_stream_t stream);
+PDU_API size_t pdu_bias_prelu_bwd_workspace_bytes(int channels);
+PDU_API int pdu_bias_prelu_bwd_f32(const float* g, const float* y, const float* bias, const float* slope, int n_slope,
+                                   float* gz, float* gbias, float* gslope, void* workspace, size_t workspace_bytes,
+                                   int batch, int channels, long plane, int layout, pdu_stream_t stream);
 /* The epilogue of a UNet encoder (or up-convolution) in one pass over the channels-last convolution
  * output y [batch, height, width, channels]:  v = prelu(y + bias, slope) is written into its slot of the
  * decoder's concatenation buffer (`skip` already points at the slot's first channel; consecutive pixels are

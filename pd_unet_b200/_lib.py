@@ -63,6 +63,9 @@ SIGNATURES = {
     "pdu_concat_f32": (C.c_int, [_p, _p, _p, _p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_long, C.c_float, C.c_int, _p]),
     "pdu_residual_slice_f32": (C.c_int, [_p, _p, _p, _p, C.c_int, C.c_int, C.c_long, C.c_int, C.c_int, C.c_int, _p]),
     "pdu_bias_prelu_f32": (C.c_int, [_p, _p, _p, C.c_int, C.c_int, C.c_int, C.c_long, C.c_int, _p]),
+    "pdu_bias_prelu_fwd_f32": (C.c_int, [_p, _p, _p, _p, C.c_int, C.c_int, C.c_int, C.c_long, C.c_int, _p]),
+    "pdu_bias_prelu_bwd_workspace_bytes": (C.c_size_t, [C.c_int]),
+    "pdu_bias_prelu_bwd_f32": (C.c_int, [_p, _p, _p, _p, C.c_int, _p, _p, _p, _p, C.c_size_t, C.c_int, C.c_int, C.c_long, C.c_int, _p]),
     "pdu_bias_prelu_place_f32": (C.c_int, [_p, _p, _p, C.c_int, _p, C.c_long, _p, C.c_int, C.c_int, C.c_int, C.c_int, _p]),
     "pdu_axpby_f32": (C.c_int, [_p, C.c_float, _p, C.c_float, _p, C.c_long, _p]),
     "pdu_angular_upsample_f32": (C.c_int, [_p, _p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _p]),

@@ -367,6 +367,169 @@ extern "C" int pdu_bias_prelu_f32(float* y, const float* bias, const float* slop
     return PDU_OK;
 }
 
+// ------------------------------------------------------------------ bias + PReLU for training: out of place + backward
+// Forward keeps the convolution output y (the backward needs the sign and value of z = y + bias) and writes
+// out = prelu(z).  Backward, ONE pass over (g, y):  gz = g * (z > 0 ? 1 : slope)  and per-channel
+//   gbias[c] = sum gz,   gslope[c] = sum g * min(z, 0)
+// accumulated in registers (a thread always sees the same four channels: the grid stride is a multiple of C / 4),
+// reduced per block in shared memory, and summed over the blocks by a second tiny kernel in a fixed order
+// (reproducible: no atomics).  ATen runs bias add, PReLU, PReLU backward (which writes a full-size slope-gradient
+// tensor) and two full-size sum reductions: 41 % of a PD-UNet training step (profiles/r01_training.md).
+namespace pdu {
+
+template <bool HAS_SLOPE>
+__global__ void __launch_bounds__(256)
+    bias_prelu_out_nhwc4_kernel(const float4* __restrict__ y, float4* __restrict__ out, const float4* __restrict__ bias,
+                                const float4* __restrict__ slope, int c4, int n_slope, long total4) {
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % c4);
+        const float4 b = __ldg(bias + c);
+        float4 v = __ldg(y + i);
+        v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+        if (HAS_SLOPE) {
+            float4 s;
+            if (n_slope == 1) { const float s1 = __ldg((const float*)slope); s = make_float4(s1, s1, s1, s1); }
+            else s = __ldg(slope + c);
+            v.x = prelu1(v.x, s.x); v.y = prelu1(v.y, s.y); v.z = prelu1(v.z, s.z); v.w = prelu1(v.w, s.w);
+        }
+        out[i] = v;
+    }
+}
+
+// d(prelu)/dz with ATen's convention at z == 0 (the negative branch)
+__device__ __forceinline__ void prelu_bwd1(float g, float z, float s, float& gz, float& sb, float& sa) {
+    const bool pos = z > 0.f;
+    gz = pos ? g : g * s;
+    sb += gz;
+    sa += pos ? 0.f : g * z;
+}
+
+__global__ void __launch_bounds__(256)
+    bias_prelu_bwd_nhwc4_kernel(const float4* __restrict__ g, const float4* __restrict__ y, const float4* __restrict__ bias,
+                                const float4* __restrict__ slope, int n_slope, float4* __restrict__ gz,
+                                float* __restrict__ partial, int c4, long total4) {
+    // gridDim.x * 256 is a multiple of c4 (host checks 256 % c4 == 0): the channel group of a thread never changes
+    const int c = threadIdx.x % c4;
+    const float4 b = __ldg(bias + c);
+    float4 s;
+    if (n_slope == 1) { const float s1 = __ldg((const float*)slope); s = make_float4(s1, s1, s1, s1); }
+    else s = __ldg(slope + c);
+    float sb[4] = {0.f, 0.f, 0.f, 0.f}, sa[4] = {0.f, 0.f, 0.f, 0.f};
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long)gridDim.x * blockDim.x) {
+        const float4 gi = __ldg(g + i), yi = __ldg(y + i);
+        float4 o;
+        prelu_bwd1(gi.x, yi.x + b.x, s.x, o.x, sb[0], sa[0]);
+        prelu_bwd1(gi.y, yi.y + b.y, s.y, o.y, sb[1], sa[1]);
+        prelu_bwd1(gi.z, yi.z + b.z, s.z, o.z, sb[2], sa[2]);
+        prelu_bwd1(gi.w, yi.w + b.w, s.w, o.w, sb[3], sa[3]);
+        gz[i] = o;
+    }
+    __shared__ float red[8][256];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        red[k][threadIdx.x] = sb[k];
+        red[4 + k][threadIdx.x] = sa[k];
+    }
+    __syncthreads();
+    // thread t < 8 c4 sums quantity q = t / c4 of channel group cc = t % c4 over the 256 / c4 threads that own it
+    for (int idx = threadIdx.x; idx < 8 * c4; idx += 256) {
+        const int q = idx / c4, cc = idx - q * c4;
+        float acc = 0.f;
+        for (int t = cc; t < 256; t += c4) acc += red[q][t];
+        // partial [block][2][C]: q < 4 -> gbias of channel 4 cc + q, q >= 4 -> gslope of channel 4 cc + q - 4
+        const int C = 4 * c4;
+        partial[((long)blockIdx.x * 2 + (q >> 2)) * C + 4 * cc + (q & 3)] = acc;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+    bias_prelu_bwd_reduce_kernel(const float* __restrict__ partial, int nblocks, int C, int n_slope, float* __restrict__ gbias,
+                                 float* __restrict__ gslope) {
+    __shared__ float s_slope[256];
+    const int t = threadIdx.x;       // one thread per (quantity, channel): 2 C <= 512 threads in two rounds
+    for (int idx = t; idx < 2 * C; idx += 256) {
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        int b = 0;
+        for (; b + 4 <= nblocks; b += 4) {
+            a0 += partial[(long)(b + 0) * 2 * C + idx];
+            a1 += partial[(long)(b + 1) * 2 * C + idx];
+            a2 += partial[(long)(b + 2) * 2 * C + idx];
+            a3 += partial[(long)(b + 3) * 2 * C + idx];
+        }
+        for (; b < nblocks; ++b) a0 += partial[(long)b * 2 * C + idx];
+        const float v = (a0 + a1) + (a2 + a3);
+        if (idx < C) gbias[idx] = v;
+        else if (n_slope == C) gslope[idx - C] = v;
+        else s_slope[idx - C] = v;
+    }
+    if (n_slope == 1) {              // one shared slope: add the channels up in a fixed order (C <= 256)
+        __syncthreads();
+        if (t == 0) {
+            float v = 0.f;
+            for (int c = 0; c < C; ++c) v += s_slope[c];
+            gslope[0] = v;
+        }
+    }
+}
+
+}  // namespace pdu
+
+static bool bias_prelu_train_ok(int channels, int layout, const void* a, const void* b, const void* c, const void* d) {
+    const int c4 = channels / 4;
+    return layout == PDU_LAYOUT_NHWC && channels % 4 == 0 && c4 >= 1 && c4 <= 64 && 256 % c4 == 0 && pdu::al16(a) && pdu::al16(b) &&
+           pdu::al16(c) && (d == nullptr || pdu::al16(d));
+}
+
+extern "C" int pdu_bias_prelu_fwd_f32(const float* y, float* out, const float* bias, const float* slope, int n_slope, int batch,
+                                      int channels, long plane, int layout, pdu_stream_t stream) {
+    using namespace pdu;
+    PDU_REQUIRE(y && out && bias && slope, "pdu_bias_prelu_fwd_f32: null pointer");
+    PDU_REQUIRE(batch > 0 && channels > 0 && plane > 0, "pdu_bias_prelu_fwd_f32: sizes must be positive");
+    PDU_REQUIRE(n_slope == 1 || n_slope == channels, "pdu_bias_prelu_fwd_f32: slope must have 1 or %d values", channels);
+    if (!bias_prelu_train_ok(channels, layout, y, out, bias, n_slope == 1 ? nullptr : slope)) {
+        set_error("pdu_bias_prelu_fwd_f32: needs a 16-byte aligned channels-last tensor with channels in {4,8,16,32,64,128,256}");
+        return PDU_EUNSUPPORTED;
+    }
+    const long total4 = (long)batch * channels * plane / 4;
+    bias_prelu_out_nhwc4_kernel<true><<<stream_grid(total4, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const float4*)y, (float4*)out, (const float4*)bias, (const float4*)slope, channels / 4, n_slope, total4);
+    PDU_LAUNCHED();
+    return PDU_OK;
+}
+
+extern "C" size_t pdu_bias_prelu_bwd_workspace_bytes(int channels) {
+    return channels > 0 ? (size_t)4 * pdu::sm_count() * 2 * channels * sizeof(float) : 0;
+}
+
+extern "C" int pdu_bias_prelu_bwd_f32(const float* g, const float* y, const float* bias, const float* slope, int n_slope,
+                                      float* gz, float* gbias, float* gslope, void* workspace, size_t workspace_bytes,
+                                      int batch, int channels, long plane, int layout, pdu_stream_t stream) {
+    using namespace pdu;
+    PDU_REQUIRE(g && y && bias && slope && gz && gbias && gslope, "pdu_bias_prelu_bwd_f32: null pointer");
+    PDU_REQUIRE(batch > 0 && channels > 0 && plane > 0, "pdu_bias_prelu_bwd_f32: sizes must be positive");
+    PDU_REQUIRE(n_slope == 1 || n_slope == channels, "pdu_bias_prelu_bwd_f32: slope must have 1 or %d values", channels);
+    if (!bias_prelu_train_ok(channels, layout, g, y, gz, bias) || (n_slope != 1 && !al16(slope))) {
+        set_error("pdu_bias_prelu_bwd_f32: needs 16-byte aligned channels-last tensors with channels in {4,8,16,32,64,128,256}");
+        return PDU_EUNSUPPORTED;
+    }
+    const size_t need = pdu_bias_prelu_bwd_workspace_bytes(channels);
+    if (!workspace || workspace_bytes < need) {
+        set_error("pdu_bias_prelu_bwd_f32: workspace of %zu bytes required, got %zu", need, workspace ? workspace_bytes : (size_t)0);
+        return PDU_ENOMEM;
+    }
+    const long total4 = (long)batch * channels * plane / 4;
+    int nblocks = 4 * sm_count();
+    if ((long)nblocks > (total4 + 255) / 256) nblocks = (int)((total4 + 255) / 256);
+    cudaStream_t st = (cudaStream_t)stream;
+    bias_prelu_bwd_nhwc4_kernel<<<nblocks, 256, 0, st>>>((const float4*)g, (const float4*)y, (const float4*)bias,
+                                                         (const float4*)slope, n_slope, (float4*)gz, (float*)workspace,
+                                                         channels / 4, total4);
+    PDU_LAUNCHED();
+    bias_prelu_bwd_reduce_kernel<<<1, 256, 0, st>>>((const float*)workspace, nblocks, channels, n_slope, gbias, gslope);
+    PDU_LAUNCHED();
+    return PDU_OK;
+}
+
 // ------------------------------------------------------------------ bias + PReLU + skip placement + 2x2 max pool
 // The epilogue of a UNet encoder block in one pass over the convolution output y (channels-last):
 //   v = prelu(y + bias, slope)  ->  written into its slot of the decoder's concatenation buffer

@@ -32,8 +32,10 @@ def _fused_epilogue_ok(x: torch.Tensor) -> bool:
 
 class ConvAct(nn.Module):
     """3x3 convolution (cuDNN) + optional PReLU.  In inference the bias add and the activation run as
-    one in-place pass of pdu_bias_prelu_f32 instead of ATen's two; with gradients on, the stock
-    modules are used so autograd sees ordinary ops.  Parameters are those of the wrapped modules."""
+    one in-place pass of pdu_bias_prelu_f32 instead of ATen's two; with gradients on, the convolution runs
+    without its bias and `updates.bias_prelu` (one forward pass, one backward pass that also yields the bias and
+    slope gradients) replaces bias add + PReLU and their backward kernels.  Parameters are those of the wrapped
+    modules, so state_dict keys do not change."""
 
     def __init__(self, cin: int, cout: int, act: bool = True, kernel: int = 3):
         super().__init__()
@@ -58,6 +60,12 @@ class ConvAct(nn.Module):
         if _fused_epilogue_ok(x):
             y = nn.functional.conv2d(x, self._weight_for(x.shape[1]), None, self.conv.stride, self.conv.padding)
             return updates.bias_prelu_(y, self.conv.bias, self.act.weight if self.act is not None else None)
+        if (self.act is not None and x.is_cuda and x.dtype == torch.float32 and x.dim() == 4
+                and x.is_contiguous(memory_format=torch.channels_last)
+                and x.shape[0] * self.conv.out_channels * x.shape[2] * x.shape[3] >= updates.FUSED_TRAIN_MIN_ELEMS):
+            # training: bias-free cuDNN convolution (autograd's own dgrad / wgrad) + the fused differentiable epilogue
+            y = nn.functional.conv2d(x, self.conv.weight, None, self.conv.stride, self.conv.padding)
+            return updates.bias_prelu(y, self.conv.bias, self.act.weight)
         y = self.conv(x)
         return self.act(y) if self.act is not None else y
 

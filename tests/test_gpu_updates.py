@@ -204,3 +204,43 @@ def test_fused_unet_path_matches_the_plain_modules():
     ref = torch.nn.functional.prelu(y + bias.view(1, -1, 1, 1), slope)
     assert torch.equal(cat[:, 8:], ref) and torch.equal(cat[:, :8], torch.zeros_like(ref))
     assert torch.equal(pooled, torch.nn.functional.max_pool2d(ref, 2))
+
+
+@pytest.mark.parametrize("C,n_slope", [(32, 32), (64, 1), (8, 8), (256, 256)])
+def test_bias_prelu_training_matches_aten(C, n_slope):
+    """The differentiable epilogue (pdu_bias_prelu_fwd_f32 / _bwd_f32) against conv2d(bias) + PReLU in ATen:
+    output, input gradient, bias gradient and slope gradient; and the reduction is bit-reproducible."""
+    torch.manual_seed(7)
+    B, H, W = 3, 24, 40
+    x = torch.randn(B, 5, H, W, device=DEV).contiguous(memory_format=torch.channels_last)
+    conv = torch.nn.Conv2d(5, C, 3, padding=1).to(DEV).to(memory_format=torch.channels_last)
+    act = torch.nn.PReLU(n_slope).to(DEV)
+    monkey = pytest.MonkeyPatch()
+    monkey.setattr(updates, "FUSED_TRAIN_MIN_ELEMS", 0)      # the test tensors are small: force the fused kernels
+    with torch.no_grad():
+        act.weight.uniform_(-0.2, 0.6)        # negative and zero-crossing slopes included
+    w = torch.randn(B, C, H, W, device=DEV)
+
+    def run(fused):
+        for p in list(conv.parameters()) + list(act.parameters()):
+            p.grad = None
+        xr = x.clone().requires_grad_()
+        if fused:
+            y = torch.nn.functional.conv2d(xr, conv.weight, None, padding=1)
+            out = pdu.updates.bias_prelu(y, conv.bias, act.weight)
+        else:
+            out = act(conv(xr))
+        (out * w).sum().backward()
+        return out.detach(), xr.grad, conv.bias.grad.clone(), act.weight.grad.clone(), conv.weight.grad.clone()
+
+    ref = run(False)
+    got = run(True)
+    again = run(True)
+    for name, a, b in zip(("out", "grad_x", "grad_bias", "grad_slope", "grad_weight"), got, ref):
+        assert rel_l2(a, b) <= 2e-5, name          # TF32 convolutions on both sides; the epilogue itself is exact fp32
+    assert torch.equal(got[2], again[2]) and torch.equal(got[3], again[3])
+    # odd layouts fall back to the ATen ops on the GPU (same numbers)
+    yp = torch.randn(2, 6, 9, 9, device=DEV, requires_grad=True)
+    o = pdu.updates.bias_prelu(yp, torch.randn(6, device=DEV), torch.full((1,), 0.25, device=DEV))
+    assert o.shape == yp.shape
+    monkey.undo()
