@@ -11,6 +11,8 @@ from __future__ import annotations
 
 from typing import Optional, Tuple
 
+import os
+
 import torch
 
 from ._lib import LAYOUT_NCHW, LAYOUT_NHWC, WRAP_MODES, PduError, check, lib, require_cuda, stream_ptr
@@ -236,10 +238,11 @@ def bias_prelu_(y: torch.Tensor, bias: torch.Tensor, slope: Optional[torch.Tenso
     return y
 
 
-# Below this size a training step is bound by the host (Python autograd.Function + ctypes calls cost more than
-# ATen's C++ nodes) and the fused epilogue loses: measured on B200, MRI 320^2 x 2 slices (6.5 M elements per
-# feature map) 17.0 -> 19.0 ms with it, CT 256^2 x 8 slices (16.8 M) 34.8 -> 27.1 ms.
-FUSED_TRAIN_MIN_ELEMS = 8 << 20
+# Below this size a training step is bound by the host (a Python autograd.Function + ctypes calls cost more than
+# ATen's C++ nodes) and the fused epilogue does not pay.  Measured on one B200 with the gate at 0 / 1 M / 4 M / 8 M
+# elements: CT 256^2 x 8 slices 24.6 / 24.6 / 25.2 / 26.9 ms (ATen ops only: 34.8); MRI 320^2 x 2 slices 17.5 / 18.3 /
+# 17.0 / 17.5 (ATen only: 17.0, i.e. neutral within noise); 128^2 x 2 slices (1 M-element maps) 7.2 ms against 6.4.
+FUSED_TRAIN_MIN_ELEMS = int(os.environ.get("PDU_FUSED_TRAIN_MIN_ELEMS", 2 << 20))
 
 
 def _bias_prelu_train_ok(y: torch.Tensor, bias: torch.Tensor, slope: Optional[torch.Tensor]) -> bool:
