@@ -197,6 +197,11 @@ PDU_API int pdu_bias_prelu_f32(float* y, const float* bias, const float* slope, 
  * Replaces nn.Conv2d's bias add + nn.PReLU forward, and PReLU backward + the bias / slope gradient reductions. */
 PDU_API int pdu_bias_prelu_fwd_f32(const float* y, float* out, const float* bias, const float* slope, int n_slope,
                                    int batch, int channels, long plane, int layout, pdu_stream_t stream);
+/* out[c] = sum over batch and plane of g[., c, .] for a channels-last tensor (same shape limits as above; workspace
+ * of pdu_bias_prelu_bwd_workspace_bytes(channels) bytes; fixed summation order).  Replaces the bias-gradient
+ * reduction of a convolution that has no activation (`grad.sum((0, 2, 3))`). */
+PDU_API int pdu_channel_sum_f32(const float* g, float* out, void* workspace, size_t workspace_bytes, int batch,
+                                int channels, long plane, int layout, pdu_stream_t stream);
 PDU_API size_t pdu_bias_prelu_bwd_workspace_bytes(int channels);
 PDU_API int pdu_bias_prelu_bwd_f32(const float* g, const float* y, const float* bias, const float* slope, int n_slope,
                                    float* gz, float* gbias, float* gslope, void* workspace, size_t workspace_bytes,

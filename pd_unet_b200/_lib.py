@@ -64,6 +64,7 @@ SIGNATURES = {
     "pdu_residual_slice_f32": (C.c_int, [_p, _p, _p, _p, C.c_int, C.c_int, C.c_long, C.c_int, C.c_int, C.c_int, _p]),
     "pdu_bias_prelu_f32": (C.c_int, [_p, _p, _p, C.c_int, C.c_int, C.c_int, C.c_long, C.c_int, _p]),
     "pdu_bias_prelu_fwd_f32": (C.c_int, [_p, _p, _p, _p, C.c_int, C.c_int, C.c_int, C.c_long, C.c_int, _p]),
+    "pdu_channel_sum_f32": (C.c_int, [_p, _p, _p, C.c_size_t, C.c_int, C.c_int, C.c_long, C.c_int, _p]),
     "pdu_bias_prelu_bwd_workspace_bytes": (C.c_size_t, [C.c_int]),
     "pdu_bias_prelu_bwd_f32": (C.c_int, [_p, _p, _p, _p, C.c_int, _p, _p, _p, _p, C.c_size_t, C.c_int, C.c_int, C.c_long, C.c_int, _p]),
     "pdu_bias_prelu_place_f32": (C.c_int, [_p, _p, _p, C.c_int, _p, C.c_long, _p, C.c_int, C.c_int, C.c_int, C.c_int, _p]),

@@ -473,6 +473,42 @@ __global__ void bias_prelu_bwd_scalar_slope_kernel(const float* __restrict__ slo
     gslope[0] = v;
 }
 
+// per-channel sum of a channels-last tensor (the bias gradient of a convolution without activation): same two stages
+__global__ void __launch_bounds__(256)
+    channel_sum_nhwc4_kernel(const float4* __restrict__ g, float* __restrict__ partial, int c4, long total4) {
+    float sb[4] = {0.f, 0.f, 0.f, 0.f};
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long)gridDim.x * blockDim.x) {
+        const float4 gi = __ldg(g + i);
+        sb[0] += gi.x; sb[1] += gi.y; sb[2] += gi.z; sb[3] += gi.w;
+    }
+    __shared__ float red[4][256];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) red[k][threadIdx.x] = sb[k];
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < 4 * c4; idx += 256) {
+        const int q = idx / c4, cc = idx - q * c4;
+        float acc = 0.f;
+        for (int t = cc; t < 256; t += c4) acc += red[q][t];
+        partial[(long)blockIdx.x * 4 * c4 + 4 * cc + q] = acc;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+    partial_rows_sum_kernel(const float* __restrict__ partial, int nblocks, int row_len, float* __restrict__ out) {
+    __shared__ float red[256];
+    const int idx = blockIdx.x, t = threadIdx.x;
+    float acc = 0.f;
+    for (int b = t; b < nblocks; b += 256) acc += partial[(long)b * row_len + idx];
+    red[t] = acc;
+    __syncthreads();
+#pragma unroll
+    for (int w = 128; w > 0; w >>= 1) {
+        if (t < w) red[t] += red[t + w];
+        __syncthreads();
+    }
+    if (t == 0) out[idx] = red[0];
+}
+
 }  // namespace pdu
 
 static bool bias_prelu_train_ok(int channels, int layout, const void* a, const void* b, const void* c, const void* d) {
@@ -494,6 +530,32 @@ extern "C" int pdu_bias_prelu_fwd_f32(const float* y, float* out, const float* b
     const long total4 = (long)batch * channels * plane / 4;
     bias_prelu_out_nhwc4_kernel<true><<<stream_grid(total4, 256), 256, 0, (cudaStream_t)stream>>>(
         (const float4*)y, (float4*)out, (const float4*)bias, (const float4*)slope, channels / 4, n_slope, total4);
+    PDU_LAUNCHED();
+    return PDU_OK;
+}
+
+extern "C" int pdu_channel_sum_f32(const float* g, float* out, void* workspace, size_t workspace_bytes, int batch, int channels,
+                                   long plane, int layout, pdu_stream_t stream) {
+    using namespace pdu;
+    PDU_REQUIRE(g && out, "pdu_channel_sum_f32: null pointer");
+    PDU_REQUIRE(batch > 0 && channels > 0 && plane > 0, "pdu_channel_sum_f32: sizes must be positive");
+    const int c4 = channels / 4;
+    if (!(layout == PDU_LAYOUT_NHWC && channels % 4 == 0 && c4 <= 64 && 256 % c4 == 0 && al16(g))) {
+        set_error("pdu_channel_sum_f32: needs a 16-byte aligned channels-last tensor with channels in {4,8,16,32,64,128,256}");
+        return PDU_EUNSUPPORTED;
+    }
+    const size_t need = (size_t)4 * sm_count() * channels * sizeof(float);
+    if (!workspace || workspace_bytes < need) {
+        set_error("pdu_channel_sum_f32: workspace of %zu bytes required, got %zu", need, workspace ? workspace_bytes : (size_t)0);
+        return PDU_ENOMEM;
+    }
+    const long total4 = (long)batch * channels * plane / 4;
+    int nblocks = 4 * sm_count();
+    if ((long)nblocks > (total4 + 255) / 256) nblocks = (int)((total4 + 255) / 256);
+    cudaStream_t st = (cudaStream_t)stream;
+    channel_sum_nhwc4_kernel<<<nblocks, 256, 0, st>>>((const float4*)g, (float*)workspace, c4, total4);
+    PDU_LAUNCHED();
+    partial_rows_sum_kernel<<<channels, 256, 0, st>>>((const float*)workspace, nblocks, channels, out);
     PDU_LAUNCHED();
     return PDU_OK;
 }

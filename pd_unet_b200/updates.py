@@ -300,6 +300,40 @@ class _BiasPReLU(torch.autograd.Function):
         return gz, gb, ga
 
 
+class _BiasAdd(torch.autograd.Function):
+    """out = y + bias[c] in place (y is the fresh output of a bias-free convolution); backward passes the gradient
+    through untouched and sums it per channel with pdu_channel_sum_f32 (two stages, fixed order)."""
+
+    @staticmethod
+    def forward(ctx, y, bias):
+        ctx.mark_dirty(y)
+        ctx.n_channels = y.shape[1]
+        ctx.bias_dtype = bias.dtype
+        return bias_prelu_(y, bias, None)
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous(memory_format=torch.channels_last)
+        gb = torch.empty(ctx.n_channels, dtype=torch.float32, device=g.device)
+        with _on_device(g.device):
+            L = lib()
+            ws = torch.empty(L.pdu_bias_prelu_bwd_workspace_bytes(g.shape[1]), dtype=torch.uint8, device=g.device)
+            check(L.pdu_channel_sum_f32(g.data_ptr(), gb.data_ptr(), ws.data_ptr(), ws.numel(), g.shape[0], g.shape[1],
+                                        _plane(g), LAYOUT_NHWC, stream_ptr()), "pdu_channel_sum_f32")
+        return g, gb
+
+
+def bias_add(y: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
+    """Differentiable y + bias[c] for the output of a bias-free (transposed) convolution without activation; large
+    channels-last maps take the in-place add and the two-stage channel sum, everything else the ATen ops."""
+    Cn = y.shape[1] if y.dim() == 4 else 0
+    if (y.is_cuda and y.dtype == torch.float32 and y.dim() == 4 and y.numel() >= FUSED_TRAIN_MIN_ELEMS and _is_channels_last(y)
+            and Cn % 4 == 0 and Cn // 4 <= 64 and 256 % (Cn // 4) == 0 and bias.numel() == Cn and y.data_ptr() % 16 == 0
+            and not y.is_leaf):        # in place: y must be the (unsaved) output of the convolution, never a user tensor
+        return _BiasAdd.apply(y, bias)
+    return y + bias.view((1, -1) + (1,) * (y.dim() - 2))
+
+
 def bias_prelu(y: torch.Tensor, bias: torch.Tensor, slope: torch.Tensor) -> torch.Tensor:
     """Differentiable prelu(y + bias[c], slope) for the output y of a bias-free convolution: the training form of
     `bias_prelu_`.  One forward pass and one backward pass (input gradient + bias and slope gradients, reproducible)

@@ -244,3 +244,27 @@ def test_bias_prelu_training_matches_aten(C, n_slope):
     o = pdu.updates.bias_prelu(yp, torch.randn(6, device=DEV), torch.full((1,), 0.25, device=DEV))
     assert o.shape == yp.shape
     monkey.undo()
+
+
+@pytest.mark.parametrize("C", [4, 32, 128])
+def test_bias_add_training_matches_aten(C):
+    """updates.bias_add (in-place add + pdu_channel_sum_f32 in the backward) against conv2d(bias=True)."""
+    torch.manual_seed(11)
+    x = torch.randn(2, 6, 20, 28, device=DEV).contiguous(memory_format=torch.channels_last)
+    conv = torch.nn.Conv2d(6, C, 3, padding=1).to(DEV).to(memory_format=torch.channels_last)
+    w = torch.randn(2, C, 20, 28, device=DEV)
+    monkey = pytest.MonkeyPatch()
+    monkey.setattr(updates, "FUSED_TRAIN_MIN_ELEMS", 0)
+
+    def run(fused):
+        conv.zero_grad(set_to_none=True)
+        xr = x.clone().requires_grad_()
+        out = updates.bias_add(torch.nn.functional.conv2d(xr, conv.weight, None, padding=1), conv.bias) if fused else conv(xr)
+        (out * w).sum().backward()
+        return out.detach(), xr.grad, conv.bias.grad.clone(), conv.weight.grad.clone()
+
+    ref, got, again = run(False), run(True), run(True)
+    monkey.undo()
+    for name, a, b in zip(("out", "grad_x", "grad_bias", "grad_weight"), got, ref):
+        assert rel_l2(a, b) <= 2e-5, name
+    assert torch.equal(got[2], again[2])
