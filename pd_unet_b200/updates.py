@@ -239,10 +239,13 @@ def bias_prelu_(y: torch.Tensor, bias: torch.Tensor, slope: Optional[torch.Tenso
 
 
 # Below this size a training step is bound by the host (a Python autograd.Function + ctypes calls cost more than
-# ATen's C++ nodes) and the fused epilogue does not pay.  Measured on one B200 with the gate at 0 / 1 M / 4 M / 8 M
-# elements: CT 256^2 x 8 slices 24.6 / 24.6 / 25.2 / 26.9 ms (ATen ops only: 34.8); MRI 320^2 x 2 slices 17.5 / 18.3 /
-# 17.0 / 17.5 (ATen only: 17.0, i.e. neutral within noise); 128^2 x 2 slices (1 M-element maps) 7.2 ms against 6.4.
-FUSED_TRAIN_MIN_ELEMS = int(os.environ.get("PDU_FUSED_TRAIN_MIN_ELEMS", 2 << 20))
+# ATen's C++ nodes; an eager PD-UNet step is ~1000 launches) and the fused epilogue does not pay.  Measured on B200:
+#   CT 256^2 x 8 slices (16.8 M-element maps), 1 GPU, gate 0 / 1 M / 4 M / 8 M: 24.6 / 24.6 / 25.2 / 26.9 ms
+#                                                                    (ATen ops only: 34.8; under 2-GPU DDP 25.5 vs 35.9)
+#   MRI 320^2 x 2 slices (6.5 M-element maps): 1 GPU neutral (17.0 .. 17.7 ms either way), 2-GPU DDP 20.5 fused vs 18.7
+#   128^2 x 2 slices (1 M): 7.2 ms fused vs 6.4
+# so the gate sits between 6.5 M and 16.8 M elements.
+FUSED_TRAIN_MIN_ELEMS = int(os.environ.get("PDU_FUSED_TRAIN_MIN_ELEMS", 8 << 20))
 
 
 def _bias_prelu_train_ok(y: torch.Tensor, bias: torch.Tensor, slope: Optional[torch.Tensor]) -> bool:
