@@ -81,14 +81,15 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // Bounded wait: a barrier that never completes must not hang the GPU box.
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
-    for (int spin = 0; spin < (1 << 22); ++spin) {
+    // every try may sleep up to the 100 us hint: 2^18 tries bound a wait that can never complete to under half a minute
+    for (int spin = 0; spin < (1 << 18); ++spin) {
         uint32_t ok;
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
             "selp.b32 %0, 1, 0, p;\n\t}"
             : "=r"(ok)
-            : "r"(addr), "r"(parity), "r"(0x989680u)     // suspend-time hint: sleep in hardware instead of spinning
+            : "r"(addr), "r"(parity), "r"(100000u)       // suspend-time hint (ns): sleep in hardware instead of spinning
             : "memory");
         if (ok) return true;
     }
