@@ -50,3 +50,58 @@ class GraphedInference:
     def replay(self) -> torch.Tensor:
         self.graph.replay()
         return self.static_out
+
+
+class GraphedTrainingStep:
+    """Captures one whole training step -- forward, loss, backward, optimizer.step() -- and replays it.
+
+    An eager PD-UNet training step is ~1000 launches (cuDNN fprop / dgrad / wgrad, the operators and their
+    adjoints, autograd glue); at a few slices per GPU the host cannot issue them as fast as the GPU retires
+    them.  Replaying a captured graph removes that bound (and with it the size gate under which the fused
+    differentiable epilogues of pd_unet_b200.updates do not pay).
+
+    model:      the module to train (a DistributedDataParallel wrapper works: PyTorch's whole-network capture
+                needs NCCL >= 2.9.6 and 11 eager warm-up steps, which this class runs)
+    optimizer:  must be capturable, e.g. torch.optim.Adam(params, lr, capturable=True)
+    loss_fn:    (output, target) -> scalar tensor
+    inputs:     tuple of example input tensors (shapes / dtypes / devices fixed from now on); non-tensor entries
+                are passed through unchanged
+    The warm-up steps are REAL optimisation steps on the example batch.
+    """
+
+    def __init__(self, model: torch.nn.Module, optimizer: torch.optim.Optimizer, loss_fn: Callable, inputs: tuple,
+                 target: torch.Tensor, warmup: int = 3):
+        if not target.is_cuda:
+            raise ValueError("GraphedTrainingStep needs CUDA tensors")
+        self.model, self.optimizer, self.loss_fn = model, optimizer, loss_fn
+        self.static_inputs = tuple(t.clone() if isinstance(t, torch.Tensor) else t for t in inputs)
+        self.static_target = target.clone()
+        dev = target.device
+        is_ddp = isinstance(model, torch.nn.parallel.DistributedDataParallel)
+        n_warm = max(warmup, 11) if is_ddp else max(warmup, 1)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(n_warm):
+                optimizer.zero_grad(set_to_none=True)
+                loss = loss_fn(model(*self.static_inputs), self.static_target)
+                loss.backward()
+                optimizer.step()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        optimizer.zero_grad(set_to_none=True)
+        with torch.cuda.graph(self.graph):
+            self.static_loss = loss_fn(model(*self.static_inputs), self.static_target)
+            self.static_loss.backward()
+            optimizer.step()
+
+    def __call__(self, inputs: tuple, target: torch.Tensor) -> torch.Tensor:
+        """Copies the batch into the captured tensors, replays the step, returns the (captured) loss tensor."""
+        for dst, src in zip(self.static_inputs, inputs):
+            if isinstance(dst, torch.Tensor) and src.data_ptr() != dst.data_ptr():
+                dst.copy_(src, non_blocking=True)
+        if target.data_ptr() != self.static_target.data_ptr():
+            self.static_target.copy_(target, non_blocking=True)
+        self.graph.replay()
+        return self.static_loss

@@ -62,13 +62,13 @@ class ConvAct(nn.Module):
             return updates.bias_prelu_(y, self.conv.bias, self.act.weight if self.act is not None else None)
         if (self.act is not None and x.is_cuda and x.dtype == torch.float32 and x.dim() == 4
                 and x.is_contiguous(memory_format=torch.channels_last)
-                and x.shape[0] * self.conv.out_channels * x.shape[2] * x.shape[3] >= updates.FUSED_TRAIN_MIN_ELEMS):
+                and x.shape[0] * self.conv.out_channels * x.shape[2] * x.shape[3] >= updates.fused_train_min_elems()):
             # training: bias-free cuDNN convolution (autograd's own dgrad / wgrad) + the fused differentiable epilogue
             y = nn.functional.conv2d(x, self.conv.weight, None, self.conv.stride, self.conv.padding)
             return updates.bias_prelu(y, self.conv.bias, self.act.weight)
         if (self.act is None and x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and torch.is_grad_enabled()
                 and x.is_contiguous(memory_format=torch.channels_last)
-                and x.shape[0] * self.conv.out_channels * x.shape[2] * x.shape[3] >= updates.FUSED_TRAIN_MIN_ELEMS):
+                and x.shape[0] * self.conv.out_channels * x.shape[2] * x.shape[3] >= updates.fused_train_min_elems()):
             return updates.bias_add(nn.functional.conv2d(x, self.conv.weight, None, self.conv.stride, self.conv.padding),
                                     self.conv.bias)
         y = self.conv(x)
@@ -88,7 +88,7 @@ class UpConv(nn.Module):
             return updates.bias_prelu_(y, self.conv.bias, None)
         if (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and torch.is_grad_enabled()
                 and x.is_contiguous(memory_format=torch.channels_last)
-                and 4 * x.shape[0] * self.conv.out_channels * x.shape[2] * x.shape[3] >= updates.FUSED_TRAIN_MIN_ELEMS):
+                and 4 * x.shape[0] * self.conv.out_channels * x.shape[2] * x.shape[3] >= updates.fused_train_min_elems()):
             return updates.bias_add(nn.functional.conv_transpose2d(x, self.conv.weight, None, 2), self.conv.bias)
         return self.conv(x)
 

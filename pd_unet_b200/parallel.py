@@ -14,9 +14,14 @@ import torch
 import torch.distributed as dist
 
 
-def init_distributed(backend: str | None = None) -> Tuple[int, int, int]:
+def init_distributed(backend: str | None = None, graph_capture: bool = False) -> Tuple[int, int, int]:
     """Initialise torch.distributed from the torchrun environment.  -> (rank, world_size, local_rank).
-    A plain `python script.py` run (no RANK in the environment) is world_size 1 and touches nothing."""
+    A plain `python script.py` run (no RANK in the environment) is world_size 1 and touches nothing.
+    graph_capture: the training step will be captured into a CUDA graph together with DDP's all-reduce
+    (pd_unet_b200.graph.GraphedTrainingStep): NCCL's asynchronous error handling (a watchdog that polls the
+    communicator from another thread) has to be off before the process group exists."""
+    if graph_capture:
+        os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "0")
     if "RANK" not in os.environ or int(os.environ.get("WORLD_SIZE", "1")) == 1:
         return 0, 1, int(os.environ.get("LOCAL_RANK", "0"))
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
@@ -87,11 +92,20 @@ def gather_batch(local: torch.Tensor, n_items: int) -> torch.Tensor | None:
     return torch.cat([o[:b - a] for o, (a, b) in zip(outs, sizes)], dim=0)
 
 
-def wrap_ddp(model: torch.nn.Module, local_rank: int) -> torch.nn.Module:
-    """DistributedDataParallel with bucket views (no extra gradient copy); identity at world_size 1."""
+def wrap_ddp(model: torch.nn.Module, local_rank: int, graph_capture: bool = False) -> torch.nn.Module:
+    """DistributedDataParallel with bucket views (no extra gradient copy); identity at world_size 1.
+    graph_capture: construct the wrapper on a side stream, as whole-step CUDA-graph capture of a DDP model needs
+    (PyTorch CUDA-graphs notes; GraphedTrainingStep then runs the 11 eager warm-up steps DDP asks for)."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return model
     from torch.nn.parallel import DistributedDataParallel as DDP
     if next(model.parameters()).is_cuda:
+        if graph_capture:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                ddp = DDP(model, device_ids=[local_rank], gradient_as_bucket_view=True)
+            torch.cuda.current_stream().wait_stream(side)
+            return ddp
         return DDP(model, device_ids=[local_rank], gradient_as_bucket_view=True)
     return DDP(model, gradient_as_bucket_view=True)

@@ -248,6 +248,12 @@ def bias_prelu_(y: torch.Tensor, bias: torch.Tensor, slope: Optional[torch.Tenso
 FUSED_TRAIN_MIN_ELEMS = int(os.environ.get("PDU_FUSED_TRAIN_MIN_ELEMS", 8 << 20))
 
 
+def fused_train_min_elems() -> int:
+    """The size gate of the fused training epilogues; 0 while a CUDA graph is being captured (a replayed step has no
+    host cost per launch, so the fused kernels win at every size: MRI 320^2 x 2 slices 15.3 -> 11.0 ms)."""
+    return 0 if torch.cuda.is_current_stream_capturing() else FUSED_TRAIN_MIN_ELEMS
+
+
 def _bias_prelu_train_ok(y: torch.Tensor, bias: torch.Tensor, slope: Optional[torch.Tensor]) -> bool:
     """Shapes the fused training epilogue serves: float32 CUDA channels-last [B, C, H, W], C in {4, 8, ..., 256}."""
     if slope is None or not y.is_cuda or y.dtype != torch.float32 or y.dim() != 4 or y.numel() == 0:
@@ -330,7 +336,7 @@ def bias_add(y: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
     """Differentiable y + bias[c] for the output of a bias-free (transposed) convolution without activation; large
     channels-last maps take the in-place add and the two-stage channel sum, everything else the ATen ops."""
     Cn = y.shape[1] if y.dim() == 4 else 0
-    if (y.is_cuda and y.dtype == torch.float32 and y.dim() == 4 and y.numel() >= FUSED_TRAIN_MIN_ELEMS and _is_channels_last(y)
+    if (y.is_cuda and y.dtype == torch.float32 and y.dim() == 4 and y.numel() >= fused_train_min_elems() and _is_channels_last(y)
             and Cn % 4 == 0 and Cn // 4 <= 64 and 256 % (Cn // 4) == 0 and bias.numel() == Cn and y.data_ptr() % 16 == 0
             and not y.is_leaf):        # in place: y must be the (unsaved) output of the convolution, never a user tensor
         return _BiasAdd.apply(y, bias)
@@ -342,7 +348,7 @@ def bias_prelu(y: torch.Tensor, bias: torch.Tensor, slope: torch.Tensor) -> torc
     `bias_prelu_`.  One forward pass and one backward pass (input gradient + bias and slope gradients, reproducible)
     instead of ATen's bias add, PReLU, PReLU backward and two full-size reductions.  Shapes the fused kernels do
     not serve (planar layout, odd channel counts) go through the equivalent ATen ops on the GPU."""
-    if _bias_prelu_train_ok(y, bias, slope) and y.numel() >= FUSED_TRAIN_MIN_ELEMS:
+    if _bias_prelu_train_ok(y, bias, slope) and y.numel() >= fused_train_min_elems():
         return _BiasPReLU.apply(y, bias, slope)
     return torch.nn.functional.prelu(y + bias.view((1, -1) + (1,) * (y.dim() - 2)), slope)
 

@@ -80,6 +80,43 @@ def test_ct_model_trains():
     assert losses[-1] < losses[0]
 
 
+def test_graphed_training_step_matches_eager():
+    """One captured training step (forward + loss + backward + Adam) replayed N times lands on the same parameters
+    as N eager steps (the fused epilogues are used at every size while capturing, so allow rounding differences)."""
+    from pd_unet_b200.graph import GraphedTrainingStep
+    n, A, up, warm, steps = 64, 32, 4, 2, 4
+    radon = pdu.Radon(n, user_angles(A))
+    x = phantom_batch(2, n).to(DEV)
+    sparse = radon.forward(x)[:, None, ::up].contiguous()
+    loss_fn = lambda out, tgt: torch.nn.functional.mse_loss(out[:, 0], tgt)
+
+    def make():
+        torch.manual_seed(3)
+        m = PrimalDualUNetCT(radon, upsample=up, n_iter=2, n_primal=2, n_dual=2, unet_base=8, unet_depth=2,
+                             dual_features=8).to(DEV)
+        return m, torch.optim.Adam(m.parameters(), 1e-3, capturable=True)
+
+    m_e, opt_e = make()
+    eager_losses = []
+    for _ in range(warm + steps):
+        opt_e.zero_grad(set_to_none=True)
+        loss = loss_fn(m_e(sparse), x)
+        loss.backward()
+        opt_e.step()
+        eager_losses.append(float(loss))
+    m_g, opt_g = make()
+    step = GraphedTrainingStep(m_g, opt_g, loss_fn, (sparse,), x, warmup=warm)
+    graph_losses = [float(step((sparse,), x)) for _ in range(steps)]
+    assert graph_losses[-1] < graph_losses[0]
+    assert abs(graph_losses[-1] - eager_losses[-1]) <= 1e-3 * abs(eager_losses[-1])
+    for pe, pg in zip(m_e.parameters(), m_g.parameters()):
+        assert rel_l2(pg, pe) <= 2e-3
+    # a different batch goes through the captured tensors
+    x2 = phantom_batch(2, n, seed=9).to(DEV)
+    s2 = radon.forward(x2)[:, None, ::up].contiguous()
+    assert torch.isfinite(step((s2,), x2))
+
+
 def test_mri_model_matches_cpu_oracle_model():
     torch.backends.cudnn.allow_tf32 = False
     im, spokes, readout, coils = (32, 32), 8, 64, 2

@@ -1,6 +1,7 @@
 """Training-step timings (BASELINE.json configs[1] and configs[3] shapes) under DDP.
   python tools/train_bench.py                       # 1 GPU
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tools/train_bench.py
+  ... --graph: the whole step (DDP all-reduce included) captured once and replayed (GraphedTrainingStep)
 One step = forward + MSE loss + backward + (DDP all-reduce) + Adam update; CUDA-event time, max over ranks."""
 import os, sys, statistics
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -9,17 +10,36 @@ import pd_unet_b200 as pdu
 from pd_unet_b200 import data, parallel
 from pd_unet_b200.model import PrimalDualUNetCT, PrimalDualUNetMRI
 
-rank, world, local = parallel.init_distributed("nccl")
+rank, world, local = parallel.init_distributed("nccl", graph_capture="--graph" in sys.argv)
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 torch.backends.cudnn.benchmark = True
 KW = dict(n_iter=4, n_primal=4, n_dual=4, unet_base=32, unet_depth=3, dual_features=32)
 
 
+GRAPH = "--graph" in sys.argv      # replay one captured training step (pd_unet_b200.graph.GraphedTrainingStep)
+
+
 def run(name, model, step_inputs, target, per_rank, steps=8, warm=3):
-    ddp = parallel.wrap_ddp(model, local)
-    opt = torch.optim.Adam(ddp.parameters(), 1e-4)
+    ddp = parallel.wrap_ddp(model, local, graph_capture=GRAPH)
+    opt = torch.optim.Adam(ddp.parameters(), 1e-4, capturable=GRAPH)
     times, losses = [], []
+    if GRAPH:
+        from pd_unet_b200.graph import GraphedTrainingStep
+        step = GraphedTrainingStep(ddp, opt, lambda o, t: (o - t).abs().pow(2).mean(), step_inputs, target, warmup=warm)
+        for it in range(steps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            parallel.barrier(); torch.cuda.synchronize()
+            a.record()
+            loss = step(step_inputs, target)
+            b.record(); torch.cuda.synchronize()
+            times.append(a.elapsed_time(b))
+            losses.append(float(loss.detach()))
+        ms = parallel.max_over_ranks(statistics.median(times), dev)
+        mem = torch.cuda.max_memory_allocated(dev) / 2 ** 30
+        if rank == 0:
+            print(f"| {name}, CUDA graph | {world} | {per_rank} | {ms:.1f} | {per_rank * world / ms * 1e3:.0f} | {mem:.1f} | {losses[0]:.4g} -> {losses[-1]:.4g} |", flush=True)
+        return
     for it in range(warm + steps):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         parallel.barrier(); torch.cuda.synchronize()
