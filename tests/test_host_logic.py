@@ -107,3 +107,17 @@ def test_world_size_2_on_gloo(tmp_path):
     net(x).pow(2).mean().backward()
     want = torch.cat([p.grad.reshape(-1) for p in net.parameters()])
     assert torch.allclose(g0, want, atol=1e-6)
+
+
+def test_graph_capture_switch_sets_nccl_env(monkeypatch):
+    """init_distributed(graph_capture=True) must turn NCCL's async error handling off before any process group
+    exists (whole-step CUDA-graph capture with DDP), and is a no-op for the communicator at world size 1."""
+    from pd_unet_b200 import parallel
+    monkeypatch.delenv("TORCH_NCCL_ASYNC_ERROR_HANDLING", raising=False)
+    monkeypatch.delenv("RANK", raising=False)
+    monkeypatch.delenv("WORLD_SIZE", raising=False)
+    assert parallel.init_distributed(graph_capture=True)[:2] == (0, 1)
+    import os
+    assert os.environ.get("TORCH_NCCL_ASYNC_ERROR_HANDLING") == "0"
+    m = torch.nn.Linear(2, 2)
+    assert parallel.wrap_ddp(m, 0, graph_capture=True) is m        # world size 1: identity
