@@ -53,8 +53,9 @@ PDU_API const char* pdu_last_error(void);
 PDU_API int pdu_version(void);                       /* 10000*major + 100*minor + patch */
 PDU_API int pdu_device_info(int* sm_count, int* cc_major, int* cc_minor);
 /* Kernel-variant switches for A/B measurement ("radon_fwd_variant", "radon_adj_variant",
- * "filter_variant", "nufft_adj_variant"); value -1 restores the default.  Returns PDU_EINVAL for
- * an unknown key.  Never changes results beyond floating-point summation order. */
+ * "filter_variant", "nufft_fwd_variant", "nufft_adj_variant"); value -1 restores the default (the
+ * numbering is documented at each entry point's dispatch in csrc/).  Returns PDU_EINVAL for an
+ * unknown key.  Never changes results beyond floating-point rounding / summation order. */
 PDU_API int pdu_set_option(const char* key, int value);
 PDU_API int pdu_get_option(const char* key, int* value);
 /* Number of kernels this library launched (all threads of the process) since the last reset. */
@@ -81,8 +82,9 @@ typedef struct pdu_radon_geom {
  * [RECALL] torch_radon BaseRadon.__init__ does). */
 PDU_API int pdu_radon_trig_f32(const float* angles, float* trig, int n_angles, pdu_stream_t stream);
 
-/* Bytes of scratch the projectors want (a transposed copy of the batch for the forward
- * projector's horizontal-major views).  0 is a valid answer. */
+/* Bytes of scratch the forward projector wants: the bilinear-cell tensors of the batch and of its
+ * transpose, 2 * batch * (n+1)^2 * 16 bytes (the float-tile variants use the head of it for a
+ * transposed copy).  0 is a valid answer. */
 PDU_API size_t pdu_radon_workspace_bytes(const pdu_radon_geom_t* g, int batch);
 
 /* img [batch, n, n] -> sino [batch, n_angles, det_count].

@@ -2,10 +2,13 @@
 // Replaces [RECALL] torchkbnufft KbNufft / KbNufftAdjoint / KbInterp / KbInterpAdjoint, which are
 // compositions of ATen ops (complex multiply, pad, torch.fft, index arithmetic, index_add_).
 //
-//   forward :  apod_pad_kernel   image (* smaps) * scaling_coef -> zero-padded grid      (1 pass)
-//              FFT               oversampled grid, in place
+//   forward :  grids 512 / 640 (the BASELINE shapes): ff_rows_fwd_kernel (apodise, * smaps, pruned row FFT of the
+//                N non-zero rows) ; ff_cols_fwd_kernel (pruned column FFT)        -- pfft_fast.cuh, 2 passes
+//              other grids: apod_pad_kernel + cuFFT, or the generic pruned FFT of pfft.cuh (variant 1)
 //              interp_fwd_kernel J x J table-weighted gather per k-space sample, * phase
-//   adjoint :  memset grid ; interp_adj_kernel (scatter, float2 atomics) ; inverse FFT ;
+//   adjoint :  trajectory used more than once: sorted (CSR) gather interp_adj_csrT_kernel on plane-interleaved
+//                kdata -- no atomics, no memset, reproducible; else memset + interp_adj_kernel (float2 atomics)
+//              inverse FFT: ff_rows_adj_kernel / ff_cols_adj_kernel (only the N kept outputs per axis), or cuFFT
 //              crop_apod_kernel  crop * scaling_coef (* conj(smaps), summed over coils)
 //
 // Grid offsets and table indices are computed with explicitly rounded float32 operations, the same

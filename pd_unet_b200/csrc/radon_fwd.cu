@@ -2,17 +2,21 @@
 // radon_forward_kernel, which samples a layered CUDA texture; here the image is staged in shared
 // memory by TMA and interpolated in exact float32.
 //
-// variant 1 (default) -- "strip marching".  A CTA owns DB detectors x AG neighbouring views of
-//   one slice.  Rays are walked in the direction of increasing major coordinate (rows for
-//   mostly-vertical rays; for mostly-horizontal views the CTA reads a transposed copy of the slice
-//   so the same code applies) through horizontal strips of TH rows.  Before marching, every ray
-//   records its column extent in every strip it crosses (shared-memory atomicMin/Max), which fixes
-//   one (TH+1) x W box per strip; thread 0 streams those boxes with cp.async.bulk.tensor
-//   (zero fill outside the image = the texture "border" mode) through an NBUF-deep mbarrier ring
-//   while all threads sample the current box with four LDS per sample.  A strip whose extent does
-//   not fit W columns falls back to global loads for that strip only.
-// variant 0 -- one thread per ray, bilinear taps through L1 (__ldg).  Kept as the A/B baseline
-//   and for shapes TMA cannot describe (n % 4 != 0, unaligned base).
+// Strip marching (both tile formats).  A CTA owns DB detectors x AG neighbouring views of one slice.  Rays are
+//   walked in the direction of increasing major coordinate (rows for mostly-vertical rays; for
+//   mostly-horizontal views the CTA reads a transposed copy of the slice so the same code applies) through
+//   horizontal strips of TH rows.  Before marching, every ray records its column extent in every strip it
+//   crosses (warp-reduced, then shared-memory atomicMin/Max by one lane), which fixes one box per strip; a
+//   producer streams those boxes with cp.async.bulk.tensor (zero fill outside the image = the texture
+//   "border" mode) through an NBUF-deep mbarrier ring while the warps sample the current box.  A strip whose
+//   extent does not fit the box falls back to global loads for that strip only.
+// variants 7 .. 14 -- cell ("quad") tiles: one float4 per bilinear cell, one LDS.128 + four FMAs per sample
+//   (radon_fwd_quad_kernel; shape 13 is the default for dense view sets).
+// variants 1 .. 6 -- float tiles: (TH+1) x W floats, four LDS.32 per sample, boxes up to 248 columns wide
+//   (radon_fwd_strip_kernel; variant 1 = its own shape heuristic, the default for sparse view sets).
+// variant 0 -- one thread per ray, bilinear taps through L1 (__ldg).  Kept as the A/B baseline and for
+//   shapes neither tensor map can describe.
+// The dispatch and the measurements behind it: pdu_radon_fwd_f32 at the end of this file, DESIGN.md 3.1.
 #include <cuda.h>
 
 #include "radon_common.cuh"
