@@ -47,6 +47,24 @@ enum Opt { OPT_RADON_FWD = 0, OPT_RADON_ADJ = 1, OPT_FILTER = 2, OPT_NUFFT_ADJ =
 static inline long cdiv(long a, long b) { return (a + b - 1) / b; }
 
 #ifdef __CUDACC__
+// cudaFuncAttributeMaxDynamicSharedMemorySize once per (kernel, device, size): the attribute belongs to the device's
+// context, so a process that drives several GPUs must set it on each of them (a plain `static bool` did it once).
+// Kern is the kernel itself (non-type template parameter): one record per kernel instantiation.
+template <auto Kern>
+inline cudaError_t ensure_dyn_smem(int bytes) {
+    static int set_bytes[64] = {};             // per device ordinal; racing first calls repeat an idempotent call
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    int& rec = set_bytes[dev & 63];
+    if (rec >= bytes) return cudaSuccess;
+    e = cudaFuncSetAttribute(Kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) rec = bytes;
+    return e;
+}
+#endif
+
+#ifdef __CUDACC__
 // packed-FP32 helpers (sm_100 FFMA2 / FADD2): a 64-bit register holds (lo, hi) floats
 typedef unsigned long long ull;
 __device__ __forceinline__ ull pk2(float lo, float hi) { ull r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }

@@ -112,11 +112,7 @@ int pdu_filter_sinogram_f32(const float* sino, float* out, const float* taps, co
         return filter_tc_launch(sino, out, workspace, rows, D, variant, (cudaStream_t)stream);
     const size_t smem = ((size_t)(2 * D - 1 + 8 + 3) / 4 * 4 + (size_t)FILT_RB * D) * sizeof(float);
     PDU_REQUIRE(smem <= 200 * 1024, "pdu_filter_sinogram_f32: det_count %d too large for the shared-memory tile", D);
-    static bool attr_set = false;
-    if (!attr_set) {
-        PDU_CUDA(cudaFuncSetAttribute(filter_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set = true;
-    }
+    PDU_CUDA(ensure_dyn_smem<filter_direct_kernel>(200 * 1024));
     const long blocks = cdiv(rows, FILT_RB);
     PDU_REQUIRE(blocks <= 2147483647L, "pdu_filter_sinogram_f32: too many rows");
     filter_direct_kernel<<<(unsigned)blocks, 256, smem, (cudaStream_t)stream>>>(sino, out, taps, rows, D);

@@ -380,11 +380,7 @@ static int tc_launch(const float* sino, float* out, const void* ws, long rows, i
     rc = tc_make_map(&th, (const float*)ws, 3L * D, D, BK);     // the three pieces stacked by rows
     if (rc) return rc;
     const int smem = SYNTH ? TcCfg<SPLIT, BK>::smem_synth(D) : TcCfg<SPLIT, BK>::SMEM;
-    static int attr_set = 0;
-    if (attr_set < smem) {
-        PDU_CUDA(cudaFuncSetAttribute(filter_tc_kernel<SPLIT, SYNTH, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_set = smem;
-    }
+    PDU_CUDA((ensure_dyn_smem<filter_tc_kernel<SPLIT, SYNTH, BK>>(smem)));
     const float* tap_pieces = (const float*)ws + 3L * D * D;
     dim3 grid((unsigned)cdiv(rows, TC_BM), (unsigned)(D / TC_BN));
     filter_tc_kernel<SPLIT, SYNTH, BK><<<grid, TC_THREADS, smem, st>>>(tx, th, tap_pieces, out, rows, D, nullptr);

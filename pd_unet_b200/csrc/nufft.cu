@@ -571,12 +571,8 @@ static int ff_forward(pdu_nufft_plan* p, const float2* image, const float2* smap
     const NufftDims d = dims_of(p);
     auto rows = ff_rows_fwd_kernel<K, FF_SEQ_ROWS>;
     auto cols = ff_cols_fwd_kernel<K, FF_SEQ_COLS>;
-    static bool attr = false;
-    if (!attr) {
-        PDU_CUDA(cudaFuncSetAttribute(rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ff_smem_bytes<K>(FF_SEQ_ROWS)));
-        PDU_CUDA(cudaFuncSetAttribute(cols, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ff_smem_bytes<K>(FF_SEQ_COLS)));
-        attr = true;
-    }
+    PDU_CUDA((ensure_dyn_smem<ff_rows_fwd_kernel<K, FF_SEQ_ROWS>>((int)ff_smem_bytes<K>(FF_SEQ_ROWS))));
+    PDU_CUDA((ensure_dyn_smem<ff_cols_fwd_kernel<K, FF_SEQ_COLS>>((int)ff_smem_bytes<K>(FF_SEQ_COLS))));
     rows<<<dim3((unsigned)cdiv(p->n0, FF_SEQ_ROWS), (unsigned)planes), FF_SEQ_ROWS * FastFft<K>::TPS, ff_smem_bytes<K>(FF_SEQ_ROWS), st>>>(
         image, smaps, T, p->d_s0, p->d_s1, p->d_w1, d, coils, smaps_batch);
     PDU_LAUNCHED();
@@ -591,12 +587,8 @@ static int ff_adjoint(pdu_nufft_plan* p, const float2* grid, float2* T, float2* 
     const NufftDims d = dims_of(p);
     auto rows = ff_rows_adj_kernel<K, FF_SEQ_ROWS>;
     auto cols = ff_cols_adj_kernel<K, FF_SEQ_COLS>;
-    static bool attr = false;
-    if (!attr) {
-        PDU_CUDA(cudaFuncSetAttribute(rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ff_smem_bytes<K>(FF_SEQ_ROWS)));
-        PDU_CUDA(cudaFuncSetAttribute(cols, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ff_smem_bytes<K>(FF_SEQ_COLS)));
-        attr = true;
-    }
+    PDU_CUDA((ensure_dyn_smem<ff_rows_adj_kernel<K, FF_SEQ_ROWS>>((int)ff_smem_bytes<K>(FF_SEQ_ROWS))));
+    PDU_CUDA((ensure_dyn_smem<ff_cols_adj_kernel<K, FF_SEQ_COLS>>((int)ff_smem_bytes<K>(FF_SEQ_COLS))));
     rows<<<dim3((unsigned)cdiv(p->k0, FF_SEQ_ROWS), (unsigned)planes), FF_SEQ_ROWS * FastFft<K>::TPS, ff_smem_bytes<K>(FF_SEQ_ROWS), st>>>(
         grid, T, p->d_w1, d);
     PDU_LAUNCHED();

@@ -658,11 +658,7 @@ static int launch_strip(const float* img, const float* imgT, float* sino, const 
     rc = make_image_map(&tmT, imgT, batch, g.n, W, C::ROWS);
     if (rc) return rc;
     auto kern = radon_fwd_strip_kernel<DB, AG, TH, W, NBUF, LD, PK>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        PDU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-        attr_set = true;
-    }
+    PDU_CUDA((ensure_dyn_smem<radon_fwd_strip_kernel<DB, AG, TH, W, NBUF, LD, PK>>(C::SMEM)));
     dim3 grid((unsigned)cdiv(g.det_count, DB), (unsigned)cdiv(g.n_angles, AG), (unsigned)batch);
     kern<<<grid, C::THREADS, C::SMEM, st>>>(tm, tmT, img, imgT, sino, trig, g);
     PDU_LAUNCHED();
@@ -703,11 +699,7 @@ static int launch_quad(const float4* q, const float4* qt, float* sino, const flo
     rc = make_quad_map(&tmT, qt, batch, g.n + 1, W, TH);
     if (rc) return rc;
     auto kern = radon_fwd_quad_kernel<DB, AG, TH, W, NBUF, LD>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        PDU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-        attr_set = true;
-    }
+    PDU_CUDA((ensure_dyn_smem<radon_fwd_quad_kernel<DB, AG, TH, W, NBUF, LD>>(C::SMEM)));
     dim3 grid((unsigned)cdiv(g.det_count, DB), (unsigned)cdiv(g.n_angles, AG), (unsigned)batch);
     kern<<<grid, C::THREADS + 32, C::SMEM, st>>>(tm, tmT, q, qt, sino, trig, g);
     PDU_LAUNCHED();
