@@ -335,6 +335,8 @@ class _BiasAdd(torch.autograd.Function):
 def bias_add(y: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
     """Differentiable y + bias[c] for the output of a bias-free (transposed) convolution without activation; large
     channels-last maps take the in-place add and the two-stage channel sum, everything else the ATen ops."""
+    if not y.is_cuda:
+        raise PduError(f"y is on {y.device}: the pd_unet_b200 operators run on CUDA only (no CPU fallback)")
     Cn = y.shape[1] if y.dim() == 4 else 0
     if (y.is_cuda and y.dtype == torch.float32 and y.dim() == 4 and y.numel() >= fused_train_min_elems() and _is_channels_last(y)
             and Cn % 4 == 0 and Cn // 4 <= 64 and 256 % (Cn // 4) == 0 and bias.numel() == Cn and y.data_ptr() % 16 == 0
@@ -348,6 +350,8 @@ def bias_prelu(y: torch.Tensor, bias: torch.Tensor, slope: torch.Tensor) -> torc
     `bias_prelu_`.  One forward pass and one backward pass (input gradient + bias and slope gradients, reproducible)
     instead of ATen's bias add, PReLU, PReLU backward and two full-size reductions.  Shapes the fused kernels do
     not serve (planar layout, odd channel counts) go through the equivalent ATen ops on the GPU."""
+    if not y.is_cuda:
+        raise PduError(f"y is on {y.device}: the pd_unet_b200 operators run on CUDA only (no CPU fallback)")
     if _bias_prelu_train_ok(y, bias, slope) and y.numel() >= fused_train_min_elems():
         return _BiasPReLU.apply(y, bias, slope)
     return torch.nn.functional.prelu(y + bias.view((1, -1) + (1,) * (y.dim() - 2)), slope)

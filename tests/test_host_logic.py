@@ -121,3 +121,13 @@ def test_graph_capture_switch_sets_nccl_env(monkeypatch):
     assert os.environ.get("TORCH_NCCL_ASYNC_ERROR_HANDLING") == "0"
     m = torch.nn.Linear(2, 2)
     assert parallel.wrap_ddp(m, 0, graph_capture=True) is m        # world size 1: identity
+
+
+def test_training_epilogues_refuse_cpu_tensors():
+    """No CPU fallback: the differentiable epilogues raise on CPU tensors like every other operator wrapper."""
+    from pd_unet_b200 import updates, PduError
+    y = torch.zeros(1, 4, 3, 3)
+    with pytest.raises(PduError):
+        updates.bias_prelu(y, torch.zeros(4), torch.zeros(4))
+    with pytest.raises(PduError):
+        updates.bias_add(y, torch.zeros(4))
