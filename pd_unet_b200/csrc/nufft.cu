@@ -510,9 +510,9 @@ __global__ void __launch_bounds__(SEQ* FastFft<K>::TPS)
     const bool live = col < d.k1;
     const float2* src = T + p * d.n0 * d.k1 + col;
     float2* dst = grid + p * K * d.k1 + col;
-    auto ld = [&](int e) { return live ? __ldg(src + (long)e * d.k1) : make_float2(0.f, 0.f); };
+    auto ld = [&](int e) { return live ? __ldcs(src + (long)e * d.k1) : make_float2(0.f, 0.f); };
     auto st = [&](int e, float2 v) {
-        if (live) dst[(long)e * d.k1] = v;
+        if (live) __stcs(dst + (long)e * d.k1, v);
     };
     ff_transform<K, 3, false, true, false>(buf + s * F::template pitch<3>(), tw, t, ld, st);
 }
@@ -530,9 +530,9 @@ __global__ void __launch_bounds__(SEQ* FastFft<K>::TPS)
     const bool live = row < d.k0;
     const float2* src = grid + (p * d.k0 + row) * K;
     float2* dst = T + (p * d.k0 + row) * d.n1;
-    auto ld = [&](int e) { return live ? __ldg(src + e) : make_float2(0.f, 0.f); };
+    auto ld = [&](int e) { return live ? __ldcs(src + e) : make_float2(0.f, 0.f); };
     auto st = [&](int e, float2 v) {
-        if (live) dst[e] = v;
+        if (live) __stcs(dst + e, v);
     };
     ff_transform<K, 4, true, false, true>(buf + s * F::template pitch<4>(), tw, t, ld, st);
 }
@@ -550,9 +550,9 @@ __global__ void __launch_bounds__(SEQ* FastFft<K>::TPS)
     const bool live = col < d.n1;
     const float2* src = T + p * K * d.n1 + col;
     float2* dst = U + p * d.n0 * d.n1 + col;
-    auto ld = [&](int e) { return live ? __ldg(src + (long)e * d.n1) : make_float2(0.f, 0.f); };
+    auto ld = [&](int e) { return live ? __ldcs(src + (long)e * d.n1) : make_float2(0.f, 0.f); };
     auto st = [&](int e, float2 v) {
-        if (live) dst[(long)e * d.n1] = v;
+        if (live) __stcs(dst + (long)e * d.n1, v);
     };
     ff_transform<K, 3, true, false, true>(buf + s * F::template pitch<3>(), tw, t, ld, st);
 }
