@@ -487,7 +487,7 @@ __global__ void __launch_bounds__(DB* AG + 32)
         const float slope = lin ? (ub - ua) / dw : 0.f;
         const float umin = fminf(ua, ub), umax = fmaxf(ua, ub);
         const int kA_w = __reduce_min_sync(0xffffffffu, kA), kB_w = __reduce_max_sync(0xffffffffu, kB);
-        float wk = (float)(kA_w * TH);
+        float wk = (float)((kA_w <= kB_w ? kA_w : 0) * TH);      // (no valid ray in the warp: kA_w == INT_MAX, loop empty)
         int Fk = (int)floorf(lin ? fminf(fmaxf(fmaf(wk - wa, slope, ua), umin), umax) : umin);
         for (int k = kA_w; k <= kB_w; ++k) {
             wk += (float)TH;
