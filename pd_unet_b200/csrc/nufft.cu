@@ -498,7 +498,7 @@ __global__ void __launch_bounds__(SEQ* FastFft<K>::TPS)
 }
 
 template <int K, int SEQ>
-__global__ void __launch_bounds__(SEQ* FastFft<K>::TPS)
+__global__ void __launch_bounds__(SEQ* FastFft<K>::TPS, 3)
     ff_cols_fwd_kernel(const float2* __restrict__ T, float2* __restrict__ grid, const float2* __restrict__ tw_g, NufftDims d) {
     using F = FastFft<K>;
     float2* buf = pf_smem<float2>();
@@ -538,7 +538,7 @@ __global__ void __launch_bounds__(SEQ* FastFft<K>::TPS)
 }
 
 template <int K, int SEQ>
-__global__ void __launch_bounds__(SEQ* FastFft<K>::TPS)
+__global__ void __launch_bounds__(SEQ* FastFft<K>::TPS, 3)
     ff_cols_adj_kernel(const float2* __restrict__ T, float2* __restrict__ U, const float2* __restrict__ tw_g, NufftDims d) {
     using F = FastFft<K>;
     float2* buf = pf_smem<float2>();
