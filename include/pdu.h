@@ -60,6 +60,19 @@ PDU_API int pdu_set_option(const char* key, int value);
 PDU_API int pdu_get_option(const char* key, int* value);
 /* Number of kernels this library launched (all threads of the process) since the last reset. */
 PDU_API long pdu_launch_count(int reset);
+/* Device-side failure word.  A kernel whose TMA / mbarrier pipeline wait times out (a fault, a
+ * regression) stores a non-zero code in a word of mapped host memory and abandons its tile instead
+ * of producing numbers from an unfilled buffer.  While the word is set every compute entry point
+ * returns PDU_ECUDA (checked on entry: a plain host read, no synchronisation; the failing launch
+ * itself has already returned PDU_OK, so callers that must know synchronise and call this).
+ * Returns the code (0 = none, 1 = forward projector, 2 = tensor-core filter, 3 = NUFFT);
+ * reset != 0 clears it.  Option "debug_fault" = 1 makes the TMA producers of those kernels skip
+ * their loads so that the path can be tested. */
+PDU_API int pdu_device_error(int reset);
+/* Name and shape of the kernel the dispatcher of an operator chose in this thread's most recent
+ * call: op in {"radon_fwd", "radon_adj", "filter", "nufft_fwd", "nufft_adj"}; "" before the first
+ * call.  The string stays valid until the thread's next call of that operator. */
+PDU_API const char* pdu_last_kernel(const char* op);
 
 /* ------------------------------------------------------------------ CT ---- */
 enum { PDU_GEOM_PARALLEL = 0, PDU_GEOM_FAN = 1 };
@@ -111,6 +124,13 @@ PDU_API int pdu_filter_prepare_f32(const float* taps, void* workspace, size_t wo
 PDU_API int pdu_filter_sinogram_f32(const float* sino, float* out, const float* taps,
                                     const void* workspace, size_t workspace_bytes, long rows,
                                     int det_count, pdu_stream_t stream);
+/* The same with sino[r, j] first multiplied by col_weight[j] (float[det_count], nullable) inside the
+ * kernel: the cosine pre-weight of fan-beam FBP (Kak & Slaney eq. 3.3.2-(95) for a flat equispaced
+ * detector) without a separate pass over the sinogram. */
+PDU_API int pdu_filter_sinogram_weighted_f32(const float* sino, float* out, const float* taps,
+                                             const float* col_weight, const void* workspace,
+                                             size_t workspace_bytes, long rows, int det_count,
+                                             pdu_stream_t stream);
 
 /* ----------------------------------------------------------------- MRI ---- */
 typedef struct pdu_nufft_plan pdu_nufft_plan_t;

@@ -60,31 +60,47 @@ class NufftSpec:
         return self.kbwidth * self.numpoints
 
 
+# kb_table / scaling_coef are written independently of pd_unet_b200/nufft.py on purpose: the
+# product evaluates np.i0 on a vector grid and the closed-form transform sinh(w)/w; here the kernel goes through the
+# exponentially scaled Bessel function entry by entry, and the apodisation is the kernel's Fourier transform by
+# Gauss-Legendre quadrature -- which also checks the closed form itself.
+def _kb(u: float, J: int, alpha: float) -> float:
+    """Kaiser-Bessel kernel of order 0 and width J at offset u (grid units): I0(alpha sqrt(1 - (2u/J)^2)) / I0(alpha)."""
+    r = 2.0 * u / J
+    if abs(r) >= 1.0:
+        return 0.0
+    s = math.sqrt(1.0 - r * r)
+    # I0(x) = i0e(x) e^x: the ratio stays in range for any alpha
+    return float(special.i0e(alpha * s) / special.i0e(alpha) * math.exp(alpha * (s - 1.0)))
+
+
 def kb_table(spec: NufftSpec, dim: int) -> np.ndarray:
-    """complex128 [J*L + 1]; entry q is the coefficient at u = q / L - J / 2."""
+    """complex128 [J*L + 1]; entry q is the coefficient at u = (q - J L / 2) / L: the kernel times the linear phase
+    exp(-i (2 pi / K) ((N - 1) / 2) u) that centres the image ([RECALL] Fessler's / torchkbnufft's table)."""
     s = spec.resolved()
     J, L = s.numpoints, s.table_oversamp
     N, K = s.im_size[dim], s.grid_size[dim]
-    u = np.arange(J * L + 1, dtype=np.float64) / L - J / 2.0
-    inside = np.abs(u) < J / 2.0
-    arg = np.sqrt(np.where(inside, 1.0 - (u / (J / 2.0)) ** 2, 0.0))
-    kb = np.where(inside, special.iv(0, s.alpha * arg) / special.iv(0, s.alpha), 0.0)
-    phase = np.exp(-1j * (2.0 * np.pi / K) * ((N - 1) / 2.0) * u)
-    return kb * phase
+    half = (J * L) // 2
+    out = np.empty(J * L + 1, dtype=np.complex128)
+    slope = (2.0 * math.pi / K) * ((N - 1) / 2.0)
+    for q in range(J * L + 1):
+        u = (q - half) / L
+        out[q] = _kb(u, J, s.alpha) * complex(math.cos(slope * u), -math.sin(slope * u))
+    return out
 
 
-def scaling_coef(spec: NufftSpec, dim: int) -> np.ndarray:
-    """float64 [N]: reciprocal of the kernel's Fourier transform at (n - (N-1)/2)/K."""
+def scaling_coef(spec: NufftSpec, dim: int, nodes: int = 96) -> np.ndarray:
+    """float64 [N]: 1 / FT{kb}((n - (N-1)/2) / K), the transform taken numerically:
+    FT(f) = int_{-J/2}^{J/2} kb(u) cos(2 pi f u) du by Gauss-Legendre quadrature (the integrand is smooth inside the
+    support and the kernel is even; 96 nodes reach 1e-15 relative for J = 6, alpha = 14)."""
     s = spec.resolved()
     J = s.numpoints
     N, K = s.im_size[dim], s.grid_size[dim]
-    om = (np.arange(N, dtype=np.float64) - (N - 1) / 2.0) / K
-    w2 = s.alpha ** 2 - (np.pi * J * om) ** 2
-    w = np.sqrt(np.abs(w2))
-    with np.errstate(divide="ignore", invalid="ignore"):
-        ratio = np.where(w2 > 0, np.sinh(w) / w, np.sin(w) / w)
-    ratio = np.where(w == 0, 1.0, ratio)
-    ft = J * ratio / special.iv(0, s.alpha)
+    x, w = np.polynomial.legendre.leggauss(nodes)
+    u = 0.5 * J * x                                              # [-J/2, J/2]
+    kb = np.array([_kb(float(v), J, s.alpha) for v in u])
+    f = (np.arange(N, dtype=np.float64) - (N - 1) / 2.0) / K
+    ft = (np.cos(2.0 * np.pi * f[:, None] * u[None, :]) * (kb * w)[None, :]).sum(1) * (0.5 * J)
     return 1.0 / ft
 
 

@@ -234,28 +234,62 @@ def radon_backprojection(sino, trig: np.ndarray, g: RadonGeom, angle_chunk: int 
 # ----------------------------------------------------------------------------
 # sinogram filtering ([RECALL] torch_radon filter_sinogram + scikit-image filters)
 # ----------------------------------------------------------------------------
-def _fourier_filter(size: int, name: str) -> np.ndarray:
-    n = np.concatenate((np.arange(1, size / 2 + 1, 2, dtype=np.int64),
-                        np.arange(size / 2 - 1, 0, -2, dtype=np.int64)))
+# Written independently of pd_unet_b200/radon.py on purpose: the product builds the response
+# the scikit-image way (np.fft of a constant table, np.hamming / np.hanning, np.fft.fftshift); here every quantity
+# comes from its closed form and plain cosine sums, so a test that compares the two compares two constructions.
+def _ramp_kernel(size: int) -> np.ndarray:
+    """Kak & Slaney eq. 61: the band-limited ramp sampled at the integers, laid out circularly on `size` points:
+    f[0] = 1/4, f[k] = -1 / (pi d)^2 for odd distance d = min(k, size - k), 0 for even d."""
+    k = np.arange(size)
+    d = np.minimum(k, size - k).astype(np.float64)
     f = np.zeros(size)
+    odd = (d % 2) == 1
+    f[odd] = -1.0 / (np.pi * d[odd]) ** 2
     f[0] = 0.25
-    f[1::2] = -1.0 / (np.pi * n) ** 2
-    ff = 2.0 * np.real(np.fft.fft(f))
+    return f
+
+
+def _cos_sum(values: np.ndarray, chunk: int = 256) -> np.ndarray:
+    """out[i] = sum_k values[k] cos(2 pi i k / P): a real DFT of an even sequence without an FFT.  The angle is
+    reduced with integer arithmetic ((i k) mod P) before the cosine, so the sum is accurate to ~1e-16 P."""
+    P = values.shape[0]
+    k = np.arange(P, dtype=np.int64)
+    out = np.empty(P)
+    for i0 in range(0, P, chunk):
+        i = np.arange(i0, min(P, i0 + chunk), dtype=np.int64)
+        out[i0:i0 + i.size] = np.cos((2.0 * np.pi / P) * ((i[:, None] * k[None, :]) % P)) @ values
+    return out
+
+
+_RESP_CACHE = {}
+
+
+def _fourier_filter(size: int, name: str) -> np.ndarray:
+    """Frequency response on `size` (even) points: 2 DFT(ramp kernel), times the named window.  Windows are written
+    out as functions of the centred frequency index c = (i + size/2) mod size (what np.fft.fftshift of a symmetric
+    window amounts to)."""
     name = name.lower()
+    key = (size, name)
+    if key in _RESP_CACHE:
+        return _RESP_CACHE[key]
+    ff = 2.0 * _cos_sum(_ramp_kernel(size))
+    i = np.arange(size)
+    c = (i + size // 2) % size
     if name in ("ramp", "ram-lak"):
         pass
     elif name == "shepp-logan":
-        omega = np.pi * np.fft.fftfreq(size)[1:]
-        ff[1:] *= np.sin(omega) / omega
+        freq = np.where(i < size - size // 2, i, i - size) / size          # cycles per sample, as np.fft.fftfreq
+        om = np.pi * freq[1:]
+        ff[1:] = ff[1:] * np.sin(om) / om
     elif name == "cosine":
-        freq = np.linspace(0, np.pi, size, endpoint=False)
-        ff *= np.fft.fftshift(np.sin(freq))
+        ff = ff * np.sin(np.pi * c / size)
     elif name == "hamming":
-        ff *= np.fft.fftshift(np.hamming(size))
+        ff = ff * (0.54 - 0.46 * np.cos(2.0 * np.pi * c / (size - 1)))
     elif name == "hann":
-        ff *= np.fft.fftshift(np.hanning(size))
+        ff = ff * (0.5 - 0.5 * np.cos(2.0 * np.pi * c / (size - 1)))
     else:
         raise ValueError(f"unknown filter {name!r}")
+    _RESP_CACHE[key] = ff
     return ff
 
 
@@ -263,11 +297,25 @@ def padded_size(det_count: int) -> int:
     return max(64, int(2 ** math.ceil(math.log2(2 * det_count))))
 
 
+_TAPS_CACHE = {}
+
+
 def filter_taps(det_count: int, name: str = "ramp") -> np.ndarray:
+    key = (det_count, name.lower())
+    if key not in _TAPS_CACHE:
+        _TAPS_CACHE[key] = _filter_taps(det_count, name)
+    return _TAPS_CACHE[key].copy()
+
+
+def _filter_taps(det_count: int, name: str = "ramp") -> np.ndarray:
     """Spatial taps h[-(D-1) .. D-1] (length 2D-1, float64) such that the padded
-    circular FFT filter equals the linear convolution q[i] = sum_j p[j] h[i-j]."""
+    circular FFT filter equals the linear convolution q[i] = sum_j p[j] h[i-j].
+    ramp: straight from the closed form (h = 2 x ramp kernel); windowed: inverse cosine sum of the response."""
     P = padded_size(det_count)
-    h = np.real(np.fft.ifft(_fourier_filter(P, name)))        # circular kernel, length P >= 2D
+    if name.lower() in ("ramp", "ram-lak"):
+        h = 2.0 * _ramp_kernel(P)
+    else:
+        h = _cos_sum(_fourier_filter(P, name)) / P                          # response is real and even
     k = np.arange(-(det_count - 1), det_count)
     return h[k % P]
 
@@ -280,8 +328,9 @@ def filter_matrix(det_count: int, n_angles: int, name: str = "ramp") -> np.ndarr
     return t[(i - j) + det_count - 1] * (np.pi / (2.0 * n_angles))
 
 
-def filter_sinogram(sino, name: str = "ramp") -> torch.Tensor:
-    """[..., A, D] float64, the FFT route exactly as [RECALL] torch_radon does it."""
+def filter_sinogram_fft(sino, name: str = "ramp") -> torch.Tensor:
+    """[..., A, D] float64, the FFT route as [RECALL] torch_radon does it: zero-pad to a power of two >= 2 D,
+    multiply the spectrum by the response, inverse, crop, scale by pi / (2 A)."""
     sino = torch.as_tensor(sino, dtype=torch.float64)
     D = sino.shape[-1]
     A = sino.shape[-2]
@@ -290,6 +339,23 @@ def filter_sinogram(sino, name: str = "ramp") -> torch.Tensor:
     pad = torch.nn.functional.pad(sino, (0, P - D))
     q = torch.fft.ifft(torch.fft.fft(pad, dim=-1) * ff, dim=-1).real
     return q[..., :D] * (math.pi / (2.0 * A))
+
+
+def filter_sinogram(sino, name: str = "ramp") -> torch.Tensor:
+    """[..., A, D] float64: the same filter as the linear convolution it is, out = sino @ H (no FFT anywhere on this
+    route; tests/test_oracle_radon.py checks it against filter_sinogram_fft)."""
+    sino = torch.as_tensor(sino, dtype=torch.float64)
+    D, A = sino.shape[-1], sino.shape[-2]
+    return sino @ torch.from_numpy(filter_matrix(D, A, name))
+
+
+def fan_cosine_weights(g: RadonGeom) -> np.ndarray:
+    """float64 [D]: the pre-weight of fan-beam FBP for a flat equispaced detector (Kak & Slaney section 3.4.2): with the
+    detector scaled back to the rotation centre, s' = u s / (s + d), the projection is multiplied by
+    s / sqrt(s^2 + s'^2) = (s + d) / sqrt((s + d)^2 + u^2), the cosine of the ray's fan angle."""
+    u = (np.arange(g.det_count, dtype=np.float64) + 0.5 - g.det_count / 2.0) * g.det_spacing
+    k = float(g.s_dist) + float(g.d_dist)
+    return k / np.sqrt(k * k + u * u)
 
 
 def fbp(sino, trig, g: RadonGeom, name: str = "ramp") -> torch.Tensor:

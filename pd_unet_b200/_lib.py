@@ -38,6 +38,8 @@ SIGNATURES = {
     "pdu_set_option": (C.c_int, [C.c_char_p, C.c_int]),
     "pdu_get_option": (C.c_int, [C.c_char_p, C.POINTER(C.c_int)]),
     "pdu_launch_count": (C.c_long, [C.c_int]),
+    "pdu_device_error": (C.c_int, [C.c_int]),
+    "pdu_last_kernel": (C.c_char_p, [C.c_char_p]),
     "pdu_radon_trig_f32": (C.c_int, [_p, _p, C.c_int, _p]),
     "pdu_radon_workspace_bytes": (C.c_size_t, [_G, C.c_int]),
     "pdu_radon_fwd_f32": (C.c_int, [_p, _p, _p, C.c_int, _G, _p, C.c_size_t, _p]),
@@ -45,6 +47,7 @@ SIGNATURES = {
     "pdu_filter_workspace_bytes": (C.c_size_t, [C.c_int]),
     "pdu_filter_prepare_f32": (C.c_int, [_p, _p, C.c_size_t, C.c_int, _p]),
     "pdu_filter_sinogram_f32": (C.c_int, [_p, _p, _p, _p, C.c_size_t, C.c_long, C.c_int, _p]),
+    "pdu_filter_sinogram_weighted_f32": (C.c_int, [_p, _p, _p, _p, _p, C.c_size_t, C.c_long, C.c_int, _p]),
     "pdu_nufft_plan_create": (C.c_int, [C.POINTER(_p), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                         C.c_int, C.c_int, _p, _p, _p, _p]),
     "pdu_nufft_plan_destroy": (C.c_int, [_p]),
@@ -122,3 +125,14 @@ def set_option(key: str, value: int) -> None:
 
 def launch_count(reset: bool = False) -> int:
     return int(lib().pdu_launch_count(1 if reset else 0))
+
+
+def last_kernel(op: str) -> str:
+    """The kernel (name, template shape, grid) the dispatcher of `op` chose in this thread's most recent call."""
+    v = lib().pdu_last_kernel(op.encode())
+    return v.decode() if v else ""
+
+
+def device_error(reset: bool = False) -> int:
+    """Non-zero if a kernel reported a pipeline time-out since the last reset (include/pdu.h)."""
+    return int(lib().pdu_device_error(1 if reset else 0))

@@ -13,7 +13,8 @@ namespace pdu {
 
 static thread_local char g_err[512] = "";
 static std::atomic<long> g_launches{0};
-static std::atomic<int> g_opts[OPT_COUNT] = {{-1}, {-1}, {-1}, {-1}, {-1}};
+static std::atomic<int> g_opts[OPT_COUNT] = {{-1}, {-1}, {-1}, {-1}, {-1}, {-1}, {-1}};
+static thread_local char g_kernel[OP_COUNT][192];
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -27,7 +28,8 @@ int option(int which) {
     const int v = g_opts[which].load(std::memory_order_relaxed);
     if (v >= 0) return v;
     static const char* names[OPT_COUNT] = {"PDU_RADON_FWD_VARIANT", "PDU_RADON_ADJ_VARIANT", "PDU_FILTER_VARIANT",
-                                           "PDU_NUFFT_ADJ_VARIANT", "PDU_NUFFT_FWD_VARIANT"};
+                                           "PDU_NUFFT_ADJ_VARIANT", "PDU_NUFFT_FWD_VARIANT", "PDU_DEBUG_FAULT",
+                                           "PDU_TEX_WEIGHTS"};
     static int env[OPT_COUNT];
     static std::once_flag once;
     std::call_once(once, [] {
@@ -39,6 +41,40 @@ int option(int which) {
     return env[which];
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+void note_kernel(int op, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_kernel[op], sizeof(g_kernel[op]), fmt, ap);
+    va_end(ap);
+}
+
+int* device_error_word() {
+    static int* word = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        if (cudaHostAlloc(&p, 64, cudaHostAllocMapped | cudaHostAllocPortable) == cudaSuccess) {
+            memset(p, 0, 64);
+            word = (int*)p;
+        } else {
+            (void)cudaGetLastError();
+        }
+    });
+    return word;
+}
+
+int check_device_error(const char* who) {
+    int* w = device_error_word();
+    const int code = w ? *(volatile int*)w : 0;
+    if (code == DEV_ERR_NONE) return PDU_OK;
+    static const char* what[] = {"", "forward projector (TMA / mbarrier wait timed out)",
+                                 "tensor-core sinogram filter (TMA / MMA pipeline wait timed out)",
+                                 "NUFFT (TMA / mbarrier wait timed out)"};
+    set_error("%s: an earlier kernel reported a device-side failure: %s; its output is invalid "
+              "(pdu_device_error(1) clears the flag)", who, what[code >= 0 && code <= 3 ? code : 0]);
+    return PDU_ECUDA;
+}
 
 int sm_count() {
     static thread_local int cached_dev = -1, cached = 0;
@@ -60,6 +96,8 @@ static int opt_index(const char* key) {
     if (!strcmp(key, "filter_variant")) return OPT_FILTER;
     if (!strcmp(key, "nufft_adj_variant")) return OPT_NUFFT_ADJ;
     if (!strcmp(key, "nufft_fwd_variant")) return OPT_NUFFT_FWD;
+    if (!strcmp(key, "debug_fault")) return OPT_DEBUG_FAULT;
+    if (!strcmp(key, "tex_weights")) return OPT_TEX_WEIGHTS;
     return -1;
 }
 
@@ -102,6 +140,22 @@ int pdu_get_option(const char* key, int* value) {
     PDU_REQUIRE(i >= 0 && value, "pdu_get_option: unknown key '%s'", key ? key : "(null)");
     *value = pdu::g_opts[i].load(std::memory_order_relaxed);
     return PDU_OK;
+}
+
+int pdu_device_error(int reset) {
+    int* w = pdu::device_error_word();
+    if (!w) return 0;
+    const int code = *(volatile int*)w;
+    if (reset) *(volatile int*)w = 0;
+    return code;
+}
+
+const char* pdu_last_kernel(const char* op) {
+    static const char* names[pdu::OP_COUNT] = {"radon_fwd", "radon_adj", "filter", "nufft_fwd", "nufft_adj"};
+    if (!op) return "";
+    for (int i = 0; i < pdu::OP_COUNT; ++i)
+        if (!strcmp(op, names[i])) return pdu::g_kernel[i];
+    return "";
 }
 
 long pdu_launch_count(int reset) {

@@ -4,8 +4,8 @@
 // so it is done directly as a Toeplitz contraction and the sinogram makes one round trip through HBM
 // instead of the FFT route's three.
 //
-// variant 1 (default when det_count % 128 == 0) -- 3xTF32 GEMM on tcgen05 tensor cores: filter_tc.cu.
-//   Measured on B200 (8192 x 256 rows): 16.4 us against 47.1 us for variant 0.
+// variant 1 (default when det_count % 128 == 0) -- exact split-TF32 GEMM on tcgen05 tensor cores: filter_tc.cu.
+//   Measured on B200 (8192 x 256 rows): 20.5 us against 47.1 us for variant 0.
 // variant 0 -- register-tiled FP32 contraction on the CUDA cores.  A CTA owns RB rows; the rows
 //   and the 2D-1 taps sit in shared memory; a thread produces a 4 (rows) x 4 (adjacent outputs)
 //   patch, sliding a 4-tap window so every inner step costs 4 broadcast row loads + 1 tap load for
@@ -18,14 +18,14 @@ namespace pdu {
 bool filter_tc_supported(int D);
 size_t filter_tc_workspace_bytes(int D);
 int filter_tc_prepare(const float* taps, void* ws, size_t ws_bytes, int D, cudaStream_t st);
-int filter_tc_launch(const float* sino, float* out, const void* ws, long rows, int D, int mode, cudaStream_t st);
+int filter_tc_launch(const float* sino, float* out, const void* ws, const float* col_weight, long rows, int D, cudaStream_t st);
 
 constexpr int FILT_RB = 16;   // rows per CTA
 
 // dynamic smem: taps[2D+6] (zero padded by 3 in front, 4 behind) | rows[RB][D]
 __global__ void __launch_bounds__(256)
     filter_direct_kernel(const float* __restrict__ sino, float* __restrict__ out, const float* __restrict__ taps,
-                         long rows, int D) {
+                         const float* __restrict__ col_weight, long rows, int D) {
     extern __shared__ float s_f[];
     const int TL = 2 * D - 1;
     float* s_taps = s_f;                 // s_taps[3 + k] = taps[k]
@@ -38,7 +38,9 @@ __global__ void __launch_bounds__(256)
     }
     for (int i = threadIdx.x; i < FILT_RB * D; i += blockDim.x) {
         const int r = i / D;
-        s_rows[i] = r < nr ? __ldg(sino + r0 * D + i) : 0.f;
+        float v = r < nr ? __ldg(sino + r0 * D + i) : 0.f;
+        if (col_weight) v *= __ldg(col_weight + (i - r * D));
+        s_rows[i] = v;
     }
     __syncthreads();
     // patches: (FILT_RB / 4) row groups x ceil(D / 4) column groups
@@ -99,25 +101,34 @@ int pdu_filter_prepare_f32(const float* taps, void* workspace, size_t workspace_
     return filter_tc_prepare(taps, workspace, workspace_bytes, det_count, (cudaStream_t)stream);
 }
 
-int pdu_filter_sinogram_f32(const float* sino, float* out, const float* taps, const void* workspace,
-                            size_t workspace_bytes, long rows, int det_count, pdu_stream_t stream) {
+int pdu_filter_sinogram_weighted_f32(const float* sino, float* out, const float* taps, const float* col_weight,
+                                     const void* workspace, size_t workspace_bytes, long rows, int det_count,
+                                     pdu_stream_t stream) {
+    PDU_CHECK_DEVICE("pdu_filter_sinogram_f32");
     PDU_REQUIRE(sino && out && taps, "pdu_filter_sinogram_f32: null pointer");
     PDU_REQUIRE(rows > 0 && det_count > 0, "pdu_filter_sinogram_f32: rows and det_count must be > 0");
     PDU_REQUIRE(sino != out, "pdu_filter_sinogram_f32: in-place filtering is not supported");
     const int D = det_count;
     int variant = option(OPT_FILTER);
-    if (variant < 0) variant = 1;      // 1 = tcgen05 split-TF32 GEMM, exact products (filter_tc.cu); 2 = its 3-product A/B form
-    if (variant >= 1 && variant <= 5 && filter_tc_supported(D) && workspace && workspace_bytes >= filter_tc_workspace_bytes(D) &&
-        (((uintptr_t)sino | (uintptr_t)out | (uintptr_t)workspace) & 15) == 0)
-        return filter_tc_launch(sino, out, workspace, rows, D, variant, (cudaStream_t)stream);
+    if (variant < 0) variant = 1;      // 1 = tcgen05 split-TF32 GEMM, exact products (filter_tc.cu); 0 = CUDA cores
+    if (variant >= 1 && filter_tc_supported(D) && workspace && workspace_bytes >= filter_tc_workspace_bytes(D) &&
+        (((uintptr_t)sino | (uintptr_t)out | (uintptr_t)workspace | (uintptr_t)col_weight) & 15) == 0)
+        return filter_tc_launch(sino, out, workspace, col_weight, rows, D, (cudaStream_t)stream);
     const size_t smem = ((size_t)(2 * D - 1 + 8 + 3) / 4 * 4 + (size_t)FILT_RB * D) * sizeof(float);
     PDU_REQUIRE(smem <= 200 * 1024, "pdu_filter_sinogram_f32: det_count %d too large for the shared-memory tile", D);
     PDU_CUDA(ensure_dyn_smem<filter_direct_kernel>(200 * 1024));
     const long blocks = cdiv(rows, FILT_RB);
     PDU_REQUIRE(blocks <= 2147483647L, "pdu_filter_sinogram_f32: too many rows");
-    filter_direct_kernel<<<(unsigned)blocks, 256, smem, (cudaStream_t)stream>>>(sino, out, taps, rows, D);
+    filter_direct_kernel<<<(unsigned)blocks, 256, smem, (cudaStream_t)stream>>>(sino, out, taps, col_weight, rows, D);
     PDU_LAUNCHED();
+    note_kernel(OP_FILTER, "filter_direct_kernel grid %ld (CUDA-core Toeplitz contraction, det_count %% 128 != 0)%s", blocks,
+                col_weight ? " + fused detector weight" : "");
     return PDU_OK;
+}
+
+int pdu_filter_sinogram_f32(const float* sino, float* out, const float* taps, const void* workspace,
+                            size_t workspace_bytes, long rows, int det_count, pdu_stream_t stream) {
+    return pdu_filter_sinogram_weighted_f32(sino, out, taps, nullptr, workspace, workspace_bytes, rows, det_count, stream);
 }
 
 }  // extern "C"

@@ -3,16 +3,17 @@
 // linear filtering; here the detector rows are staged in shared memory and interpolated in exact
 // float32.
 //
-// variant 1 (default) -- a CTA owns a TX x TY pixel tile of one slice (each thread PY = 8 pixels in a
+// variant 3 (default) -- a CTA owns a TX x TY pixel tile of one slice (each thread PY = 8 pixels in a
 //   column of the tile).  Views are consumed in chunks of AC: for every view of the chunk the CTA
 //   computes, in float64 and relative to the tile, the detector interval the tile projects onto and
-//   copies it -- zero filled outside [0, D) (the texture "border" mode), as (value, next - value)
-//   pairs -- into a SEG-entry shared row; then every pixel takes its tap per view with one 8-byte
-//   load and one FMA, two pixels per packed-FP32 instruction, no bounds test.
+//   copies it -- zero filled outside [0, D) (the texture "border" mode), in LINE FORM (A, B) with
+//   tap(t) = A + t B -- into a SEG-entry shared row; then every pixel takes its tap per view with one
+//   8-byte load and one FMA, two pixels per packed-FP32 instruction, no bounds test.
 //   A chunk in which some view's interval does not fit SEG entries is served from global memory.
-// variant 2 -- the same with 4 pixels per thread (A/B).
 // variant 0 -- every tap from global memory with float64 coordinates (slow; the reference form of
 //   the fallback above).
+// (r01 also carried the (value, difference) tap form with 8 and 4 pixels per thread and a forced 96-entry
+//  segment -- 254 / 281 / 194 us against 182 -- deleted in r02.)
 #include "common.cuh"
 
 namespace pdu {
@@ -34,8 +35,8 @@ struct AdjGeom {
 // fit its shared segment: wide magnification near the source, coarse detectors) evaluates the detector
 // coordinate in float64 and splits it into integer tap and float32 fraction, so it is as accurate as the
 // tile-relative shared-memory path no matter how large the coordinate gets.
-__device__ __noinline__ float tap_global(const AdjGeom& g, const float* __restrict__ row, float cs, float sn, float dx,
-                                            float dy) {
+__device__ __forceinline__ float tap_global_inl(const AdjGeom& g, const float* __restrict__ row, float cs, float sn, float dx,
+                                                float dy) {
     const double p = (double)cs * dx + (double)sn * dy;
     const double ids = 1.0 / (double)g.det_spacing;
     double t, w = 1.0;
@@ -52,6 +53,16 @@ __device__ __noinline__ float tap_global(const AdjGeom& g, const float* __restri
     const float s0 = (unsigned)i0 < (unsigned)D ? __ldg(row + i0) : 0.f;
     const float s1 = (unsigned)(i0 + 1) < (unsigned)D ? __ldg(row + i0 + 1) : 0.f;
     return (float)w * fmaf(fr, s1 - s0, s0);
+}
+// Inlined into the parallel-beam tile kernel (no stack frame, no spill: ptxas -v), called from the fan-beam one
+// (there the inlined float64 sequence would push the tap loop's registers over the 5-CTAs-per-SM cap).
+__device__ __noinline__ float tap_global_call(const AdjGeom& g, const float* __restrict__ row, float cs, float sn, float dx,
+                                              float dy) {
+    return tap_global_inl(g, row, cs, sn, dx, dy);
+}
+template <bool CALL>
+__device__ __forceinline__ float tap_global(const AdjGeom& g, const float* __restrict__ row, float cs, float sn, float dx, float dy) {
+    return CALL ? tap_global_call(g, row, cs, sn, dx, dy) : tap_global_inl(g, row, cs, sn, dx, dy);
 }
 
 template <int TX, int TY, int PY>
@@ -73,7 +84,7 @@ __global__ void __launch_bounds__(TX*(TY / PY))
 #pragma unroll
             for (int k = 0; k < PY; ++k) {
                 const float dy = (float)(y0 + k * (TY / PY)) - g.half;
-                acc[k] += tap_global(g, row, cs, sn, dx, dy);
+                acc[k] += tap_global<true>(g, row, cs, sn, dx, dy);
             }
         }
     }
@@ -96,9 +107,7 @@ __global__ void __launch_bounds__(TX*(TY / PY))
 // (lx, ly) = pixel offset inside the tile, lo = first detector bin of the staged segment.
 // parallel beam: cap the registers so that 7 (PY = 8) / 3 (PY = 4) CTAs fit an SM -- B N^2 / PY threads then
 // make one balanced wave; the rarely taken float64 fallback is what would otherwise raise the count
-// MODE 0 (r01): the segment holds (value, next - value) and the tap is value + frac * diff: floor, fraction, masked
-//   index -- 7 instructions per tap.
-// MODE 1: the segment holds the line through the two samples in the segment's own coordinate, (A, B) with
+// The segment holds the line through the two samples in the segment's own coordinate, (A, B) with
 //   tap(t) = A + t B, A = value - c B for entry c.  No fraction is needed, only floor(t) for the index, and the byte
 //   address comes from the magic-number bit pattern with one IMAD (the constant exponent part is folded into the
 //   per-view base, mod 2^32): 4.5 instructions per tap.  A is rounded at the magnitude of c |B| (c < SEG = 96),
@@ -157,7 +166,7 @@ __device__ __forceinline__ void fan_taps_line(const float* __restrict__ view, ui
     }
 }
 
-template <int TX, int TY, int PY, int AC, int SEG, bool FAN, int MODE = 0>
+template <int TX, int TY, int PY, int AC, int SEG, bool FAN>
 __global__ void __launch_bounds__(TX*(TY / PY), FAN ? (PY == 8 ? 5 : 2) : (PY == 8 ? 7 : 3))
     radon_adj_tile_kernel(const float* __restrict__ sino, float* __restrict__ img, const float* __restrict__ trig,
                           const AdjGeom g) {
@@ -185,7 +194,7 @@ __global__ void __launch_bounds__(TX*(TY / PY), FAN ? (PY == 8 ? 5 : 2) : (PY ==
     float acc[PY];
 #pragma unroll
     for (int k = 0; k < PY; ++k) acc[k] = 0.f;
-    ull acc2[PY / 2];        // MODE 1, parallel beam: packed accumulators of the pixel pairs
+    ull acc2[PY / 2];        // parallel beam: packed accumulators of the pixel pairs
 #pragma unroll
     for (int k = 0; k < PY / 2; ++k) acc2[k] = pk2(0.f, 0.f);
     constexpr float MAGIC = 8388608.f;
@@ -243,7 +252,7 @@ __global__ void __launch_bounds__(TX*(TY / PY), FAN ? (PY == 8 ? 5 : 2) : (PY ==
         const bool big = s_big != 0;
         const bool close = s_close != 0;
         if (!big) {
-            if (MODE) {
+            {
                 // one warp per view, lanes along the segment: each bin is loaded once and its right neighbour comes
                 // from the next lane (SHFL) -- half the loads and none of the index arithmetic of the generic loop
                 static_assert(SEG % 32 == 0, "segment = whole warps of bins");
@@ -267,16 +276,6 @@ __global__ void __launch_bounds__(TX*(TY / PY), FAN ? (PY == 8 ? 5 : 2) : (PY ==
                         s_seg[al][c] = make_float2(fmaf(-(float)c, dv, v[i]), dv);
                     }
                 }
-            } else {
-            for (int i = tid; i < na * SEG; i += THREADS) {
-                const int al = i / SEG, c = i - al * SEG;
-                const int d = s_lo[al] + c;
-                const float* row = sb + (long)(a0 + al) * g.det_count;
-                const float v0 = (unsigned)d < (unsigned)g.det_count ? __ldg(row + d) : 0.f;
-                const float v1 = (unsigned)(d + 1) < (unsigned)g.det_count ? __ldg(row + d + 1) : 0.f;
-                const float dv = v1 - v0;
-                s_seg[al][c] = MODE ? make_float2(fmaf(-(float)c, dv, v0), dv) : make_float2(v0, dv);
-            }
             }
             __syncthreads();
             if (x < g.n) {
@@ -284,15 +283,14 @@ __global__ void __launch_bounds__(TX*(TY / PY), FAN ? (PY == 8 ? 5 : 2) : (PY ==
                 // coordinate, its floor and its fraction.  ly_pk holds the row offsets of the pixel pairs,
                 // clamped to the image so that padding rows of an edge tile stay inside the staged interval
                 // (no per-tap clamp).
-                const ull p_m = pk2(MAGIC, MAGIC);
 #pragma unroll 2
                 for (int al = 0; al < na; ++al) {
                     const float2* seg = s_seg[al];
                     if (!FAN) {
                         const float4 v = *reinterpret_cast<const float4*>(s_view[al]);
                         const float tx = fmaf(v.x, lx, v.z);
-                        const ull p_tx = pk2(tx, tx), p_b = pk2(v.y, v.y);
-                        if (MODE) {
+                        const ull p_tx = pk2(tx, tx), p_b = pk2(v.y, v.y), p_m = pk2(MAGIC, MAGIC);
+                        {
                             // bits(t + 2^23) = 0x4B000000 + floor(t): fold the constant into the base (mod 2^32)
                             const uint32_t cbase = (uint32_t)__cvta_generic_to_shared(seg) - g.koff;
 #pragma unroll
@@ -306,55 +304,11 @@ __global__ void __launch_bounds__(TX*(TY / PY), FAN ? (PY == 8 ? 5 : 2) : (PY ==
                                 const float2 s1 = lds64((uint32_t)__float_as_int(t1) * 8u + cbase);
                                 acc2[k / 2] = add2(acc2[k / 2], pk2(fmaf(c0, s0.y, s0.x), fmaf(c1, s1.y, s1.x)));
                             }
-                        } else {
-#pragma unroll
-                        for (int k = 0; k < PY; k += 2) {
-                            const ull p_tl = fma2(p_b, ly_pk[k / 2], p_tx);        // >= 1 by construction
-                            const ull p_t = add2_rm(p_tl, p_m);
-                            const ull p_fr = sub2(p_tl, sub2(p_t, p_m));
-                            float t0, t1, f0, f1;
-                            upk2(p_t, t0, t1);
-                            upk2(p_fr, f0, f1);
-                            const float2 s0 = seg[__float_as_int(t0) & 0x7fffff];
-                            const float2 s1 = seg[__float_as_int(t1) & 0x7fffff];
-                            acc[k] += fmaf(f0, s0.y, s0.x);
-                            acc[k + 1] += fmaf(f1, s1.y, s1.x);
                         }
-                        }
-                    } else if (MODE) {
+                    } else {
                         const uint32_t cbase = (uint32_t)__cvta_generic_to_shared(seg) - g.koff;
                         if (close) fan_taps_line<PY, SEG, false>(s_view[al], cbase, lx, ly_pk, g.k, acc);
                         else fan_taps_line<PY, SEG, true>(s_view[al], cbase, lx, ly_pk, g.k, acc);
-                    } else {
-                        const float4 v = *reinterpret_cast<const float4*>(s_view[al]);
-                        const float2 tr = *reinterpret_cast<const float2*>(s_view[al] + 4);
-                        const float nx_ = fmaf(v.y, lx, v.x), dx_ = fmaf(tr.x, lx, v.w);
-                        const ull p_nx = pk2(nx_, nx_), p_dx = pk2(dx_, dx_);
-                        const ull p_ny = pk2(v.z, v.z), p_dy = pk2(-tr.y, -tr.y);
-                        const ull p_one = pk2(1.f, 1.f), p_k = pk2(g.k, g.k), p_zero = pk2(0.f, 0.f);
-#pragma unroll
-                        for (int k = 0; k < PY; k += 2) {
-                            const ull p_num = fma2(p_ny, ly_pk[k / 2], p_nx);
-                            const ull p_den = fma2(p_dy, ly_pk[k / 2], p_dx);
-                            float d0, d1;
-                            upk2(p_den, d0, d1);
-                            ull p_r = pk2(__fdividef(1.f, d0), __fdividef(1.f, d1));
-                            p_r = fma2(p_r, sub2(p_one, mul2(p_den, p_r)), p_r);   // one Newton step: ~1 ulp
-                            float q0, q1;
-                            upk2(mul2(p_num, p_r), q0, q1);
-                            const ull p_tl = pk2(fmaxf(q0, 0.f), fmaxf(q1, 0.f));
-                            const ull p_t = add2_rm(p_tl, p_m);
-                            const ull p_fr = sub2(p_tl, sub2(p_t, p_m));
-                            float t0, t1, f0, f1, w0, w1;
-                            upk2(p_t, t0, t1);
-                            upk2(p_fr, f0, f1);
-                            upk2(mul2(p_k, p_r), w0, w1);
-                            const float2 s0 = seg[min(__float_as_int(t0) & 0x7fffff, SEG - 1)];
-                            const float2 s1 = seg[min(__float_as_int(t1) & 0x7fffff, SEG - 1)];
-                            acc[k] = fmaf(w0, fmaf(f0, s0.y, s0.x), acc[k]);
-                            acc[k + 1] = fmaf(w1, fmaf(f1, s1.y, s1.x), acc[k + 1]);
-                        }
-                        (void)p_zero;
                     }
                 }
             }
@@ -366,13 +320,13 @@ __global__ void __launch_bounds__(TX*(TY / PY), FAN ? (PY == 8 ? 5 : 2) : (PY ==
 #pragma unroll
                 for (int k = 0; k < PY; ++k) {
                     const float dy = (float)(y0 + k * RY) - g.half;
-                    acc[k] += tap_global(g, row, cs, sn, dx, dy);
+                    acc[k] += tap_global<FAN>(g, row, cs, sn, dx, dy);
                 }
             }
         }
     }
     const float dx = (float)x - g.half;
-    if (MODE && !FAN) {
+    if (!FAN) {
 #pragma unroll
         for (int k = 0; k < PY; k += 2) {
             float a0, a1;
@@ -412,6 +366,7 @@ extern "C" int pdu_radon_adj_f32(const float* sino, float* img, const float* tri
     if (g->geom == PDU_GEOM_FAN)
         PDU_REQUIRE(g->s_dist > 0.f && g->d_dist >= 0.f, "pdu_radon_adj_f32: fan beam needs s_dist > 0, d_dist >= 0");
     PDU_REQUIRE(sino && img && trig, "pdu_radon_adj_f32: null pointer");
+    PDU_CHECK_DEVICE("pdu_radon_adj_f32");
 
     AdjGeom ag;
     ag.n = g->n;
@@ -430,24 +385,22 @@ extern "C" int pdu_radon_adj_f32(const float* sino, float* img, const float* tri
 
     cudaStream_t st = (cudaStream_t)stream;
     int variant = option(OPT_RADON_ADJ);
-    if (variant < 0) variant = 3;
+    if (variant != 0) variant = 3;
     constexpr int TX = 32, TY = 32;
     dim3 grid((unsigned)cdiv(g->n, TX), (unsigned)cdiv(g->n, TY), (unsigned)batch);
     if (variant == 0) {
         radon_adj_gather_kernel<TX, TY, 4><<<grid, dim3(TX, TY / 4), 0, st>>>(sino, img, trig, ag);
-    } else if (variant == 2) {        // A/B: 4 pixels per thread, 256 threads
-        if (ag.fan) radon_adj_tile_kernel<TX, TY, 4, 32, 96, true><<<grid, dim3(TX, TY / 4), 0, st>>>(sino, img, trig, ag);
-        else radon_adj_tile_kernel<TX, TY, 4, 32, 96, false><<<grid, dim3(TX, TY / 4), 0, st>>>(sino, img, trig, ag);
-    } else if (variant == 3 || variant == 4) {   // line-form taps (MODE 1), 8 pixels per thread: the default
+        note_kernel(OP_RADON_ADJ, "radon_adj_gather_kernel grid %ux%ux%u (float64 taps through L1)", grid.x, grid.y, grid.z);
+    } else {
+        // line-form taps, 8 pixels per thread, 128 threads: B N^2 / 8 threads fit one balanced wave.
         // a 32 x 32 tile projects onto at most 32 sqrt(2) / det_spacing bins: a 64-entry segment is enough for
-        // parallel beams with det_spacing >= 0.8 (a third less staging work); variant 4 forces 96 for A/B
-        const bool seg64 = variant == 3 && !ag.fan && 46.f * ag.ids + 5.f <= 64.f;
-        if (ag.fan) radon_adj_tile_kernel<TX, TY, 8, 32, 96, true, 1><<<grid, dim3(TX, TY / 8), 0, st>>>(sino, img, trig, ag);
-        else if (seg64) radon_adj_tile_kernel<TX, TY, 8, 32, 64, false, 1><<<grid, dim3(TX, TY / 8), 0, st>>>(sino, img, trig, ag);
-        else radon_adj_tile_kernel<TX, TY, 8, 32, 96, false, 1><<<grid, dim3(TX, TY / 8), 0, st>>>(sino, img, trig, ag);
-    } else {                          // 8 pixels per thread, 128 threads: B N^2 / 8 threads fit one balanced wave
+        // parallel beams with det_spacing >= 0.8 (a third less staging work)
+        const bool seg64 = !ag.fan && 46.f * ag.ids + 5.f <= 64.f;
         if (ag.fan) radon_adj_tile_kernel<TX, TY, 8, 32, 96, true><<<grid, dim3(TX, TY / 8), 0, st>>>(sino, img, trig, ag);
+        else if (seg64) radon_adj_tile_kernel<TX, TY, 8, 32, 64, false><<<grid, dim3(TX, TY / 8), 0, st>>>(sino, img, trig, ag);
         else radon_adj_tile_kernel<TX, TY, 8, 32, 96, false><<<grid, dim3(TX, TY / 8), 0, st>>>(sino, img, trig, ag);
+        note_kernel(OP_RADON_ADJ, "radon_adj_tile_kernel<32,32,8,32,%d,%s> grid %ux%ux%u (line-form taps in shared memory, packed FP32)",
+                    ag.fan ? 96 : (seg64 ? 64 : 96), ag.fan ? "fan" : "parallel", grid.x, grid.y, grid.z);
     }
     PDU_LAUNCHED();
     return PDU_OK;

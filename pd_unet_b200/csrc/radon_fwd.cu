@@ -10,12 +10,15 @@
 //   producer streams those boxes with cp.async.bulk.tensor (zero fill outside the image = the texture
 //   "border" mode) through an NBUF-deep mbarrier ring while the warps sample the current box.  A strip whose
 //   extent does not fit the box falls back to global loads for that strip only.
-// variants 7 .. 14 -- cell ("quad") tiles: one float4 per bilinear cell, one LDS.128 + four FMAs per sample
-//   (radon_fwd_quad_kernel; shape 13 is the default for dense view sets).
-// variants 1 .. 6 -- float tiles: (TH+1) x W floats, four LDS.32 per sample, boxes up to 248 columns wide
-//   (radon_fwd_strip_kernel; variant 1 = its own shape heuristic, the default for sparse view sets).
+// variants 9 / 11 / 13 -- cell ("quad") tiles: one float4 per bilinear cell, one LDS.128 + four FMAs per sample
+//   (radon_fwd_quad_kernel; shape 13 is the default for dense view sets, 9 / 11 serve sparser ones when the float
+//   tile cannot be used).
+// variant 1 -- float tiles: (TH+1) x W floats, four LDS.32 per sample, boxes up to 248 columns wide
+//   (radon_fwd_strip_kernel with its own shape heuristic, the default for sparse view sets).
 // variant 0 -- one thread per ray, bilinear taps through L1 (__ldg).  Kept as the A/B baseline and for
 //   shapes neither tensor map can describe.
+// Every mbarrier wait is bounded; a time-out is reported through the device error word (common.cuh) and the CTA gives
+// up instead of sampling an unfilled tile -- the next library call returns PDU_ECUDA.
 // The dispatch and the measurements behind it: pdu_radon_fwd_f32 at the end of this file, DESIGN.md 3.1.
 #include <cuda.h>
 
@@ -82,23 +85,16 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// Bounded wait: a barrier that never completes must not hang the GPU box.
-__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
-    const uint32_t addr = smem_u32(bar);
-    // every try may sleep up to the 100 us hint: 2^18 tries bound a wait that can never complete to under half a minute
-    for (int spin = 0; spin < (1 << 18); ++spin) {
-        uint32_t ok;
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-            "selp.b32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok)
-            : "r"(addr), "r"(parity), "r"(100000u)       // suspend-time hint (ns): sleep in hardware instead of spinning
-            : "memory");
-        if (ok) return true;
-    }
-    return false;
+// Bounded wait (common.cuh): false on time-out -- the caller reports and abandons the tile.
+__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, unsigned long long timeout_ns) {
+    return mbar_wait_bounded(smem_u32(bar), parity, timeout_ns);
 }
+// what the kernels need to report a pipeline failure (and, for the tests, to provoke one)
+struct FaultCtl {
+    int* err_word;                    // device_error_word(), may be null
+    unsigned long long timeout_ns;
+    int fault;                        // debug_fault option: the producer skips its TMA loads
+};
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, int c0, int c1, int c2, uint64_t* bar) {
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
@@ -118,11 +114,11 @@ struct FwdCfg {
     static_assert(W % 4 == 0 && W % 32 != 0 && W <= 256, "box width: 16-byte multiple, not a multiple of 32 banks");
 };
 
-template <int DB, int AG, int TH, int W, int NBUF, int LD, bool PK>
+template <int DB, int AG, int TH, int W, int NBUF, int LD>
 __global__ void __launch_bounds__(DB* AG)
     radon_fwd_strip_kernel(const __grid_constant__ CUtensorMap tm_img, const __grid_constant__ CUtensorMap tm_imgT,
                            const float* __restrict__ img, const float* __restrict__ imgT, float* __restrict__ sino,
-                           const float* __restrict__ trig, const pdu_radon_geom_t g) {
+                           const float* __restrict__ trig, const pdu_radon_geom_t g, const FaultCtl fc) {
     using C = FwdCfg<DB, AG, TH, W, NBUF>;
     // indexed directly (no re-aligned generic pointer) so that the tile reads compile to LDS
     extern __shared__ __align__(1024) unsigned char smem_dyn[];
@@ -223,25 +219,29 @@ __global__ void __launch_bounds__(DB* AG)
     const float* src = (use_t ? imgT : img) + (long)b * N * N;
 
     int k_issue = 0, seq_issue = 0;   // producer state (thread 0)
-    auto issue = [&]() {
+    auto issue = [&]() -> bool {
         while (k_issue < n_strips && s_umin[k_issue] > s_umax[k_issue]) ++k_issue;
         if (k_issue < n_strips) {
             const int buf = seq_issue % NBUF;
             // the buffer's previous strip must have been read by every warp (they run ahead of each other
             // by up to NBUF - 1 strips: there is no block-wide barrier in the marching loop)
-            if (seq_issue >= NBUF) mbar_wait(empty + buf, ((seq_issue / NBUF) - 1) & 1);
+            if (seq_issue >= NBUF && !mbar_wait(empty + buf, ((seq_issue / NBUF) - 1) & 1, fc.timeout_ns)) {
+                report_device_error(fc.err_word, DEV_ERR_RADON_FWD);
+                return false;                // stop producing: the consumers time out and give up as well
+            }
             // TMA needs the innermost start coordinate on a 16-byte boundary (measured: any c0 % 4 != 0
             // raises "illegal instruction" on sm_100a, negative values are fine) -> round down to 4 floats
             const int lo = s_umin[k_issue] & ~3;
             if (tma_ok && s_umax[k_issue] - lo + 1 <= W) {
                 mbar_expect_tx(full + buf, C::TILE_BYTES);
-                tma_load_3d(smem_dyn + buf * C::TILE_STRIDE, tm, lo, k_issue * TH - 1, b, full + buf);
+                if (!fc.fault) tma_load_3d(smem_dyn + buf * C::TILE_STRIDE, tm, lo, k_issue * TH - 1, b, full + buf);
             } else {
                 mbar_arrive(full + buf);
             }
             ++seq_issue;
             ++k_issue;
         }
+        return true;
     };
     if (tid == 0) {
 #pragma unroll
@@ -256,9 +256,12 @@ __global__ void __launch_bounds__(DB* AG)
         const int hi = s_umax[k];
         if (s_umin[k] > hi) continue;
         const int lo = s_umin[k] & ~3;
-        if (tid == 0) issue();
+        if (tid == 0 && !issue()) return;
         const int buf = seq % NBUF;
-        mbar_wait(full + buf, (seq / NBUF) & 1);
+        if (!mbar_wait(full + buf, (seq / NBUF) & 1, fc.timeout_ns)) {
+            report_device_error(fc.err_word, DEV_ERR_RADON_FWD);     // never sample an unfilled tile
+            return;
+        }
         // strip-local coordinates: both subtractions are exact (result is a multiple of the operands' ulp)
         const float w0l = w0 - (float)(k * TH - 1);
         const float u0l = u0 - (float)lo;
@@ -279,7 +282,7 @@ __global__ void __launch_bounds__(DB* AG)
         if (tma_ok && hi - lo + 1 <= W) {
             const float* tile = (const float*)(smem_dyn + buf * C::TILE_STRIDE);
             int i = 0;
-            if (PK) {
+            {
                 // Packed-FP32 inner loop (Blackwell FFMA2 / FADD2): the (w, u) coordinate pair, its floor
                 // and fraction, and the two horizontal lerps each take one instruction for both lanes of
                 // the pair; the tile is addressed straight from the magic-number bit patterns.
@@ -411,10 +414,10 @@ struct QuadCfg {
 };
 
 template <int DB, int AG, int TH, int W, int NBUF, int LD>
-__global__ void __launch_bounds__(DB* AG + 32)
+__global__ void __launch_bounds__(DB* AG + 32, 5)      // 5: ptxas settles at 40 registers without a spill (4: 56 registers WITH one)
     radon_fwd_quad_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_qt,
                           const float4* __restrict__ q, const float4* __restrict__ qt, float* __restrict__ sino,
-                          const float* __restrict__ trig, const pdu_radon_geom_t g) {
+                          const float* __restrict__ trig, const pdu_radon_geom_t g, const FaultCtl fc) {
     using C = QuadCfg<DB, AG, TH, W, NBUF>;
     extern __shared__ __align__(1024) unsigned char smem_dyn[];
     uint64_t* full = (uint64_t*)(smem_dyn + NBUF * C::TILE_BYTES);
@@ -512,26 +515,30 @@ __global__ void __launch_bounds__(DB* AG + 32)
     const float4* src = (use_t ? qt : q) + (long)b * N1 * N1;
 
     int k_issue = 0, seq_issue = 0;   // producer state
-    auto issue = [&]() {
+    auto issue = [&]() -> bool {      // false: a consumer never released the buffer (time-out) -- stop producing
         while (k_issue < n_strips && s_umin[k_issue] > s_umax[k_issue]) ++k_issue;
         if (k_issue < n_strips) {
             const int buf = seq_issue % NBUF;
-            if (seq_issue >= NBUF) mbar_wait(empty + buf, ((seq_issue / NBUF) - 1) & 1);
+            if (seq_issue >= NBUF && !mbar_wait(empty + buf, ((seq_issue / NBUF) - 1) & 1, fc.timeout_ns)) {
+                report_device_error(fc.err_word, DEV_ERR_RADON_FWD);
+                return false;
+            }
             const int lo = s_umin[k_issue];
             if (tma_ok && s_umax[k_issue] - lo + 1 <= W) {
                 mbar_expect_tx(full + buf, C::TILE_BYTES);
                 // the map describes the cells as pairs of doubles: start = 2 lo (always 16-byte aligned)
-                tma_load_3d(smem_dyn + buf * C::TILE_BYTES, tm, 2 * lo, k_issue * TH, b, full + buf);
+                if (!fc.fault) tma_load_3d(smem_dyn + buf * C::TILE_BYTES, tm, 2 * lo, k_issue * TH, b, full + buf);
             } else {
                 mbar_arrive(full + buf);
             }
             ++seq_issue;
             ++k_issue;
         }
+        return true;
     };
     if (producer) {
         if (lane == 0)
-            while (k_issue < n_strips) issue();
+            while (k_issue < n_strips && issue()) {}
         return;
     }
 
@@ -546,7 +553,10 @@ __global__ void __launch_bounds__(DB* AG + 32)
         const int lo = s_umin[k];
         if (lo > hi) continue;
         const int buf = seq % NBUF;
-        mbar_wait(full + buf, (seq / NBUF) & 1);
+        if (!mbar_wait(full + buf, (seq / NBUF) & 1, fc.timeout_ns)) {
+            report_device_error(fc.err_word, DEV_ERR_RADON_FWD);     // never sample an unfilled tile
+            return;
+        }
         const float w0l = w0 - (float)(k * TH);
         const float u0l = u0 - (float)lo;
         int cnt = 0;
@@ -648,7 +658,12 @@ static int make_image_map(CUtensorMap* tm, const float* ptr, int batch, int n, i
     return PDU_OK;
 }
 
-template <int DB, int AG, int TH, int W, int NBUF, int LD = 32, bool PK = true>
+static FaultCtl fault_ctl() {
+    const int fault = option(OPT_DEBUG_FAULT) > 0 ? 1 : 0;
+    return FaultCtl{device_error_word(), fault ? MBAR_TIMEOUT_FAULT_NS : MBAR_TIMEOUT_NS, fault};
+}
+
+template <int DB, int AG, int TH, int W, int NBUF, int LD = 32>
 static int launch_strip(const float* img, const float* imgT, float* sino, const float* trig, int batch,
                         const pdu_radon_geom_t& g, cudaStream_t st) {
     using C = FwdCfg<DB, AG, TH, W, NBUF>;
@@ -657,11 +672,13 @@ static int launch_strip(const float* img, const float* imgT, float* sino, const 
     if (rc) return rc;
     rc = make_image_map(&tmT, imgT, batch, g.n, W, C::ROWS);
     if (rc) return rc;
-    auto kern = radon_fwd_strip_kernel<DB, AG, TH, W, NBUF, LD, PK>;
-    PDU_CUDA((ensure_dyn_smem<radon_fwd_strip_kernel<DB, AG, TH, W, NBUF, LD, PK>>(C::SMEM)));
+    auto kern = radon_fwd_strip_kernel<DB, AG, TH, W, NBUF, LD>;
+    PDU_CUDA((ensure_dyn_smem<radon_fwd_strip_kernel<DB, AG, TH, W, NBUF, LD>>(C::SMEM)));
     dim3 grid((unsigned)cdiv(g.det_count, DB), (unsigned)cdiv(g.n_angles, AG), (unsigned)batch);
-    kern<<<grid, C::THREADS, C::SMEM, st>>>(tm, tmT, img, imgT, sino, trig, g);
+    kern<<<grid, C::THREADS, C::SMEM, st>>>(tm, tmT, img, imgT, sino, trig, g, fault_ctl());
     PDU_LAUNCHED();
+    note_kernel(OP_RADON_FWD, "transpose_kernel + radon_fwd_strip_kernel<%d,%d,%d,%d,%d,%d> grid %ux%ux%u (float tiles, TMA ring)", DB, AG,
+                TH, W, NBUF, LD, grid.x, grid.y, grid.z);
     return PDU_OK;
 }
 
@@ -701,8 +718,10 @@ static int launch_quad(const float4* q, const float4* qt, float* sino, const flo
     auto kern = radon_fwd_quad_kernel<DB, AG, TH, W, NBUF, LD>;
     PDU_CUDA((ensure_dyn_smem<radon_fwd_quad_kernel<DB, AG, TH, W, NBUF, LD>>(C::SMEM)));
     dim3 grid((unsigned)cdiv(g.det_count, DB), (unsigned)cdiv(g.n_angles, AG), (unsigned)batch);
-    kern<<<grid, C::THREADS + 32, C::SMEM, st>>>(tm, tmT, q, qt, sino, trig, g);
+    kern<<<grid, C::THREADS + 32, C::SMEM, st>>>(tm, tmT, q, qt, sino, trig, g, fault_ctl());
     PDU_LAUNCHED();
+    note_kernel(OP_RADON_FWD, "quad_build_kernel + radon_fwd_quad_kernel<%d,%d,%d,%d,%d,%d> grid %ux%ux%u (bilinear-cell tiles, TMA ring)",
+                DB, AG, TH, W, NBUF, LD, grid.x, grid.y, grid.z);
     return PDU_OK;
 }
 
@@ -743,6 +762,7 @@ int pdu_radon_fwd_f32(const float* img, float* sino, const float* trig, int batc
                       void* workspace, size_t workspace_bytes, pdu_stream_t stream) {
     int rc = check_geom(g, batch, "pdu_radon_fwd_f32");
     if (rc) return rc;
+    PDU_CHECK_DEVICE("pdu_radon_fwd_f32");
     PDU_REQUIRE(img && sino && trig, "pdu_radon_fwd_f32: null pointer");
     cudaStream_t st = (cudaStream_t)stream;
     int variant = option(OPT_RADON_FWD);
@@ -752,6 +772,7 @@ int pdu_radon_fwd_f32(const float* img, float* sino, const float* trig, int batc
         dim3 grid((unsigned)cdiv(g->det_count, 64), (unsigned)cdiv(g->n_angles, 4), (unsigned)batch);
         radon_fwd_gather_kernel<<<grid, block, 0, st>>>(img, sino, trig, *g);
         PDU_LAUNCHED();
+        note_kernel(OP_RADON_FWD, "radon_fwd_gather_kernel grid %ux%ux%u (one thread per ray, L1 gather)", grid.x, grid.y, grid.z);
         return PDU_OK;
     }
     // columns one view step moves a ray across the slice (assumes evenly spread views; a wrong guess costs
@@ -772,13 +793,15 @@ int pdu_radon_fwd_f32(const float* img, float* sino, const float* trig, int batc
         else if (quad_ok) variant = 7.f * drift <= 63.f ? 11 : 9;
         else variant = 0;
     }
+    if (variant >= 2 && variant != 9 && variant != 11) variant = 13;      // the only explicit choices: 0, 1, 9, 11, 13
     if (variant >= 7 && !quad_ok) variant = tile_ok ? 1 : 0;
-    if (variant >= 1 && variant <= 6 && !tile_ok) variant = quad_ok ? 9 : 0;
+    if (variant == 1 && !tile_ok) variant = quad_ok ? 9 : 0;
     if (variant == 0) {
         dim3 block(64, 4);
         dim3 grid((unsigned)cdiv(g->det_count, 64), (unsigned)cdiv(g->n_angles, 4), (unsigned)batch);
         radon_fwd_gather_kernel<<<grid, block, 0, st>>>(img, sino, trig, *g);
         PDU_LAUNCHED();
+        note_kernel(OP_RADON_FWD, "radon_fwd_gather_kernel grid %ux%ux%u (one thread per ray, L1 gather)", grid.x, grid.y, grid.z);
         return PDU_OK;
     }
     const size_t need = variant >= 7 ? quad_bytes(g->n, batch) : (size_t)batch * g->n * g->n * sizeof(float);
@@ -797,17 +820,12 @@ int pdu_radon_fwd_f32(const float* img, float* sino, const float* trig, int batc
             quad_build_kernel<<<grid, block, 0, st>>>(img, q, qt, g->n);
             PDU_LAUNCHED();
         }
-        switch (variant) {                                        // explicit shapes for A/B measurement
-            case 8: return launch_quad<32, 8, 32, 104, 2, 8>(q, qt, sino, trig, batch, *g, st);    // 32-row strips
+        // shapes the dispatcher uses (every other shape measured in r01 -- 32-row strips, 512-thread CTAs, 3-deep rings,
+        // 84/76/88/89-cell pitches, 8- and 16-detector quarter-warps -- lost by 2-20 % and was deleted)
+        switch (variant) {
             case 9: return launch_quad<32, 4, 16, 120, 2, 8>(q, qt, sino, trig, batch, *g, st);    // 4 views / CTA (sparser views)
-            case 10: return launch_quad<32, 16, 16, 92, 2, 8>(q, qt, sino, trig, batch, *g, st);   // 512 threads: 16 views share a box
             case 11: return launch_quad<32, 8, 16, 128, 2, 8>(q, qt, sino, trig, batch, *g, st);   // widest cell box (sparser views)
-            case 12: return launch_quad<32, 8, 16, 88, 2, 4>(q, qt, sino, trig, batch, *g, st);    // quarter-warp = 4 detectors x 2 views
-            case 13: return launch_quad<32, 8, 16, 92, 2, 4>(q, qt, sino, trig, batch, *g, st);    // same, rows 4 bank groups apart
-            case 14: return launch_quad<32, 16, 16, 92, 2, 2>(q, qt, sino, trig, batch, *g, st);   // quarter-warp = 2 detectors x 4 views (16 views / CTA)
-            // (r02 also measured 3-deep rings, 84/76/89-cell pitches, 16-detector warps and 8-row strips:
-            //  520..600 us against 513 for shape 7 -- dropped)
-            default: return launch_quad<32, 8, 16, 88, 2, 8>(q, qt, sino, trig, batch, *g, st);    // 7: quarter-warp = 8 detectors of one view
+            default: return launch_quad<32, 8, 16, 92, 2, 4>(q, qt, sino, trig, batch, *g, st);    // 13: quarter-warp = 4 detectors x 2 views
         }
     }
     float* imgT = (float*)workspace;
@@ -816,14 +834,6 @@ int pdu_radon_fwd_f32(const float* img, float* sino, const float* trig, int batc
         dim3 grid((unsigned)cdiv(g->n, 32), (unsigned)cdiv(g->n, 32), (unsigned)batch);
         transpose_kernel<<<grid, block, 0, st>>>(img, imgT, g->n);
         PDU_LAUNCHED();
-    }
-    switch (variant) {                                            // float-tile shapes (r01 A/B)
-        case 2: return launch_strip<128, 2, 32, 248, 3, 32>(img, imgT, sino, trig, batch, *g, st);   // widest box (sparse view sets)
-        case 3: return launch_strip<64, 4, 32, 168, 2, 32>(img, imgT, sino, trig, batch, *g, st);    // 32-detector warps
-        case 4: return launch_strip<64, 4, 32, 168, 2, 16>(img, imgT, sino, trig, batch, *g, st);    // 16 det x 2 views / warp
-        case 5: return launch_strip<32, 8, 32, 136, 2, 8>(img, imgT, sino, trig, batch, *g, st);     // 8 det x 4 views / warp
-        case 6: return launch_strip<32, 8, 32, 136, 2, 8, false>(img, imgT, sino, trig, batch, *g, st);   // scalar inner loop
-        default: break;
     }
     // variant 1: the r01 default -- as many neighbouring views per CTA as keep the strip box inside W
     if (7.f * drift <= 40.f) return launch_strip<32, 8, 32, 136, 2, 8>(img, imgT, sino, trig, batch, *g, st);

@@ -60,7 +60,7 @@ def _reset_variants():
         pdu.set_option(k, -1)
 
 
-@pytest.mark.parametrize("variant", [-1, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14])
+@pytest.mark.parametrize("variant", [-1, 0, 1, 9, 11, 13])     # default, L1 gather, float tiles, three cell-tile shapes
 @pytest.mark.parametrize("name", CASES)
 def test_forward_matches_oracle(name, variant):
     op, g, internal = _case(name)
@@ -72,7 +72,7 @@ def test_forward_matches_oracle(name, variant):
     assert rel_l2(got, want) <= TOL
 
 
-@pytest.mark.parametrize("variant", [-1, 0, 1, 2, 3, 4])
+@pytest.mark.parametrize("variant", [-1, 0])                    # default (line-form tile kernel), float64 gather
 @pytest.mark.parametrize("name", CASES)
 def test_backprojection_matches_oracle(name, variant):
     op, g, internal = _case(name)
@@ -204,7 +204,7 @@ def test_filter_tensor_core_variant(D, A, B):
     obj = op.forward(phantom_batch(B, D, seed=5).to(DEV)).cpu()
     for s in (noise, obj, obj + 0.01 * noise):
         want = oracle.filter_sinogram(s)
-        for variant in (1, 3, 4, 5, 0):
+        for variant in (1, 0):
             try:
                 pdu.set_option("filter_variant", variant)
                 got = op.filter_sinogram(s.to(DEV))
@@ -215,8 +215,6 @@ def test_filter_tensor_core_variant(D, A, B):
     try:
         pdu.set_option("filter_variant", 1)
         assert rel_l2(op.filter_sinogram(obj.to(DEV), "hann"), oracle.filter_sinogram(obj, "hann")) <= TOL
-        pdu.set_option("filter_variant", 2)      # 3-product A/B form: fine on noise, documented as short on objects
-        assert rel_l2(op.filter_sinogram(noise.to(DEV)), oracle.filter_sinogram(noise)) <= TOL
     finally:
         pdu.set_option("filter_variant", -1)
 
@@ -243,3 +241,51 @@ def test_unsorted_angles_and_odd_geometries_take_the_fallback_paths_correctly():
     assert rel_l2(fan.forward(x.to(DEV)), oracle.radon_forward(x, trig, gf)) <= TOL
     s = seeded((1, 11, 180), 10)
     assert rel_l2(fan.backprojection(s.to(DEV)), oracle.radon_backprojection(s, trig, gf)) <= TOL
+
+
+def test_a_pipeline_timeout_is_reported_not_silently_wrong():
+    """a timed-out mbarrier wait must not yield a quietly wrong sinogram.  `debug_fault` makes the TMA
+    producers skip their loads; the kernels must give up within their (shortened) time-out, raise the device error
+    word, and every later library call must fail with PDU_ECUDA until the word is cleared."""
+    from pd_unet_b200 import _lib
+    L = _lib.lib()
+    n, A = 256, 64
+    dense = pdu.Radon(n, user_angles(512))           # cell ("quad") kernel
+    sparse = pdu.Radon(n, user_angles(A))            # float-tile kernel
+    x = phantom_batch(1, n).to(DEV)
+    good = dense.forward(x)
+    s = sparse.forward(x)
+    good_f = sparse.filter_sinogram(s)
+    torch.cuda.synchronize()
+    assert L.pdu_device_error(0) == 0
+    for name, call, code in (("cell projector", lambda: dense._project(x), 1), ("tile projector", lambda: sparse._project(x), 1),
+                             ("tensor-core filter", lambda: sparse._filter(s, "ramp"), 2)):
+        try:
+            pdu.set_option("debug_fault", 1)
+            call()                                   # the launch itself succeeds ...
+            torch.cuda.synchronize()
+        finally:
+            pdu.set_option("debug_fault", -1)
+        assert L.pdu_device_error(0) == code, name   # ... the kernel reports
+        with pytest.raises(_lib.PduError, match="device-side failure"):
+            dense.forward(x)                         # and the next call refuses to run
+        assert L.pdu_device_error(1) == code         # read and clear
+        assert L.pdu_device_error(0) == 0
+    # the library works again and gives the same numbers as before
+    assert torch.equal(dense.forward(x), good)
+    assert torch.equal(sparse.filter_sinogram(s), good_f)
+
+
+def test_last_kernel_names_the_dispatch():
+    from pd_unet_b200 import _lib
+    n = 256
+    x = phantom_batch(1, n).to(DEV)
+    dense, sparse = pdu.Radon(n, user_angles(512)), pdu.Radon(n, user_angles(64))
+    dense.forward(x)
+    assert "radon_fwd_quad_kernel<32,8,16,92,2,4>" in _lib.last_kernel("radon_fwd")
+    s = sparse.forward(x)
+    assert "radon_fwd_strip_kernel" in _lib.last_kernel("radon_fwd")
+    sparse.filter_sinogram(s)
+    assert "filter_tc_kernel" in _lib.last_kernel("filter")
+    sparse.backprojection(s)
+    assert "radon_adj_tile_kernel<32,32,8,32,64,parallel>" in _lib.last_kernel("radon_adj")

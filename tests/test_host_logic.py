@@ -21,6 +21,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 @pytest.mark.parametrize("name", FILTERS)
 @pytest.mark.parametrize("D,A", [(64, 24), (77, 33), (256, 512)])
 def test_filter_taps_equal_the_fft_route(name, D, A):
+    """Two constructions: the product's (scikit-image style: np.fft of the constant table, numpy windows, fftshift)
+    against the oracle's (closed-form ramp kernel, windows as explicit functions of the frequency index, plain
+    cosine sums, direct Toeplitz product) -- they share no code."""
     taps = filter_taps(D, A, name)
     assert taps.shape == (2 * D - 1,)
     assert np.allclose(taps, taps[::-1], atol=1e-15)                 # even => symmetric Toeplitz => self-adjoint
@@ -34,6 +37,8 @@ def test_filter_taps_equal_the_fft_route(name, D, A):
 
 @pytest.mark.parametrize("n,k", [(32, 64), (320, 640), (48, 80)])
 def test_kaiser_bessel_tables_equal_the_oracle(n, k):
+    """Two constructions: np.i0 on a vector grid + the closed-form transform sinh(w)/w (product) against scipy's
+    exponentially scaled i0e entry by entry + Gauss-Legendre quadrature of the kernel's Fourier integral (oracle)."""
     spec = oracle.NufftSpec((n, n), grid_size=(k, k))
     assert np.allclose(kaiser_bessel_table(n, k, 6, 1024, 2.34), oracle.kb_table(spec, 0), atol=1e-14)
     assert np.allclose(kaiser_bessel_scaling(n, k, 6, 2.34), oracle.scaling_coef(spec, 0), rtol=1e-13)

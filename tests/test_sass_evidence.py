@@ -35,7 +35,7 @@ def _mnemonics(text):
 
 @pytest.mark.parametrize("kernel,needles", [
     ("radon_fwd_quad_kernel", ["UTMALDG.3D", "LDS.128", "FFMA2", "FADD2.RM", "SYNCS.PHASECHK.TRANS64.TRYWAIT", "CREDUX.MIN.S32"]),
-    ("radon_fwd_strip_kernel", ["UTMALDG.3D", "SYNCS.PHASECHK.TRANS64.TRYWAIT", "CREDUX.MIN.S32"]),   # (one shape is the scalar A/B form: no FFMA2)
+    ("radon_fwd_strip_kernel", ["UTMALDG.3D", "FFMA2", "SYNCS.PHASECHK.TRANS64.TRYWAIT", "CREDUX.MIN.S32"]),
     ("radon_adj_tile_kernel", ["LDS.64", "FFMA2", "FADD2.RM"]),
     ("filter_tc_kernel", ["UTMALDG.2D", "UTCHMMA", "LDTM", "UTCBAR"]),
     ("ff_cols_fwd_kernel", ["LDG", "STG", "BAR.SYNC"]),
@@ -50,10 +50,12 @@ def test_kernel_uses_the_hardware_path(sass, kernel, needles):
             assert any(m.startswith(n) for m in have), f"{n} missing from {name[:90]}"
 
 
-def test_no_local_memory_traffic_in_the_forward_projector(sass):
-    """The cell projector was tuned at 40 registers without spills; STL / LDL in it is a regression.  (The backprojector
-    keeps a small stack frame for its rarely taken float64 fallback call, so it is not checked here.)"""
+def test_no_local_memory_traffic_in_the_projectors(sass):
+    """The cell projector was tuned at 40 registers without spills and the parallel-beam backprojector's float64
+    fallback is inlined (r02: no stack frame, no spill); STL / LDL in either is a regression.  The fan-beam
+    backprojector passes its geometry struct to the out-of-line fallback through a 56-byte stack frame -- parameter
+    passing, not a spill (ptxas -v: 0 bytes spill stores) -- so it is not checked here."""
     for name, text in _functions(sass).items():
-        if "radon_fwd_quad_kernel" in name:
+        if "radon_fwd_quad_kernel" in name or ("radon_adj_tile_kernel" in name and "Lb0E" in name):
             body = _mnemonics(text)
             assert not any(m.startswith("STL") or m.startswith("LDL") for m in body), f"local-memory traffic in {name[:90]}"
