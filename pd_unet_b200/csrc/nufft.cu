@@ -1047,6 +1047,11 @@ static int nufft_fwd_chunk(pdu_nufft_plan_t* p, const float2* image, float2* kda
         rc = run_fft(p, grid, planes, CUFFT_FORWARD, st);
         if (rc) return rc;
     }
+    note_kernel(OP_NUFFT_FWD, "%s + interp_fwd_kernel<%d> (%d planes of %dx%d, M=%ld)",
+                variant == 2 ? "ff_rows_fwd_kernel + ff_cols_fwd_kernel (register-resident pruned FFT)"
+                             : (variant == 1 && p->pfft_ok ? "pfft_rows_fwd_kernel + pfft_cols_fwd_kernel (generic pruned FFT)"
+                                                           : "apod_pad_kernel + cuFFT C2C"),
+                p->J == 6 ? 6 : 0, planes, p->k0, p->k1, m);
     return launch_interp_fwd(p, grid, kdata, omega, planes, m, scale, st);
 }
 
@@ -1071,6 +1076,13 @@ static int nufft_adj_chunk(pdu_nufft_plan_t* p, const float2* kdata, float2* ima
     int variant = option(OPT_NUFFT_ADJ);
     if (variant < 0) variant = ff_supported(p) ? 2 : 0;      // see nufft_fwd_chunk
     if (variant == 2 && !ff_supported(p)) variant = 0;
+    note_kernel(OP_NUFFT_ADJ, "%s + %s + crop_apod_kernel (%d planes of %dx%d, M=%ld)",
+                csr ? "transpose_kdata_kernel + interp_adj_csrT_kernel + interp_adj_csr_long_kernel (sorted gather)"
+                    : "interp_adj_kernel (float2 atomics)",
+                variant == 2 ? "ff_rows_adj_kernel + ff_cols_adj_kernel (register-resident pruned FFT)"
+                             : (variant == 1 && p->pfft_ok ? "pfft_rows_adj_kernel + pfft_cols_adj_kernel (generic pruned FFT)"
+                                                           : "cuFFT C2C"),
+                planes, p->k0, p->k1, m);
     if (variant == 2) {
         float2* T = grid + (long)planes * p->k0 * p->k1;
         float2* U = T + (long)planes * std::max((long)p->n0 * p->k1, (long)p->k0 * p->n1);
@@ -1121,6 +1133,7 @@ int pdu_nufft_fwd_c64(pdu_nufft_plan_t* p, const float* image, float* kdata, con
                       pdu_stream_t stream) {
     int rc = check_call(p, image, kdata, omega, batch, coils, smaps_batch, smaps, m, "pdu_nufft_fwd_c64");
     if (rc) return rc;
+    PDU_CHECK_DEVICE("pdu_nufft_fwd_c64");
     const int cb = batch_chunk(p, batch, coils);
     const size_t need = pdu_nufft_workspace_bytes(p, cb * coils);
     if (!workspace || workspace_bytes < need) {
@@ -1171,6 +1184,7 @@ int pdu_nufft_adj_csr_c64(pdu_nufft_plan_t* p, const float* kdata, float* image,
                           size_t workspace_bytes, pdu_stream_t stream) {
     int rc = check_call(p, kdata, image, omega, batch, coils, smaps_batch, smaps, m, "pdu_nufft_adj_c64");
     if (rc) return rc;
+    PDU_CHECK_DEVICE("pdu_nufft_adj_c64");
     const int cb = batch_chunk(p, batch, coils);
     const size_t need = pdu_nufft_workspace_bytes(p, cb * coils);
     if (!workspace || workspace_bytes < need) {

@@ -195,3 +195,40 @@ def test_fan_beam_ct_model_matches_cpu_oracle_model():
                                   lambda im: oracle.radon_forward(im[:, 0], trig, g)[:, None],
                                   lambda s: oracle.fbp(s[:, 0], trig, g)[:, None])
     assert rel_l2(got, want) < 1e-4
+
+
+@pytest.mark.parametrize("tf32", [False, True])
+def test_ct_model_at_the_benched_size_matches_cpu_oracle_model(tf32):
+    """PSNR-within-0.01-dB proven at the size and model bench.py times (configs[1]: 256^2,
+    64 -> 512 views, n_iter 4, UNet base 32 depth 3), on 2 slices, against the same weights on the CPU in float64 with
+    the oracle's operators (OpenMP C restatement).  tf32=False: cuDNN in plain fp32 -- the north_star tolerance.
+    tf32=True: PyTorch's default for convolutions (what bench.py and the reference run with); the operators stay
+    fp32, the convolutions round their inputs to 10 mantissa bits -- a looser, measured bound."""
+    from oracle import c_port
+    import bench
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = tf32
+    try:
+        n, up, A = bench.N, bench.UP, bench.A_FULL
+        ang = user_angles(A)
+        radon = pdu.Radon(n, ang)
+        torch.manual_seed(1234)
+        model = PrimalDualUNetCT(radon, upsample=up, adjoint="fbp", **bench.MODEL_KW).to(DEV).eval()
+        x = phantom_batch(2, n, seed=100)
+        g = oracle.RadonGeom(n=n, n_angles=A, det_count=n)
+        trig = oracle.trig_table(-ang)
+        sparse = c_port.radon_forward(x, trig, g).float()[:, None, ::up].contiguous()
+        with torch.no_grad():
+            got = model(sparse.to(DEV))
+            gg = ou.angular_upsample(sparse[:, 0].double(), up, "flip")[:, None] / model.op_scale
+            want = _reference_forward(model, gg, (n, n),
+                                      lambda im: c_port.radon_forward(im[:, 0], trig, g)[:, None],
+                                      lambda s: c_port.fbp(s[:, 0], trig, g)[:, None])
+        err = rel_l2(got, want)
+        mse = lambda a: float(((a.double().cpu() - x[:, None].double()) ** 2).mean())
+        dpsnr = abs(10 * np.log10(mse(got) / mse(want)))
+        print(f"benched-size model, cudnn tf32={tf32}: rel-L2 {err:.2e}, |dPSNR| {dpsnr:.5f} dB")
+        assert err < (5e-3 if tf32 else 1e-4)
+        assert dpsnr < 0.01
+    finally:
+        torch.backends.cudnn.allow_tf32 = old

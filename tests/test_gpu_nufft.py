@@ -205,3 +205,37 @@ def test_non_default_numpoints(numpoints):
     A, AH = pdu.KbNufft(im, numpoints=numpoints), pdu.KbNufftAdjoint(im, numpoints=numpoints)
     assert rel_l2(A(x.to(DEV), omd), oracle.nufft_forward(x, om, spec)) <= TOL
     assert rel_l2(AH(k.to(DEV), omd), oracle.nufft_adjoint(k, om, spec)) <= TOL
+
+
+def test_default_path_at_the_cfg4_share_matches_oracle():
+    """the DEFAULT kernels at BASELINE configs[3]'s per-GPU share (320^2, 8 coils, batch 8,
+    48 spokes: 64 planes -> own FFT, sorted / binned gathers, fused coil combine) compared with the float64 oracle
+    itself, not only through properties.  The oracle runs batch element 5 (all 8 coils) and, without coil maps, planes
+    (0, 0) and (7, 7) of a 64-plane call: seconds on the CPU."""
+    from pd_unet_b200 import _lib
+    n, coils, batch, spokes = 320, 8, 8, 48
+    im = (n, n)
+    spec = oracle.NufftSpec(im)
+    om = _traj(spokes, 2 * n)
+    omd = torch.from_numpy(om).to(DEV)
+    A, AH = pdu.KbNufft(im), pdu.KbNufftAdjoint(im)
+    sm = coil_maps(coils, n)[None]
+    x = seeded((batch, 1) + im, 61, complex_=True)
+    k = seeded((batch, coils, om.shape[1]), 62, complex_=True)
+    y = A(x.to(DEV), omd, smaps=sm.to(DEV), norm="ortho")
+    fwd_kernel = _lib.last_kernel("nufft_fwd")
+    xa = AH(k.to(DEV), omd, smaps=sm.to(DEV), norm="ortho")
+    adj_kernel = _lib.last_kernel("nufft_adj")
+    assert "cufft" not in fwd_kernel.lower() and "cufft" not in adj_kernel.lower(), (fwd_kernel, adj_kernel)
+    b = 5
+    assert rel_l2(y[b:b + 1], oracle.nufft_forward(x[b:b + 1], om, spec, smaps=sm, norm="ortho")) <= TOL
+    assert rel_l2(xa[b:b + 1], oracle.nufft_adjoint(k[b:b + 1], om, spec, smaps=sm, norm="ortho")) <= TOL
+    # no coil maps: 64 independent planes in one call
+    x64 = seeded((batch, coils) + im, 63, complex_=True)
+    y64 = A(x64.to(DEV), omd)
+    xa64 = AH(k.to(DEV), omd)
+    for bb, cc in ((0, 0), (7, 7)):
+        assert rel_l2(y64[bb, cc], oracle.nufft_forward(x64[bb:bb + 1, cc:cc + 1], om, spec)[0, 0]) <= TOL
+        assert rel_l2(xa64[bb, cc], oracle.nufft_adjoint(k[bb:bb + 1, cc:cc + 1], om, spec)[0, 0]) <= TOL
+    # the adjoint of a fixed trajectory is bit-reproducible (no atomics on the default path)
+    assert torch.equal(AH(k.to(DEV), omd, smaps=sm.to(DEV), norm="ortho"), xa)

@@ -24,15 +24,15 @@ def timed(name, fn):
     print(f"{name:28s} median {statistics.median(ts)*1e3:9.1f} us  min {min(ts)*1e3:9.1f} us", flush=True)
 
 
-for v in (1, 7, 12, 13, 14):
+for v in (1, 13):
     pdu.set_option("radon_fwd_variant", v)
     timed(f"radon_fwd variant {v}", lambda: op._project(x))
 pdu.set_option("radon_fwd_variant", -1)
-for v in (1, 3, 4):
+for v in (3,):
     pdu.set_option("radon_adj_variant", v)
     timed(f"radon_adj variant {v}", lambda: op._backproject(s))
 pdu.set_option("radon_adj_variant", -1)
-for v in (0, 1, 2, 3, 4, 5):
+for v in (0, 1):
     pdu.set_option("filter_variant", v)
     timed(f"filter variant {v}", lambda: op._filter(s, "ramp"))
 pdu.set_option("filter_variant", -1)
@@ -40,16 +40,16 @@ pdu.set_option("filter_variant", -1)
 fan = pdu.RadonFanbeam(512, np.linspace(0, 2 * np.pi, 1024, endpoint=False), 1024.0)
 xf = torch.rand(8, 512, 512, device=dev)
 sf = torch.rand(8, 1024, 512, device=dev)
-for v in (1, 7, 12, 13, 14):
+for v in (1, 13):
     pdu.set_option("radon_fwd_variant", v)
     timed(f"fan512 fwd variant {v}", lambda: fan._project(xf))
 pdu.set_option("radon_fwd_variant", -1)
 timed("fan512 fwd", lambda: fan._project(xf))
-for v in (1, 3):
+for v in (3,):
     pdu.set_option("radon_adj_variant", v)
     timed(f"fan512 adj variant {v}", lambda: fan._backproject(sf))
 pdu.set_option("radon_adj_variant", -1)
-for v in (0, 1, 2, 3, 4, 5):
+for v in (0, 1):
     pdu.set_option("filter_variant", v)
     timed(f"fan512 filter variant {v}", lambda: fan._filter(sf, "ramp"))
 pdu.set_option("filter_variant", -1)
