@@ -168,6 +168,9 @@ PDU_API int pdu_nufft_adj_c64(pdu_nufft_plan_t* plan, const float* kdata, float*
  * (csr == NULL falls back to the atomic scatter).
  * Replaces [RECALL] torchkbnufft's precomputed `interp_mats` path (calc_tensor_spmatrix + sparse matmul). */
 PDU_API size_t pdu_nufft_csr_bytes(const pdu_nufft_plan_t* plan, long m);
+/* The same size, and in *persist_bytes how much of the buffer (its head) the apply calls read: the rest is
+ * build scratch that may be released once pdu_nufft_csr_build has been enqueued. */
+PDU_API size_t pdu_nufft_csr_bytes2(const pdu_nufft_plan_t* plan, long m, size_t* persist_bytes);
 PDU_API int pdu_nufft_csr_build(pdu_nufft_plan_t* plan, const float* omega, long m, void* csr,
                                 size_t csr_bytes, pdu_stream_t stream);
 PDU_API int pdu_nufft_interp_adj_csr_c64(pdu_nufft_plan_t* plan, const float* kdata, float* grid,
@@ -176,6 +179,34 @@ PDU_API int pdu_nufft_adj_csr_c64(pdu_nufft_plan_t* plan, const float* kdata, fl
                                   const float* omega, const float* smaps, int batch, int coils,
                                   int smaps_batch, long m, float scale, const void* csr, void* workspace,
                                   size_t workspace_bytes, pdu_stream_t stream);
+/* Fused path for the BASELINE grids (k = 2 n in {256, 512, 640, 1024, 2048}, numpoints 6, square): the separable
+ * Kaiser-Bessel interpolation is split along the two grid axes and fused into the two passes of the library's own
+ * pruned FFT, so the oversampled grid is never written to memory and neither direction needs atomics
+ * (csrc/nufft_fused.cu).  It needs the trajectory's "row bins" -- every (sample, row tap) entry sorted by grid row and
+ * first column -- built once per trajectory:
+ *   pdu_nufft_bins_bytes   size of the device buffer the build needs (256-byte aligned); the first *persist_bytes of
+ *                          it must be kept for the calls below, the rest is build scratch and may be released
+ *   pdu_nufft_bins_build   omega [2, m] -> bins
+ * flags: PDU_NUFFT_IMAGE_SPLIT -- the image side is [batch, ci, 2, n0, n1] float32 (real plane, imaginary plane) instead
+ * of complex64 [batch, ci, n0, n1]; PDU_NUFFT_KDATA_SPLIT -- likewise [batch, coils, 2, m] for the samples: the layouts
+ * PD-UNet's CNN blocks use, so no permute / view_as_complex passes surround the operator.  kweight (nullable):
+ * float32 [m] multiplied into the samples on load (the density compensation of the adjoint).
+ * Replace [RECALL] torchkbnufft KbNufft / KbNufftAdjoint with precomputed interpolation (`interp_mats`). */
+enum { PDU_NUFFT_IMAGE_SPLIT = 1, PDU_NUFFT_KDATA_SPLIT = 2 };
+PDU_API int pdu_nufft_has_fused_path(const pdu_nufft_plan_t* plan);
+PDU_API size_t pdu_nufft_bins_bytes(const pdu_nufft_plan_t* plan, long m, size_t* persist_bytes);
+PDU_API int pdu_nufft_bins_build(pdu_nufft_plan_t* plan, const float* omega, long m, void* bins,
+                                 size_t bins_bytes, pdu_stream_t stream);
+PDU_API size_t pdu_nufft_binned_workspace_bytes(const pdu_nufft_plan_t* plan, int planes, long m);
+PDU_API int pdu_nufft_fwd_binned_c64(pdu_nufft_plan_t* plan, const float* image, float* kdata,
+                                     const float* smaps, int batch, int coils, int smaps_batch, long m,
+                                     float scale, const void* bins, int flags, void* workspace,
+                                     size_t workspace_bytes, pdu_stream_t stream);
+PDU_API int pdu_nufft_adj_binned_c64(pdu_nufft_plan_t* plan, const float* kdata, float* image,
+                                     const float* smaps, const float* kweight, int batch, int coils,
+                                     int smaps_batch, long m, float scale, const void* bins, int flags,
+                                     void* workspace, size_t workspace_bytes, pdu_stream_t stream);
+
 /* Table interpolation only: grid [planes, k0, k1] <-> kdata [planes, m].
  * Replace [RECALL] torchkbnufft `KbInterp.forward` / `KbInterpAdjoint.forward`; the adjoint
  * ACCUMULATES into grid (zero it first). */

@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libpdu_b200.so")
 PDU_GEOM_PARALLEL, PDU_GEOM_FAN = 0, 1
 WRAP_MODES = {"flip": 0, "periodic": 1, "clamp": 2}
 LAYOUT_NCHW, LAYOUT_NHWC = 0, 1
+NUFFT_IMAGE_SPLIT, NUFFT_KDATA_SPLIT = 1, 2
 
 
 class PduError(RuntimeError):
@@ -57,6 +58,15 @@ SIGNATURES = {
     "pdu_nufft_adj_c64": (C.c_int, [_p, _p, _p, _p, _p, C.c_int, C.c_int, C.c_int, C.c_long, C.c_float, _p,
                                     C.c_size_t, _p]),
     "pdu_nufft_csr_bytes": (C.c_size_t, [_p, C.c_long]),
+    "pdu_nufft_csr_bytes2": (C.c_size_t, [_p, C.c_long, C.POINTER(C.c_size_t)]),
+    "pdu_nufft_has_fused_path": (C.c_int, [_p]),
+    "pdu_nufft_bins_bytes": (C.c_size_t, [_p, C.c_long, C.POINTER(C.c_size_t)]),
+    "pdu_nufft_bins_build": (C.c_int, [_p, _p, C.c_long, _p, C.c_size_t, _p]),
+    "pdu_nufft_binned_workspace_bytes": (C.c_size_t, [_p, C.c_int, C.c_long]),
+    "pdu_nufft_fwd_binned_c64": (C.c_int, [_p, _p, _p, _p, C.c_int, C.c_int, C.c_int, C.c_long, C.c_float, _p, C.c_int, _p,
+                                           C.c_size_t, _p]),
+    "pdu_nufft_adj_binned_c64": (C.c_int, [_p, _p, _p, _p, _p, C.c_int, C.c_int, C.c_int, C.c_long, C.c_float, _p, C.c_int, _p,
+                                           C.c_size_t, _p]),
     "pdu_nufft_csr_build": (C.c_int, [_p, _p, C.c_long, _p, C.c_size_t, _p]),
     "pdu_nufft_interp_adj_csr_c64": (C.c_int, [_p, _p, _p, _p, C.c_int, C.c_long, _p]),
     "pdu_nufft_adj_csr_c64": (C.c_int, [_p, _p, _p, _p, _p, C.c_int, C.c_int, C.c_int, C.c_long, C.c_float, _p, _p,

@@ -13,8 +13,6 @@
 //
 // Grid offsets and table indices are computed with explicitly rounded float32 operations, the same
 // sequence oracle/nufft.py::_tap_indices_f32 performs, so both read the same table entries.
-#include <cufft.h>
-
 #include <cub/device/device_radix_sort.cuh>
 
 #include <math.h>
@@ -24,74 +22,9 @@
 #include <mutex>
 #include <vector>
 
-#include "common.cuh"
-#include "pfft.cuh"
-#include "pfft_fast.cuh"
-
-struct pdu_nufft_plan {
-    int n0, n1, k0, k1, J, L, shift0, shift1;
-    int device;
-    float2* d_t0;
-    float2* d_t1;
-    float* d_s0;
-    float* d_s1;
-    std::map<int, cufftHandle> fft;   // batched 2-D C2C plans keyed by number of planes
-    std::mutex mu;
-    // own pruned FFT (pfft.cuh): per-axis radix plans and float64-computed twiddle tables; pfft_ok == false
-    // (a grid size with a prime factor above 5) keeps the cuFFT path
-    bool pfft_ok;
-    pdu::PfftPlan pf0, pf1;
-    float2* d_w0;
-    float2* d_w1;
-};
+#include "nufft_common.cuh"
 
 namespace pdu {
-
-constexpr int MAXJ = 8;
-
-struct NufftDims {
-    int n0, n1, k0, k1, J, L;
-    float gam0, gam1;       // float32(2 pi / K)
-    double shift0, shift1;
-};
-
-__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
-    return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
-}
-__device__ __forceinline__ float2 cmul_conj(float2 a, float2 b) {   // a * conj(b)
-    return make_float2(fmaf(a.x, b.x, a.y * b.y), fmaf(a.y, b.x, -a.x * b.y));
-}
-
-// per-axis taps of one sample: wrapped grid index and table coefficient.  JT > 0: compile-time tap count (the
-// default J = 6 gets straight-line code, 6-entry register arrays and no per-tap branches); JT == 0: run-time J <= MAXJ
-template <int JT = 0>
-__device__ __forceinline__ void axis_taps(float om, float gam, int K, int Jrt, int L, const float2* __restrict__ table,
-                                          int* gi, float2* co) {
-    const int J = JT > 0 ? JT : Jrt;
-    constexpr int N = JT > 0 ? JT : MAXJ;
-    const float tm = __fdiv_rn(om, gam);
-    const int koff = (int)floorf(__fsub_rn(tm, 0.5f * (float)J));
-    const int half = (J * L) / 2;
-#pragma unroll
-    for (int j = 0; j < N; ++j) {
-        if (j < J) {
-            const int g = koff + 1 + j;
-            const float dist = __fmul_rn(__fsub_rn(tm, (float)g), (float)L);
-            int q = (int)rintf(dist) + half;
-            q = min(max(q, 0), J * L);
-            co[j] = __ldg(table + q);
-            int gw = g % K;
-            if (gw < 0) gw += K;
-            gi[j] = gw;
-        }
-    }
-}
-
-__device__ __forceinline__ float2 shift_phase(float om0, float om1, double s0, double s1) {
-    double sn, cs;
-    sincos((double)om0 * s0 + (double)om1 * s1, &sn, &cs);
-    return make_float2((float)cs, (float)sn);
-}
 
 // ------------------------------------------------------------------ apodise + zero pad
 // one thread = two neighbouring grid cells (one 16-byte store); three quarters of the stores are zeros
@@ -137,7 +70,7 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256)
     crop_apod_kernel(const float2* __restrict__ grid, const float2* __restrict__ smaps, float2* __restrict__ image,
                      const float* __restrict__ s0, const float* __restrict__ s1, NufftDims d, int coils, int smaps_batch,
-                     float scale, long total) {
+                     float scale, long total, int split = 0) {
     const long plane = (long)d.n0 * d.n1;
     const long gplane = (long)d.k0 * d.k1;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
@@ -179,7 +112,13 @@ __global__ void __launch_bounds__(256)
         } else {
             v = __ldg(grid + q * gplane + gp);
         }
-        image[i] = make_float2(v.x * w, v.y * w);
+        if (split) {              // [planes][2][n0][n1] float32: real plane, imaginary plane
+            float* o = reinterpret_cast<float*>(image) + 2 * q * plane + (long)c0 * d.n1 + c1;
+            o[0] = v.x * w;
+            o[plane] = v.y * w;
+        } else {
+            image[i] = make_float2(v.x * w, v.y * w);
+        }
     }
 }
 
@@ -262,16 +201,6 @@ __global__ void __launch_bounds__(128)
             }
         }
     }
-}
-
-static NufftDims dims_of(const pdu_nufft_plan* p) {
-    NufftDims d;
-    d.n0 = p->n0; d.n1 = p->n1; d.k0 = p->k0; d.k1 = p->k1; d.J = p->J; d.L = p->L;
-    d.gam0 = (float)(2.0 * 3.14159265358979323846 / p->k0);
-    d.gam1 = (float)(2.0 * 3.14159265358979323846 / p->k1);
-    d.shift0 = (double)p->shift0;
-    d.shift1 = (double)p->shift1;
-    return d;
 }
 
 static unsigned stream_grid(long items) {
@@ -636,8 +565,6 @@ struct CsrView {
     size_t total;
 };
 
-static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
-
 static CsrView csr_layout(const pdu_nufft_plan* p, long M, void* base, bool with_scratch = true) {
     const size_t n = (size_t)M * p->J * p->J, cells = (size_t)p->k0 * p->k1;
     CsrView v;
@@ -900,6 +827,19 @@ static int launch_interp_adj_csr(pdu_nufft_plan* p, const float2* kdata, float2*
     return PDU_OK;
 }
 
+// cropped planes U [planes][n0][n1] -> image (x apodisation x scale, x conj(smaps) summed over coils); nufft_fused.cu
+int launch_crop_apod(pdu_nufft_plan* p, const float2* U, const float2* smaps, float2* image, int out_planes, int coils,
+                     int smaps_batch, float scale, int split, cudaStream_t st) {
+    NufftDims dc = dims_of(p);          // the cropped result is a dense [n0][n1] "grid"
+    dc.k0 = dc.n0;
+    dc.k1 = dc.n1;
+    const long total = (long)out_planes * p->n0 * p->n1;
+    crop_apod_kernel<<<stream_grid(total), 256, 0, st>>>(U, smaps, image, p->d_s0, p->d_s1, dc, coils, smaps_batch, scale, total,
+                                                         split);
+    PDU_LAUNCHED();
+    return PDU_OK;
+}
+
 static int check_call(const pdu_nufft_plan* p, const void* a, const void* b, const void* omega, int batch, int coils,
                       int smaps_batch, const void* smaps, long m, const char* who) {
     PDU_REQUIRE(p != nullptr, "%s: plan is null", who);
@@ -952,7 +892,7 @@ int pdu_nufft_plan_create(pdu_nufft_plan_t** plan, int n0, int n1, int k0, int k
     if (e == cudaSuccess) e = cudaMemcpy(p->d_t1, table1, tl * sizeof(float2), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(p->d_s0, scal0, (size_t)n0 * sizeof(float), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(p->d_s1, scal1, (size_t)n1 * sizeof(float), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess && p->pfft_ok) {
+    if (e == cudaSuccess && (p->pfft_ok || (fast_fft_size(k0) && fast_fft_size(k1)))) {
         for (int ax = 0; ax < 2 && e == cudaSuccess; ++ax) {
             const int K = ax == 0 ? k0 : k1;
             std::vector<float2> w((size_t)K);
@@ -1157,6 +1097,15 @@ size_t pdu_nufft_csr_bytes(const pdu_nufft_plan_t* p, long m) {
     return csr_layout(p, m, nullptr).total;
 }
 
+size_t pdu_nufft_csr_bytes2(const pdu_nufft_plan_t* p, long m, size_t* persist_bytes) {
+    if (persist_bytes) *persist_bytes = 0;
+    if (!p || m <= 0) return 0;
+    const CsrView v = csr_layout(p, m, nullptr);
+    // row_ptr | n_long | long_rows | samp | w are what applying the matrix reads; everything behind is sort scratch
+    if (persist_bytes) *persist_bytes = (size_t)((char*)v.key_in - (char*)nullptr);
+    return v.total;
+}
+
 int pdu_nufft_csr_build(pdu_nufft_plan_t* p, const float* omega, long m, void* csr, size_t csr_bytes, pdu_stream_t stream) {
     PDU_REQUIRE(p && omega && m > 0, "pdu_nufft_csr_build: null pointer or m <= 0");
     return csr_build(p, omega, m, csr, csr_bytes, (cudaStream_t)stream);
@@ -1201,6 +1150,45 @@ int pdu_nufft_adj_csr_c64(pdu_nufft_plan_t* p, const float* kdata, float* image,
         if (rc) return rc;
     }
     return PDU_OK;
+}
+
+int pdu_nufft_fwd_binned_c64(pdu_nufft_plan_t* p, const float* image, float* kdata, const float* smaps, int batch, int coils,
+                             int smaps_batch, long m, float scale, const void* bins, int flags, void* workspace,
+                             size_t workspace_bytes, pdu_stream_t stream) {
+    int rc = check_call(p, image, kdata, bins, batch, coils, smaps_batch, smaps, m, "pdu_nufft_fwd_binned_c64");
+    if (rc) return rc;
+    PDU_CHECK_DEVICE("pdu_nufft_fwd_binned_c64");
+    if (!fused_supported(p)) {
+        set_error("pdu_nufft_fwd_binned_c64: grid %d x %d (J = %d) has no fused path; use pdu_nufft_fwd_c64", p->k0, p->k1, p->J);
+        return PDU_EUNSUPPORTED;
+    }
+    const size_t need = fused_workspace_bytes(p, batch * coils, m);
+    if (!workspace || workspace_bytes < need || ((uintptr_t)workspace & 255)) {
+        set_error("pdu_nufft_fwd_binned_c64: workspace of %zu bytes (256-byte aligned) required, got %zu", need,
+                  workspace ? workspace_bytes : (size_t)0);
+        return PDU_ENOMEM;
+    }
+    return fused_forward(p, image, kdata, smaps, batch, coils, smaps_batch, m, scale, bins, flags, workspace, (cudaStream_t)stream);
+}
+
+int pdu_nufft_adj_binned_c64(pdu_nufft_plan_t* p, const float* kdata, float* image, const float* smaps, const float* kweight,
+                             int batch, int coils, int smaps_batch, long m, float scale, const void* bins, int flags,
+                             void* workspace, size_t workspace_bytes, pdu_stream_t stream) {
+    int rc = check_call(p, kdata, image, bins, batch, coils, smaps_batch, smaps, m, "pdu_nufft_adj_binned_c64");
+    if (rc) return rc;
+    PDU_CHECK_DEVICE("pdu_nufft_adj_binned_c64");
+    if (!fused_supported(p)) {
+        set_error("pdu_nufft_adj_binned_c64: grid %d x %d (J = %d) has no fused path; use pdu_nufft_adj_c64", p->k0, p->k1, p->J);
+        return PDU_EUNSUPPORTED;
+    }
+    const size_t need = fused_workspace_bytes(p, batch * coils, m);
+    if (!workspace || workspace_bytes < need || ((uintptr_t)workspace & 255)) {
+        set_error("pdu_nufft_adj_binned_c64: workspace of %zu bytes (256-byte aligned) required, got %zu", need,
+                  workspace ? workspace_bytes : (size_t)0);
+        return PDU_ENOMEM;
+    }
+    return fused_adjoint(p, kdata, image, smaps, kweight, batch, coils, smaps_batch, m, scale, bins, flags, workspace,
+                         (cudaStream_t)stream);
 }
 
 int pdu_nufft_interp_fwd_c64(pdu_nufft_plan_t* p, const float* grid, float* kdata, const float* omega, int planes,

@@ -1,9 +1,10 @@
-// Register-resident pruned FFT for the two oversampled-grid sizes of the BASELINE MRI shapes
-// (K = 512 for 256^2 images, K = 640 for 320^2): compile-time radices 8 x 8 x (K / 64), three
-// butterflies per thread with two shared-memory exchanges in between.  The first butterfly reads
-// its inputs straight from global memory and the last one writes its outputs straight back, so a
-// sequence crosses shared memory twice (pfft.cuh's generic run-time-radix passes: five times) and
-// there is no index arithmetic that is not a shift or a compile-time constant.
+// Register-resident pruned FFT for the oversampled-grid sizes of the BASELINE shapes (grid = 2 x image):
+//   K = 256 (128^2 images), 512 (256^2), 640 (320^2), 1024 (512^2), 2048 (1024^2)
+// compile-time radices 8 x 8 x (K / 64) (2048: 8 x 16 x 16): three butterflies per thread with two shared-memory
+// exchanges in between.  The first butterfly reads its inputs through a caller-supplied functor (global memory, or the
+// sequence's own shared buffer when an interpolation stage has just filled it) and the last one hands its
+// outputs to another functor, so a sequence crosses shared memory twice (pfft.cuh's generic run-time-radix
+// passes: five times) and there is no index arithmetic that is not a shift or a compile-time constant.
 //
 // Stockham autosort, natural order in and out; pass with radix R, Ns = product of earlier radices:
 //   butterfly j (0 <= j < K/R):  k = j mod Ns, hi = j / Ns
@@ -17,10 +18,11 @@ namespace pdu {
 
 template <int K>
 struct FastFft {
-    static constexpr bool ok = (K == 512 || K == 640);
-    static constexpr int TPS = K / 8;     // threads per sequence (radix-8 butterflies per pass)
-    static constexpr int R3 = K / 64;     // radix of the last pass: 8 or 10
-    // Padding: one slot every 2^PS elements, chosen per thread layout (measured, ncu r02):
+    static constexpr bool ok = (K == 256 || K == 512 || K == 640 || K == 1024 || K == 2048);
+    static constexpr int TPS = K / 8;                 // threads per sequence (one radix-8 butterfly each in the first pass)
+    static constexpr int R2 = K == 2048 ? 16 : 8;     // radix of the second pass
+    static constexpr int R3 = K / (8 * R2);           // radix of the last pass: 4, 8, 10, 16 (8 R2 butterflies)
+    // Padding: one slot every 2^PS elements, chosen per thread layout (measured, ncu r01):
     //  PS = 3 (column kernels: a half-warp is 8 neighbouring sequences x 2 butterflies) -- element 8 t + r sits at
     //    9 t + r; with the pitch == 2 (mod 16) float2 every access of the three passes is conflict free;
     //  PS = 4 (row kernels: a half-warp is 16 consecutive butterflies of one sequence) -- the unit-stride loads of
@@ -29,6 +31,7 @@ struct FastFft {
     template <int PS>
     __host__ __device__ static constexpr int pitch() { return (K + (K >> PS) + 13) / 16 * 16 + 2; }
 };
+static inline bool fast_fft_size(int K) { return K == 256 || K == 512 || K == 640 || K == 1024 || K == 2048; }
 template <int PS>
 __device__ __forceinline__ int ff_pos(int e) { return e + (e >> PS); }
 
@@ -73,10 +76,54 @@ __device__ __forceinline__ void ff_r10(float2* v) {
     }
 }
 
+// radix 16 = 4 x 4 and radix 32 = 4 x 8 inside one thread's registers (Cooley-Tukey, n = n1 + 4 n2, k = R2 k1 + k2):
+// four DFT_R2 over the stride-4 subsequences, twiddles W_R^(n1 k2), then R2 DFT_4 across the subsequences.
+template <bool INV, int R>
+__device__ __forceinline__ void ff_r4xN(float2* v) {
+    static_assert(R == 16 || R == 32, "radix 16 or 32");
+    constexpr int R2 = R / 4;
+    // exp(+2 pi i j / 32), j = 0 .. 31
+    constexpr float C32[32] = {1.f, 0.98078528040323043f, 0.92387953251128674f, 0.83146961230254524f, 0.70710678118654757f, 0.55557023301960229f, 0.38268343236508984f, 0.19509032201612833f, 0.f, -0.19509032201612819f, -0.38268343236508973f, -0.55557023301960196f, -0.70710678118654746f, -0.83146961230254535f, -0.92387953251128674f, -0.98078528040323043f, -1.f, -0.98078528040323043f, -0.92387953251128685f, -0.83146961230254546f, -0.70710678118654768f, -0.55557023301960218f, -0.38268343236509034f, -0.19509032201612866f, 0.f, 0.1950903220161283f, 0.38268343236509f, 0.55557023301960184f, 0.70710678118654735f, 0.83146961230254524f, 0.92387953251128652f, 0.98078528040323032f};
+    constexpr float S32[32] = {0.f, 0.19509032201612825f, 0.38268343236508978f, 0.55557023301960218f, 0.70710678118654746f, 0.83146961230254524f, 0.92387953251128674f, 0.98078528040323043f, 1.f, 0.98078528040323043f, 0.92387953251128674f, 0.83146961230254546f, 0.70710678118654757f, 0.55557023301960218f, 0.38268343236508989f, 0.19509032201612861f, 0.f, -0.19509032201612836f, -0.38268343236508967f, -0.55557023301960196f, -0.70710678118654746f, -0.83146961230254524f, -0.92387953251128652f, -0.98078528040323032f, -1.f, -0.98078528040323043f, -0.92387953251128663f, -0.83146961230254546f, -0.70710678118654768f, -0.55557023301960218f, -0.38268343236509039f, -0.19509032201612872f};
+    float2 y[4][R2];
+#pragma unroll
+    for (int n1 = 0; n1 < 4; ++n1) {
+#pragma unroll
+        for (int n2 = 0; n2 < R2; ++n2) y[n1][n2] = v[n1 + 4 * n2];
+        if constexpr (R2 == 4) pf_r4<INV>(y[n1]);
+        else pf_r8<INV>(y[n1]);
+    }
+#pragma unroll
+    for (int k2 = 0; k2 < R2; ++k2) {
+        float2 z[4];
+        z[0] = y[0][k2];
+#pragma unroll
+        for (int n1 = 1; n1 < 4; ++n1) {
+            constexpr int STEP = 32 / R;
+            const int j = (n1 * k2 * STEP) & 31;
+            const float2 w = make_float2(C32[j], INV ? S32[j] : -S32[j]);
+            z[n1] = (n1 * k2 == 0) ? y[n1][k2] : pf_mul(y[n1][k2], w);
+        }
+        pf_r4<INV>(z);
+#pragma unroll
+        for (int k1 = 0; k1 < 4; ++k1) v[R2 * k1 + k2] = z[k1];
+    }
+}
+
+template <bool INV, int R>
+__device__ __forceinline__ void ff_small(float2* v) {
+    if constexpr (R == 4) pf_r4<INV>(v);
+    else if constexpr (R == 8) pf_r8<INV>(v);
+    else if constexpr (R == 10) ff_r10<INV>(v);
+    else ff_r4xN<INV, R>(v);
+}
+
 // One sequence of length K held by the TPS threads t = 0 .. TPS-1 of a CTA (every thread of the CTA must call
 // this: it synchronises).  buf = this sequence's pitch<PS>() float2 of shared memory, tw = the K-entry table
 // exp(-2 pi i m / K) in shared memory.  ld(e) returns input element e, st(e, v) consumes output element e.
-template <int K, int PS, bool INV, bool HALF_IN, bool HALF_OUT, class LD, class ST>
+// LD_BUF: ld reads this CTA's `buf`s (an interpolation stage filled them) -- every load must be complete before
+//   the first exchange store;  ST_BUF: st writes the `buf`s -- every last-pass load must be complete before it.
+template <int K, int PS, bool INV, bool HALF_IN, bool HALF_OUT, bool LD_BUF = false, bool ST_BUF = false, class LD, class ST>
 __device__ __forceinline__ void ff_transform(float2* __restrict__ buf, const float2* __restrict__ tw, int t, LD ld, ST st) {
     using F = FastFft<K>;
     constexpr int TPS = F::TPS, R3 = F::R3;
@@ -84,36 +131,70 @@ __device__ __forceinline__ void ff_transform(float2* __restrict__ buf, const flo
     // pass 1: radix 8, Ns = 1
 #pragma unroll
     for (int r = 0; r < 8; ++r) v[r] = (HALF_IN && r >= 4) ? make_float2(0.f, 0.f) : ld(t + r * TPS);
+    if (LD_BUF) __syncthreads();
     pf_r8<INV>(v);
 #pragma unroll
     for (int r = 0; r < 8; ++r) buf[ff_pos<PS>(t * 8 + r)] = v[r];
     __syncthreads();
-    // pass 2: radix 8, Ns = 8
+    // pass 2: radix R2, Ns = 8; K / R2 butterflies
+    constexpr int R2 = F::R2, NB2 = K / R2, NS3 = 8 * R2;
+    float2 w2[R2];
+    if (t < NB2) {
 #pragma unroll
-    for (int r = 0; r < 8; ++r) v[r] = buf[ff_pos<PS>(t + r * TPS)];
-    __syncthreads();
-    {
-        const int k = t & 7;
-#pragma unroll
-        for (int r = 1; r < 8; ++r) v[r] = pf_mul(v[r], ff_tw<INV>(tw, r * k * (K / 64)));
-        pf_r8<INV>(v);
-        const int o0 = (t >> 3) * 64 + k;
-#pragma unroll
-        for (int r = 0; r < 8; ++r) buf[ff_pos<PS>(o0 + r * 8)] = v[r];
+        for (int r = 0; r < R2; ++r) w2[r] = buf[ff_pos<PS>(t + r * NB2)];
     }
     __syncthreads();
-    // pass 3: radix K / 64, Ns = 64; 64 butterflies
-    if (t < 64) {
-        float2 u[R3];
+    if (t < NB2) {
+        const int k = t & 7;
 #pragma unroll
-        for (int r = 0; r < R3; ++r) u[r] = buf[ff_pos<PS>(t + r * 64)];
+        for (int r = 1; r < R2; ++r) w2[r] = pf_mul(w2[r], ff_tw<INV>(tw, r * k * (K / NS3)));
+        ff_small<INV, R2>(w2);
+        const int o0 = (t >> 3) * NS3 + k;
 #pragma unroll
-        for (int r = 1; r < R3; ++r) u[r] = pf_mul(u[r], ff_tw<INV>(tw, r * t));
-        if constexpr (R3 == 8) pf_r8<INV>(u);
-        else ff_r10<INV>(u);
+        for (int r = 0; r < R2; ++r) buf[ff_pos<PS>(o0 + r * 8)] = w2[r];
+    }
+    __syncthreads();
+    // pass 3: radix R3, Ns = 8 R2; NS3 butterflies (TPS = 32: two per thread)
+    constexpr int PER = TPS >= NS3 ? 1 : NS3 / TPS;
+    if (!ST_BUF) {
 #pragma unroll
-        for (int r = 0; r < R3; ++r)
-            if (!HALF_OUT || r < R3 / 2) st(t + r * 64, u[r]);
+        for (int i = 0; i < PER; ++i) {
+            const int j = t + i * TPS;
+            if (j < NS3) {
+                float2 u[R3];
+#pragma unroll
+                for (int r = 0; r < R3; ++r) u[r] = buf[ff_pos<PS>(j + r * NS3)];
+#pragma unroll
+                for (int r = 1; r < R3; ++r) u[r] = pf_mul(u[r], ff_tw<INV>(tw, r * j));
+                ff_small<INV, R3>(u);
+#pragma unroll
+                for (int r = 0; r < R3; ++r)
+                    if (!HALF_OUT || r < R3 / 2) st(j + r * NS3, u[r]);
+            }
+        }
+    } else {
+        float2 u[PER][R3];
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+            const int j = t + i * TPS;
+            if (j < NS3) {
+#pragma unroll
+                for (int r = 0; r < R3; ++r) u[i][r] = buf[ff_pos<PS>(j + r * NS3)];
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+            const int j = t + i * TPS;
+            if (j < NS3) {
+#pragma unroll
+                for (int r = 1; r < R3; ++r) u[i][r] = pf_mul(u[i][r], ff_tw<INV>(tw, r * j));
+                ff_small<INV, R3>(u[i]);
+#pragma unroll
+                for (int r = 0; r < R3; ++r)
+                    if (!HALF_OUT || r < R3 / 2) st(j + r * NS3, u[i][r]);
+            }
+        }
     }
 }
 

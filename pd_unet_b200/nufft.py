@@ -26,7 +26,7 @@ import numpy as np
 import torch
 from torch import nn
 
-from ._lib import PduError, check, lib, require_cuda, stream_ptr
+from ._lib import NUFFT_IMAGE_SPLIT, NUFFT_KDATA_SPLIT, PduError, check, lib, require_cuda, stream_ptr
 
 
 # ----------------------------------------------------------------------------- tables (host, float64)
@@ -74,33 +74,93 @@ class _Plan:
         self.scaling = [kaiser_bessel_scaling(n, k, self.numpoints, self.kbwidth).astype(np.float32)
                         for n, k in zip(self.im_size, self.grid_size)]
         self._handles: Dict[int, C.c_void_p] = {}
-        # adjoint interpolators (CSR, sorted by grid cell) of the most recent trajectories:
-        # key -> (omega kept alive so its address cannot be reused, device buffer)
-        self._csr: "OrderedDict[tuple, tuple]" = OrderedDict()
+        # per-trajectory precomputation (row bins of the fused path, CSR form of the adjoint interpolator), keyed by
+        # the trajectory tensor's identity; a fixed trajectory is reused by every unrolled iteration / training step
+        self._traj: "OrderedDict[tuple, dict]" = OrderedDict()
+        self.traj_cache_bytes = 512 << 20
         # "auto": the gather where it is faster (measured on B200: >= 16 planes per call; with fewer planes
         # the atomic scatter wins -- 54 vs 138 us at 256 spokes x 1 plane, 165 vs 157 us at 16 planes, 597 vs
-        # 437 us at 64 planes); True: always (bit-reproducible adjoint); False: never
+        # 437 us at 64 planes); True: always (bit-reproducible adjoint); False: never.  Only the generic path
+        # (grids without a fused path, KbInterpAdjoint) looks at it.
         self.use_csr = "auto"
+        # the fused path (csrc/nufft_fused.cu) wherever the library has one for the grid; False forces the generic path
+        self.use_fused = True
+
+    # -------------------------------------------------------------- per-trajectory cache
+    def _entry(self, omega: torch.Tensor) -> dict:
+        key = (omega.data_ptr(), omega._version, tuple(omega.shape), omega.device)
+        ent = self._traj.get(key)
+        if ent is None:
+            ent = {"omega": omega, "bins": None, "csr": None, "events": []}   # omega kept alive: its address cannot be reused
+            self._traj[key] = ent
+        else:
+            self._traj.move_to_end(key)
+        return ent
+
+    def _trim(self) -> None:
+        def nbytes(e):
+            return sum(t.numel() for t in (e["bins"], e["csr"]) if t is not None)
+        while len(self._traj) > 1 and (len(self._traj) > 16 or sum(nbytes(e) for e in self._traj.values()) > self.traj_cache_bytes):
+            self._traj.popitem(last=False)
+
+    @staticmethod
+    def _built(ent: dict) -> None:
+        """Remember where the build ran so that a later use on another stream can wait for it."""
+        ev = torch.cuda.Event()
+        ev.record()
+        ent["events"].append((torch.cuda.current_stream(), ev))
+
+    @staticmethod
+    def _wait(ent: dict) -> None:
+        cur = torch.cuda.current_stream()
+        if torch.cuda.is_current_stream_capturing():
+            return                      # graph capture follows eager warm-up calls and a device synchronisation
+        for st, ev in ent["events"]:
+            if st != cur:
+                cur.wait_event(ev)
+
+    def _keep_prefix(self, buf: torch.Tensor, persist: int) -> torch.Tensor:
+        """Only the head of a build buffer is needed afterwards; the sort scratch behind it (about two thirds) goes
+        back to the allocator (stream-ordered, so the pending build kernels are safe)."""
+        return buf[:persist].clone() if persist < buf.numel() else buf
+
+    def _bins_for(self, omega: torch.Tensor):
+        """Row bins of the fused path for this trajectory (None when the grid has no fused path)."""
+        L, h = lib(), self.handle(omega.device)
+        if not self.use_fused or not L.pdu_nufft_has_fused_path(h):
+            return None
+        ent = self._entry(omega)
+        if ent["bins"] is None:
+            persist = C.c_size_t(0)
+            nbytes = L.pdu_nufft_bins_bytes(h, omega.shape[1], C.byref(persist))
+            buf = torch.empty(nbytes, dtype=torch.uint8, device=omega.device)
+            check(L.pdu_nufft_bins_build(h, omega.data_ptr(), omega.shape[1], buf.data_ptr(), buf.numel(), stream_ptr()),
+                  "pdu_nufft_bins_build")
+            ent["bins"] = self._keep_prefix(buf, persist.value)
+            self._built(ent)
+            self._trim()
+        else:
+            self._wait(ent)
+        return ent["bins"]
 
     def _csr_for(self, omega: torch.Tensor, planes: int = 1 << 30):
-        """The sorted-gather form of the adjoint interpolator for this trajectory, built on first use and
-        kept for the last few trajectories (a fixed trajectory is reused by every unrolled iteration)."""
+        """The sorted-gather form of the adjoint interpolator for this trajectory, built on first use."""
         if self.use_csr is False or (self.use_csr == "auto" and planes < 16):
             return None
-        key = (omega.data_ptr(), omega._version, tuple(omega.shape), omega.device)
-        hit = self._csr.get(key)
-        if hit is not None:
-            self._csr.move_to_end(key)
-            return hit[1]
-        L, h = lib(), self.handle(omega.device)
-        nbytes = L.pdu_nufft_csr_bytes(h, omega.shape[1])
-        buf = torch.empty(nbytes, dtype=torch.uint8, device=omega.device)
-        check(L.pdu_nufft_csr_build(h, omega.data_ptr(), omega.shape[1], buf.data_ptr(), buf.numel(), stream_ptr()),
-              "pdu_nufft_csr_build")
-        self._csr[key] = (omega, buf)
-        while len(self._csr) > 4:
-            self._csr.popitem(last=False)
-        return buf
+        ent = self._entry(omega)
+        if ent["csr"] is None:
+            L, h = lib(), self.handle(omega.device)
+            persist = C.c_size_t(0)
+            nbytes = L.pdu_nufft_csr_bytes2(h, omega.shape[1], C.byref(persist))
+            buf = torch.empty(nbytes, dtype=torch.uint8, device=omega.device)
+            check(L.pdu_nufft_csr_build(h, omega.data_ptr(), omega.shape[1], buf.data_ptr(), buf.numel(), stream_ptr()),
+                  "pdu_nufft_csr_build")
+            ent["csr"] = self._keep_prefix(buf, persist.value)
+            self._built(ent)
+            self._trim()
+        else:
+            self._wait(ent)
+        return ent["csr"]
 
     def handle(self, device: torch.device) -> C.c_void_p:
         idx = device.index if device.index is not None else torch.cuda.current_device()
@@ -155,45 +215,106 @@ class _Plan:
             raise ValueError(f"smaps must be [1 or {batch}, coils, {self.im_size[0]}, {self.im_size[1]}]")
         return smaps, smaps.shape[1], smaps.shape[0]
 
-    def forward(self, image, omega, smaps, norm):
-        image = require_cuda(image, torch.complex64, "image")
-        if image.dim() != 4 or tuple(image.shape[-2:]) != self.im_size:
+    # Layouts.  split=False: complex64 tensors, image [B, C, N0, N1], data [B, C, M] (torchkbnufft's).
+    # split=True: float32 tensors with the real and imaginary parts as neighbouring channels, image [B, 2 C, N0, N1],
+    # data [B, 2 C, M] -- what PD-UNet's CNN blocks carry, so the model needs no permute / view_as_complex passes.
+    @staticmethod
+    def _split_to_complex(x: torch.Tensor) -> torch.Tensor:
+        B, C2 = x.shape[:2]
+        return torch.complex(x.reshape(B, C2 // 2, 2, *x.shape[2:])[:, :, 0], x.reshape(B, C2 // 2, 2, *x.shape[2:])[:, :, 1])
+
+    @staticmethod
+    def _complex_to_split(z: torch.Tensor) -> torch.Tensor:
+        B, Cc = z.shape[:2]
+        return torch.stack([z.real, z.imag], dim=2).reshape(B, 2 * Cc, *z.shape[2:]).contiguous()
+
+    def _chunks(self, L, h, B: int, coils: int, M: int):
+        """Batch chunks that keep the fused path's scratch under 1 GiB."""
+        per = max(1, L.pdu_nufft_binned_workspace_bytes(h, coils, M))
+        cb = max(1, min(B, (1 << 30) // per))
+        return [(b0, min(B, b0 + cb)) for b0 in range(0, B, cb)]
+
+    def forward(self, image, omega, smaps, norm, split: bool = False):
+        image = require_cuda(image, torch.float32 if split else torch.complex64, "image")
+        if image.dim() != 4 or tuple(image.shape[-2:]) != self.im_size or (split and image.shape[1] % 2):
             raise ValueError(f"image must be [B, C, {self.im_size[0]}, {self.im_size[1]}], got {tuple(image.shape)}")
         omega = self._omega(omega)
         B, M = image.shape[0], omega.shape[1]
+        ci = image.shape[1] // 2 if split else image.shape[1]
         smaps, coils, sb = self._smaps(smaps, B)
         if smaps is None:
-            coils = image.shape[1]
-        elif image.shape[1] != 1:
+            coils = ci
+        elif ci != 1:
             raise ValueError("with smaps the image must have one channel")
-        out = torch.empty((B, coils, M), dtype=torch.complex64, device=image.device)
+        out = (torch.empty((B, 2 * coils, M), dtype=torch.float32, device=image.device) if split else
+               torch.empty((B, coils, M), dtype=torch.complex64, device=image.device))
         if B == 0 or M == 0:
             return out
         with torch.cuda.device(image.device):
             L, h = lib(), self.handle(image.device)
+            bins = self._bins_for(omega)
+            if bins is not None:
+                flags = (NUFFT_IMAGE_SPLIT | NUFFT_KDATA_SPLIT) if split else 0
+                for b0, b1 in self._chunks(L, h, B, coils, M):
+                    nb = b1 - b0
+                    ws = torch.empty(L.pdu_nufft_binned_workspace_bytes(h, nb * coils, M), dtype=torch.uint8, device=image.device)
+                    sm = None if smaps is None else (smaps if sb == 1 else smaps[b0:b1])
+                    check(L.pdu_nufft_fwd_binned_c64(h, image[b0:b1].data_ptr(), out[b0:b1].data_ptr(),
+                                                     sm.data_ptr() if sm is not None else None, nb, coils, 1 if sb == 1 else nb, M,
+                                                     self.scale(norm), bins.data_ptr(), flags, ws.data_ptr(), ws.numel(),
+                                                     stream_ptr()), "pdu_nufft_fwd_binned_c64")
+                return out
+            if split:
+                return self._complex_to_split(self.forward(self._split_to_complex(image), omega, smaps, norm))
             ws = torch.empty(L.pdu_nufft_workspace_bytes(h, B * coils), dtype=torch.uint8, device=image.device)
             check(L.pdu_nufft_fwd_c64(h, image.data_ptr(), out.data_ptr(), omega.data_ptr(),
                                       smaps.data_ptr() if smaps is not None else None, B, coils, sb, M,
                                       self.scale(norm), ws.data_ptr(), ws.numel(), stream_ptr()), "pdu_nufft_fwd_c64")
         return out
 
-    def adjoint(self, data, omega, smaps, norm):
-        data = require_cuda(data, torch.complex64, "data")
+    def adjoint(self, data, omega, smaps, norm, split: bool = False, kweight: Optional[torch.Tensor] = None):
+        """kweight: float32 [M] multiplied into the samples first (density compensation)."""
+        data = require_cuda(data, torch.float32 if split else torch.complex64, "data")
         omega = self._omega(omega)
-        if data.dim() != 3 or data.shape[-1] != omega.shape[1]:
+        if data.dim() != 3 or data.shape[-1] != omega.shape[1] or (split and data.shape[1] % 2):
             raise ValueError(f"data must be [B, C, {omega.shape[1]}], got {tuple(data.shape)}")
-        B, coils, M = data.shape
+        B, M = data.shape[0], data.shape[2]
+        coils = data.shape[1] // 2 if split else data.shape[1]
         smaps, sc, sb = self._smaps(smaps, B)
         if smaps is not None and sc != coils:
             raise ValueError(f"data has {coils} coils, smaps {sc}")
-        out = torch.empty((B, 1 if smaps is not None else coils) + self.im_size, dtype=torch.complex64,
-                          device=data.device)
+        if kweight is not None:
+            kweight = require_cuda(kweight, torch.float32, "kweight").reshape(-1)
+            if kweight.numel() != M:
+                raise ValueError(f"kweight must have {M} entries")
+        co = 1 if smaps is not None else coils
+        out = (torch.empty((B, 2 * co) + self.im_size, dtype=torch.float32, device=data.device) if split else
+               torch.empty((B, co) + self.im_size, dtype=torch.complex64, device=data.device))
         if B == 0:
             return out
         if M == 0:
             return out.zero_()
         with torch.cuda.device(data.device):
             L, h = lib(), self.handle(data.device)
+            bins = self._bins_for(omega)
+            if bins is not None:
+                flags = (NUFFT_IMAGE_SPLIT | NUFFT_KDATA_SPLIT) if split else 0
+                for b0, b1 in self._chunks(L, h, B, coils, M):
+                    nb = b1 - b0
+                    ws = torch.empty(L.pdu_nufft_binned_workspace_bytes(h, nb * coils, M), dtype=torch.uint8, device=data.device)
+                    sm = None if smaps is None else (smaps if sb == 1 else smaps[b0:b1])
+                    check(L.pdu_nufft_adj_binned_c64(h, data[b0:b1].data_ptr(), out[b0:b1].data_ptr(),
+                                                     sm.data_ptr() if sm is not None else None,
+                                                     kweight.data_ptr() if kweight is not None else None, nb, coils,
+                                                     1 if sb == 1 else nb, M, self.scale(norm), bins.data_ptr(), flags,
+                                                     ws.data_ptr(), ws.numel(), stream_ptr()), "pdu_nufft_adj_binned_c64")
+                return out
+            if split or kweight is not None:
+                z = self._split_to_complex(data) if split else data
+                if kweight is not None:
+                    z = z * kweight
+                x = self.adjoint(z, omega, smaps, norm)
+                return self._complex_to_split(x) if split else x
             ws = torch.empty(L.pdu_nufft_workspace_bytes(h, B * coils), dtype=torch.uint8, device=data.device)
             csr = self._csr_for(omega, B * coils)
             check(L.pdu_nufft_adj_csr_c64(h, data.data_ptr(), out.data_ptr(), omega.data_ptr(),
@@ -253,18 +374,24 @@ def _per_trajectory(fn, x, omega, smaps, *rest):
 
 class _NufftFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, omega, smaps, plan, norm, adjoint):
-        ctx.plan, ctx.norm, ctx.adjoint = plan, norm, adjoint
+    def forward(ctx, x, omega, smaps, plan, norm, adjoint, split=False, kweight=None):
+        ctx.plan, ctx.norm, ctx.adjoint, ctx.split, ctx.kweight = plan, norm, adjoint, split, kweight
         ctx.save_for_backward(omega, smaps) if smaps is not None else ctx.save_for_backward(omega)
-        fn = plan.adjoint if adjoint else plan.forward
-        return _per_trajectory(fn, x, omega, smaps, norm)
+        if adjoint:
+            return _per_trajectory(plan.adjoint, x, omega, smaps, norm, split, kweight)
+        return _per_trajectory(plan.forward, x, omega, smaps, norm, split)
 
     @staticmethod
     def backward(ctx, grad):
         saved = ctx.saved_tensors
         omega, smaps = saved[0], (saved[1] if len(saved) > 1 else None)
-        fn = ctx.plan.forward if ctx.adjoint else ctx.plan.adjoint
-        return _per_trajectory(fn, grad.contiguous(), omega, smaps, ctx.norm), None, None, None, None, None
+        if ctx.adjoint:       # x = A^H (w y)  =>  dy = w A dx
+            g = _per_trajectory(ctx.plan.forward, grad.contiguous(), omega, smaps, ctx.norm, ctx.split)
+            if ctx.kweight is not None:
+                g = g * ctx.kweight.reshape(-1)
+        else:
+            g = _per_trajectory(ctx.plan.adjoint, grad.contiguous(), omega, smaps, ctx.norm, ctx.split)
+        return g, None, None, None, None, None, None, None
 
 
 class _InterpFn(torch.autograd.Function):
@@ -302,17 +429,22 @@ class _KbModule(nn.Module):
 class KbNufft(_KbModule):
     """image [B, C, N0, N1] -> k-space samples [B, C (or coils), M].  [RECALL] torchkbnufft.KbNufft."""
 
-    def forward(self, image, omega, interp_mats=None, smaps=None, norm: Optional[str] = None):
+    def forward(self, image, omega, interp_mats=None, smaps=None, norm: Optional[str] = None, split: bool = False):
+        """split=True (an extension): image float32 [B, 2 C, N0, N1] with (re, im) as neighbouring channels ->
+        float32 [B, 2 coils, M]; no complex tensors, no layout passes around the operator."""
         self._no_interp_mats(interp_mats)
-        return _NufftFn.apply(image, omega, smaps, self._plan, norm, False)
+        return _NufftFn.apply(image, omega, smaps, self._plan, norm, False, split)
 
 
 class KbNufftAdjoint(_KbModule):
     """samples [B, C, M] -> image [B, C (or 1), N0, N1].  [RECALL] torchkbnufft.KbNufftAdjoint."""
 
-    def forward(self, data, omega, interp_mats=None, smaps=None, norm: Optional[str] = None):
+    def forward(self, data, omega, interp_mats=None, smaps=None, norm: Optional[str] = None, split: bool = False,
+                kweight: Optional[torch.Tensor] = None):
+        """Extensions: split=True as in KbNufft; kweight float32 [M] is multiplied into the samples on load (the
+        density compensation that otherwise is a separate pass over the data)."""
         self._no_interp_mats(interp_mats)
-        return _NufftFn.apply(data, omega, smaps, self._plan, norm, True)
+        return _NufftFn.apply(data, omega, smaps, self._plan, norm, True, split, kweight)
 
 
 class KbInterp(_KbModule):

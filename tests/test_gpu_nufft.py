@@ -239,3 +239,55 @@ def test_default_path_at_the_cfg4_share_matches_oracle():
         assert rel_l2(xa64[bb, cc], oracle.nufft_adjoint(k[bb:bb + 1, cc:cc + 1], om, spec)[0, 0]) <= TOL
     # the adjoint of a fixed trajectory is bit-reproducible (no atomics on the default path)
     assert torch.equal(AH(k.to(DEV), omd, smaps=sm.to(DEV), norm="ortho"), xa)
+
+
+@pytest.mark.parametrize("n,planes,spokes", [(128, 3, 24), (256, 9, 20), (320, 2, 17), (512, 3, 12), (1024, 2, 6)])
+def test_fused_path_every_grid_size(n, planes, spokes):
+    """csrc/nufft_fused.cu on each grid it is compiled for (256, 512, 640, 1024, 2048), with plane counts that are
+    not multiples of the CTA's plane group, against the float64 oracle -- and against the generic path."""
+    from pd_unet_b200 import _lib
+    im = (n, n)
+    spec = oracle.NufftSpec(im)
+    om = _traj(spokes, 2 * n)
+    omd = torch.from_numpy(om).to(DEV)
+    A, AH = pdu.KbNufft(im), pdu.KbNufftAdjoint(im)
+    x = seeded((1, planes) + im, 71, complex_=True)
+    k = seeded((1, planes, om.shape[1]), 72, complex_=True)
+    y, xa = A(x.to(DEV), omd), AH(k.to(DEV), omd)
+    assert "fz_rows_fwd_kernel" in _lib.last_kernel("nufft_fwd") and "fz_rows_adj_kernel" in _lib.last_kernel("nufft_adj")
+    check = [0, planes - 1]
+    assert rel_l2(y[:, check], oracle.nufft_forward(x[:, check], om, spec)) <= TOL
+    assert rel_l2(xa[:, check], oracle.nufft_adjoint(k[:, check], om, spec)) <= TOL
+    A._plan.use_fused = AH._plan.use_fused = False
+    assert rel_l2(A(x.to(DEV), omd), y) <= 2e-6 and rel_l2(AH(k.to(DEV), omd), xa) <= 2e-6
+    assert "fz_" not in _lib.last_kernel("nufft_fwd")
+
+
+def test_split_layout_and_density_weights():
+    """The (re, im)-as-channels layout and the fused density compensation give the same numbers as the complex API
+    followed by the layout passes -- with and without coil maps, on the fused path and on the generic one."""
+    for n, coils in ((256, 1), (320, 4), (48, 3)):
+        im = (n, n)
+        om = torch.from_numpy(_traj(11, 2 * n)).to(DEV)
+        M = om.shape[1]
+        A, AH = pdu.KbNufft(im), pdu.KbNufftAdjoint(im)
+        sm = coil_maps(coils, n)[None].to(DEV) if coils > 1 else None
+        x = seeded((2, 1) + im, 81, complex_=True).to(DEV)
+        k = seeded((2, coils, M), 82, complex_=True).to(DEV)
+        w = torch.rand(M, generator=torch.Generator().manual_seed(3)).to(DEV) + 0.5
+        xs = torch.stack([x.real, x.imag], 2).reshape(2, 2, n, n).contiguous()
+        ks = torch.stack([k.real, k.imag], 2).reshape(2, 2 * coils, M).contiguous()
+        y = A(x, om, smaps=sm, norm="ortho")
+        ys = A(xs, om, smaps=sm, norm="ortho", split=True)
+        assert ys.shape == (2, 2 * coils, M) and ys.dtype == torch.float32
+        assert rel_l2(torch.complex(ys.reshape(2, coils, 2, M)[:, :, 0], ys.reshape(2, coils, 2, M)[:, :, 1]), y) <= 1e-6
+        xa = AH(k * w, om, smaps=sm, norm="ortho")
+        xas = AH(ks, om, smaps=sm, norm="ortho", split=True, kweight=w)
+        co = xa.shape[1]
+        assert xas.shape == (2, 2 * co, n, n)
+        assert rel_l2(torch.complex(xas.reshape(2, co, 2, n, n)[:, :, 0], xas.reshape(2, co, 2, n, n)[:, :, 1]), xa) <= 1e-6
+        # gradients flow through the split / weighted forms: <A^H(w k), x> differentiated in k is w A x
+        ksr = ks.clone().requires_grad_()
+        (AH(ksr, om, smaps=sm, norm="ortho", split=True, kweight=w) * xs[:, :2 * co]).sum().backward()
+        want = A(xs, om, smaps=sm, norm="ortho", split=True) * w
+        assert rel_l2(ksr.grad, want) <= 1e-5
