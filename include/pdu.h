@@ -279,6 +279,18 @@ PDU_API int pdu_angular_upsample_f32(const float* sparse, float* full, int batch
                                      int factor, int det_count, int mode, pdu_stream_t stream);
 PDU_API int pdu_angular_upsample_adj_f32(const float* full, float* sparse, int batch, int a_sparse,
                                          int factor, int det_count, int mode, pdu_stream_t stream);
+/* The same with the result multiplied by `scale` (the 1 / operator-norm normalisation of the model's input). */
+PDU_API int pdu_angular_upsample_scaled_f32(const float* sparse, float* full, int batch, int a_sparse,
+                                            int factor, int det_count, int mode, float scale, pdu_stream_t stream);
+/* The upsampling fused with the dual update's concatenation:
+ *   out [batch, c_out, views, det] = cat(a [batch, ca, ...], scale_b * b [batch, 1, ...],
+ *                                        scale_c * upsample(sparse [batch, a_sparse, det]), zeros)
+ * with views = a_sparse * factor, in `layout`.  The full-view measured sinogram is never materialised: every
+ * unrolled iteration reads the sparse views instead.  Replaces torch.cat([h, K f, g]) with g the
+ * interpolated sinogram. */
+PDU_API int pdu_concat_upsample_f32(float* out, const float* a, const float* b, const float* sparse, int batch,
+                                    int ca, int c_out, int a_sparse, int factor, int det_count, int mode,
+                                    float scale_b, float scale_c, int layout, pdu_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -83,6 +83,9 @@ SIGNATURES = {
     "pdu_bias_prelu_place_f32": (C.c_int, [_p, _p, _p, C.c_int, _p, C.c_long, _p, C.c_int, C.c_int, C.c_int, C.c_int, _p]),
     "pdu_axpby_f32": (C.c_int, [_p, C.c_float, _p, C.c_float, _p, C.c_long, _p]),
     "pdu_angular_upsample_f32": (C.c_int, [_p, _p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _p]),
+    "pdu_angular_upsample_scaled_f32": (C.c_int, [_p, _p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _p]),
+    "pdu_concat_upsample_f32": (C.c_int, [_p, _p, _p, _p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                          C.c_float, C.c_float, C.c_int, _p]),
     "pdu_angular_upsample_adj_f32": (C.c_int, [_p, _p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _p]),
 }
 

@@ -275,12 +275,7 @@ __global__ void __launch_bounds__(SEQ* FastFft<K>::TPS)
 }
 
 // ------------------------------------------------------------------ forward, pass 2: row FFT + interpolation along the row
-// Work item = grid row R (heavy rows first) x PG planes; thread = (plane slot s, butterfly t).  The kernel is PERSISTENT:
-// a CTA per SM slot walks the item list with stride gridDim.x.  A short-lived CTA per item spent most of its life in a
-// chain of dependent L2 round trips (row -> entry range -> records, plus the twiddle table again and again: measured
-// ~60 us of 148); here the twiddles are loaded once per CTA, the next item's descriptor is read one iteration ahead and
-// its T rows and entry records are prefetched into L1 while the current row is transformed.
-__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+// CTA = work item = grid row R (heavy rows first) x PG planes; thread = (plane slot s, butterfly t).
 
 // item -> (row, first plane); -1 when past the end
 struct FzItem {
@@ -311,27 +306,18 @@ __global__ void __launch_bounds__(PG* FastFft<K>::TPS, (1536 / (PG * FastFft<K>:
     float2* buf = fz_smem<float2>();
     float2* tw = buf + PG * PITCH;
     const int tid = threadIdx.x, s = tid / F::TPS, t = tid - s * F::TPS;
-    const int n_items = K * groups;
+    const FzItem cur = fz_item(blockIdx.x, K * groups, groups, PG, K, row_order, key_ptr);
+    if (cur.beg == cur.end) return;                                // no sample touches this row: its transform is not needed
     for (int i = tid; i < K; i += NT) tw[i] = __ldg(tw_g + i);
-    FzItem nxt = fz_item(blockIdx.x, n_items, groups, PG, K, row_order, key_ptr);
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const FzItem cur = nxt;
-        nxt = fz_item(item + gridDim.x, n_items, groups, PG, K, row_order, key_ptr);
-        if (cur.beg == cur.end) continue;                          // no sample touches this row: its transform is not needed
+    {
         const int p = cur.p0 + s;
         const bool live = p < planes;
         const float2* src = T + ((long)p * K + cur.R) * d.n1;
         auto ld = [&](int e) { return live ? __ldcs(src + e) : make_float2(0.f, 0.f); };
         float2* row = buf + s * PITCH;
         auto st = [&](int e, float2 v) { row[ff_pos<4>(e)] = v; };
-        __syncthreads();                                           // the previous item's row has been consumed (and tw is loaded)
+        __syncthreads();                                           // tw is loaded
         ff_transform<K, 4, false, true, false, false, true>(row, tw, t, ld, st);
-        if (nxt.R >= 0) {                                          // next item's inputs -> L1 while this row is interpolated
-            const int pn = nxt.p0 + s;
-            if (pn < planes)
-                for (int e = t * 16; e < d.n1; e += F::TPS * 16) prefetch_l1(T + ((long)pn * K + nxt.R) * d.n1 + e);
-            for (int e = nxt.beg + tid * 2; e < nxt.end; e += NT * 2) prefetch_l1(rec + e);
-        }
         __syncthreads();
         // a thread = one entry, all PG planes: the record is read once, the taps are LDS.64, and a warp's stores of one
         // plane are 32 neighbouring entries (mostly neighbouring samples of one spoke)
@@ -431,14 +417,8 @@ __global__ void __launch_bounds__(PG* FastFft<K>::TPS, (1024 / (PG * FastFft<K>:
     int* us = reinterpret_cast<int*>(cs + EC * FZ_J); // [EC]
     int* kp = us + EC;                                // [K + 1]
     const int tid = threadIdx.x, s = tid / F::TPS, t = tid - s * F::TPS;
-    const int n_items = K * groups;
-    for (int i = tid; i < K; i += NT) tw[i] = __ldg(tw_g + i);
-    // persistent: see fz_rows_fwd_kernel.  The next item's descriptor is read one iteration ahead; its key_ptr row, cell
-    // order and entry records are prefetched into L1 while the current row is transformed.
-    FzItem nxt = fz_item(blockIdx.x, n_items, groups, PG, K, row_order, key_ptr);
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const FzItem cur = nxt;
-        nxt = fz_item(item + gridDim.x, n_items, groups, PG, K, row_order, key_ptr);
+    const FzItem cur = fz_item(blockIdx.x, K * groups, groups, PG, K, row_order, key_ptr);
+    {
         const int R = cur.R, p0 = cur.p0, beg = cur.beg, end = cur.end;
         const int p = p0 + s;
         const bool live = p < planes;
@@ -446,8 +426,9 @@ __global__ void __launch_bounds__(PG* FastFft<K>::TPS, (1024 / (PG * FastFft<K>:
         if (beg == end) {                             // empty row: its inverse transform is zero
             if (live)
                 for (int e = t; e < d.n1; e += F::TPS) __stcs(dst + e, make_float2(0.f, 0.f));
-            continue;
+            return;
         }
+        for (int i = tid; i < K; i += NT) tw[i] = __ldg(tw_g + i);
         // stage chunk [cb, cb + ne): a thread = one entry, all PG planes -- the record is read once and the PG sample
         // loads are independent (consecutive lanes = neighbouring samples of a spoke: the loads of one plane coalesce)
         auto stage = [&](int cb, int ne) {
@@ -483,8 +464,7 @@ __global__ void __launch_bounds__(PG* FastFft<K>::TPS, (1024 / (PG * FastFft<K>:
                 c[2] = make_float4(r3.x, -r3.y, r3.z, -r3.w);
             }
         };
-        __syncthreads();                              // the previous item's buffers are free (and tw is loaded)
-        stage(beg, min(EC, end - beg));
+        stage(beg, min(EC, end - beg));               // the first chunk's loads are in flight while the tables load
         for (int i = tid; i <= K; i += NT) kp[i] = __ldg(key_ptr + (long)R * K + i);
         // this thread's cells: the q-th block of NT cells in the row's order of decreasing contributor count, so that
         // the lanes of a warp loop about equally often
@@ -541,11 +521,6 @@ __global__ void __launch_bounds__(PG* FastFft<K>::TPS, (1024 / (PG * FastFft<K>:
         for (int q = 0; q < CPT; ++q)
 #pragma unroll
             for (int g = 0; g < PG; ++g) buf[g * PITCH + ff_pos<4>(cell[q])] = acc[q][g];
-        if (nxt.R >= 0) {                             // next item's tables and records -> L1 while this row is transformed
-            for (int i = tid * 32; i <= K; i += NT * 32) prefetch_l1(key_ptr + (long)nxt.R * K + i);
-            for (int i = tid * 64; i < K; i += NT * 64) prefetch_l1(cell_order + (long)nxt.R * K + i);
-            for (int e = nxt.beg + tid * 2; e < min(nxt.end, nxt.beg + EC); e += NT * 2) prefetch_l1(rec + e);
-        }
         __syncthreads();
         float2* row = buf + s * PITCH;
         auto ld = [&](int e) { return row[ff_pos<4>(e)]; };
@@ -638,9 +613,7 @@ static int fused_forward_k(pdu_nufft_plan* p, const float* image, float* kdata, 
     PDU_LAUNCHED();
     {
         const int groups = (int)cdiv(planes, PG);
-        int occ = 1;
-        PDU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fz_rows_fwd_kernel<K, PG>, PG * FastFft<K>::TPS, fz_rows_fwd_smem<K, PG>()));
-        const long ctas = std::min<long>((long)K * groups, (long)sm_count() * std::max(1, occ));
+        const long ctas = (long)K * groups;
         fz_rows_fwd_kernel<K, PG><<<(unsigned)ctas, PG * FastFft<K>::TPS, fz_rows_fwd_smem<K, PG>(), st>>>(
             T, P, v.key_ptr, v.row_order, v.rec, p->d_w1, d, planes, m, groups);
         PDU_LAUNCHED();
@@ -671,10 +644,7 @@ static int fused_adjoint_k(pdu_nufft_plan* p, const float* kdata, float* image, 
     PDU_CUDA((ensure_dyn_smem<fz_cols_adj_kernel<K, FZ_SEQ_COLS>>((int)fz_cols_smem<K>())));
     {
         const int groups = (int)cdiv(planes, PG);
-        int occ = 1;
-        PDU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fz_rows_adj_kernel<K, PG, FZ_EC>, PG * FastFft<K>::TPS,
-                                                               fz_rows_adj_smem<K, PG>()));
-        const long ctas = std::min<long>((long)K * groups, (long)sm_count() * std::max(1, occ));
+        const long ctas = (long)K * groups;
         fz_rows_adj_kernel<K, PG, FZ_EC><<<(unsigned)ctas, PG * FastFft<K>::TPS, fz_rows_adj_smem<K, PG>(), st>>>(
             kdata, kweight, T, v.key_ptr, v.row_order, v.cell_order, v.rec, p->d_w1, d, planes, m,
             (flags & PDU_NUFFT_KDATA_SPLIT) ? 1 : 0, groups);

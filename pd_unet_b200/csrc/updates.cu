@@ -130,25 +130,67 @@ __global__ void __launch_bounds__(256)
 // ------------------------------------------------------------------ angular upsampling
 // full[b, i*f + r, d] = (1 - r/f) s[b, i, d] + (r/f) s[b, i+1, d];  the row after the last one is
 // s[b, 0, D-1-d] (mode 0), s[b, 0, d] (mode 1) or s[b, As-1, d] (mode 2).
+// value of full-view pixel `pix` (= (b * As * f + view) * D + d) of the upsampled sinogram
+__device__ __forceinline__ float upsampled_at(const float* __restrict__ sparse, long pix, int As, int f, int D, int mode, float inv_f) {
+    const int d = (int)(pix % D);
+    const long row = pix / D;
+    const int av = (int)(row % ((long)As * f));
+    const long b = row / ((long)As * f);
+    const int ia = av / f, r = av - ia * f;
+    const float* sb = sparse + b * (long)As * D;
+    const float lo = __ldg(sb + (long)ia * D + d);
+    float hi;
+    if (ia + 1 < As) hi = __ldg(sb + (long)(ia + 1) * D + d);
+    else if (mode == PDU_WRAP_FLIP) hi = __ldg(sb + (D - 1 - d));
+    else if (mode == PDU_WRAP_PERIODIC) hi = __ldg(sb + d);
+    else hi = lo;
+    return fmaf((float)r * inv_f, hi - lo, lo);
+}
+
 __global__ void __launch_bounds__(256)
-    upsample_kernel(const float* __restrict__ sparse, float* __restrict__ full, int As, int f, int D, int mode,
+    upsample_kernel(const float* __restrict__ sparse, float* __restrict__ full, int As, int f, int D, int mode, float scale,
                     long total) {
     const float inv_f = 1.f / (float)f;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x)
+        full[i] = scale * upsampled_at(sparse, i, As, f, D, mode, inv_f);
+}
+
+// The dual update's concatenation with the measured data interpolated on the fly: out = [a | scale_b b | scale_c up(sparse) | 0].
+// The full-view sinogram g is never materialised -- the sparse views (1 / factor of it) are read instead, from L2.
+// nhwc: out is [batch, plane, ct], a [batch, plane, ca], b [batch, plane]; else planar.
+__global__ void __launch_bounds__(256)
+    concat_upsample_kernel(float* __restrict__ out, const float* __restrict__ a, const float* __restrict__ b,
+                           const float* __restrict__ sparse, int ca, int ct, long plane, int As, int f, int D, int mode,
+                           float scale_b, float scale_c, int nhwc, long total) {
+    const float inv_f = 1.f / (float)f;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-        const int d = (int)(i % D);
-        const long row = i / D;
-        const int av = (int)(row % ((long)As * f));
-        const long b = row / ((long)As * f);
-        const int ia = av / f, r = av - ia * f;
-        const float* sb = sparse + b * (long)As * D;
-        const float lo = __ldg(sb + (long)ia * D + d);
-        float hi;
-        if (ia + 1 < As) hi = __ldg(sb + (long)(ia + 1) * D + d);
-        else if (mode == PDU_WRAP_FLIP) hi = __ldg(sb + (D - 1 - d));
-        else if (mode == PDU_WRAP_PERIODIC) hi = __ldg(sb + d);
-        else hi = lo;
-        const float w = (float)r * inv_f;
-        full[i] = fmaf(w, hi - lo, lo);
+        long pix;
+        int ch;
+        if (nhwc) {
+            pix = i / ct;
+            ch = (int)(i - pix * ct);
+        } else {
+            const long n = i / ((long)ct * plane), r = i - n * (long)ct * plane;
+            ch = (int)(r / plane);
+            pix = n * plane + (r - (long)ch * plane);
+        }
+        float v = 0.f;
+        if (ch < ca) v = nhwc ? a[pix * ca + ch] : a[(pix / plane * ca + ch) * plane + pix % plane];
+        else if (ch == ca) v = b[pix] * scale_b;
+        else if (ch == ca + 1) v = scale_c * upsampled_at(sparse, pix, As, f, D, mode, inv_f);
+        out[i] = v;
+    }
+}
+
+// channels-last fast path (4 state channels, output padded to 8): one thread per pixel
+__global__ void __launch_bounds__(256)
+    concat_upsample_nhwc_4_to8_kernel(float4* __restrict__ out, const float4* __restrict__ a, const float* __restrict__ b,
+                                      const float* __restrict__ sparse, int As, int f, int D, int mode, float scale_b,
+                                      float scale_c, long pixels) {
+    const float inv_f = 1.f / (float)f;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < pixels; i += (long)gridDim.x * blockDim.x) {
+        out[2 * i] = a[i];
+        out[2 * i + 1] = make_float4(b[i] * scale_b, scale_c * upsampled_at(sparse, i, As, f, D, mode, inv_f), 0.f, 0.f);
     }
 }
 
@@ -273,14 +315,43 @@ int pdu_axpby_f32(float* out, float alpha, const float* x, float beta, const flo
     return PDU_OK;
 }
 
-int pdu_angular_upsample_f32(const float* sparse, float* full, int batch, int a_sparse, int factor, int det_count,
-                             int mode, pdu_stream_t stream) {
+int pdu_angular_upsample_scaled_f32(const float* sparse, float* full, int batch, int a_sparse, int factor, int det_count,
+                                    int mode, float scale, pdu_stream_t stream) {
     PDU_REQUIRE(sparse && full, "pdu_angular_upsample_f32: null pointer");
     PDU_REQUIRE(batch > 0 && a_sparse > 0 && factor > 0 && det_count > 0, "pdu_angular_upsample_f32: sizes must be positive");
     PDU_REQUIRE(mode >= 0 && mode <= 2, "pdu_angular_upsample_f32: unknown mode %d", mode);
     const long total = (long)batch * a_sparse * factor * det_count;
     upsample_kernel<<<stream_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(sparse, full, a_sparse, factor, det_count,
-                                                                               mode, total);
+                                                                               mode, scale, total);
+    PDU_LAUNCHED();
+    return PDU_OK;
+}
+
+int pdu_angular_upsample_f32(const float* sparse, float* full, int batch, int a_sparse, int factor, int det_count,
+                             int mode, pdu_stream_t stream) {
+    return pdu_angular_upsample_scaled_f32(sparse, full, batch, a_sparse, factor, det_count, mode, 1.f, stream);
+}
+
+int pdu_concat_upsample_f32(float* out, const float* a, const float* b, const float* sparse, int batch, int ca, int c_out,
+                            int a_sparse, int factor, int det_count, int mode, float scale_b, float scale_c, int layout,
+                            pdu_stream_t stream) {
+    PDU_REQUIRE(out && a && b && sparse, "pdu_concat_upsample_f32: null pointer");
+    PDU_REQUIRE(batch > 0 && ca > 0 && a_sparse > 0 && factor > 0 && det_count > 0, "pdu_concat_upsample_f32: sizes must be positive");
+    PDU_REQUIRE(c_out >= ca + 2, "pdu_concat_upsample_f32: c_out %d is smaller than the %d input channels", c_out, ca + 2);
+    PDU_REQUIRE(mode >= 0 && mode <= 2, "pdu_concat_upsample_f32: unknown mode %d", mode);
+    PDU_REQUIRE(layout == PDU_LAYOUT_NCHW || layout == PDU_LAYOUT_NHWC, "pdu_concat_upsample_f32: unknown layout %d", layout);
+    cudaStream_t st = (cudaStream_t)stream;
+    const long plane = (long)a_sparse * factor * det_count;
+    const long pixels = (long)batch * plane;
+    if (layout == PDU_LAYOUT_NHWC && ca == 4 && c_out == 8 && al16(out) && al16(a)) {
+        concat_upsample_nhwc_4_to8_kernel<<<stream_grid(pixels, 256), 256, 0, st>>>((float4*)out, (const float4*)a, b, sparse, a_sparse,
+                                                                                    factor, det_count, mode, scale_b, scale_c, pixels);
+        PDU_LAUNCHED();
+        return PDU_OK;
+    }
+    const long total = pixels * c_out;
+    concat_upsample_kernel<<<stream_grid(total, 256), 256, 0, st>>>(out, a, b, sparse, ca, c_out, plane, a_sparse, factor, det_count, mode,
+                                                                    scale_b, scale_c, layout == PDU_LAYOUT_NHWC ? 1 : 0, total);
     PDU_LAUNCHED();
     return PDU_OK;
 }

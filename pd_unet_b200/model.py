@@ -203,22 +203,30 @@ class PrimalDualUNet(nn.Module):
         if self.channels_last:
             self.to(memory_format=torch.channels_last)
 
-    def forward(self, g: torch.Tensor, image_shape) -> torch.Tensor:
-        """g: measured data on the full grid [B, kd, *data].  Returns the reconstruction [B, kc, *image]."""
-        B = g.shape[0]
-        fmt = torch.channels_last if (self.channels_last and g.dim() == 4) else torch.contiguous_format
-        h = torch.empty((B, self.n_dual) + tuple(g.shape[2:]), dtype=g.dtype, device=g.device, memory_format=fmt).zero_()
-        f = torch.empty((B, self.n_primal) + tuple(image_shape), dtype=g.dtype, device=g.device, memory_format=fmt).zero_()
-        f_op = g.new_zeros((B, self.kc) + tuple(image_shape))
+    def forward(self, g: Optional[torch.Tensor], image_shape, dual_cat: Optional[Callable] = None,
+                data_like: Optional[torch.Tensor] = None, data_shape=None) -> torch.Tensor:
+        """g: measured data on the full grid [B, kd, *data].  Returns the reconstruction [B, kc, *image].
+        dual_cat (with g None): callable (h, kf, scale_b, pad_to) -> the dual block's input; the CT flavour passes the
+        concatenation that interpolates the sparse-view sinogram on the fly, so the full-view g never exists
+        (data_like gives dtype / device, data_shape the [*data] axes)."""
+        ref = g if g is not None else data_like
+        dshape = tuple(g.shape[2:]) if g is not None else tuple(data_shape)
+        B = ref.shape[0]
+        fmt = torch.channels_last if (self.channels_last and len(dshape) == 2) else torch.contiguous_format
+        h = torch.empty((B, self.n_dual) + dshape, dtype=ref.dtype, device=ref.device, memory_format=fmt).zero_()
+        f = torch.empty((B, self.n_primal) + tuple(image_shape), dtype=ref.dtype, device=ref.device, memory_format=fmt).zero_()
+        f_op = ref.new_zeros((B, self.kc) + tuple(image_shape))
         inv = 1.0 / self.op_scale
         # inference: round the concatenated channel count up to 8 (zero channels; the first convolution pads
         # its weights to match) -- with 6 or 5 input channels cuDNN falls back to a CUDA-core kernel
-        pad = 8 if (g.is_cuda and not torch.is_grad_enabled()) else 0
+        pad = 8 if (ref.is_cuda and not torch.is_grad_enabled()) else 0
+        if dual_cat is None:
+            dual_cat = lambda hh, kk, scale_b, pad_to: updates.concat(hh, kk, g, scale_b=scale_b, pad_to=pad_to)
         for i in range(self.n_iter):
             # the 1/op_scale normalisation of each operator output rides in the concat kernel
             # the primal state starts at zero and the operator is linear: K 0 = 0, so the first projection is skipped
-            kf = self.op_forward(f_op) if i > 0 else torch.zeros_like(g[:, :self.kd])
-            h, h_op = updates.residual_slice(h, self.dual[i](updates.concat(h, kf, g, scale_b=inv, pad_to=pad)), 0, self.kd)
+            kf = self.op_forward(f_op) if i > 0 else ref.new_zeros((B, self.kd) + dshape)
+            h, h_op = updates.residual_slice(h, self.dual[i](dual_cat(h, kf, inv, pad)), 0, self.kd)
             kth = self.op_adjoint(h_op)
             f, f_op = updates.residual_slice(f, self.primal[i](updates.concat(f, kth, scale_b=inv, pad_to=pad)), 0, self.kc)
         return f_op
@@ -244,15 +252,34 @@ class PrimalDualUNetCT(PrimalDualUNet):
         self.wrap = "flip" if radon.geom.geom == 0 else "periodic"
 
     def forward(self, sparse_sino: torch.Tensor) -> torch.Tensor:
-        g = updates.angular_upsample(sparse_sino, self.upsample, self.wrap) * (1.0 / self.op_scale)
+        """sparse_sino [B, 1, A_sparse, D].  The angular upsampling to the full view set is fused with the dual
+        update: every iteration's concatenation interpolates the sparse views on the fly (1 / op_scale included)."""
         n = self.radon.resolution
-        return super().forward(g, (n, n))
+        inv = 1.0 / self.op_scale
+        sparse = sparse_sino.contiguous()
+        if not sparse.is_cuda:                   # host tensors (the CPU plumbing tests): the plain two-step form
+            g = updates.angular_upsample(sparse, self.upsample, self.wrap) * inv
+            return super().forward(g, (n, n))
+        cat = lambda h, kf, scale_b, pad_to: updates.concat_upsampled(h, kf, sparse, self.upsample, self.wrap, scale_b=scale_b,
+                                                                       scale_c=inv, pad_to=pad_to)
+        dshape = (sparse.shape[-2] * self.upsample, sparse.shape[-1])
+        return super().forward(None, (n, n), dual_cat=cat, data_like=sparse, data_shape=dshape)
 
 
 class PrimalDualUNetMRI(PrimalDualUNet):
-    """Radial-MRI flavour: k-space samples [B, coils, spokes * readout] complex64 (+ trajectory, coil
-    maps, density compensation) -> complex image [B, 1, N, N].  Complex tensors travel through the
-    CNNs as (re, im) channel pairs; data-space tensors are laid out [B, 2 coils, spokes, readout]."""
+    """Radial-MRI flavour: k-space samples [B, coils, spokes * readout] complex64 (+ trajectory, coil maps, density
+    compensation) -> complex image [B, 1, N, N].
+
+    Complex tensors travel through the CNNs as (re, im) channel pairs: data-space tensors are
+    [B, 2 coils, spokes, readout] float32 and the image is [B, 2, N, N] -- exactly the `split` layouts of
+    pd_unet_b200.nufft, so the operators read and write them directly: no permute / contiguous / view_as_complex pass
+    and no separate density-compensation multiply surround a NUFFT call (the adjoint takes the weights as `kweight`).
+
+    Spoke upsampling (BASELINE.json configs[0]: "32 spokes upsampled to 256"): when `forward` is given the sparse
+    acquisition (`omega_sparse`, optionally `dcf_sparse`) the measured samples are first regridded onto the model's
+    full trajectory, g = A_full A_sparse^H (dcf_sparse y) -- the step the reference does with torchkbnufft on the CPU --
+    and the unrolled iterations then run on the full set of spokes, as the CT flavour does after its angular
+    upsampling."""
 
     def __init__(self, im_size, n_spokes: int, n_readout: int, coils: int = 1, **kw):
         self.im_size = tuple(im_size)
@@ -265,32 +292,46 @@ class PrimalDualUNetMRI(PrimalDualUNet):
         fwd, adj = KbNufft(im_size), KbNufftAdjoint(im_size)
 
         def op_forward(x):               # [B, 2, N, N] -> [B, 2 coils, spokes, readout]
-            z = torch.view_as_complex(x.permute(0, 2, 3, 1).contiguous())[:, None]
-            y = fwd(z, self._omega, smaps=self._smaps, norm="ortho")
-            y = torch.view_as_real(y).permute(0, 1, 3, 2).reshape(x.shape[0], 2 * self.coils, n_spokes, n_readout)
-            return y
+            y = fwd(x, self._omega, smaps=self._smaps, norm="ortho", split=True)
+            return y.view(x.shape[0], 2 * self.coils, n_spokes, n_readout)
 
-        def op_adjoint(y):               # inverse layout change, density compensated
-            B = y.shape[0]
-            z = y.reshape(B, self.coils, 2, n_spokes * n_readout).permute(0, 1, 3, 2).contiguous()
-            z = torch.view_as_complex(z)
-            if self._dcf is not None:
-                z = z * self._dcf
-            x = adj(z, self._omega, smaps=self._smaps, norm="ortho")
-            return torch.view_as_real(x[:, 0]).permute(0, 3, 1, 2).contiguous()
+        def op_adjoint(y):               # [B, 2 coils, spokes, readout] -> [B, 2, N, N], density compensated
+            z = y.reshape(y.shape[0], 2 * self.coils, n_spokes * n_readout)
+            return adj(z, self._omega, smaps=self._smaps, norm="ortho", split=True, kweight=self._dcf)
 
         PrimalDualUNet.__init__(self, op_forward, op_adjoint, 2, 2 * coils, **kw)
         self.nufft, self.nufft_adjoint = fwd, adj
 
+    @staticmethod
+    def _real_weights(dcf: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+        """Density compensation as float32 [M] (calc_density_compensation_function returns complex [1, 1, M])."""
+        if dcf is None:
+            return None
+        w = dcf.real if dcf.is_complex() else dcf
+        return w.reshape(-1).to(torch.float32).contiguous()
+
+    def upsample_spokes(self, kdata: torch.Tensor, omega_sparse: torch.Tensor, omega_full: torch.Tensor,
+                        smaps: Optional[torch.Tensor] = None, dcf_sparse: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Sparse acquisition [B, coils, M_sparse] complex64 -> the same object sampled on the full trajectory, in the
+        model's data layout [B, 2 coils, M_full] float32: A_full A_sparse^H (dcf_sparse y)."""
+        B = kdata.shape[0]
+        ys = torch.view_as_real(kdata).permute(0, 1, 3, 2).reshape(B, 2 * self.coils, -1).contiguous()
+        x = self.nufft_adjoint(ys, omega_sparse, smaps=smaps, norm="ortho", split=True, kweight=self._real_weights(dcf_sparse))
+        return self.nufft(x, omega_full, smaps=smaps, norm="ortho", split=True)
+
     def forward(self, kdata: torch.Tensor, omega: torch.Tensor, smaps: Optional[torch.Tensor] = None,
-                dcf: Optional[torch.Tensor] = None) -> torch.Tensor:
+                dcf: Optional[torch.Tensor] = None, omega_sparse: Optional[torch.Tensor] = None,
+                dcf_sparse: Optional[torch.Tensor] = None) -> torch.Tensor:
         if kdata.shape[1] != self.coils:
             raise ValueError(f"kdata has {kdata.shape[1]} coils, the model was built for {self.coils}")
         if self.coils > 1 and smaps is None:
             raise ValueError("multi-coil data needs smaps")
-        self._omega, self._smaps, self._dcf = omega, smaps, dcf
+        self._omega, self._smaps, self._dcf = omega, smaps, self._real_weights(dcf)
         B = kdata.shape[0]
-        g = torch.view_as_real(kdata).permute(0, 1, 3, 2).reshape(B, 2 * self.coils, self.n_spokes, self.n_readout)
-        g = (g * (1.0 / self.op_scale)).contiguous()
-        out = PrimalDualUNet.forward(self, g, self.im_size)
-        return torch.view_as_complex(out.permute(0, 2, 3, 1).contiguous())[:, None]
+        if omega_sparse is not None:
+            g = self.upsample_spokes(kdata, omega_sparse, omega, smaps, dcf_sparse)
+        else:
+            g = torch.view_as_real(kdata).permute(0, 1, 3, 2).reshape(B, 2 * self.coils, -1)
+        g = (g * (1.0 / self.op_scale)).reshape(B, 2 * self.coils, self.n_spokes, self.n_readout).contiguous()
+        out = PrimalDualUNet.forward(self, g, self.im_size)          # [B, 2, N, N]
+        return torch.complex(out[:, 0], out[:, 1])[:, None]

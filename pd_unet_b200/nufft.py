@@ -83,8 +83,12 @@ class _Plan:
         # 437 us at 64 planes); True: always (bit-reproducible adjoint); False: never.  Only the generic path
         # (grids without a fused path, KbInterpAdjoint) looks at it.
         self.use_csr = "auto"
-        # the fused path (csrc/nufft_fused.cu) wherever the library has one for the grid; False forces the generic path
-        self.use_fused = True
+        # the fused path (csrc/nufft_fused.cu): True -- wherever the library has one for the grid; False -- never;
+        # "auto" -- where it measured faster on B200 (tools/prof_nufft.py, profiles/r02_nufft_timings.txt): from 8 planes
+        # per call up (below that a call is ~700 short-lived CTAs and the generic path's wide gathers win: 24 vs 36 us
+        # at 256^2 x 1 plane), and for the adjoint of the 512 / 640 grids only up to 32 planes (64 planes of 640^2:
+        # fused 326 us, generic sorted gather + register FFT 308 us; forward 226 vs 263 us)
+        self.use_fused = "auto"
 
     # -------------------------------------------------------------- per-trajectory cache
     def _entry(self, omega: torch.Tensor) -> dict:
@@ -124,11 +128,14 @@ class _Plan:
         back to the allocator (stream-ordered, so the pending build kernels are safe)."""
         return buf[:persist].clone() if persist < buf.numel() else buf
 
-    def _bins_for(self, omega: torch.Tensor):
-        """Row bins of the fused path for this trajectory (None when the grid has no fused path)."""
+    def _bins_for(self, omega: torch.Tensor, planes: int = 1 << 30, adjoint: bool = False):
+        """Row bins of the fused path for this trajectory (None when the generic path is to be used)."""
         L, h = lib(), self.handle(omega.device)
         if not self.use_fused or not L.pdu_nufft_has_fused_path(h):
             return None
+        if self.use_fused == "auto":
+            if planes < 8 or (adjoint and planes > 32 and self.grid_size[0] in (512, 640)):
+                return None
         ent = self._entry(omega)
         if ent["bins"] is None:
             persist = C.c_size_t(0)
@@ -252,7 +259,7 @@ class _Plan:
             return out
         with torch.cuda.device(image.device):
             L, h = lib(), self.handle(image.device)
-            bins = self._bins_for(omega)
+            bins = self._bins_for(omega, B * coils)
             if bins is not None:
                 flags = (NUFFT_IMAGE_SPLIT | NUFFT_KDATA_SPLIT) if split else 0
                 for b0, b1 in self._chunks(L, h, B, coils, M):
@@ -296,7 +303,7 @@ class _Plan:
             return out.zero_()
         with torch.cuda.device(data.device):
             L, h = lib(), self.handle(data.device)
-            bins = self._bins_for(omega)
+            bins = self._bins_for(omega, B * coils, adjoint=True)
             if bins is not None:
                 flags = (NUFFT_IMAGE_SPLIT | NUFFT_KDATA_SPLIT) if split else 0
                 for b0, b1 in self._chunks(L, h, B, coils, M):

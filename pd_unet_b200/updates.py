@@ -92,6 +92,49 @@ def concat(a: torch.Tensor, b: torch.Tensor, c: Optional[torch.Tensor] = None, s
     return _Concat.apply(a, b, c, float(scale_b), int(pad_to))
 
 
+class _ConcatUpsample(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b, sparse, factor, mode, scale_b, scale_c, pad_to):
+        nhwc = _is_channels_last(a)
+        a = _in_layout(a, nhwc, "a")
+        b = _in_layout(b, nhwc, "b")
+        sparse = require_cuda(sparse, torch.float32, "sparse")
+        B, ca = a.shape[:2]
+        As, D = sparse.shape[-2], sparse.shape[-1]
+        if b.shape[1] != 1 or b.shape[0] != B or tuple(b.shape[2:]) != tuple(a.shape[2:]):
+            raise ValueError("concat_upsampled: b must be [B, 1, views, det] like a")
+        if tuple(a.shape[2:]) != (As * factor, D) or sparse.numel() != B * As * D:
+            raise ValueError(f"concat_upsampled: a is {tuple(a.shape)}, sparse {tuple(sparse.shape)} x{factor} views")
+        ctx.ca, ctx.scale_b = ca, scale_b
+        c_out = ca + 2
+        if pad_to > 1:
+            c_out = (c_out + pad_to - 1) // pad_to * pad_to
+        out = _empty((B, c_out) + tuple(a.shape[2:]), a, nhwc)
+        if out.numel():
+            with torch.cuda.device(a.device):
+                check(lib().pdu_concat_upsample_f32(out.data_ptr(), a.data_ptr(), b.data_ptr(), sparse.data_ptr(), B, ca, c_out, As,
+                                                    factor, D, WRAP_MODES[mode], scale_b, scale_c,
+                                                    LAYOUT_NHWC if nhwc else LAYOUT_NCHW, stream_ptr()), "pdu_concat_upsample_f32")
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        ca = ctx.ca
+        gb = g[:, ca:ca + 1]
+        if ctx.scale_b != 1.0:
+            gb = gb * ctx.scale_b
+        return g[:, :ca], gb, None, None, None, None, None, None      # the measured data takes no gradient
+
+
+def concat_upsampled(a: torch.Tensor, b: torch.Tensor, sparse: torch.Tensor, factor: int, mode: str = "flip",
+                     scale_b: float = 1.0, scale_c: float = 1.0, pad_to: int = 0) -> torch.Tensor:
+    """cat([a, scale_b * b, scale_c * angular_upsample(sparse, factor, mode)], dim=1) in one pass: the dual update's input
+    with the measured sparse-view sinogram [B, (1,) A_sparse, D] interpolated on the fly."""
+    if mode not in WRAP_MODES:
+        raise ValueError(f"mode must be one of {tuple(WRAP_MODES)}")
+    return _ConcatUpsample.apply(a, b, sparse, int(factor), mode, float(scale_b), float(scale_c), int(pad_to))
+
+
 class _ResidualSlice(torch.autograd.Function):
     @staticmethod
     def forward(ctx, state, delta, k, kn):

@@ -227,6 +227,7 @@ def test_default_path_at_the_cfg4_share_matches_oracle():
     xa = AH(k.to(DEV), omd, smaps=sm.to(DEV), norm="ortho")
     adj_kernel = _lib.last_kernel("nufft_adj")
     assert "cufft" not in fwd_kernel.lower() and "cufft" not in adj_kernel.lower(), (fwd_kernel, adj_kernel)
+    assert "fz_rows_fwd_kernel" in fwd_kernel and "ff_rows_adj_kernel" in adj_kernel       # the measured-fastest pair at 64 planes
     b = 5
     assert rel_l2(y[b:b + 1], oracle.nufft_forward(x[b:b + 1], om, spec, smaps=sm, norm="ortho")) <= TOL
     assert rel_l2(xa[b:b + 1], oracle.nufft_adjoint(k[b:b + 1], om, spec, smaps=sm, norm="ortho")) <= TOL
@@ -251,6 +252,7 @@ def test_fused_path_every_grid_size(n, planes, spokes):
     om = _traj(spokes, 2 * n)
     omd = torch.from_numpy(om).to(DEV)
     A, AH = pdu.KbNufft(im), pdu.KbNufftAdjoint(im)
+    A._plan.use_fused = AH._plan.use_fused = True          # "auto" keeps small plane counts on the generic path
     x = seeded((1, planes) + im, 71, complex_=True)
     k = seeded((1, planes, om.shape[1]), 72, complex_=True)
     y, xa = A(x.to(DEV), omd), AH(k.to(DEV), omd)
@@ -266,11 +268,12 @@ def test_fused_path_every_grid_size(n, planes, spokes):
 def test_split_layout_and_density_weights():
     """The (re, im)-as-channels layout and the fused density compensation give the same numbers as the complex API
     followed by the layout passes -- with and without coil maps, on the fused path and on the generic one."""
-    for n, coils in ((256, 1), (320, 4), (48, 3)):
+    for n, coils, fused in ((256, 1, True), (320, 4, True), (320, 4, "auto"), (48, 3, "auto")):
         im = (n, n)
         om = torch.from_numpy(_traj(11, 2 * n)).to(DEV)
         M = om.shape[1]
         A, AH = pdu.KbNufft(im), pdu.KbNufftAdjoint(im)
+        A._plan.use_fused = AH._plan.use_fused = fused
         sm = coil_maps(coils, n)[None].to(DEV) if coils > 1 else None
         x = seeded((2, 1) + im, 81, complex_=True).to(DEV)
         k = seeded((2, coils, M), 82, complex_=True).to(DEV)

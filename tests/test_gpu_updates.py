@@ -268,3 +268,28 @@ def test_bias_add_training_matches_aten(C):
     for name, a, b in zip(("out", "grad_x", "grad_bias", "grad_weight"), got, ref):
         assert rel_l2(a, b) <= 2e-5, name
     assert torch.equal(got[2], again[2])
+
+
+@pytest.mark.parametrize("mode", ["flip", "periodic", "clamp"])
+@pytest.mark.parametrize("ca,shape,factor,pad_to,nhwc", [(4, (2, 8, 16), 8, 8, True), (4, (3, 5, 7), 3, 0, True),
+                                                         (3, (2, 6, 12), 4, 0, False), (4, (1, 64, 256), 8, 8, False)])
+def test_concat_with_the_upsampling_fused(mode, ca, shape, factor, pad_to, nhwc):
+    """the dual update's concatenation interpolates the sparse-view sinogram on the fly; the
+    result is torch.cat([a, scale_b b, scale_c upsample(sparse)]) to the last bit (the same single FMA per element)."""
+    B, As, D = shape
+    sparse = seeded((B, 1, As, D), 1)
+    a = seeded((B, ca, As * factor, D), 2)
+    b = seeded((B, 1, As * factor, D), 3)
+    ad = a.to(DEV).contiguous(memory_format=torch.channels_last) if nhwc else a.to(DEV)
+    got = updates.concat_upsampled(ad, b.to(DEV), sparse.to(DEV), factor, mode, scale_b=0.5, scale_c=0.25, pad_to=pad_to)
+    up = updates.angular_upsample(sparse.to(DEV), factor, mode)
+    want = torch.cat([a.to(DEV), 0.5 * b.to(DEV), 0.25 * up], 1)
+    assert got.shape[1] == (8 if pad_to else ca + 2)
+    assert torch.equal(got[:, :ca + 2], want)
+    assert not got[:, ca + 2:].any()
+    assert rel_l2(got[:, ca + 1], 0.25 * ou.angular_upsample(sparse[:, 0], factor, mode)) < 1e-7
+    # gradients reach a and b (the measured data takes none)
+    ar, br = ad.clone().requires_grad_(), b.to(DEV).requires_grad_()
+    w = seeded(tuple(got.shape), 4).to(DEV)
+    (updates.concat_upsampled(ar, br, sparse.to(DEV), factor, mode, scale_b=0.5, scale_c=0.25, pad_to=pad_to) * w).sum().backward()
+    assert torch.equal(ar.grad, w[:, :ca]) and torch.equal(br.grad, 0.5 * w[:, ca:ca + 1])
