@@ -14,6 +14,12 @@ to a host result.  `roofline`: the Radon forward-projection call timed live with
 those same K steps.  `cpu_baseline` / `--impl reference`: the CPU oracle port of the same model
 on the host cores, on a bounded sample (the reference's own operators, torch_radon, are CUDA-only
 and not mounted: SURVEY.md section 8c/8d).
+`operators`: every hot-path operator alone (L2 flushed): Radon forward / adjoint / filter at configs[1], NUFFT
+forward / adjoint at configs[0] and at the configs[3] per-GPU share, GSamples/s and fraction of the HBM roof.
+`extras` (skip with --no-extras): the other BASELINE configs as model-level legs -- configs[0] radial-MRI inference
+(256^2, 32 -> 256 spokes, one slice, CUDA graph), configs[2] fan-beam CT (512^2, 128 -> 1024 views, 8 slices per GPU),
+configs[3] radial-MRI training step (320^2, 8 coils, 48 spokes; forward + loss + backward + Adam captured in one CUDA
+graph, DDP's NCCL all-reduce inside it when --gpus N > 1).
 """
 from __future__ import annotations
 
@@ -39,6 +45,12 @@ MODEL_KW = dict(n_iter=4, n_primal=4, n_dual=4, unet_base=32, unet_depth=3, dual
 METRIC = "PD-UNet recon slices/sec"
 WORKLOAD = ("configs[1]: parallel-beam CT PD-UNet 256x256, 64->512 views sinogram upsampling, "
             "batch 16 per GPU (inference pass, 4 unrolled iterations)")
+
+
+# ncu --set full numbers that bench.py does not measure itself (labelled as such in the JSON line)
+STATIC_TRAFFIC = {"cold": 33847040 + 378368, "in_step": 512 + 105984,
+                  "source": "profiles/r01_ncu_full_summary.md + profiles/r01_traffic_in_step.csv (ncu captures of commit 05ca706, "
+                            "radon_fwd_quad_kernel<32,8,16,92,2,4>; not re-measured by this run)"}
 
 
 def peaks():
@@ -121,7 +133,7 @@ def run_ours(args):
     from pd_unet_b200 import parallel, radon as radon_mod
     from pd_unet_b200.graph import GraphedInference
 
-    rank, world, local = parallel.init_distributed("nccl")
+    rank, world, local = parallel.init_distributed("nccl", graph_capture=not args.no_extras)
     if world != args.gpus:
         if rank == 0:
             print(f"bench.py: --gpus {args.gpus} but WORLD_SIZE={world}; launch with torch.distributed.run",
@@ -214,7 +226,13 @@ def run_ours(args):
     e2e_ms = parallel.max_over_ranks(sum(s.elapsed_time(e) for s, e in ev2), dev)
 
     # ---- operator microbenchmarks (each call alone, L2 flushed): GSamples/s and HBM fraction
+    from pd_unet_b200 import _lib
+    fwd_kernel = _lib.last_kernel("radon_fwd")         # what the dispatcher chose for the steps above
     ops = operator_microbench(radon, dev, flush) if rank == 0 else {}
+    # ---- the other BASELINE configs as model-level legs (every rank takes part: the training leg is DDP)
+    del graphed
+    torch.cuda.empty_cache()
+    extras = {} if args.no_extras else extra_legs(dev, flush, rank, world, local, args)
 
     if rank != 0:
         return
@@ -227,6 +245,7 @@ def run_ours(args):
         "metric": METRIC, "value": slices / (total_ms * 1e-3), "unit": "slices/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "dtype_note": "operators float32 throughout; cuDNN convolutions with TF32 allowed (PyTorch default, as the reference runs)",
         "config": {"workload": WORKLOAD, "image": N, "views_sparse": A_SPARSE, "views_full": A_FULL,
                    "batch_per_gpu": BATCH, "model": MODEL_KW, "weights": "random init (seed 1234)",
                    "parallelism": f"slice-sharded x{world}, no collective",
@@ -237,14 +256,14 @@ def run_ours(args):
                 "d2h_bytes_per_step": host_out.numel() * 4},
         "gpu_launches": int(launches),
         "clocks": clocks.summary(),
-        "roofline": {"bound": "hbm", "kernel": "pdu_radon_fwd_f32 (quad_build_kernel + radon_fwd_quad_kernel<32,8,16,92,2,4>), 512 views",
+        "roofline": {"bound": "hbm", "kernel": "pdu_radon_fwd_f32: " + fwd_kernel,       # pdu_last_kernel(): the dispatcher's choice in this run
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     # dram__bytes_read.sum + dram__bytes_write.sum of the quad kernel in one ncu --set full capture
-                     # (profiles/r01_ncu_full_summary.md).  ncu flushes the caches before every kernel, so this is the
-                     # cold figure: the two 16.9 MB cell tensors quad_build_kernel has just written.  Inside a step they
-                     # are still in L2 (traffic_in_step: the same counters with --cache-control none,
-                     # profiles/r01_traffic_in_step.csv).
-                     "traffic": 33847040 + 378368, "traffic_in_step": 512 + 105984,
+                     # NOT measured in this run: dram__bytes_read.sum + dram__bytes_write.sum of the projector kernel from
+                     # a committed ncu --set full capture (see traffic_source).  ncu flushes the caches before every
+                     # kernel, so it is the cold figure: the two 16.9 MB cell tensors quad_build_kernel has just written;
+                     # inside a step they are still in L2 (traffic_in_step, --cache-control none).
+                     "traffic": STATIC_TRAFFIC["cold"], "traffic_in_step": STATIC_TRAFFIC["in_step"],
+                     "traffic_source": STATIC_TRAFFIC["source"],
                      "peak_source": peak_src, "algorithmic_bytes": alg_bytes, "avg_launch_ms": fwd_avg_ms,
                      "launches_timed": len(fwd_ms),
                      "gsamples_per_s": BATCH * A_FULL * N * N / (fwd_avg_ms * 1e-3) / 1e9,
@@ -254,6 +273,7 @@ def run_ours(args):
                              "ncu: L1/shared pipe 74 % busy (1.56 wavefronts per ideal one: bank conflicts of the 16-byte "
                              "cell loads), issue 72 %. DESIGN.md section 3"},
         "operators": ops,
+        "extras": extras,
     }
     if not args.no_cpu and world == 1:                 # the CPU leg is reported at N = 1 only
         line["cpu_baseline"] = cpu_baseline(sample_slices=4)
@@ -284,16 +304,112 @@ def operator_microbench(radon, dev, flush, reps=10):
 
     rb = 4.0 * BATCH * (N * N + A_FULL * N)
     out = {}
-    for name, fn, nbytes, samples in (
-            ("radon_fwd", lambda: radon._project(x), rb, BATCH * A_FULL * N * N),
-            ("radon_adj", lambda: radon._backproject(s), rb, BATCH * N * N * A_FULL),
-            ("filter", lambda: radon._filter(s, "ramp"), 4.0 * (2 * BATCH * A_FULL * N + N * N), None),
-            ("residual_slice", lambda: pdu.updates.residual_slice(h, h, 0), 4.0 * h.numel() * 3 + 4.0 * h.numel() / 4,
-             None)):
+    from pd_unet_b200 import _lib
+    from pd_unet_b200.data import radial_trajectory
+    from pd_unet_b200.phantoms import coil_maps
+    cases = [("radon_fwd", lambda: radon._project(x), rb, BATCH * A_FULL * N * N, "radon_fwd"),
+             ("radon_adj", lambda: radon._backproject(s), rb, BATCH * N * N * A_FULL, "radon_adj"),
+             ("filter", lambda: radon._filter(s, "ramp"), 4.0 * (2 * BATCH * A_FULL * N + N * N), None, "filter"),
+             ("residual_slice", lambda: pdu.updates.residual_slice(h, h, 0), 4.0 * h.numel() * 3 + 4.0 * h.numel() / 4,
+              None, None)]
+    # NUFFT: configs[0] (256^2, one coil, one slice; the 32 measured spokes and the 256 of the upsampled grid) and the
+    # configs[3] per-GPU share (320^2, 8 coils, batch 8, 48 spokes).  Algorithmic bytes 8 B C (N^2 + M) + 8 M (+ 8 C N^2 maps).
+    keep = []
+    for tag, n, coils, B, spokes in (("cfg1_32sp", 256, 1, 1, 32), ("cfg1_256sp", 256, 1, 1, 256), ("cfg4_share", 320, 8, 8, 48)):
+        om = radial_trajectory(spokes, 2 * n, device=dev)
+        M = om.shape[1]
+        fw, ad = pdu.KbNufft((n, n)), pdu.KbNufftAdjoint((n, n))
+        sm = coil_maps(coils, n)[None].to(dev) if coils > 1 else None
+        img = torch.randn(B, 1, n, n, dtype=torch.complex64, device=dev)
+        kd = torch.randn(B, coils, M, dtype=torch.complex64, device=dev)
+        nb = 8.0 * B * coils * (n * n + M) + 8.0 * M + (8.0 * coils * n * n if coils > 1 else 0.0)
+        taps = B * coils * M * 36
+        keep.append((om, sm, img, kd, fw, ad))
+        cases.append((f"nufft_fwd_{tag}", (lambda fw=fw, img=img, om=om, sm=sm: fw(img, om, smaps=sm, norm="ortho")), nb, taps, "nufft_fwd"))
+        cases.append((f"nufft_adj_{tag}", (lambda ad=ad, kd=kd, om=om, sm=sm: ad(kd, om, smaps=sm, norm="ortho")), nb, taps, "nufft_adj"))
+    for name, fn, nbytes, samples, op in cases:
         ms = timed(fn)
-        out[name] = {"ms": ms, "GB/s": nbytes / ms / 1e6, "hbm_frac": nbytes / ms / 1e6 / peak}
+        out[name] = {"ms": ms, "GB/s": nbytes / ms / 1e6, "hbm_frac": nbytes / ms / 1e6 / peak, "algorithmic_bytes": nbytes}
         if samples:
             out[name]["GSamples/s"] = samples / ms / 1e6
+        if op:
+            out[name]["kernel"] = _lib.last_kernel(op)
+    return out
+
+
+# ============================================================================= the other BASELINE configs
+def _timed_steps(run, flush, steps, dev):
+    from pd_unet_b200 import parallel
+    for _ in range(3):
+        run()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    parallel.barrier()
+    torch.cuda.synchronize()
+    for a, b in ev:
+        flush.zero_()
+        a.record()
+        run()
+        b.record()
+    torch.cuda.synchronize()
+    parallel.barrier()
+    return parallel.max_over_ranks(sum(a.elapsed_time(b) for a, b in ev), dev) / steps
+
+
+def extra_legs(dev, flush, rank, world, local, args):
+    """configs[0], configs[2] and configs[3] at model level (see the module docstring).  Every leg is weak scaling
+    (fixed work per GPU); values are whole-job aggregates over the `world` GPUs, CUDA-event time, max over ranks."""
+    import pd_unet_b200 as pdu
+    from pd_unet_b200 import data, parallel
+    from pd_unet_b200.graph import GraphedInference, GraphedTrainingStep
+    from pd_unet_b200.model import PrimalDualUNetCT, PrimalDualUNetMRI
+    steps = max(3, min(args.steps, 10))
+    out = {}
+    # ---- configs[0]: radial-MRI inference, 256^2, 32 measured spokes regridded to 256, one slice per GPU
+    n, sp_s, sp_f = 256, 32, 256
+    torch.manual_seed(1234)
+    mri = PrimalDualUNetMRI((n, n), sp_f, 2 * n, coils=1, **MODEL_KW).to(dev).eval()
+    d = data.make_mri_batch((n, n), sp_s, 1, 1, seed=200 + rank, device=dev)
+    om_full = data.radial_trajectory(sp_f, 2 * n, device=dev)
+    dcf_full = pdu.calc_density_compensation_function(om_full, (n, n))
+    fn = lambda kd: mri(kd, om_full, None, dcf_full, omega_sparse=d["omega"], dcf_sparse=d["dcf"])
+    with torch.no_grad():
+        g = GraphedInference(fn, d["kdata"], warmup=2)
+    ms = _timed_steps(g.replay, flush, steps, dev)
+    out["cfg1_mri_inference"] = {"workload": "configs[0]: radial-MRI PD-UNet 256x256, 32 spokes regridded to 256 on the GPU (own NUFFT), "
+                                             "1 slice per GPU, CUDA graph", "ms_per_step": ms, "slices_per_s": world / (ms * 1e-3)}
+    del g, mri, d
+    torch.cuda.empty_cache()
+    # ---- configs[2]: fan-beam CT, 512^2, 128 -> 1024 views, 8 slices per GPU (batch 64 over 8 GPUs)
+    n, a_s, up, b = 512, 128, 8, 8
+    fan = pdu.RadonFanbeam(n, np.linspace(0.0, 2.0 * np.pi, a_s * up, endpoint=False), 2.0 * n)
+    torch.manual_seed(1234)
+    ct = PrimalDualUNetCT(fan, upsample=up, adjoint="fbp", **MODEL_KW).to(dev).eval()
+    sparse = data.make_ct_batch(fan, b, up, seed=300 + rank, device=dev)["sino_sparse"]
+    with torch.no_grad():
+        g = GraphedInference(ct, sparse, warmup=2)
+    ms = _timed_steps(g.replay, flush, steps, dev)
+    out["cfg3_fan_ct_inference"] = {"workload": "configs[2]: fan-beam CT PD-UNet 512x512, 128->1024 views, 8 slices per GPU, CUDA graph",
+                                    "ms_per_step": ms, "slices_per_s": b * world / (ms * 1e-3),
+                                    "peak_mem_GiB": torch.cuda.max_memory_allocated(dev) / 2 ** 30}
+    del g, ct, sparse, fan
+    torch.cuda.empty_cache()
+    # ---- configs[3]: radial-MRI training step, 320^2, 8 coils, 48 spokes, 2 slices per GPU, DDP when world > 1
+    n, coils, sp, b = 320, 8, 48, 2
+    torch.manual_seed(1234)
+    m = PrimalDualUNetMRI((n, n), sp, 2 * n, coils=coils, n_iter=4, n_primal=4, n_dual=2 * coils, unet_base=32, unet_depth=3,
+                          dual_features=32).to(dev)
+    d = data.make_mri_batch((n, n), sp, coils, b, seed=400 + rank, device=dev)
+    ddp = parallel.wrap_ddp(m, local, graph_capture=True)
+    opt = torch.optim.Adam(ddp.parameters(), 1e-4, capturable=True)
+    loss_fn = lambda o, t: (o - t).abs().pow(2).mean()
+    step = GraphedTrainingStep(ddp, opt, loss_fn, (d["kdata"], d["omega"], d["smaps"], d["dcf"]), d["image"], warmup=3)
+    ms = _timed_steps(step.graph.replay, flush, steps, dev)
+    out["cfg4_mri_training"] = {"workload": "configs[3]: radial-MRI PD-UNet 320x320, 8 coils, 48 spokes, training step (forward + MSE + "
+                                            "backward + Adam), 2 slices per GPU, one CUDA graph" + (", DDP NCCL all-reduce inside" if world > 1 else ""),
+                                "ms_per_step": ms, "slices_per_s": b * world / (ms * 1e-3), "loss": float(step.static_loss.detach()),
+                                "peak_mem_GiB": torch.cuda.max_memory_allocated(dev) / 2 ** 30}
+    del step, ddp, opt, m, d
+    torch.cuda.empty_cache()
     return out
 
 
@@ -418,6 +534,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the configs[0] / [2] / [3] model-level legs")
     args = ap.parse_args()
     global _STDOUT
     _STDOUT = StdoutToStderr()

@@ -114,6 +114,14 @@ PDU_API int pdu_radon_adj_f32(const float* sino, float* img, const float* trig, 
                               const pdu_radon_geom_t* g, void* workspace, size_t workspace_bytes,
                               pdu_stream_t stream);
 
+/* The same with fan-beam FBP's distance weighting: fbp_weight != 0 multiplies every tap of a fan-beam view once more
+ * by s_dist / (s_dist - t), t the pixel's depth along the central ray -- together with the magnification weight the
+ * plain adjoint already applies this is the 1 / U^2 of Kak & Slaney section 3.4.2 for a flat equispaced detector
+ * (views over 2 pi).  Ignored for parallel beams. */
+PDU_API int pdu_radon_adj_weighted_f32(const float* sino, float* img, const float* trig, int batch,
+                                       const pdu_radon_geom_t* g, int fbp_weight, void* workspace,
+                                       size_t workspace_bytes, pdu_stream_t stream);
+
 /* out[r, i] = sum_j sino[r, j] * taps[(i - j) + det_count - 1],  r < rows.
  * taps: 2*det_count - 1 spatial filter taps (already scaled by pi / (2 n_angles)).
  * Replaces [RECALL] torch_radon `Radon.filter_sinogram` (pad, rfft, multiply, irfft, crop, scale).

@@ -136,12 +136,20 @@ def ray_setup_f32(g: RadonGeom, trig: np.ndarray):
                 step=np.where(hit, step, z), n_steps=n_steps)
 
 
-def _bilinear_zero(img_flat: torch.Tensor, n: int, xc: torch.Tensor, yc: torch.Tensor):
+def _texq(f: torch.Tensor) -> torch.Tensor:
+    """An interpolation fraction as the texture unit holds it: 9-bit fixed point with 8 fractional bits (CUDA C
+    programming guide, linear filtering) -- round to nearest (even) multiple of 2^-8."""
+    return torch.round(f * 256.0) / 256.0
+
+
+def _bilinear_zero(img_flat: torch.Tensor, n: int, xc: torch.Tensor, yc: torch.Tensor, tex_weights: bool = False):
     """img_flat [B, n*n] float64; xc, yc [...] float64 pixel-centre coords -> [B, ...]."""
     ix = torch.floor(xc)
     iy = torch.floor(yc)
     fx = xc - ix
     fy = yc - iy
+    if tex_weights:
+        fx, fy = _texq(fx), _texq(fy)
     ix = ix.long()
     iy = iy.long()
     out = None
@@ -157,9 +165,12 @@ def _bilinear_zero(img_flat: torch.Tensor, n: int, xc: torch.Tensor, yc: torch.T
     return out
 
 
-def radon_forward(img, trig: np.ndarray, g: RadonGeom, angle_chunk: int = 8) -> torch.Tensor:
+def radon_forward(img, trig: np.ndarray, g: RadonGeom, angle_chunk: int = 8, tex_weights: bool = False) -> torch.Tensor:
     """img [B, n, n] -> sinogram [B, A, D] float64.  Restates [RECALL] torch_radon
-    radon_forward_kernel (ray driven, clipped, unit-ish step, texture bilinear)."""
+    radon_forward_kernel (ray driven, clipped, unit-ish step, texture bilinear).
+    tex_weights: emulate the texture unit's 8-bit interpolation weights (the twin of the library's "tex_weights"
+    option).  The sample coordinates are then rounded to float32 like the kernel's single FMA, so that both sides
+    quantise the same fractions."""
     img = torch.as_tensor(img, dtype=torch.float64)
     B = img.shape[0]
     n, A, D = g.n, g.n_angles, g.det_count
@@ -179,15 +190,21 @@ def radon_forward(img, trig: np.ndarray, g: RadonGeom, angle_chunk: int = 8) -> 
         vx = torch.from_numpy(rs["vx"][a0:a1]).double()[..., None]
         vy = torch.from_numpy(rs["vy"][a0:a1]).double()[..., None]
         live = (j <= ns[..., None].double())
-        vals = _bilinear_zero(flat, n, x0 + j * vx, y0 + j * vy)
+        xs, ys = x0 + j * vx, y0 + j * vy
+        if tex_weights:
+            xs, ys = xs.float().double(), ys.float().double()
+        vals = _bilinear_zero(flat, n, xs, ys, tex_weights)
         s = (vals * live).sum(-1)
         out[:, a0:a1] = s * torch.from_numpy(rs["step"][a0:a1]).double()
     return out
 
 
-def radon_backprojection(sino, trig: np.ndarray, g: RadonGeom, angle_chunk: int = 16) -> torch.Tensor:
+def radon_backprojection(sino, trig: np.ndarray, g: RadonGeom, angle_chunk: int = 16, fbp_weight: bool = False,
+                         tex_weights: bool = False) -> torch.Tensor:
     """sinogram [B, A, D] -> image [B, n, n] float64.  Restates [RECALL] torch_radon
-    radon_backward_kernel (pixel driven, linear along the detector, zero border)."""
+    radon_backward_kernel (pixel driven, linear along the detector, zero border).
+    fbp_weight (fan beam): every tap once more times s / (s - t) -- with the magnification weight this is the
+    1 / U^2 of fan-beam FBP."""
     sino = torch.as_tensor(sino, dtype=torch.float64)
     B = sino.shape[0]
     n, A, D = g.n, g.n_angles, g.det_count
@@ -212,10 +229,12 @@ def radon_backprojection(sino, trig: np.ndarray, g: RadonGeom, angle_chunk: int 
             den = float(np.float32(g.s_dist)) + sn * dx - cs * dy
             iden = k / den
             jc = (cs * dx + sn * dy) * ids * iden + cr
-            w = iden
+            w = iden * (float(np.float32(g.s_dist)) / den) if fbp_weight else iden
         jb = jc - 0.5
         i0 = torch.floor(jb)
         fr = jb - i0
+        if tex_weights:
+            fr = _texq(fr)
         i0 = i0.long()
         rows = sino[:, a0:a1, :]                                   # [B, a, D]
         tot = torch.zeros(B, a1 - a0, n, n, dtype=torch.float64)
@@ -358,5 +377,10 @@ def fan_cosine_weights(g: RadonGeom) -> np.ndarray:
     return k / np.sqrt(k * k + u * u)
 
 
-def fbp(sino, trig, g: RadonGeom, name: str = "ramp") -> torch.Tensor:
+def fbp(sino, trig, g: RadonGeom, name: str = "ramp", fan_weights: bool = True) -> torch.Tensor:
+    """Parallel beam: backprojection(filter(s)).  Fan beam with fan_weights (Kak & Slaney section 3.4.2, flat equispaced
+    detector, views over 2 pi): cosine pre-weight, ramp filter, backprojection weighted by 1 / U^2."""
+    if g.geom == FAN and fan_weights:
+        s = torch.as_tensor(sino, dtype=torch.float64) * torch.from_numpy(fan_cosine_weights(g))
+        return radon_backprojection(filter_sinogram(s, name), trig, g, fbp_weight=True)
     return radon_backprojection(filter_sinogram(sino, name), trig, g)

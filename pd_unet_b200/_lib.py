@@ -45,6 +45,7 @@ SIGNATURES = {
     "pdu_radon_workspace_bytes": (C.c_size_t, [_G, C.c_int]),
     "pdu_radon_fwd_f32": (C.c_int, [_p, _p, _p, C.c_int, _G, _p, C.c_size_t, _p]),
     "pdu_radon_adj_f32": (C.c_int, [_p, _p, _p, C.c_int, _G, _p, C.c_size_t, _p]),
+    "pdu_radon_adj_weighted_f32": (C.c_int, [_p, _p, _p, C.c_int, _G, C.c_int, _p, C.c_size_t, _p]),
     "pdu_filter_workspace_bytes": (C.c_size_t, [C.c_int]),
     "pdu_filter_prepare_f32": (C.c_int, [_p, _p, C.c_size_t, C.c_int, _p]),
     "pdu_filter_sinogram_f32": (C.c_int, [_p, _p, _p, _p, C.c_size_t, C.c_long, C.c_int, _p]),

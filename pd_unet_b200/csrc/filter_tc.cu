@@ -327,7 +327,7 @@ int filter_tc_launch(const float* sino, float* out, const void* ws, const float*
     if (rc) return rc;
     PDU_CUDA((ensure_dyn_smem<filter_tc_kernel>(TC_SMEM)));
     dim3 grid((unsigned)cdiv(rows, TC_BM), (unsigned)(D / TC_BN));
-    const int fault = option(OPT_DEBUG_FAULT) > 0 ? 1 : 0;
+    const int fault = option(OPT_DEBUG_FAULT) == 1 ? 1 : 0;
     filter_tc_kernel<<<grid, TC_THREADS, TC_SMEM, st>>>(tx, th, col_weight, out, rows, D, device_error_word(),
                                                         fault ? MBAR_TIMEOUT_FAULT_NS : MBAR_TIMEOUT_NS, fault);
     PDU_LAUNCHED();

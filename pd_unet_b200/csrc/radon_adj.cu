@@ -14,7 +14,7 @@
 //   the fallback above).
 // (r01 also carried the (value, difference) tap form with 8 and 4 pixels per thread and a forced 96-entry
 //  segment -- 254 / 281 / 194 us against 182 -- deleted in r02.)
-#include "common.cuh"
+#include "radon_common.cuh"
 
 namespace pdu {
 
@@ -28,6 +28,8 @@ struct AdjGeom {
     float cr;       // det_count / 2 - 0.5  (detector coordinate of u = 0, in tap units)
     float half;     // n / 2 - 0.5
     uint32_t koff;  // 0x4B000000 * 8 mod 2^32, passed at run time so that ptxas keeps `base - koff` in one register
+    int texq;       // tex_weights option: the interpolation fraction rounded to 8 bits (radon_common.cuh)
+    int fbp;        // fan beam only: weight every tap by (s / den) once more -- the 1 / U^2 of fan-beam FBP (Kak & Slaney 3.4.2)
 };
 
 // detector coordinate (in tap units: value = (1-fr) s[i0] + fr s[i0+1], i0 = floor(t)) and weight
@@ -41,14 +43,17 @@ __device__ __forceinline__ float tap_global_inl(const AdjGeom& g, const float* _
     const double ids = 1.0 / (double)g.det_spacing;
     double t, w = 1.0;
     if (g.fan) {
-        w = ((double)g.s_dist + (double)g.d_dist) / ((double)g.s_dist + (double)sn * dx - (double)cs * dy);
+        const double den = (double)g.s_dist + (double)sn * dx - (double)cs * dy;
+        w = ((double)g.s_dist + (double)g.d_dist) / den;
         t = p * ids * w + (double)g.cr;
+        if (g.fbp) w *= (double)g.s_dist / den;
     } else {
         t = p * ids + (double)g.cr;
     }
     const double tf = floor(t);
     if (!(tf > -2.0 && tf < (double)g.det_count)) return 0.f;       // both taps outside the detector (or NaN)
-    const float fr = (float)(t - tf);
+    float fr = (float)(t - tf);
+    if (g.texq) fr = texq(fr);
     const int i0 = (int)tf, D = g.det_count;
     const float s0 = (unsigned)i0 < (unsigned)D ? __ldg(row + i0) : 0.f;
     const float s1 = (unsigned)(i0 + 1) < (unsigned)D ? __ldg(row + i0 + 1) : 0.f;
@@ -130,9 +135,9 @@ __device__ __forceinline__ float rcp_approx(float d) {
     return r;
 }
 
-template <int PY, int SEG, bool SAFE>
+template <int PY, int SEG, bool SAFE, bool TQ>
 __device__ __forceinline__ void fan_taps_line(const float* __restrict__ view, uint32_t cbase, float lx,
-                                              const ull* __restrict__ ly_pk, float kk, float* __restrict__ acc) {
+                                              const ull* __restrict__ ly_pk, float kk, float sfbp, float* __restrict__ acc) {
     constexpr float MAGIC = 8388608.f;
     const float4 v = *reinterpret_cast<const float4*>(view);
     const float2 tr = *reinterpret_cast<const float2*>(view + 4);
@@ -149,6 +154,7 @@ __device__ __forceinline__ void fan_taps_line(const float* __restrict__ view, ui
         ull p_r = pk2(rcp_approx(d0), rcp_approx(d1));
         if (!SAFE) p_r = fma2(p_r, sub2(p_one, mul2(p_den, p_r)), p_r);
         ull p_c = mul2(p_num, p_r);
+        if (TQ) p_c = sub2(add2(p_c, pk2(TEXQ_MAGIC, TEXQ_MAGIC)), pk2(TEXQ_MAGIC, TEXQ_MAGIC));
         float c0, c1;
         upk2(p_c, c0, c1);
         if (!SAFE) {
@@ -158,7 +164,9 @@ __device__ __forceinline__ void fan_taps_line(const float* __restrict__ view, ui
         }
         float t0, t1, w0, w1;
         upk2(add2_rm(p_c, p_m), t0, t1);
-        upk2(mul2(p_k, p_r), w0, w1);
+        ull p_w = mul2(p_k, p_r);
+        if (sfbp != 0.f) p_w = mul2(p_w, mul2(pk2(sfbp, sfbp), p_r));     // fan-beam FBP: k s / den^2 (uniform branch)
+        upk2(p_w, w0, w1);
         const float2 s0 = lds64((uint32_t)__float_as_int(t0) * 8u + cbase);
         const float2 s1 = lds64((uint32_t)__float_as_int(t1) * 8u + cbase);
         acc[k] = fmaf(w0, fmaf(c0, s0.y, s0.x), acc[k]);
@@ -166,7 +174,7 @@ __device__ __forceinline__ void fan_taps_line(const float* __restrict__ view, ui
     }
 }
 
-template <int TX, int TY, int PY, int AC, int SEG, bool FAN>
+template <int TX, int TY, int PY, int AC, int SEG, bool FAN, bool TQ>
 __global__ void __launch_bounds__(TX*(TY / PY), FAN ? (PY == 8 ? 5 : 2) : (PY == 8 ? 7 : 3))
     radon_adj_tile_kernel(const float* __restrict__ sino, float* __restrict__ img, const float* __restrict__ trig,
                           const AdjGeom g) {
@@ -295,7 +303,8 @@ __global__ void __launch_bounds__(TX*(TY / PY), FAN ? (PY == 8 ? 5 : 2) : (PY ==
                             const uint32_t cbase = (uint32_t)__cvta_generic_to_shared(seg) - g.koff;
 #pragma unroll
                             for (int k = 0; k < PY; k += 2) {
-                                const ull p_tl = fma2(p_b, ly_pk[k / 2], p_tx);        // >= 1 by construction
+                                ull p_tl = fma2(p_b, ly_pk[k / 2], p_tx);              // >= 1 by construction
+                                if (TQ) p_tl = sub2(add2(p_tl, pk2(TEXQ_MAGIC, TEXQ_MAGIC)), pk2(TEXQ_MAGIC, TEXQ_MAGIC));
                                 const ull p_t = add2_rm(p_tl, p_m);
                                 float t0, t1, c0, c1;
                                 upk2(p_t, t0, t1);
@@ -307,8 +316,9 @@ __global__ void __launch_bounds__(TX*(TY / PY), FAN ? (PY == 8 ? 5 : 2) : (PY ==
                         }
                     } else {
                         const uint32_t cbase = (uint32_t)__cvta_generic_to_shared(seg) - g.koff;
-                        if (close) fan_taps_line<PY, SEG, false>(s_view[al], cbase, lx, ly_pk, g.k, acc);
-                        else fan_taps_line<PY, SEG, true>(s_view[al], cbase, lx, ly_pk, g.k, acc);
+                        const float sfbp = g.fbp ? g.s_dist : 0.f;
+                        if (close) fan_taps_line<PY, SEG, false, TQ>(s_view[al], cbase, lx, ly_pk, g.k, sfbp, acc);
+                        else fan_taps_line<PY, SEG, true, TQ>(s_view[al], cbase, lx, ly_pk, g.k, sfbp, acc);
                     }
                 }
             }
@@ -351,9 +361,19 @@ __global__ void __launch_bounds__(TX*(TY / PY), FAN ? (PY == 8 ? 5 : 2) : (PY ==
 
 using namespace pdu;
 
+extern "C" int pdu_radon_adj_weighted_f32(const float* sino, float* img, const float* trig, int batch,
+                                          const pdu_radon_geom_t* g, int fbp_weight, void* workspace, size_t workspace_bytes,
+                                          pdu_stream_t stream);
+
 extern "C" int pdu_radon_adj_f32(const float* sino, float* img, const float* trig, int batch,
                                  const pdu_radon_geom_t* g, void* workspace, size_t workspace_bytes,
                                  pdu_stream_t stream) {
+    return pdu_radon_adj_weighted_f32(sino, img, trig, batch, g, 0, workspace, workspace_bytes, stream);
+}
+
+extern "C" int pdu_radon_adj_weighted_f32(const float* sino, float* img, const float* trig, int batch,
+                                          const pdu_radon_geom_t* g, int fbp_weight, void* workspace, size_t workspace_bytes,
+                                          pdu_stream_t stream) {
     (void)workspace;
     (void)workspace_bytes;
     PDU_REQUIRE(g != nullptr, "pdu_radon_adj_f32: geom is null");
@@ -382,6 +402,8 @@ extern "C" int pdu_radon_adj_f32(const float* sino, float* img, const float* tri
     ag.cr = 0.5f * (float)g->det_count - 0.5f;
     ag.half = 0.5f * (float)g->n - 0.5f;
     ag.koff = 0x4B000000u * 8u;
+    ag.fbp = (fbp_weight && ag.fan) ? 1 : 0;
+    ag.texq = option(OPT_TEX_WEIGHTS) > 0 ? 1 : 0;
 
     cudaStream_t st = (cudaStream_t)stream;
     int variant = option(OPT_RADON_ADJ);
@@ -396,9 +418,16 @@ extern "C" int pdu_radon_adj_f32(const float* sino, float* img, const float* tri
         // a 32 x 32 tile projects onto at most 32 sqrt(2) / det_spacing bins: a 64-entry segment is enough for
         // parallel beams with det_spacing >= 0.8 (a third less staging work)
         const bool seg64 = !ag.fan && 46.f * ag.ids + 5.f <= 64.f;
-        if (ag.fan) radon_adj_tile_kernel<TX, TY, 8, 32, 96, true><<<grid, dim3(TX, TY / 8), 0, st>>>(sino, img, trig, ag);
-        else if (seg64) radon_adj_tile_kernel<TX, TY, 8, 32, 64, false><<<grid, dim3(TX, TY / 8), 0, st>>>(sino, img, trig, ag);
-        else radon_adj_tile_kernel<TX, TY, 8, 32, 96, false><<<grid, dim3(TX, TY / 8), 0, st>>>(sino, img, trig, ag);
+        const dim3 blk(TX, TY / 8);
+        if (ag.texq) {
+            if (ag.fan) radon_adj_tile_kernel<TX, TY, 8, 32, 96, true, true><<<grid, blk, 0, st>>>(sino, img, trig, ag);
+            else if (seg64) radon_adj_tile_kernel<TX, TY, 8, 32, 64, false, true><<<grid, blk, 0, st>>>(sino, img, trig, ag);
+            else radon_adj_tile_kernel<TX, TY, 8, 32, 96, false, true><<<grid, blk, 0, st>>>(sino, img, trig, ag);
+        } else {
+            if (ag.fan) radon_adj_tile_kernel<TX, TY, 8, 32, 96, true, false><<<grid, blk, 0, st>>>(sino, img, trig, ag);
+            else if (seg64) radon_adj_tile_kernel<TX, TY, 8, 32, 64, false, false><<<grid, blk, 0, st>>>(sino, img, trig, ag);
+            else radon_adj_tile_kernel<TX, TY, 8, 32, 96, false, false><<<grid, blk, 0, st>>>(sino, img, trig, ag);
+        }
         note_kernel(OP_RADON_ADJ, "radon_adj_tile_kernel<32,32,8,32,%d,%s> grid %ux%ux%u (line-form taps in shared memory, packed FP32)",
                     ag.fan ? 96 : (seg64 ? 64 : 96), ag.fan ? "fan" : "parallel", grid.x, grid.y, grid.z);
     }

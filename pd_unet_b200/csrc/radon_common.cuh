@@ -85,10 +85,21 @@ __device__ __forceinline__ Ray ray_setup(const pdu_radon_geom_t& g, float cs, fl
     return r;
 }
 
+// Texture-unit weight emulation (option "tex_weights"): [RECALL] torch_radon samples through CUDA texture filtering,
+// whose interpolation weights are 9-bit fixed point with 8 fractional bits (CUDA C programming guide, "Linear
+// filtering").  Rounding a fraction in [0, 1] to a multiple of 2^-8: adding 2^15 makes the float32 ulp 2^-8, round to
+// nearest even does the rest.  The oracle twin is oracle.radon_forward(..., tex_weights=True).
+constexpr float TEXQ_MAGIC = 32768.f;
+__device__ __forceinline__ float texq(float f) { return __fsub_rn(__fadd_rn(f, TEXQ_MAGIC), TEXQ_MAGIC); }
+
 // Bilinear sample with a zero border straight from global memory (any coordinates).
-__device__ __forceinline__ float bilinear_global(const float* __restrict__ img, int n, float xc, float yc) {
+__device__ __forceinline__ float bilinear_global(const float* __restrict__ img, int n, float xc, float yc, bool tq = false) {
     const float xf = floorf(xc), yf = floorf(yc);
-    const float fx = xc - xf, fy = yc - yf;
+    float fx = xc - xf, fy = yc - yf;
+    if (tq) {
+        fx = texq(fx);
+        fy = texq(fy);
+    }
     const int ix = (int)xf, iy = (int)yf;
     const bool x0 = (unsigned)ix < (unsigned)n, x1 = (unsigned)(ix + 1) < (unsigned)n;
     const bool y0 = (unsigned)iy < (unsigned)n, y1 = (unsigned)(iy + 1) < (unsigned)n;

@@ -55,7 +55,7 @@ __global__ void transpose_kernel(const float* __restrict__ in, float* __restrict
 
 // ------------------------------------------------------------------ variant 0
 __global__ void __launch_bounds__(256) radon_fwd_gather_kernel(const float* __restrict__ img, float* __restrict__ sino,
-                                                               const float* __restrict__ trig, pdu_radon_geom_t g) {
+                                                               const float* __restrict__ trig, pdu_radon_geom_t g, int tq) {
     const int d = blockIdx.x * blockDim.x + threadIdx.x;
     const int a = blockIdx.y * blockDim.y + threadIdx.y;
     const int b = blockIdx.z;
@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(256) radon_fwd_gather_kernel(const float* __re
     const float* src = img + (long)b * g.n * g.n;
     for (int j = 0; j <= r.n_steps; ++j) {
         const float jf = (float)j;
-        acc += bilinear_global(src, g.n, fmaf(jf, r.vx, r.xc0), fmaf(jf, r.vy, r.yc0));
+        acc += bilinear_global(src, g.n, fmaf(jf, r.vx, r.xc0), fmaf(jf, r.vy, r.yc0), tq != 0);
     }
     sino[((long)b * g.n_angles + a) * g.det_count + d] = acc * r.step;
 }
@@ -94,6 +94,7 @@ struct FaultCtl {
     int* err_word;                    // device_error_word(), may be null
     unsigned long long timeout_ns;
     int fault;                        // debug_fault option: the producer skips its TMA loads
+    int texq;                         // tex_weights option: interpolation fractions rounded to 8 bits (radon_common.cuh)
 };
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, int c0, int c1, int c2, uint64_t* bar) {
     asm volatile(
@@ -296,7 +297,8 @@ __global__ void __launch_bounds__(DB* AG)
                     for (; i < cnt; ++i) {
                         const ull p_c = fma2(p_j, p_v, p_0);            // (wl, ul)
                         const ull p_t = add2_rm(p_c, p_m);              // (floor + 2^23) each
-                        const ull p_f = sub2(p_c, sub2(p_t, p_m));      // (fw, fu)
+                        ull p_f = sub2(p_c, sub2(p_t, p_m));            // (fw, fu)
+                        if (fc.texq) p_f = sub2(add2(p_f, pk2(TEXQ_MAGIC, TEXQ_MAGIC)), pk2(TEXQ_MAGIC, TEXQ_MAGIC));
                         float tw, tu, fw, fu;
                         upk2(p_t, tw, tu);
                         upk2(p_f, fw, fu);
@@ -324,7 +326,11 @@ __global__ void __launch_bounds__(DB* AG)
                 const float ul = fmaf(jf, vu, u0l);
                 const float tw = __fadd_rd(wl, MAGIC), tu = __fadd_rd(ul, MAGIC);
                 const int iw = __float_as_int(tw) & 0x7fffff, iu = __float_as_int(tu) & 0x7fffff;
-                const float fw = wl - (tw - MAGIC), fu = ul - (tu - MAGIC);
+                float fw = wl - (tw - MAGIC), fu = ul - (tu - MAGIC);
+                if (fc.texq) {
+                    fw = texq(fw);
+                    fu = texq(fu);
+                }
                 const float* p = tile + iw * W + iu;
                 const float v00 = p[0], v01 = p[1], v10 = p[W], v11 = p[W + 1];
                 const float top = fmaf(fu, v01 - v00, v00);
@@ -334,7 +340,7 @@ __global__ void __launch_bounds__(DB* AG)
             }
         } else {
             for (int i = 0; i < cnt; ++i) {
-                acc += bilinear_global(src, N, fmaf(jf, vu, u0), fmaf(jf, vw, w0));
+                acc += bilinear_global(src, N, fmaf(jf, vu, u0), fmaf(jf, vw, w0), fc.texq != 0);
                 jf += dj;
             }
         }
@@ -396,12 +402,16 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
 }
 
 // one cell straight from global memory (oversize strips only); (wc, uc) are cell coordinates
-__device__ __forceinline__ float quad_global(const float4* __restrict__ q, int n1, float wc, float uc) {
+__device__ __forceinline__ float quad_global(const float4* __restrict__ q, int n1, float wc, float uc, bool tq) {
     const float wf = floorf(wc), uf = floorf(uc);
     const int R = (int)wf, Cc = (int)uf;
     if ((unsigned)R >= (unsigned)n1 || (unsigned)Cc >= (unsigned)n1) return 0.f;
     const float4 c = __ldg(q + (long)R * n1 + Cc);
-    const float fw = wc - wf, fu = uc - uf;
+    float fw = wc - wf, fu = uc - uf;
+    if (tq) {
+        fw = texq(fw);
+        fu = texq(fu);
+    }
     return fmaf(fu, c.z, c.x) + fw * fmaf(fu, c.w, c.y);
 }
 
@@ -413,7 +423,7 @@ struct QuadCfg {
     static_assert(W <= 128 && (TH * W) % 8 == 0, "one TMA box of 2 W doubles; 128-byte aligned buffers");
 };
 
-template <int DB, int AG, int TH, int W, int NBUF, int LD>
+template <int DB, int AG, int TH, int W, int NBUF, int LD, bool TEXQ>
 __global__ void __launch_bounds__(DB* AG + 32, 5)      // 5: ptxas settles at 40 registers without a spill (4: 56 registers WITH one)
     radon_fwd_quad_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_qt,
                           const float4* __restrict__ q, const float4* __restrict__ qt, float* __restrict__ sino,
@@ -580,7 +590,8 @@ __global__ void __launch_bounds__(DB* AG + 32, 5)      // 5: ptxas settles at 40
                 // a first sample an ulp before the strip: clamp it onto the strip's first cell row
                 const float ul = fmaf(jf, vu, u0l);
                 const float tu = __fadd_rd(ul, MAGIC);
-                const float fu = ul - (tu - MAGIC);
+                float fu = ul - (tu - MAGIC);
+                if (TEXQ) fu = texq(fu);
                 const uint32_t addr = smem_base + (uint32_t)(buf * C::TILE_BYTES) + (((uint32_t)__float_as_int(tu) & 0x7fffffu) << 4);
                 const float4 c = lds128(addr);
                 acc0 += fmaf(fu, c.z, c.x);
@@ -593,7 +604,8 @@ __global__ void __launch_bounds__(DB* AG + 32, 5)      // 5: ptxas settles at 40
             for (; i < cnt; ++i) {
                 const ull p_c = fma2(p_j, p_v, p_0);            // (wl, ul)
                 const ull p_t = add2_rm(p_c, p_m);              // (floor + 2^23) each
-                const ull p_f = sub2(p_c, sub2(p_t, p_m));      // (fw, fu)
+                ull p_f = sub2(p_c, sub2(p_t, p_m));            // (fw, fu)
+                if (TEXQ) p_f = sub2(add2(p_f, pk2(TEXQ_MAGIC, TEXQ_MAGIC)), pk2(TEXQ_MAGIC, TEXQ_MAGIC));
                 float tw, tu, fw, fu;
                 upk2(p_t, tw, tu);
                 upk2(p_f, fw, fu);
@@ -607,7 +619,7 @@ __global__ void __launch_bounds__(DB* AG + 32, 5)      // 5: ptxas settles at 40
             upk2(p_j, jf, j_hi);
         } else {
             for (int i = 0; i < cnt; ++i) {
-                acc0 += quad_global(src, N1, fmaf(jf, vw, w0), fmaf(jf, vu, u0));
+                acc0 += quad_global(src, N1, fmaf(jf, vw, w0), fmaf(jf, vu, u0), TEXQ);
                 jf += dj;
             }
         }
@@ -659,8 +671,8 @@ static int make_image_map(CUtensorMap* tm, const float* ptr, int batch, int n, i
 }
 
 static FaultCtl fault_ctl() {
-    const int fault = option(OPT_DEBUG_FAULT) > 0 ? 1 : 0;
-    return FaultCtl{device_error_word(), fault ? MBAR_TIMEOUT_FAULT_NS : MBAR_TIMEOUT_NS, fault};
+    const int fault = option(OPT_DEBUG_FAULT) == 1 ? 1 : 0;
+    return FaultCtl{device_error_word(), fault ? MBAR_TIMEOUT_FAULT_NS : MBAR_TIMEOUT_NS, fault, option(OPT_TEX_WEIGHTS) > 0 ? 1 : 0};
 }
 
 template <int DB, int AG, int TH, int W, int NBUF, int LD = 32>
@@ -715,10 +727,15 @@ static int launch_quad(const float4* q, const float4* qt, float* sino, const flo
     if (rc) return rc;
     rc = make_quad_map(&tmT, qt, batch, g.n + 1, W, TH);
     if (rc) return rc;
-    auto kern = radon_fwd_quad_kernel<DB, AG, TH, W, NBUF, LD>;
-    PDU_CUDA((ensure_dyn_smem<radon_fwd_quad_kernel<DB, AG, TH, W, NBUF, LD>>(C::SMEM)));
+    const FaultCtl fc = fault_ctl();
     dim3 grid((unsigned)cdiv(g.det_count, DB), (unsigned)cdiv(g.n_angles, AG), (unsigned)batch);
-    kern<<<grid, C::THREADS + 32, C::SMEM, st>>>(tm, tmT, q, qt, sino, trig, g, fault_ctl());
+    if (fc.texq) {
+        PDU_CUDA((ensure_dyn_smem<radon_fwd_quad_kernel<DB, AG, TH, W, NBUF, LD, true>>(C::SMEM)));
+        radon_fwd_quad_kernel<DB, AG, TH, W, NBUF, LD, true><<<grid, C::THREADS + 32, C::SMEM, st>>>(tm, tmT, q, qt, sino, trig, g, fc);
+    } else {
+        PDU_CUDA((ensure_dyn_smem<radon_fwd_quad_kernel<DB, AG, TH, W, NBUF, LD, false>>(C::SMEM)));
+        radon_fwd_quad_kernel<DB, AG, TH, W, NBUF, LD, false><<<grid, C::THREADS + 32, C::SMEM, st>>>(tm, tmT, q, qt, sino, trig, g, fc);
+    }
     PDU_LAUNCHED();
     note_kernel(OP_RADON_FWD, "quad_build_kernel + radon_fwd_quad_kernel<%d,%d,%d,%d,%d,%d> grid %ux%ux%u (bilinear-cell tiles, TMA ring)",
                 DB, AG, TH, W, NBUF, LD, grid.x, grid.y, grid.z);
@@ -770,7 +787,7 @@ int pdu_radon_fwd_f32(const float* img, float* sino, const float* trig, int batc
     if (variant == 0) {
         dim3 block(64, 4);
         dim3 grid((unsigned)cdiv(g->det_count, 64), (unsigned)cdiv(g->n_angles, 4), (unsigned)batch);
-        radon_fwd_gather_kernel<<<grid, block, 0, st>>>(img, sino, trig, *g);
+        radon_fwd_gather_kernel<<<grid, block, 0, st>>>(img, sino, trig, *g, option(OPT_TEX_WEIGHTS) > 0 ? 1 : 0);
         PDU_LAUNCHED();
         note_kernel(OP_RADON_FWD, "radon_fwd_gather_kernel grid %ux%ux%u (one thread per ray, L1 gather)", grid.x, grid.y, grid.z);
         return PDU_OK;
@@ -799,7 +816,7 @@ int pdu_radon_fwd_f32(const float* img, float* sino, const float* trig, int batc
     if (variant == 0) {
         dim3 block(64, 4);
         dim3 grid((unsigned)cdiv(g->det_count, 64), (unsigned)cdiv(g->n_angles, 4), (unsigned)batch);
-        radon_fwd_gather_kernel<<<grid, block, 0, st>>>(img, sino, trig, *g);
+        radon_fwd_gather_kernel<<<grid, block, 0, st>>>(img, sino, trig, *g, option(OPT_TEX_WEIGHTS) > 0 ? 1 : 0);
         PDU_LAUNCHED();
         note_kernel(OP_RADON_FWD, "radon_fwd_gather_kernel grid %ux%ux%u (one thread per ray, L1 gather)", grid.x, grid.y, grid.z);
         return PDU_OK;

@@ -128,12 +128,14 @@ class _Plan:
         back to the allocator (stream-ordered, so the pending build kernels are safe)."""
         return buf[:persist].clone() if persist < buf.numel() else buf
 
-    def _bins_for(self, omega: torch.Tensor, planes: int = 1 << 30, adjoint: bool = False):
+    def _bins_for(self, omega: torch.Tensor, planes: int = 1 << 30, adjoint: bool = False, split: bool = False):
         """Row bins of the fused path for this trajectory (None when the generic path is to be used)."""
         L, h = lib(), self.handle(omega.device)
         if not self.use_fused or not L.pdu_nufft_has_fused_path(h):
             return None
-        if self.use_fused == "auto":
+        # split-layout calls (the model's) stay on the fused path at every size: the generic kernels speak complex64
+        # only, and the layout passes around them cost what the fused path loses at small plane counts
+        if self.use_fused == "auto" and not split:
             if planes < 8 or (adjoint and planes > 32 and self.grid_size[0] in (512, 640)):
                 return None
         ent = self._entry(omega)
@@ -259,7 +261,7 @@ class _Plan:
             return out
         with torch.cuda.device(image.device):
             L, h = lib(), self.handle(image.device)
-            bins = self._bins_for(omega, B * coils)
+            bins = self._bins_for(omega, B * coils, split=split)
             if bins is not None:
                 flags = (NUFFT_IMAGE_SPLIT | NUFFT_KDATA_SPLIT) if split else 0
                 for b0, b1 in self._chunks(L, h, B, coils, M):
@@ -303,7 +305,7 @@ class _Plan:
             return out.zero_()
         with torch.cuda.device(data.device):
             L, h = lib(), self.handle(data.device)
-            bins = self._bins_for(omega, B * coils, adjoint=True)
+            bins = self._bins_for(omega, B * coils, adjoint=True, split=split)
             if bins is not None:
                 flags = (NUFFT_IMAGE_SPLIT | NUFFT_KDATA_SPLIT) if split else 0
                 for b0, b1 in self._chunks(L, h, B, coils, M):

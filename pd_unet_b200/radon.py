@@ -102,6 +102,21 @@ class _Backprojection(torch.autograd.Function):
         return ctx.op._project(grad), None
 
 
+class _FanFbp(torch.autograd.Function):
+    """Fan-beam FBP (cosine pre-weight fused into the filter, 1 / U^2 weighting in the backprojector).  Inference only:
+    the transpose of the distance-weighted backprojector is a pixel-driven scatter this library does not have, and
+    unlike for the plain pair there is no partner operator to stand in as its gradient."""
+
+    @staticmethod
+    def forward(ctx, sino, op, name):
+        return op._backproject(op._filter(sino, name, weighted=True), fbp_weight=True)
+
+    @staticmethod
+    def backward(ctx, grad):
+        raise NotImplementedError("fan-beam FBP with its distance weighting is not differentiable here; train through "
+                                  "RadonFanbeam.backprojection (adjoint='backprojection') or fbp(..., fan_weights=False)")
+
+
 class _Filter(torch.autograd.Function):
     @staticmethod
     def forward(ctx, sino, op, name):
@@ -136,6 +151,7 @@ class _BaseRadon:
         self._trig_host = np.stack([np.cos(self._internal), np.sin(self._internal)], axis=-1).astype(np.float32)
         self._trig: Dict[torch.device, torch.Tensor] = {}
         self._taps: Dict[Tuple[torch.device, str], torch.Tensor] = {}
+        self._cosw: Dict[torch.device, torch.Tensor] = {}
 
     # ------------------------------------------------------------------ public API
     @property
@@ -156,7 +172,13 @@ class _BaseRadon:
     def filter_sinogram(self, sinogram: torch.Tensor, filter_name: str = "ramp") -> torch.Tensor:
         return _Filter.apply(sinogram, self, filter_name)
 
-    def fbp(self, sinogram: torch.Tensor, filter_name: str = "ramp") -> torch.Tensor:
+    def fbp(self, sinogram: torch.Tensor, filter_name: str = "ramp", fan_weights: bool = True) -> torch.Tensor:
+        """Filtered backprojection.  Parallel beam: backprojection(filter_sinogram(s)).  Fan beam (views over 2 pi, flat
+        equispaced detector), fan_weights=True: Kak & Slaney section 3.4.2 -- the projections are multiplied by the cosine
+        of the fan angle (inside the filter kernel), ramp filtered, and backprojected with the 1 / U^2 distance weight;
+        fan_weights=False gives the unweighted composition (differentiable, like the parallel-beam form)."""
+        if self.geom.geom == PDU_GEOM_FAN and fan_weights:
+            return _FanFbp.apply(sinogram, self, filter_name)
         return self.backprojection(self.filter_sinogram(sinogram, filter_name))
 
     __call__ = forward
@@ -194,7 +216,7 @@ class _BaseRadon:
             timer.__exit__()
         return out.reshape(*lead, A, D)
 
-    def _backproject(self, s: torch.Tensor) -> torch.Tensor:
+    def _backproject(self, s: torch.Tensor, fbp_weight: bool = False) -> torch.Tensor:
         s = require_cuda(s, torch.float32, "sinogram")
         n, A, D = self.resolution, self.n_angles, self.det_count
         if s.dim() < 2 or s.shape[-1] != D or s.shape[-2] != A:
@@ -211,12 +233,19 @@ class _BaseRadon:
             timer.__enter__()
             for b0 in range(0, flat.shape[0], 65535):
                 part = flat[b0:b0 + 65535]
-                check(L.pdu_radon_adj_f32(part.data_ptr(), out[b0:].data_ptr(), trig.data_ptr(), part.shape[0],
-                                          C.byref(self.geom), None, 0, stream_ptr()), "pdu_radon_adj_f32")
+                check(L.pdu_radon_adj_weighted_f32(part.data_ptr(), out[b0:].data_ptr(), trig.data_ptr(), part.shape[0],
+                                                   C.byref(self.geom), 1 if fbp_weight else 0, None, 0, stream_ptr()),
+                      "pdu_radon_adj_f32")
             timer.__exit__()
         return out.reshape(*lead, n, n)
 
-    def _filter(self, s: torch.Tensor, name: str) -> torch.Tensor:
+    def fan_cosine_weights(self) -> np.ndarray:
+        """float64 [D]: cos of the fan angle of every detector bin, (s + d) / sqrt((s + d)^2 + u^2)."""
+        u = (np.arange(self.det_count, dtype=np.float64) + 0.5 - self.det_count / 2.0) * self.det_spacing
+        k = float(self.geom.s_dist) + float(self.geom.d_dist)
+        return k / np.sqrt(k * k + u * u)
+
+    def _filter(self, s: torch.Tensor, name: str, weighted: bool = False) -> torch.Tensor:
         s = require_cuda(s, torch.float32, "sinogram")
         A, D = self.n_angles, self.det_count
         if s.dim() < 2 or s.shape[-1] != D or s.shape[-2] != A:
@@ -237,9 +266,16 @@ class _BaseRadon:
                 entry = (taps, ws)
                 self._taps[key] = entry
             taps, ws = entry
+            cw = None
+            if weighted:
+                cw = self._cosw.get(s.device)
+                if cw is None:
+                    cw = torch.from_numpy(self.fan_cosine_weights().astype(np.float32)).to(s.device)
+                    self._cosw[s.device] = cw
             with _Timed("filter"):
-                check(L.pdu_filter_sinogram_f32(s.data_ptr(), out.data_ptr(), taps.data_ptr(), ws.data_ptr(),
-                                                ws.numel(), rows, D, stream_ptr()), "pdu_filter_sinogram_f32")
+                check(L.pdu_filter_sinogram_weighted_f32(s.data_ptr(), out.data_ptr(), taps.data_ptr(),
+                                                         cw.data_ptr() if cw is not None else None, ws.data_ptr(),
+                                                         ws.numel(), rows, D, stream_ptr()), "pdu_filter_sinogram_f32")
         return out
 
 

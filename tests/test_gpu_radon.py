@@ -289,3 +289,66 @@ def test_last_kernel_names_the_dispatch():
     assert "filter_tc_kernel" in _lib.last_kernel("filter")
     sparse.backprojection(s)
     assert "radon_adj_tile_kernel<32,32,8,32,64,parallel>" in _lib.last_kernel("radon_adj")
+
+
+def test_fan_beam_fbp_with_its_weights_matches_the_oracle():
+    """the cosine pre-weight rides in the filter kernel (tensor-core path: D % 128 == 0, CUDA-core
+    path otherwise), the distance weight in the backprojector; both against the float64 oracle, PSNR within 0.01 dB."""
+    from pd_unet_b200.phantoms import shepp_logan
+    for n, A, D, sp, s_, d_ in ((128, 180, 256, 2.0, 1.0, 1.0), (96, 120, 200, 1.7, 1.3, 0.6)):
+        ang = user_angles(A, 2 * np.pi)
+        op = pdu.RadonFanbeam(n, ang, s_ * n, det_distance=d_ * n, det_count=D, det_spacing=sp)
+        g = oracle.RadonGeom(n=n, n_angles=A, det_count=D, det_spacing=sp, geom=FAN, s_dist=s_ * n, d_dist=d_ * n)
+        trig = oracle.trig_table(-ang)
+        x = torch.from_numpy(shepp_logan(n)).float()[None]
+        sino = op.forward(x.to(DEV))
+        rec = op.fbp(sino)
+        want = oracle.fbp(sino.cpu(), trig, g)
+        assert rel_l2(rec, want) <= TOL
+        assert rel_l2(op.fbp(sino, fan_weights=False), oracle.fbp(sino.cpu(), trig, g, fan_weights=False)) <= TOL
+        mse = lambda a: float(((a.double().cpu() - x.double()) ** 2).mean())
+        assert abs(10 * np.log10(mse(rec) / mse(want))) < 0.01
+        # the weights remove the bias of the plain composition (8 % low for a source one image width away)
+        c = np.arange(n) - n / 2 + 0.5
+        inner = torch.from_numpy((c[None, :] ** 2 + c[:, None] ** 2) < (0.2 * n) ** 2)
+        m = float(x[0][inner].mean())
+        assert abs(float(rec[0].cpu()[inner].mean()) - m) < 0.01 * m
+        assert abs(float(op.fbp(sino, fan_weights=False)[0].cpu()[inner].mean()) - m) > 0.03 * m
+        with pytest.raises(NotImplementedError):
+            s2 = sino.clone().requires_grad_()
+            op.fbp(s2).sum().backward()
+
+
+@pytest.mark.parametrize("name", ["par64", "par256_sparse", "fan96", "par63_no_tma"])
+def test_texture_weight_emulation_switch(name):
+    """[RECALL] torch_radon interpolates through the texture unit (8-bit weights).  The option
+    "tex_weights" makes every projector round its interpolation fractions the same way; the oracle has the twin.  The
+    two conventions differ by 2e-4 on a phantom -- far more than the 1e-5 budget -- which is why the switch exists.
+    Tolerances: a fraction within float32 rounding of a 2^-9 tie rounds differently in the kernels (strip- / tile-local
+    float32 coordinates) and in the oracle (float64, or float32 at image magnitude); each such sample is off by
+    2^-8 x the local difference of its neighbours -- 1e-5-level on images and object sinograms, 1e-4-level on white noise."""
+    op, g, internal = _case(name)
+    trig = oracle.trig_table(internal)
+    x = phantom_batch(2, g.n, seed=3)
+    s_obj = oracle.radon_forward(x, trig, g).float()
+    s_noise = seeded((2, g.n_angles, g.det_count), 7)
+    exact_f = oracle.radon_forward(x, trig, g)
+    try:
+        pdu.set_option("tex_weights", 1)
+        got_f = op.forward(x.to(DEV))
+        got_b = op.backprojection(s_obj.to(DEV))
+        got_bn = op.backprojection(s_noise.to(DEV))
+        dense = pdu.Radon(g.n, user_angles(8 * g.n_angles), det_count=g.det_count) if name == "par64" else None
+        got_d = dense.forward(x.to(DEV)) if dense is not None else None       # the cell-tile kernel
+    finally:
+        pdu.set_option("tex_weights", -1)
+    want_f = oracle.radon_forward(x, trig, g, tex_weights=True)
+    assert rel_l2(got_f, want_f) <= 3e-5
+    assert rel_l2(got_b, oracle.radon_backprojection(s_obj, trig, g, tex_weights=True)) <= 3e-5
+    assert rel_l2(got_bn, oracle.radon_backprojection(s_noise, trig, g, tex_weights=True)) <= 5e-4
+    assert rel_l2(want_f, exact_f) > 3e-5                              # the conventions really differ (6e-5 .. 2e-4)
+    assert rel_l2(got_f, exact_f) > 3e-5
+    if dense is not None:
+        gd = oracle.RadonGeom(n=g.n, n_angles=8 * g.n_angles, det_count=g.det_count)
+        assert rel_l2(got_d, oracle.radon_forward(x, oracle.trig_table(-user_angles(8 * g.n_angles)), gd, tex_weights=True)) <= 3e-5
+    assert rel_l2(op.forward(x.to(DEV)), exact_f) <= TOL               # and the switch is off again

@@ -149,3 +149,25 @@ def test_fbp_reconstructs_the_phantom():
     c = np.arange(n) - n / 2 + 0.5
     inner = (c[None, :] ** 2 + c[:, None] ** 2) < (0.2 * n) ** 2
     assert abs(rec[inner].mean() - img[inner].mean()) < 0.02
+
+
+def test_fan_beam_fbp_reconstructs_the_phantom():
+    """fan-beam FBP = cosine pre-weight + ramp filter + 1 / U^2-weighted backprojection
+    (Kak & Slaney section 3.4.2).  With a source one image width away the weights matter: the weighted form recovers the
+    object's mean to 0.2 %, the unweighted composition is 8 % low."""
+    n, A = 128, 360
+    ang = np.linspace(0, 2 * np.pi, A, endpoint=False)
+    g = RadonGeom(n=n, n_angles=A, det_count=320, det_spacing=2.0, geom=FAN, s_dist=1.0 * n, d_dist=1.0 * n)
+    trig = oracle.trig_table(-ang)
+    img = shepp_logan(n)
+    sino = oracle.radon_forward(img[None], trig, g)
+    psnr = lambda rec: 10 * np.log10(img.max() ** 2 / np.mean((rec - img) ** 2))
+    rec = oracle.fbp(sino, trig, g)[0].numpy()
+    plain = oracle.fbp(sino, trig, g, fan_weights=False)[0].numpy()
+    assert psnr(rec) > 25.5, psnr(rec)
+    assert psnr(rec) > psnr(plain) + 0.5, (psnr(rec), psnr(plain))
+    c = np.arange(n) - n / 2 + 0.5
+    inner = (c[None, :] ** 2 + c[:, None] ** 2) < (0.2 * n) ** 2
+    m = img[inner].mean()
+    assert abs(rec[inner].mean() - m) < 0.005 * m
+    assert abs(plain[inner].mean() - m) > 0.05 * m
