@@ -219,7 +219,10 @@ static int plane_chunk(int planes, long M) {
     return pc;
 }
 
-static int get_fft(pdu_nufft_plan* p, int planes, cudaStream_t st, cufftHandle* out) {
+// The cuFFT handle of a plan is shared state (stream binding, work area): the plan's mutex is held from the
+// cufftSetStream to the end of the exec call, so two host threads that share a plan cannot retarget each other's
+// transform.  (Kernels of one handle still run in the order they were enqueued; use one plan per stream for overlap.)
+static int run_fft(pdu_nufft_plan* p, float2* grid, int planes, int dir, cudaStream_t st) {
     std::lock_guard<std::mutex> lock(p->mu);
     auto it = p->fft.find(planes);
     if (it == p->fft.end()) {
@@ -237,15 +240,7 @@ static int get_fft(pdu_nufft_plan* p, int planes, cudaStream_t st, cufftHandle* 
         set_error("cufftSetStream failed with %d", (int)r);
         return PDU_EFFT;
     }
-    *out = it->second;
-    return PDU_OK;
-}
-
-static int run_fft(pdu_nufft_plan* p, float2* grid, int planes, int dir, cudaStream_t st) {
-    cufftHandle h;
-    int rc = get_fft(p, planes, st, &h);
-    if (rc) return rc;
-    cufftResult r = cufftExecC2C(h, (cufftComplex*)grid, (cufftComplex*)grid, dir);
+    r = cufftExecC2C(it->second, (cufftComplex*)grid, (cufftComplex*)grid, dir);
     if (r != CUFFT_SUCCESS) {
         set_error("cufftExecC2C failed with %d", (int)r);
         return PDU_EFFT;
@@ -427,7 +422,7 @@ __global__ void __launch_bounds__(SEQ* FastFft<K>::TPS)
 }
 
 template <int K, int SEQ>
-__global__ void __launch_bounds__(SEQ* FastFft<K>::TPS, 3)
+__global__ void __launch_bounds__(SEQ* FastFft<K>::TPS, K <= 640 ? 3 : 1)
     ff_cols_fwd_kernel(const float2* __restrict__ T, float2* __restrict__ grid, const float2* __restrict__ tw_g, NufftDims d) {
     using F = FastFft<K>;
     float2* buf = pf_smem<float2>();
@@ -467,7 +462,7 @@ __global__ void __launch_bounds__(SEQ* FastFft<K>::TPS)
 }
 
 template <int K, int SEQ>
-__global__ void __launch_bounds__(SEQ* FastFft<K>::TPS, 3)
+__global__ void __launch_bounds__(SEQ* FastFft<K>::TPS, K <= 640 ? 3 : 1)
     ff_cols_adj_kernel(const float2* __restrict__ T, float2* __restrict__ U, const float2* __restrict__ tw_g, NufftDims d) {
     using F = FastFft<K>;
     float2* buf = pf_smem<float2>();
@@ -486,18 +481,21 @@ __global__ void __launch_bounds__(SEQ* FastFft<K>::TPS, 3)
     ff_transform<K, 3, true, false, true>(buf + s * F::template pitch<3>(), tw, t, ld, st);
 }
 
-constexpr int FF_SEQ_ROWS = 4, FF_SEQ_COLS = 8;
+constexpr int FF_SEQ_ROWS = 4;
+template <int K>
+static constexpr int ff_seq_cols() { return K <= 1024 ? 8 : 4; }     // SEQ * K / 8 threads <= 1024
 template <int K>
 static constexpr size_t ff_smem_bytes(int seq) { return ((size_t)seq * FastFft<K>::template pitch<3>() + K) * sizeof(float2); }   // PS = 3 is the larger pitch
 
 static bool ff_supported(const pdu_nufft_plan* p) {
-    return p->k0 == p->k1 && p->k0 == 2 * p->n0 && p->k1 == 2 * p->n1 && (p->k0 == 512 || p->k0 == 640) && p->pfft_ok;
+    return p->k0 == p->k1 && p->k0 == 2 * p->n0 && p->k1 == 2 * p->n1 && fast_fft_size(p->k0) && p->d_w0 && p->d_w1;
 }
 
 template <int K>
 static int ff_forward(pdu_nufft_plan* p, const float2* image, const float2* smaps, float2* T, float2* grid, int planes,
                       int coils, int smaps_batch, cudaStream_t st) {
     const NufftDims d = dims_of(p);
+    constexpr int FF_SEQ_COLS = ff_seq_cols<K>();
     auto rows = ff_rows_fwd_kernel<K, FF_SEQ_ROWS>;
     auto cols = ff_cols_fwd_kernel<K, FF_SEQ_COLS>;
     PDU_CUDA((ensure_dyn_smem<ff_rows_fwd_kernel<K, FF_SEQ_ROWS>>((int)ff_smem_bytes<K>(FF_SEQ_ROWS))));
@@ -514,6 +512,7 @@ static int ff_forward(pdu_nufft_plan* p, const float2* image, const float2* smap
 template <int K>
 static int ff_adjoint(pdu_nufft_plan* p, const float2* grid, float2* T, float2* U, int planes, cudaStream_t st) {
     const NufftDims d = dims_of(p);
+    constexpr int FF_SEQ_COLS = ff_seq_cols<K>();
     auto rows = ff_rows_adj_kernel<K, FF_SEQ_ROWS>;
     auto cols = ff_cols_adj_kernel<K, FF_SEQ_COLS>;
     PDU_CUDA((ensure_dyn_smem<ff_rows_adj_kernel<K, FF_SEQ_ROWS>>((int)ff_smem_bytes<K>(FF_SEQ_ROWS))));
@@ -956,13 +955,20 @@ static int nufft_fwd_chunk(pdu_nufft_plan_t* p, const float2* image, float2* kda
     // 640^2): the pruned passes move 2.5x fewer bytes but are still ~1.7x slower than cuFFT's register-resident
     // radix kernels (row+column 407 us vs 238 us), so cuFFT stays the default until they are.
     int variant = option(OPT_NUFFT_FWD);
-    if (variant < 0) variant = ff_supported(p) ? 2 : 0;      // register-resident pruned FFT where it exists (r02)
+    // default: the register-resident pruned FFT on the BASELINE grids, the generic pruned FFT on every other grid
+    // that factors into 2, 3, 5 (slower than cuFFT, but the library's own); cuFFT only for other prime factors
+    if (variant < 0) variant = ff_supported(p) ? 2 : (p->pfft_ok ? 1 : 0);
     int rc;
     if (variant == 2 && !ff_supported(p)) variant = 0;
     if (variant == 2) {
         float2* T = grid + total;
-        rc = p->k0 == 512 ? ff_forward<512>(p, image, smaps, T, grid, planes, coils, smaps_batch, st)
-                          : ff_forward<640>(p, image, smaps, T, grid, planes, coils, smaps_batch, st);
+        switch (p->k0) {
+            case 256: rc = ff_forward<256>(p, image, smaps, T, grid, planes, coils, smaps_batch, st); break;
+            case 512: rc = ff_forward<512>(p, image, smaps, T, grid, planes, coils, smaps_batch, st); break;
+            case 640: rc = ff_forward<640>(p, image, smaps, T, grid, planes, coils, smaps_batch, st); break;
+            case 1024: rc = ff_forward<1024>(p, image, smaps, T, grid, planes, coils, smaps_batch, st); break;
+            default: rc = ff_forward<2048>(p, image, smaps, T, grid, planes, coils, smaps_batch, st); break;
+        }
         if (rc) return rc;
     } else if (variant == 1 && p->pfft_ok) {
         // pruned FFT: apodise + pad + transform the n0 non-zero rows, then every column
@@ -1014,7 +1020,7 @@ static int nufft_adj_chunk(pdu_nufft_plan_t* p, const float2* kdata, float2* ima
     const int out_planes = smaps ? batch : planes;
     const long total = (long)out_planes * p->n0 * p->n1;
     int variant = option(OPT_NUFFT_ADJ);
-    if (variant < 0) variant = ff_supported(p) ? 2 : 0;      // see nufft_fwd_chunk
+    if (variant < 0) variant = ff_supported(p) ? 2 : (p->pfft_ok ? 1 : 0);      // see nufft_fwd_chunk
     if (variant == 2 && !ff_supported(p)) variant = 0;
     note_kernel(OP_NUFFT_ADJ, "%s + %s + crop_apod_kernel (%d planes of %dx%d, M=%ld)",
                 csr ? "transpose_kdata_kernel + interp_adj_csrT_kernel + interp_adj_csr_long_kernel (sorted gather)"
@@ -1026,7 +1032,13 @@ static int nufft_adj_chunk(pdu_nufft_plan_t* p, const float2* kdata, float2* ima
     if (variant == 2) {
         float2* T = grid + (long)planes * p->k0 * p->k1;
         float2* U = T + (long)planes * std::max((long)p->n0 * p->k1, (long)p->k0 * p->n1);
-        rc = p->k0 == 512 ? ff_adjoint<512>(p, grid, T, U, planes, st) : ff_adjoint<640>(p, grid, T, U, planes, st);
+        switch (p->k0) {
+            case 256: rc = ff_adjoint<256>(p, grid, T, U, planes, st); break;
+            case 512: rc = ff_adjoint<512>(p, grid, T, U, planes, st); break;
+            case 640: rc = ff_adjoint<640>(p, grid, T, U, planes, st); break;
+            case 1024: rc = ff_adjoint<1024>(p, grid, T, U, planes, st); break;
+            default: rc = ff_adjoint<2048>(p, grid, T, U, planes, st); break;
+        }
         if (rc) return rc;
         NufftDims dc = dims_of(p);          // the cropped result is a dense [n0][n1] "grid"
         dc.k0 = dc.n0;

@@ -115,7 +115,7 @@ struct FwdCfg {
     static_assert(W % 4 == 0 && W % 32 != 0 && W <= 256, "box width: 16-byte multiple, not a multiple of 32 banks");
 };
 
-template <int DB, int AG, int TH, int W, int NBUF, int LD>
+template <int DB, int AG, int TH, int W, int NBUF, int LD, bool TEXQ>
 __global__ void __launch_bounds__(DB* AG)
     radon_fwd_strip_kernel(const __grid_constant__ CUtensorMap tm_img, const __grid_constant__ CUtensorMap tm_imgT,
                            const float* __restrict__ img, const float* __restrict__ imgT, float* __restrict__ sino,
@@ -298,7 +298,7 @@ __global__ void __launch_bounds__(DB* AG)
                         const ull p_c = fma2(p_j, p_v, p_0);            // (wl, ul)
                         const ull p_t = add2_rm(p_c, p_m);              // (floor + 2^23) each
                         ull p_f = sub2(p_c, sub2(p_t, p_m));            // (fw, fu)
-                        if (fc.texq) p_f = sub2(add2(p_f, pk2(TEXQ_MAGIC, TEXQ_MAGIC)), pk2(TEXQ_MAGIC, TEXQ_MAGIC));
+                        if (TEXQ) p_f = sub2(add2(p_f, pk2(TEXQ_MAGIC, TEXQ_MAGIC)), pk2(TEXQ_MAGIC, TEXQ_MAGIC));
                         float tw, tu, fw, fu;
                         upk2(p_t, tw, tu);
                         upk2(p_f, fw, fu);
@@ -327,7 +327,7 @@ __global__ void __launch_bounds__(DB* AG)
                 const float tw = __fadd_rd(wl, MAGIC), tu = __fadd_rd(ul, MAGIC);
                 const int iw = __float_as_int(tw) & 0x7fffff, iu = __float_as_int(tu) & 0x7fffff;
                 float fw = wl - (tw - MAGIC), fu = ul - (tu - MAGIC);
-                if (fc.texq) {
+                if (TEXQ) {
                     fw = texq(fw);
                     fu = texq(fu);
                 }
@@ -340,7 +340,7 @@ __global__ void __launch_bounds__(DB* AG)
             }
         } else {
             for (int i = 0; i < cnt; ++i) {
-                acc += bilinear_global(src, N, fmaf(jf, vu, u0), fmaf(jf, vw, w0), fc.texq != 0);
+                acc += bilinear_global(src, N, fmaf(jf, vu, u0), fmaf(jf, vw, w0), TEXQ);
                 jf += dj;
             }
         }
@@ -418,9 +418,15 @@ __device__ __forceinline__ float quad_global(const float4* __restrict__ q, int n
 template <int DB, int AG, int TH, int W, int NBUF>
 struct QuadCfg {
     static constexpr int THREADS = DB * AG;
-    static constexpr int TILE_BYTES = TH * W * 16;
-    static constexpr int SMEM = NBUF * TILE_BYTES + 2 * NBUF * 8 + 2 * MAX_STRIPS * 4;
-    static_assert(W <= 128 && (TH * W) % 8 == 0, "one TMA box of 2 W doubles; 128-byte aligned buffers");
+    // TH + 1 cell rows: the last one is the first row of the next strip again.  With that slack row the number of
+    // samples a ray takes in a strip is ONE estimate -- "those with local row < TH + 1/2" -- and rounding in the estimate
+    // only moves a sample between a strip's slack row and the next strip's first row (the same cells); the r01 kernel
+    // settled the count exactly with two fix-up loops per ray and strip and clamped samples an ulp before a strip.
+    static constexpr int ROWS = TH + 1;
+    static constexpr int TILE_BYTES = ROWS * W * 16;
+    static constexpr int TILE_STRIDE = (TILE_BYTES + 127) / 128 * 128;
+    static constexpr int SMEM = NBUF * TILE_STRIDE + 2 * NBUF * 8 + 2 * MAX_STRIPS * 4;
+    static_assert(W <= 128, "one TMA box of 2 W doubles");
 };
 
 template <int DB, int AG, int TH, int W, int NBUF, int LD, bool TEXQ>
@@ -430,7 +436,7 @@ __global__ void __launch_bounds__(DB* AG + 32, 5)      // 5: ptxas settles at 40
                           const float* __restrict__ trig, const pdu_radon_geom_t g, const FaultCtl fc) {
     using C = QuadCfg<DB, AG, TH, W, NBUF>;
     extern __shared__ __align__(1024) unsigned char smem_dyn[];
-    uint64_t* full = (uint64_t*)(smem_dyn + NBUF * C::TILE_BYTES);
+    uint64_t* full = (uint64_t*)(smem_dyn + NBUF * C::TILE_STRIDE);
     uint64_t* empty = full + NBUF;
     int* s_umin = (int*)(empty + NBUF);
     int* s_umax = s_umin + MAX_STRIPS;
@@ -483,6 +489,7 @@ __global__ void __launch_bounds__(DB* AG + 32, 5)      // 5: ptxas settles at 40
     const float inv_aw = aw > 1e-3f ? __fdividef(1.f, aw) : 0.f;
 
     __syncthreads();
+    int k_first = INT_MAX;            // the first strip this ray registered in: it takes no sample from an earlier one
     {
         // strip boxes: warp-reduced extents, one lane per warp touches the shared box (see the float-tile kernel).
         // u is monotone along the ray, so its range inside strip k is [U_k, U_k+1] clamped to the ray's own range,
@@ -495,20 +502,25 @@ __global__ void __launch_bounds__(DB* AG + 32, 5)      // 5: ptxas settles at 40
         constexpr float EPS = 1e-3f;
         const int kA = n >= 0 ? max((int)floorf(wa - EPS), 0) / TH : INT_MAX;
         const int kB = n >= 0 ? min(max((int)floorf(wb + EPS), 0) / TH, n_strips - 1) : -1;
+        k_first = kA;
         const float dw = wb - wa;
         const bool lin = dw > 0.f;
         const float slope = lin ? (ub - ua) / dw : 0.f;
         const float umin = fminf(ua, ub), umax = fmaxf(ua, ub);
         const int kA_w = __reduce_min_sync(0xffffffffu, kA), kB_w = __reduce_max_sync(0xffffffffu, kB);
-        float wk = (float)((kA_w <= kB_w ? kA_w : 0) * TH);      // (no valid ray in the warp: kA_w == INT_MAX, loop empty)
-        int Fk = (int)floorf(lin ? fminf(fmaxf(fmaf(wk - wa, slope, ua), umin), umax) : umin);
+        // a strip takes this ray's samples with row coordinate in [k TH - 1/2, (k + 1) TH + 1/2) (slack row, see QuadCfg):
+        // Us = u at k TH - 1/2, Ue = u at (k + 1) TH + 1/2 = (next strip's Us) + slope
+        auto u_at = [&](float w) { return lin ? fminf(fmaxf(fmaf(w - wa, slope, ua), umin), umax) : umin; };
+        float wk = (float)((kA_w <= kB_w ? kA_w : 0) * TH) - 0.5f;      // (no valid ray in the warp: kA_w == INT_MAX, loop empty)
+        int Fs = (int)floorf(u_at(wk));
         for (int k = kA_w; k <= kB_w; ++k) {
             wk += (float)TH;
-            const int Fk1 = (int)floorf(lin ? fminf(fmaxf(fmaf(wk - wa, slope, ua), umin), umax) : umax);
+            const int Fs1 = (int)floorf(u_at(wk));
+            const int Fe = (int)floorf(lin ? u_at(wk + 1.f) : umax);
             int lo_k = INT_MAX, hi_k = INT_MIN;
             if (k >= kA && k <= kB) {
-                lo_k = min(Fk, Fk1) - 1;
-                hi_k = max(Fk, Fk1) + 1;
+                lo_k = min(Fs, Fe) - 1;
+                hi_k = max(Fs, Fe) + 1;
             }
             lo_k = __reduce_min_sync(0xffffffffu, lo_k);
             hi_k = __reduce_max_sync(0xffffffffu, hi_k);
@@ -516,7 +528,7 @@ __global__ void __launch_bounds__(DB* AG + 32, 5)      // 5: ptxas settles at 40
                 atomicMin(&s_umin[k], lo_k);
                 atomicMax(&s_umax[k], hi_k);
             }
-            Fk = lin ? Fk1 : (int)floorf(umin);
+            Fs = Fs1;
         }
     }
     __syncthreads();
@@ -537,7 +549,7 @@ __global__ void __launch_bounds__(DB* AG + 32, 5)      // 5: ptxas settles at 40
             if (tma_ok && s_umax[k_issue] - lo + 1 <= W) {
                 mbar_expect_tx(full + buf, C::TILE_BYTES);
                 // the map describes the cells as pairs of doubles: start = 2 lo (always 16-byte aligned)
-                if (!fc.fault) tma_load_3d(smem_dyn + buf * C::TILE_BYTES, tm, 2 * lo, k_issue * TH, b, full + buf);
+                if (!fc.fault) tma_load_3d(smem_dyn + buf * C::TILE_STRIDE, tm, 2 * lo, k_issue * TH, b, full + buf);
             } else {
                 mbar_arrive(full + buf);
             }
@@ -569,35 +581,16 @@ __global__ void __launch_bounds__(DB* AG + 32, 5)      // 5: ptxas settles at 40
         }
         const float w0l = w0 - (float)(k * TH);
         const float u0l = u0 - (float)lo;
+        // samples of this ray in this strip: those whose local row is below TH + 1/2 (the tile has the slack row)
         int cnt = 0;
         const int left = n - s + 1;
-        bool first_low = false;
-        if (left > 0) {
-            const float wl = fmaf(jf, vw, w0l);
-            if (wl < (float)TH) {
-                int m = inv_aw > 0.f ? (int)(((float)TH - wl) * inv_aw) + 1 : 1;
-                m = max(1, min(m, left));
-                while (m > 1 && fmaf(jf + (float)(m - 1) * dj, vw, w0l) >= (float)TH) --m;
-                while (m < left && fmaf(jf + (float)m * dj, vw, w0l) < (float)TH) ++m;
-                cnt = m;
-                first_low = wl < 0.f;
-            }
+        if (left > 0 && k >= k_first) {
+            const float room = ((float)TH + 0.5f) - fmaf(jf, vw, w0l);
+            if (room > 0.f) cnt = inv_aw > 0.f ? min((int)(room * inv_aw) + 1, left) : left;
         }
         if (tma_ok && hi - lo + 1 <= W) {
-            const uint32_t cbase = smem_base + (uint32_t)(buf * C::TILE_BYTES) - KOFF;
+            const uint32_t cbase = smem_base + (uint32_t)(buf * C::TILE_STRIDE) - KOFF;
             int i = 0;
-            if (first_low && cnt > 0) {
-                // a first sample an ulp before the strip: clamp it onto the strip's first cell row
-                const float ul = fmaf(jf, vu, u0l);
-                const float tu = __fadd_rd(ul, MAGIC);
-                float fu = ul - (tu - MAGIC);
-                if (TEXQ) fu = texq(fu);
-                const uint32_t addr = smem_base + (uint32_t)(buf * C::TILE_BYTES) + (((uint32_t)__float_as_int(tu) & 0x7fffffu) << 4);
-                const float4 c = lds128(addr);
-                acc0 += fmaf(fu, c.z, c.x);
-                jf += dj;
-                i = 1;
-            }
             const ull p_v = pk2(vw, vu), p_0 = pk2(w0l, u0l), p_m = pk2(MAGIC, MAGIC), p_dj = pk2(dj, dj);
             ull p_j = pk2(jf, jf);
 #pragma unroll 4
@@ -684,10 +677,15 @@ static int launch_strip(const float* img, const float* imgT, float* sino, const 
     if (rc) return rc;
     rc = make_image_map(&tmT, imgT, batch, g.n, W, C::ROWS);
     if (rc) return rc;
-    auto kern = radon_fwd_strip_kernel<DB, AG, TH, W, NBUF, LD>;
-    PDU_CUDA((ensure_dyn_smem<radon_fwd_strip_kernel<DB, AG, TH, W, NBUF, LD>>(C::SMEM)));
+    const FaultCtl fc = fault_ctl();
     dim3 grid((unsigned)cdiv(g.det_count, DB), (unsigned)cdiv(g.n_angles, AG), (unsigned)batch);
-    kern<<<grid, C::THREADS, C::SMEM, st>>>(tm, tmT, img, imgT, sino, trig, g, fault_ctl());
+    if (fc.texq) {
+        PDU_CUDA((ensure_dyn_smem<radon_fwd_strip_kernel<DB, AG, TH, W, NBUF, LD, true>>(C::SMEM)));
+        radon_fwd_strip_kernel<DB, AG, TH, W, NBUF, LD, true><<<grid, C::THREADS, C::SMEM, st>>>(tm, tmT, img, imgT, sino, trig, g, fc);
+    } else {
+        PDU_CUDA((ensure_dyn_smem<radon_fwd_strip_kernel<DB, AG, TH, W, NBUF, LD, false>>(C::SMEM)));
+        radon_fwd_strip_kernel<DB, AG, TH, W, NBUF, LD, false><<<grid, C::THREADS, C::SMEM, st>>>(tm, tmT, img, imgT, sino, trig, g, fc);
+    }
     PDU_LAUNCHED();
     note_kernel(OP_RADON_FWD, "transpose_kernel + radon_fwd_strip_kernel<%d,%d,%d,%d,%d,%d> grid %ux%ux%u (float tiles, TMA ring)", DB, AG,
                 TH, W, NBUF, LD, grid.x, grid.y, grid.z);
@@ -723,9 +721,9 @@ static int launch_quad(const float4* q, const float4* qt, float* sino, const flo
                        const pdu_radon_geom_t& g, cudaStream_t st) {
     using C = QuadCfg<DB, AG, TH, W, NBUF>;
     CUtensorMap tm, tmT;
-    int rc = make_quad_map(&tm, q, batch, g.n + 1, W, TH);
+    int rc = make_quad_map(&tm, q, batch, g.n + 1, W, C::ROWS);
     if (rc) return rc;
-    rc = make_quad_map(&tmT, qt, batch, g.n + 1, W, TH);
+    rc = make_quad_map(&tmT, qt, batch, g.n + 1, W, C::ROWS);
     if (rc) return rc;
     const FaultCtl fc = fault_ctl();
     dim3 grid((unsigned)cdiv(g.det_count, DB), (unsigned)cdiv(g.n_angles, AG), (unsigned)batch);
