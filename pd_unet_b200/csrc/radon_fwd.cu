@@ -836,7 +836,10 @@ int pdu_radon_fwd_f32(const float* img, float* sino, const float* trig, int batc
             PDU_LAUNCHED();
         }
         // shapes the dispatcher uses (every other shape measured in r01 -- 32-row strips, 512-thread CTAs, 3-deep rings,
-        // 84/76/88/89-cell pitches, 8- and 16-detector quarter-warps -- lost by 2-20 % and was deleted)
+        // 84/76/88/89-cell pitches, 8- and 16-detector quarter-warps -- lost by 2-20 % and was deleted; r02 with the
+        // slack row, configs[1]: 12 / 16 / 20 / 24-row strips 474 / 451 / 458 / 445 us, 3-deep ring 589 us, coordinates of
+        // four samples from per-strip origins (one FMA2 per sample, no per-sample counter): 454 us at 56 registers --
+        // the loop is paced by the LDS.128 wavefronts, not by those two instructions)
         switch (variant) {
             case 9: return launch_quad<32, 4, 16, 120, 2, 8>(q, qt, sino, trig, batch, *g, st);    // 4 views / CTA (sparser views)
             case 11: return launch_quad<32, 8, 16, 128, 2, 8>(q, qt, sino, trig, batch, *g, st);   // widest cell box (sparser views)
