@@ -215,6 +215,12 @@ PDU_API int pdu_nufft_adj_binned_c64(pdu_nufft_plan_t* plan, const float* kdata,
                                      int smaps_batch, long m, float scale, const void* bins, int flags,
                                      void* workspace, size_t workspace_bytes, pdu_stream_t stream);
 
+/* The layout change on its own, for the generic (complex64) entry points: split [planes, 2, n] float32 <-> complex64
+ * [planes, n]; `weight` (nullable, float32 [n]) multiplies element e of every plane (the density compensation). */
+PDU_API int pdu_complex_from_split_f32(const float* split, float* out_c64, const float* weight, long planes, long n,
+                                       pdu_stream_t stream);
+PDU_API int pdu_split_from_complex_f32(const float* in_c64, float* split, long planes, long n, pdu_stream_t stream);
+
 /* Table interpolation only: grid [planes, k0, k1] <-> kdata [planes, m].
  * Replace [RECALL] torchkbnufft `KbInterp.forward` / `KbInterpAdjoint.forward`; the adjoint
  * ACCUMULATES into grid (zero it first). */

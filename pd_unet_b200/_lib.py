@@ -68,6 +68,8 @@ SIGNATURES = {
                                            C.c_size_t, _p]),
     "pdu_nufft_adj_binned_c64": (C.c_int, [_p, _p, _p, _p, _p, C.c_int, C.c_int, C.c_int, C.c_long, C.c_float, _p, C.c_int, _p,
                                            C.c_size_t, _p]),
+    "pdu_complex_from_split_f32": (C.c_int, [_p, _p, _p, C.c_long, C.c_long, _p]),
+    "pdu_split_from_complex_f32": (C.c_int, [_p, _p, C.c_long, C.c_long, _p]),
     "pdu_nufft_csr_build": (C.c_int, [_p, _p, C.c_long, _p, C.c_size_t, _p]),
     "pdu_nufft_interp_adj_csr_c64": (C.c_int, [_p, _p, _p, _p, C.c_int, C.c_long, _p]),
     "pdu_nufft_adj_csr_c64": (C.c_int, [_p, _p, _p, _p, _p, C.c_int, C.c_int, C.c_int, C.c_long, C.c_float, _p, _p,

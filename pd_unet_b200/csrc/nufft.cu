@@ -826,6 +826,28 @@ static int launch_interp_adj_csr(pdu_nufft_plan* p, const float2* kdata, float2*
     return PDU_OK;
 }
 
+// [planes][2][n] float32 (real plane, imaginary plane) <-> [planes][n] complex64: the layout change between the CNN
+// side of PD-UNet and the generic (complex64) operator path, one pass, optionally times a real weight per element index
+// (density compensation).  The fused path reads and writes the split layout directly and does not need these.
+__global__ void __launch_bounds__(256)
+    layout_to_complex_kernel(const float* __restrict__ split, float2* __restrict__ out, const float* __restrict__ weight, long n,
+                             long total) {
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const long p = i / n, e = i - p * n;
+        const float w = weight ? __ldg(weight + e) : 1.f;
+        out[i] = make_float2(w * __ldg(split + (2 * p) * n + e), w * __ldg(split + (2 * p + 1) * n + e));
+    }
+}
+__global__ void __launch_bounds__(256)
+    layout_to_split_kernel(const float2* __restrict__ in, float* __restrict__ split, long n, long total) {
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const long p = i / n, e = i - p * n;
+        const float2 v = __ldg(in + i);
+        split[(2 * p) * n + e] = v.x;
+        split[(2 * p + 1) * n + e] = v.y;
+    }
+}
+
 // cropped planes U [planes][n0][n1] -> image (x apodisation x scale, x conj(smaps) summed over coils); nufft_fused.cu
 int launch_crop_apod(pdu_nufft_plan* p, const float2* U, const float2* smaps, float2* image, int out_planes, int coils,
                      int smaps_batch, float scale, int split, cudaStream_t st) {
@@ -1201,6 +1223,20 @@ int pdu_nufft_adj_binned_c64(pdu_nufft_plan_t* p, const float* kdata, float* ima
     }
     return fused_adjoint(p, kdata, image, smaps, kweight, batch, coils, smaps_batch, m, scale, bins, flags, workspace,
                          (cudaStream_t)stream);
+}
+
+int pdu_complex_from_split_f32(const float* split, float* out, const float* weight, long planes, long n, pdu_stream_t stream) {
+    PDU_REQUIRE(split && out && planes > 0 && n > 0, "pdu_complex_from_split_f32: null pointer or empty tensor");
+    layout_to_complex_kernel<<<stream_grid(planes * n), 256, 0, (cudaStream_t)stream>>>(split, (float2*)out, weight, n, planes * n);
+    PDU_LAUNCHED();
+    return PDU_OK;
+}
+
+int pdu_split_from_complex_f32(const float* in, float* split, long planes, long n, pdu_stream_t stream) {
+    PDU_REQUIRE(split && in && planes > 0 && n > 0, "pdu_split_from_complex_f32: null pointer or empty tensor");
+    layout_to_split_kernel<<<stream_grid(planes * n), 256, 0, (cudaStream_t)stream>>>((const float2*)in, split, n, planes * n);
+    PDU_LAUNCHED();
+    return PDU_OK;
 }
 
 int pdu_nufft_interp_fwd_c64(pdu_nufft_plan_t* p, const float* grid, float* kdata, const float* omega, int planes,

@@ -133,9 +133,7 @@ class _Plan:
         L, h = lib(), self.handle(omega.device)
         if not self.use_fused or not L.pdu_nufft_has_fused_path(h):
             return None
-        # split-layout calls (the model's) stay on the fused path at every size: the generic kernels speak complex64
-        # only, and the layout passes around them cost what the fused path loses at small plane counts
-        if self.use_fused == "auto" and not split:
+        if self.use_fused == "auto":
             if planes < 8 or (adjoint and planes > 32 and self.grid_size[0] in (512, 640)):
                 return None
         ent = self._entry(omega)
@@ -228,14 +226,24 @@ class _Plan:
     # split=True: float32 tensors with the real and imaginary parts as neighbouring channels, image [B, 2 C, N0, N1],
     # data [B, 2 C, M] -- what PD-UNet's CNN blocks carry, so the model needs no permute / view_as_complex passes.
     @staticmethod
-    def _split_to_complex(x: torch.Tensor) -> torch.Tensor:
+    def _split_to_complex(x: torch.Tensor, weight: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """[B, 2 C, *s] float32 -> [B, C, *s] complex64 (x weight[*s]), one pass of the library's layout kernel."""
         B, C2 = x.shape[:2]
-        return torch.complex(x.reshape(B, C2 // 2, 2, *x.shape[2:])[:, :, 0], x.reshape(B, C2 // 2, 2, *x.shape[2:])[:, :, 1])
+        out = torch.empty((B, C2 // 2) + tuple(x.shape[2:]), dtype=torch.complex64, device=x.device)
+        n = out[0, 0].numel()
+        if out.numel():
+            check(lib().pdu_complex_from_split_f32(x.data_ptr(), out.data_ptr(), weight.data_ptr() if weight is not None else None,
+                                                   B * (C2 // 2), n, stream_ptr()), "pdu_complex_from_split_f32")
+        return out
 
     @staticmethod
     def _complex_to_split(z: torch.Tensor) -> torch.Tensor:
         B, Cc = z.shape[:2]
-        return torch.stack([z.real, z.imag], dim=2).reshape(B, 2 * Cc, *z.shape[2:]).contiguous()
+        out = torch.empty((B, 2 * Cc) + tuple(z.shape[2:]), dtype=torch.float32, device=z.device)
+        if out.numel():
+            check(lib().pdu_split_from_complex_f32(z.data_ptr(), out.data_ptr(), B * Cc, z[0, 0].numel(), stream_ptr()),
+                  "pdu_split_from_complex_f32")
+        return out
 
     def _chunks(self, L, h, B: int, coils: int, M: int):
         """Batch chunks that keep the fused path's scratch under 1 GiB."""
@@ -318,12 +326,10 @@ class _Plan:
                                                      1 if sb == 1 else nb, M, self.scale(norm), bins.data_ptr(), flags,
                                                      ws.data_ptr(), ws.numel(), stream_ptr()), "pdu_nufft_adj_binned_c64")
                 return out
-            if split or kweight is not None:
-                z = self._split_to_complex(data) if split else data
-                if kweight is not None:
-                    z = z * kweight
-                x = self.adjoint(z, omega, smaps, norm)
-                return self._complex_to_split(x) if split else x
+            if split:            # generic path: the library's layout kernels around the complex64 entry points
+                return self._complex_to_split(self.adjoint(self._split_to_complex(data, kweight), omega, smaps, norm))
+            if kweight is not None:
+                return self.adjoint(data * kweight, omega, smaps, norm)
             ws = torch.empty(L.pdu_nufft_workspace_bytes(h, B * coils), dtype=torch.uint8, device=data.device)
             csr = self._csr_for(omega, B * coils)
             check(L.pdu_nufft_adj_csr_c64(h, data.data_ptr(), out.data_ptr(), omega.data_ptr(),
