@@ -243,6 +243,12 @@ enum { PDU_LAYOUT_NCHW = 0, PDU_LAYOUT_NHWC = 1 };
 PDU_API int pdu_concat_f32(float* out, const float* a, const float* b, const float* c, int batch,
                            int ca, int cb, int cc, int c_out, long plane, float scale_b, int layout,
                            pdu_stream_t stream);
+/* The channels-last form of the same concatenation when b and / or c are still planar [batch, channels, plane] (the
+ * operators' output layout): out and a are channels-last, b_planar / c_planar say how b and c are stored.  Saves the
+ * separate layout-conversion pass per operand and iteration. */
+PDU_API int pdu_concat_mixed_f32(float* out, const float* a, const float* b, const float* c, int batch,
+                                 int ca, int cb, int cc, int c_out, long plane, float scale_b, int b_planar,
+                                 int c_planar, pdu_stream_t stream);
 /* out = state + delta (all three in `layout`);  slice [batch, kn, plane] = out[:, k:k+kn], always
  * planar because it is the next operator's input (slice may be NULL).  out may alias state.  Replaces
  * `h = h + net(...)` followed by `h[:, k:k+kn]` (kn = 1 for CT, 2 = (re, im) for MRI). */

@@ -77,6 +77,8 @@ SIGNATURES = {
     "pdu_nufft_interp_fwd_c64": (C.c_int, [_p, _p, _p, _p, C.c_int, C.c_long, _p]),
     "pdu_nufft_interp_adj_c64": (C.c_int, [_p, _p, _p, _p, C.c_int, C.c_long, _p]),
     "pdu_concat_f32": (C.c_int, [_p, _p, _p, _p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_long, C.c_float, C.c_int, _p]),
+    "pdu_concat_mixed_f32": (C.c_int, [_p, _p, _p, _p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_long, C.c_float, C.c_int,
+                                       C.c_int, _p]),
     "pdu_residual_slice_f32": (C.c_int, [_p, _p, _p, _p, C.c_int, C.c_int, C.c_long, C.c_int, C.c_int, C.c_int, _p]),
     "pdu_bias_prelu_f32": (C.c_int, [_p, _p, _p, C.c_int, C.c_int, C.c_int, C.c_long, C.c_int, _p]),
     "pdu_bias_prelu_fwd_f32": (C.c_int, [_p, _p, _p, _p, C.c_int, C.c_int, C.c_int, C.c_long, C.c_int, _p]),

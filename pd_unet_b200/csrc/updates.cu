@@ -66,6 +66,27 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// channels-last output and state, but b and / or c still PLANAR ([batch, channels, plane]: what the operators write):
+// the layout change happens in the concatenation instead of in a separate copy pass per operand.  A warp covers a few
+// pixels x all channels; the planar reads of one channel are 4-byte pieces of a line that the following warps reuse
+// from L1.
+__global__ void __launch_bounds__(256)
+    concat_nhwc_mixed_kernel(float* __restrict__ out, const float* __restrict__ a, const float* __restrict__ b,
+                             const float* __restrict__ c, int ca, int cb, int cc, int ct, long plane, float scale_b,
+                             int b_planar, int c_planar, long total) {
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const long pix = i / ct;
+        const int ch = (int)(i - pix * ct);
+        const long n = pix / plane, p = pix - n * plane;
+        float v;
+        if (ch < ca) v = a[pix * ca + ch];
+        else if (ch < ca + cb) v = (b_planar ? __ldg(b + (n * cb + (ch - ca)) * plane + p) : b[pix * cb + (ch - ca)]) * scale_b;
+        else if (ch < ca + cb + cc) v = c_planar ? __ldg(c + (n * cc + (ch - ca - cb)) * plane + p) : c[pix * cc + (ch - ca - cb)];
+        else v = 0.f;
+        out[i] = v;
+    }
+}
+
 // ------------------------------------------------------------------ residual + slice
 template <typename V>
 __device__ __forceinline__ V vadd(V a, V b);
@@ -271,6 +292,19 @@ int pdu_concat_f32(float* out, const float* a, const float* b, const float* c, i
     } else {
         concat_kernel<float><<<stream_grid(total, 256), 256, 0, st>>>(out, a, b, c, la, lb, lc, lz, scale_b, total);
     }
+    PDU_LAUNCHED();
+    return PDU_OK;
+}
+
+int pdu_concat_mixed_f32(float* out, const float* a, const float* b, const float* c, int batch, int ca, int cb, int cc,
+                         int c_out, long plane, float scale_b, int b_planar, int c_planar, pdu_stream_t stream) {
+    PDU_REQUIRE(out && a && b, "pdu_concat_mixed_f32: null pointer");
+    PDU_REQUIRE(batch > 0 && ca > 0 && cb > 0 && cc >= 0 && plane > 0, "pdu_concat_mixed_f32: sizes must be positive");
+    PDU_REQUIRE((c != nullptr) == (cc > 0), "pdu_concat_mixed_f32: c must be given exactly when cc > 0");
+    PDU_REQUIRE(c_out >= ca + cb + cc, "pdu_concat_mixed_f32: c_out %d is smaller than the %d input channels", c_out, ca + cb + cc);
+    const long total = (long)batch * plane * c_out;
+    concat_nhwc_mixed_kernel<<<stream_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(out, a, b, c, ca, cb, cc, c_out, plane, scale_b,
+                                                                                        b_planar ? 1 : 0, c_planar ? 1 : 0, total);
     PDU_LAUNCHED();
     return PDU_OK;
 }

@@ -54,8 +54,16 @@ class _Concat(torch.autograd.Function):
     def forward(ctx, a, b, c, scale_b, pad_to):
         nhwc = _is_channels_last(a)          # the state tensor decides; one-channel inputs fit either layout
         a = _in_layout(a, nhwc, "a")
-        b = _in_layout(b, nhwc, "b")
-        if c is not None:
+        # channels-last state with multi-channel b / c that are still planar (operator outputs): the layout change is
+        # done inside the concatenation (pdu_concat_mixed_f32) instead of by a copy pass per operand
+        planar = [False, False]
+        if nhwc:
+            for j, t in enumerate((b, c)):
+                planar[j] = (t is not None and t.is_cuda and t.dtype == torch.float32 and t.dim() == 4 and t.shape[1] > 1
+                             and t.is_contiguous())
+        if not planar[0]:
+            b = _in_layout(b, nhwc, "b")
+        if c is not None and not planar[1]:
             c = _in_layout(c, nhwc, "c")
         for t in (b, c):
             if t is not None and (t.shape[0] != a.shape[0] or t.shape[2:] != a.shape[2:]):
@@ -68,10 +76,16 @@ class _Concat(torch.autograd.Function):
         out = _empty((a.shape[0], c_out) + tuple(a.shape[2:]), a, nhwc)
         if out.numel():
             with torch.cuda.device(a.device):
-                check(lib().pdu_concat_f32(out.data_ptr(), a.data_ptr(), b.data_ptr(),
-                                           c.data_ptr() if c is not None else None, a.shape[0], ca, cb, cc,
-                                           c_out, _plane(a), scale_b, LAYOUT_NHWC if nhwc else LAYOUT_NCHW, stream_ptr()),
-                      "pdu_concat_f32")
+                if planar[0] or planar[1]:
+                    check(lib().pdu_concat_mixed_f32(out.data_ptr(), a.data_ptr(), b.data_ptr(),
+                                                     c.data_ptr() if c is not None else None, a.shape[0], ca, cb, cc, c_out,
+                                                     _plane(a), scale_b, int(planar[0]), int(planar[1]), stream_ptr()),
+                          "pdu_concat_mixed_f32")
+                else:
+                    check(lib().pdu_concat_f32(out.data_ptr(), a.data_ptr(), b.data_ptr(),
+                                               c.data_ptr() if c is not None else None, a.shape[0], ca, cb, cc,
+                                               c_out, _plane(a), scale_b, LAYOUT_NHWC if nhwc else LAYOUT_NCHW, stream_ptr()),
+                          "pdu_concat_f32")
         return out
 
     @staticmethod

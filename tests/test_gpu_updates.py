@@ -293,3 +293,18 @@ def test_concat_with_the_upsampling_fused(mode, ca, shape, factor, pad_to, nhwc)
     w = seeded(tuple(got.shape), 4).to(DEV)
     (updates.concat_upsampled(ar, br, sparse.to(DEV), factor, mode, scale_b=0.5, scale_c=0.25, pad_to=pad_to) * w).sum().backward()
     assert torch.equal(ar.grad, w[:, :ca]) and torch.equal(br.grad, 0.5 * w[:, ca:ca + 1])
+
+
+@pytest.mark.parametrize("ca,cb,cc,pad_to", [(4, 16, 16, 0), (4, 2, 0, 8), (3, 5, 1, 0)])
+def test_concat_takes_planar_operands_into_a_channels_last_state(ca, cb, cc, pad_to):
+    """The MRI data-space update concatenates a channels-last state with the NUFFT's planar multi-channel output: the
+    layout change happens inside the concatenation (pdu_concat_mixed_f32), with torch.cat's values to the last bit."""
+    B, plane = 2, (12, 20)
+    a = seeded((B, ca) + plane, 1).to(DEV).contiguous(memory_format=torch.channels_last)
+    b = seeded((B, cb) + plane, 2).to(DEV)                      # planar
+    c = seeded((B, cc) + plane, 3).to(DEV) if cc else None
+    got = updates.concat(a, b, c, scale_b=0.25, pad_to=pad_to)
+    want = torch.cat([a, 0.25 * b] + ([c] if cc else []), 1)
+    assert got.is_contiguous(memory_format=torch.channels_last)
+    assert torch.equal(got[:, :ca + cb + cc], want)
+    assert not got[:, ca + cb + cc:].any()

@@ -8,11 +8,12 @@ start = next(i for i, r in enumerate(rows) if r and r[0] == "ID")
 hdr = rows[start]
 ki, vi, mi = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Name")
 data = [(r[ki], float(r[vi].replace(",", ""))) for r in rows[start + 1:] if len(r) > vi and r[mi] == "gpu__time_duration.sum"]
+per_step = int(sys.argv[3]) if len(sys.argv) > 3 else 1       # marker launches per step
 if marker:
     marks = [i for i, (k, _) in enumerate(data) if marker in k]
-    # the last full step: from the last marker that has a successor ... to the end / next marker
-    a = marks[-1]
-    data = data[a:]
+    # one full step: from the first marker of the last-but-one step to the first marker of the last step
+    a, b = marks[-2 * per_step], marks[-per_step]
+    data = data[a:b]
 tot = sum(v for _, v in data)
 agg = collections.OrderedDict()
 for k, v in data:
