@@ -389,34 +389,37 @@ __global__ void __launch_bounds__(256)
 // Same four passes as above for K = 512 / 640 (grid = 2 x image).  Row kernels: thread = (row s, butterfly t),
 // consecutive threads along the row; column kernels: consecutive threads across the SEQ neighbouring columns so
 // that a warp touches whole 64-byte runs of every grid row.
+// These kernels run only for grid == 2 x image (ff_supported): N = K / 2 is a compile-time constant, every element
+// address is base(thread) + r * constant.
 template <int K, int SEQ>
 __global__ void __launch_bounds__(SEQ* FastFft<K>::TPS)
     ff_rows_fwd_kernel(const float2* __restrict__ image, const float2* __restrict__ smaps, float2* __restrict__ T,
                        const float* __restrict__ s0, const float* __restrict__ s1, const float2* __restrict__ tw_g, NufftDims d,
                        int coils, int smaps_batch) {
     using F = FastFft<K>;
+    constexpr int N = K / 2, TPS = F::TPS, NS3 = F::NS3;
     float2* buf = pf_smem<float2>();
     float2* tw = buf + SEQ * F::template pitch<4>();
-    const int tid = threadIdx.x, s = tid / F::TPS, t = tid - s * F::TPS;
-    const long p = blockIdx.y;
+    const int tid = threadIdx.x, s = tid / TPS, t = tid - s * TPS;
+    const int p = blockIdx.y;
     const int row = blockIdx.x * SEQ + s;
-    for (int i = tid; i < K; i += SEQ * F::TPS) tw[i] = __ldg(tw_g + i);
-    const long plane = (long)d.n0 * d.n1;
-    const long b = p / coils, c = p - b * coils;
-    const bool live = row < d.n0;
+    for (int i = tid; i < K; i += SEQ * TPS) tw[i] = __ldg(tw_g + i);
+    const int b = p / coils, c = p - b * coils;
+    const bool live = row < N;
     const float w0 = live ? __ldg(s0 + row) : 0.f;
-    const float2* src = image + (smaps ? b : p) * plane + (long)row * d.n1;
-    const float2* sm = smaps ? smaps + ((smaps_batch == 1 ? 0 : b) * coils + c) * plane + (long)row * d.n1 : nullptr;
-    auto ld = [&](int e) {
+    const float2* src = image + ((long)(smaps ? b : p) * N + row) * N + t;
+    const float2* sm = smaps ? smaps + ((long)((smaps_batch == 1 ? 0 : b) * coils + c) * N + row) * N + t : nullptr;
+    const float* s1t = s1 + t;
+    auto ld = [&](int r) {                     // element t + r TPS < N
         if (!live) return make_float2(0.f, 0.f);
-        float2 v = __ldg(src + e);
-        if (sm) v = cmul(v, __ldg(sm + e));
-        const float w = w0 * __ldg(s1 + e);
+        float2 v = __ldg(src + r * TPS);
+        if (sm) v = cmul(v, __ldg(sm + r * TPS));
+        const float w = w0 * __ldg(s1t + r * TPS);
         return make_float2(v.x * w, v.y * w);
     };
-    float2* dst = T + (p * d.n0 + row) * K;
-    auto st = [&](int e, float2 v) {
-        if (live) dst[e] = v;
+    float2* dst = T + ((long)p * N + row) * K;
+    auto st = [&](int j, int r, float2 v) {
+        if (live) dst[j + r * NS3] = v;
     };
     ff_transform<K, 4, false, true, false>(buf + s * F::template pitch<4>(), tw, t, ld, st);
 }
@@ -425,18 +428,19 @@ template <int K, int SEQ>
 __global__ void __launch_bounds__(SEQ* FastFft<K>::TPS, K <= 640 ? 3 : 1)
     ff_cols_fwd_kernel(const float2* __restrict__ T, float2* __restrict__ grid, const float2* __restrict__ tw_g, NufftDims d) {
     using F = FastFft<K>;
+    constexpr int N = K / 2, TPS = F::TPS, NS3 = F::NS3;
     float2* buf = pf_smem<float2>();
     float2* tw = buf + SEQ * F::template pitch<3>();
     const int tid = threadIdx.x, t = tid / SEQ, s = tid - t * SEQ;
-    const long p = blockIdx.y;
+    const int p = blockIdx.y;
     const int col = blockIdx.x * SEQ + s;
-    for (int i = tid; i < K; i += SEQ * F::TPS) tw[i] = __ldg(tw_g + i);
-    const bool live = col < d.k1;
-    const float2* src = T + p * d.n0 * d.k1 + col;
-    float2* dst = grid + p * K * d.k1 + col;
-    auto ld = [&](int e) { return live ? __ldcs(src + (long)e * d.k1) : make_float2(0.f, 0.f); };
-    auto st = [&](int e, float2 v) {
-        if (live) __stcs(dst + (long)e * d.k1, v);
+    for (int i = tid; i < K; i += SEQ * TPS) tw[i] = __ldg(tw_g + i);
+    const bool live = col < K;
+    const float2* src = T + ((long)p * N + t) * K + col;
+    float2* dst = grid + (long)p * K * K + col;
+    auto ld = [&](int r) { return live ? __ldcs(src + r * (TPS * K)) : make_float2(0.f, 0.f); };
+    auto st = [&](int j, int r, float2 v) {
+        if (live) __stcs(dst + j * K + r * (NS3 * K), v);
     };
     ff_transform<K, 3, false, true, false>(buf + s * F::template pitch<3>(), tw, t, ld, st);
 }
@@ -445,18 +449,19 @@ template <int K, int SEQ>
 __global__ void __launch_bounds__(SEQ* FastFft<K>::TPS)
     ff_rows_adj_kernel(const float2* __restrict__ grid, float2* __restrict__ T, const float2* __restrict__ tw_g, NufftDims d) {
     using F = FastFft<K>;
+    constexpr int N = K / 2, TPS = F::TPS, NS3 = F::NS3;
     float2* buf = pf_smem<float2>();
     float2* tw = buf + SEQ * F::template pitch<4>();
-    const int tid = threadIdx.x, s = tid / F::TPS, t = tid - s * F::TPS;
-    const long p = blockIdx.y;
+    const int tid = threadIdx.x, s = tid / TPS, t = tid - s * TPS;
+    const int p = blockIdx.y;
     const int row = blockIdx.x * SEQ + s;
-    for (int i = tid; i < K; i += SEQ * F::TPS) tw[i] = __ldg(tw_g + i);
-    const bool live = row < d.k0;
-    const float2* src = grid + (p * d.k0 + row) * K;
-    float2* dst = T + (p * d.k0 + row) * d.n1;
-    auto ld = [&](int e) { return live ? __ldcs(src + e) : make_float2(0.f, 0.f); };
-    auto st = [&](int e, float2 v) {
-        if (live) __stcs(dst + e, v);
+    for (int i = tid; i < K; i += SEQ * TPS) tw[i] = __ldg(tw_g + i);
+    const bool live = row < K;
+    const float2* src = grid + ((long)p * K + row) * K + t;
+    float2* dst = T + ((long)p * K + row) * N;
+    auto ld = [&](int r) { return live ? __ldcs(src + r * TPS) : make_float2(0.f, 0.f); };
+    auto st = [&](int j, int r, float2 v) {
+        if (live) __stcs(dst + j + r * NS3, v);
     };
     ff_transform<K, 4, true, false, true>(buf + s * F::template pitch<4>(), tw, t, ld, st);
 }
@@ -465,18 +470,19 @@ template <int K, int SEQ>
 __global__ void __launch_bounds__(SEQ* FastFft<K>::TPS, K <= 640 ? 3 : 1)
     ff_cols_adj_kernel(const float2* __restrict__ T, float2* __restrict__ U, const float2* __restrict__ tw_g, NufftDims d) {
     using F = FastFft<K>;
+    constexpr int N = K / 2, TPS = F::TPS, NS3 = F::NS3;
     float2* buf = pf_smem<float2>();
     float2* tw = buf + SEQ * F::template pitch<3>();
     const int tid = threadIdx.x, t = tid / SEQ, s = tid - t * SEQ;
-    const long p = blockIdx.y;
+    const int p = blockIdx.y;
     const int col = blockIdx.x * SEQ + s;
-    for (int i = tid; i < K; i += SEQ * F::TPS) tw[i] = __ldg(tw_g + i);
-    const bool live = col < d.n1;
-    const float2* src = T + p * K * d.n1 + col;
-    float2* dst = U + p * d.n0 * d.n1 + col;
-    auto ld = [&](int e) { return live ? __ldcs(src + (long)e * d.n1) : make_float2(0.f, 0.f); };
-    auto st = [&](int e, float2 v) {
-        if (live) __stcs(dst + (long)e * d.n1, v);
+    for (int i = tid; i < K; i += SEQ * TPS) tw[i] = __ldg(tw_g + i);
+    const bool live = col < N;
+    const float2* src = T + ((long)p * K + t) * N + col;
+    float2* dst = U + (long)p * N * N + col;
+    auto ld = [&](int r) { return live ? __ldcs(src + r * (TPS * N)) : make_float2(0.f, 0.f); };
+    auto st = [&](int j, int r, float2 v) {
+        if (live) __stcs(dst + j * N + r * (NS3 * N), v);
     };
     ff_transform<K, 3, true, false, true>(buf + s * F::template pitch<3>(), tw, t, ld, st);
 }

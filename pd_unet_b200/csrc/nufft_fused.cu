@@ -246,30 +246,34 @@ __global__ void __launch_bounds__(SEQ* FastFft<K>::TPS)
                        const float* __restrict__ s0, const float* __restrict__ s1, const float2* __restrict__ tw_g, NufftDims d,
                        int coils, int smaps_batch, int split) {
     using F = FastFft<K>;
+    constexpr int N = K / 2, TPS = F::TPS, NS3 = F::NS3;            // grid == 2 x image: every address is base + r * constant
     float2* buf = fz_smem<float2>();
     float2* tw = buf + SEQ * F::template pitch<3>();
     const int tid = threadIdx.x, t = tid / SEQ, s = tid - t * SEQ;
-    const long p = blockIdx.y;
+    const int p = blockIdx.y;
     const int col = blockIdx.x * SEQ + s;
-    for (int i = tid; i < K; i += SEQ * F::TPS) tw[i] = __ldg(tw_g + i);
-    const bool live = col < d.n1;
-    const long plane = (long)d.n0 * d.n1;
-    const long b = p / coils, c = p - b * coils;
-    const long ip = smaps ? b : p;                                  // image plane feeding this grid plane
-    const float2* sm = smaps ? smaps + ((smaps_batch == 1 ? 0 : b) * coils + c) * plane + col : nullptr;
+    for (int i = tid; i < K; i += SEQ * TPS) tw[i] = __ldg(tw_g + i);
+    const bool live = col < N;
+    const int b = p / coils, c = p - b * coils;
+    const int ip = smaps ? b : p;                                   // image plane feeding this grid plane
+    const long pix0 = (long)t * N + col;                            // pixel (row t, this column)
+    const float2* sm = smaps ? smaps + (long)((smaps_batch == 1 ? 0 : b) * coils + c) * N * N + pix0 : nullptr;
+    const float2* src_c = reinterpret_cast<const float2*>(image) + (long)ip * N * N + pix0;
+    const float* src_re = image + (long)(2 * ip) * N * N + pix0;
     const float w1 = live ? __ldg(s1 + col) : 0.f;
-    auto ld = [&](int e) {                                          // e < n0 (HALF_IN)
+    const float* s0t = s0 + t;
+    auto ld = [&](int r) {                                          // image row t + r TPS < N (HALF_IN)
         if (!live) return make_float2(0.f, 0.f);
         float2 v;
-        if (split) v = make_float2(__ldg(image + (2 * ip) * plane + (long)e * d.n1 + col), __ldg(image + (2 * ip + 1) * plane + (long)e * d.n1 + col));
-        else v = __ldg(reinterpret_cast<const float2*>(image) + ip * plane + (long)e * d.n1 + col);
-        if (sm) v = cmul(v, __ldg(sm + (long)e * d.n1));
-        const float w = w1 * __ldg(s0 + e);
+        if (split) v = make_float2(__ldg(src_re + r * (TPS * N)), __ldg(src_re + N * N + r * (TPS * N)));
+        else v = __ldg(src_c + r * (TPS * N));
+        if (sm) v = cmul(v, __ldg(sm + r * (TPS * N)));
+        const float w = w1 * __ldg(s0t + r * TPS);
         return make_float2(v.x * w, v.y * w);
     };
-    float2* dst = T + p * K * d.n1 + col;
-    auto st = [&](int e, float2 v) {
-        if (live) dst[(long)e * d.n1] = v;
+    float2* dst = T + (long)p * K * N + col;
+    auto st = [&](int j, int r, float2 v) {
+        if (live) dst[j * N + r * (NS3 * N)] = v;
     };
     ff_transform<K, 3, false, true, false>(buf + s * F::template pitch<3>(), tw, t, ld, st);
 }
@@ -312,10 +316,11 @@ __global__ void __launch_bounds__(PG* FastFft<K>::TPS, (1536 / (PG * FastFft<K>:
     {
         const int p = cur.p0 + s;
         const bool live = p < planes;
-        const float2* src = T + ((long)p * K + cur.R) * d.n1;
-        auto ld = [&](int e) { return live ? __ldcs(src + e) : make_float2(0.f, 0.f); };
+        const float2* src = T + ((long)p * K + cur.R) * (K / 2) + t;
+        auto ld = [&](int r) { return live ? __ldcs(src + r * F::TPS) : make_float2(0.f, 0.f); };
         float2* row = buf + s * PITCH;
-        auto st = [&](int e, float2 v) { row[ff_pos<4>(e)] = v; };
+        // output element j + r NS3 at its padded position pos(j) + r (NS3 + NS3 / 16)
+        auto st = [&](int j, int r, float2 v) { row[(j + (j >> 4)) + r * (F::NS3 + F::NS3 / 16)] = v; };
         __syncthreads();                                           // tw is loaded
         ff_transform<K, 4, false, true, false, false, true>(row, tw, t, ld, st);
         __syncthreads();
@@ -523,9 +528,10 @@ __global__ void __launch_bounds__(PG* FastFft<K>::TPS, (1024 / (PG * FastFft<K>:
             for (int g = 0; g < PG; ++g) buf[g * PITCH + ff_pos<4>(cell[q])] = acc[q][g];
         __syncthreads();
         float2* row = buf + s * PITCH;
-        auto ld = [&](int e) { return row[ff_pos<4>(e)]; };
-        auto st = [&](int e, float2 v) {
-            if (live) __stcs(dst + e, v);
+        const float2* row_t = row + (t + (t >> 4));      // input element t + r TPS at pos(t) + r (TPS + TPS / 16)
+        auto ld = [&](int r) { return row_t[r * (F::TPS + F::TPS / 16)]; };
+        auto st = [&](int j, int r, float2 v) {
+            if (live) __stcs(dst + j + r * F::NS3, v);
         };
         ff_transform<K, 4, true, false, true, true, false>(row, tw, t, ld, st);
     }
@@ -539,30 +545,31 @@ __global__ void __launch_bounds__(SEQ* FastFft<K>::TPS, K <= 640 ? 3 : 1)
     fz_cols_adj_kernel(const float2* __restrict__ T, float* __restrict__ out, const float* __restrict__ s0, const float* __restrict__ s1,
                        const float2* __restrict__ tw_g, NufftDims d, float scale, int finish, int split) {
     using F = FastFft<K>;
+    constexpr int N = K / 2, TPS = F::TPS, NS3 = F::NS3;
     float2* buf = fz_smem<float2>();
     float2* tw = buf + SEQ * F::template pitch<3>();
     const int tid = threadIdx.x, t = tid / SEQ, s = tid - t * SEQ;
-    const long p = blockIdx.y;
+    const int p = blockIdx.y;
     const int col = blockIdx.x * SEQ + s;
-    for (int i = tid; i < K; i += SEQ * F::TPS) tw[i] = __ldg(tw_g + i);
-    const bool live = col < d.n1;
-    const float2* src = T + p * K * d.n1 + col;
-    const long plane = (long)d.n0 * d.n1;
+    for (int i = tid; i < K; i += SEQ * TPS) tw[i] = __ldg(tw_g + i);
+    const bool live = col < N;
+    const float2* src = T + ((long)p * K + t) * N + col;
     const float w1 = (finish && live) ? __ldg(s1 + col) * scale : 1.f;
-    auto ld = [&](int e) { return live ? __ldcs(src + (long)e * d.n1) : make_float2(0.f, 0.f); };
-    auto st = [&](int e, float2 v) {                                 // e < n0 (HALF_OUT)
+    float2* out_c = reinterpret_cast<float2*>(out) + (long)p * N * N + col;
+    float* out_re = out + (long)(2 * p) * N * N + col;
+    auto ld = [&](int r) { return live ? __ldcs(src + r * (TPS * N)) : make_float2(0.f, 0.f); };
+    auto st = [&](int j, int r, float2 v) {                          // image row j + r NS3 < N (HALF_OUT)
         if (!live) return;
         if (finish) {
-            const float w = w1 * __ldg(s0 + e);
+            const float w = w1 * __ldg(s0 + j + r * NS3);
             v.x *= w;
             v.y *= w;
         }
-        const long pix = (long)e * d.n1 + col;
         if (split) {
-            out[(2 * p) * plane + pix] = v.x;
-            out[(2 * p + 1) * plane + pix] = v.y;
+            out_re[j * N + r * (NS3 * N)] = v.x;
+            out_re[N * N + j * N + r * (NS3 * N)] = v.y;
         } else {
-            __stcs(reinterpret_cast<float2*>(out) + p * plane + pix, v);
+            __stcs(out_c + j * N + r * (NS3 * N), v);
         }
     };
     ff_transform<K, 3, true, false, true>(buf + s * F::template pitch<3>(), tw, t, ld, st);

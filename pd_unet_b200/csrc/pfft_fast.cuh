@@ -22,6 +22,7 @@ struct FastFft {
     static constexpr int TPS = K / 8;                 // threads per sequence (one radix-8 butterfly each in the first pass)
     static constexpr int R2 = K == 2048 ? 16 : 8;     // radix of the second pass
     static constexpr int R3 = K / (8 * R2);           // radix of the last pass: 4, 8, 10, 16 (8 R2 butterflies)
+    static constexpr int NS3 = 8 * R2;                // butterflies of the last pass = stride of its elements
     // Padding: one slot every 2^PS elements, chosen per thread layout (measured, ncu r01):
     //  PS = 3 (column kernels: a half-warp is 8 neighbouring sequences x 2 butterflies) -- element 8 t + r sits at
     //    9 t + r; with the pitch == 2 (mod 16) float2 every access of the three passes is conflict free;
@@ -120,28 +121,43 @@ __device__ __forceinline__ void ff_small(float2* v) {
 
 // One sequence of length K held by the TPS threads t = 0 .. TPS-1 of a CTA (every thread of the CTA must call
 // this: it synchronises).  buf = this sequence's pitch<PS>() float2 of shared memory, tw = the K-entry table
-// exp(-2 pi i m / K) in shared memory.  ld(e) returns input element e, st(e, v) consumes output element e.
+// exp(-2 pi i m / K) in shared memory.  ld(r) returns input element t + r TPS (r = 0 .. 7, a compile-time constant after
+// unrolling); st(j, r, v) consumes output element j + r NS3 (NS3 = 8 R2; j = t, or t + TPS when TPS < NS3): the caller's
+// functors form base(t) + r * constant addresses as well (no 64-bit index arithmetic per element).
 // LD_BUF: ld reads this CTA's `buf`s (an interpolation stage filled them) -- every load must be complete before
 //   the first exchange store;  ST_BUF: st writes the `buf`s -- every last-pass load must be complete before it.
+//
+// Shared-memory addressing (r02): the padded position of an element is e + (e >> PS), and every access of the three
+// passes is  base(t) + r * constant  -- because the strides (TPS, 8, 8 R2 and K / R2) are multiples of 2^PS or smaller
+// than it in a way that commutes with the shift (derivations at each pass).  The first version called ff_pos() per
+// access and the compiler could not see through the shift: 39 % of the instructions of a transform were integer address
+// arithmetic (SASS histogram of fz_cols_fwd_kernel<640, 8>: 326 LEA / IMAD / IADD3 / LOP3 / SHF against 302 FP).
 template <int K, int PS, bool INV, bool HALF_IN, bool HALF_OUT, bool LD_BUF = false, bool ST_BUF = false, class LD, class ST>
 __device__ __forceinline__ void ff_transform(float2* __restrict__ buf, const float2* __restrict__ tw, int t, LD ld, ST st) {
     using F = FastFft<K>;
-    constexpr int TPS = F::TPS, R3 = F::R3;
+    constexpr int TPS = F::TPS, R2 = F::R2, R3 = F::R3, NB2 = K / R2, NS3 = 8 * R2;
+    constexpr int PADM = (1 << PS);
+    static_assert(PS == 3 || PS == 4, "padding every 8 or 16 elements");
+    static_assert(TPS % PADM == 0 && NB2 % PADM == 0 && NS3 % PADM == 0, "strides commute with the padding shift");
     float2 v[8];
-    // pass 1: radix 8, Ns = 1
+    // pass 1: radix 8, Ns = 1.  loads: elements t + r TPS (through the functor)
 #pragma unroll
-    for (int r = 0; r < 8; ++r) v[r] = (HALF_IN && r >= 4) ? make_float2(0.f, 0.f) : ld(t + r * TPS);
+    for (int r = 0; r < 8; ++r) v[r] = (HALF_IN && r >= 4) ? make_float2(0.f, 0.f) : ld(r);
     if (LD_BUF) __syncthreads();
     pf_r8<INV>(v);
+    {   // stores: elements 8 t + r, r < 8: (8 t + r) >> PS == (8 t) >> PS  =>  position = pos(8 t) + r
+        float2* p1 = buf + (8 * t + ((8 * t) >> PS));
 #pragma unroll
-    for (int r = 0; r < 8; ++r) buf[ff_pos<PS>(t * 8 + r)] = v[r];
+        for (int r = 0; r < 8; ++r) p1[r] = v[r];
+    }
     __syncthreads();
-    // pass 2: radix R2, Ns = 8; K / R2 butterflies
-    constexpr int R2 = F::R2, NB2 = K / R2, NS3 = 8 * R2;
+    // pass 2: radix R2, Ns = 8; K / R2 butterflies.  loads: elements t + r NB2, NB2 a multiple of 2^PS
+    //   => position = pos(t) + r (NB2 + NB2 / 2^PS)
     float2 w2[R2];
+    const float2* p2 = buf + (t + (t >> PS));
     if (t < NB2) {
 #pragma unroll
-        for (int r = 0; r < R2; ++r) w2[r] = buf[ff_pos<PS>(t + r * NB2)];
+        for (int r = 0; r < R2; ++r) w2[r] = p2[r * (NB2 + NB2 / PADM)];
     }
     __syncthreads();
     if (t < NB2) {
@@ -149,27 +165,34 @@ __device__ __forceinline__ void ff_transform(float2* __restrict__ buf, const flo
 #pragma unroll
         for (int r = 1; r < R2; ++r) w2[r] = pf_mul(w2[r], ff_tw<INV>(tw, r * k * (K / NS3)));
         ff_small<INV, R2>(w2);
+        // stores: elements o0 + 8 r with o0 = (t >> 3) NS3 + k, k < 8, NS3 a multiple of 2^PS:
+        //   PS == 3: (o0 + 8 r) >> 3 == (o0 >> 3) + r        => position = pos(o0) + 9 r
+        //   PS == 4: (o0 + 8 r) >> 4 == (o0 >> 4) + (r >> 1) => position = pos(o0) + 8 r + (r >> 1)
         const int o0 = (t >> 3) * NS3 + k;
+        float2* p2s = buf + (o0 + (o0 >> PS));
 #pragma unroll
-        for (int r = 0; r < R2; ++r) buf[ff_pos<PS>(o0 + r * 8)] = w2[r];
+        for (int r = 0; r < R2; ++r) p2s[PS == 3 ? 9 * r : 8 * r + (r >> 1)] = w2[r];
     }
     __syncthreads();
-    // pass 3: radix R3, Ns = 8 R2; NS3 butterflies (TPS = 32: two per thread)
+    // pass 3: radix R3, Ns = 8 R2; NS3 butterflies (TPS = 32: two per thread).  loads: elements j + r NS3
+    //   => position = pos(j) + r (NS3 + NS3 / 2^PS)
     constexpr int PER = TPS >= NS3 ? 1 : NS3 / TPS;
+    constexpr int S3 = NS3 + NS3 / PADM;
     if (!ST_BUF) {
 #pragma unroll
         for (int i = 0; i < PER; ++i) {
             const int j = t + i * TPS;
             if (j < NS3) {
                 float2 u[R3];
+                const float2* p3 = buf + (j + (j >> PS));
 #pragma unroll
-                for (int r = 0; r < R3; ++r) u[r] = buf[ff_pos<PS>(j + r * NS3)];
+                for (int r = 0; r < R3; ++r) u[r] = p3[r * S3];
 #pragma unroll
                 for (int r = 1; r < R3; ++r) u[r] = pf_mul(u[r], ff_tw<INV>(tw, r * j));
                 ff_small<INV, R3>(u);
 #pragma unroll
                 for (int r = 0; r < R3; ++r)
-                    if (!HALF_OUT || r < R3 / 2) st(j + r * NS3, u[r]);
+                    if (!HALF_OUT || r < R3 / 2) st(j, r, u[r]);
             }
         }
     } else {
@@ -178,8 +201,9 @@ __device__ __forceinline__ void ff_transform(float2* __restrict__ buf, const flo
         for (int i = 0; i < PER; ++i) {
             const int j = t + i * TPS;
             if (j < NS3) {
+                const float2* p3 = buf + (j + (j >> PS));
 #pragma unroll
-                for (int r = 0; r < R3; ++r) u[i][r] = buf[ff_pos<PS>(j + r * NS3)];
+                for (int r = 0; r < R3; ++r) u[i][r] = p3[r * S3];
             }
         }
         __syncthreads();
@@ -192,7 +216,7 @@ __device__ __forceinline__ void ff_transform(float2* __restrict__ buf, const flo
                 ff_small<INV, R3>(u[i]);
 #pragma unroll
                 for (int r = 0; r < R3; ++r)
-                    if (!HALF_OUT || r < R3 / 2) st(j + r * NS3, u[i][r]);
+                    if (!HALF_OUT || r < R3 / 2) st(j, r, u[i][r]);
             }
         }
     }
