@@ -322,7 +322,7 @@ __global__ void __launch_bounds__(PG* FastFft<K>::TPS, (1536 / (PG * FastFft<K>:
         // output element j + r NS3 at its padded position pos(j) + r (NS3 + NS3 / 16)
         auto st = [&](int j, int r, float2 v) { row[(j + (j >> 4)) + r * (F::NS3 + F::NS3 / 16)] = v; };
         __syncthreads();                                           // tw is loaded
-        ff_transform<K, 4, false, true, false, false, true>(row, tw, t, ld, st);
+        ff_transform<K, 4, false, true, false, false, true, true>(row, tw, t, ld, st);
         __syncthreads();
         // a thread = one entry, all PG planes: the record is read once, the taps are LDS.64, and a warp's stores of one
         // plane are 32 neighbouring entries (mostly neighbouring samples of one spoke)
@@ -533,7 +533,7 @@ __global__ void __launch_bounds__(PG* FastFft<K>::TPS, (1024 / (PG * FastFft<K>:
         auto st = [&](int j, int r, float2 v) {
             if (live) __stcs(dst + j + r * F::NS3, v);
         };
-        ff_transform<K, 4, true, false, true, true, false>(row, tw, t, ld, st);
+        ff_transform<K, 4, true, false, true, true, false, true>(row, tw, t, ld, st);
     }
 }
 

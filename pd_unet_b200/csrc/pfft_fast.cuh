@@ -132,7 +132,16 @@ __device__ __forceinline__ void ff_small(float2* v) {
 // than it in a way that commutes with the shift (derivations at each pass).  The first version called ff_pos() per
 // access and the compiler could not see through the shift: 39 % of the instructions of a transform were integer address
 // arithmetic (SASS histogram of fz_cols_fwd_kernel<640, 8>: 326 LEA / IMAD / IADD3 / LOP3 / SHF against 302 FP).
-template <int K, int PS, bool INV, bool HALF_IN, bool HALF_OUT, bool LD_BUF = false, bool ST_BUF = false, class LD, class ST>
+// twiddles w^r, r = 1 .. R-1, from w^1 by products of depth log2(r) (w[r] = w[r / 2] w[r - r / 2]): trades R - 2
+// shared-memory loads for 4 (R - 2) FMAs where the shared-memory pipe, not instruction issue, is the busier one
+template <int R>
+__device__ __forceinline__ void ff_tw_powers(float2 w1, float2* w) {
+    w[1] = w1;
+#pragma unroll
+    for (int r = 2; r < R; ++r) w[r] = pf_mul(w[r / 2], w[r - r / 2]);
+}
+
+template <int K, int PS, bool INV, bool HALF_IN, bool HALF_OUT, bool LD_BUF = false, bool ST_BUF = false, bool TWREC = false, class LD, class ST>
 __device__ __forceinline__ void ff_transform(float2* __restrict__ buf, const float2* __restrict__ tw, int t, LD ld, ST st) {
     using F = FastFft<K>;
     constexpr int TPS = F::TPS, R2 = F::R2, R3 = F::R3, NB2 = K / R2, NS3 = 8 * R2;
@@ -162,8 +171,15 @@ __device__ __forceinline__ void ff_transform(float2* __restrict__ buf, const flo
     __syncthreads();
     if (t < NB2) {
         const int k = t & 7;
+        if (TWREC) {
+            float2 wp[R2];
+            ff_tw_powers<R2>(ff_tw<INV>(tw, k * (K / NS3)), wp);
 #pragma unroll
-        for (int r = 1; r < R2; ++r) w2[r] = pf_mul(w2[r], ff_tw<INV>(tw, r * k * (K / NS3)));
+            for (int r = 1; r < R2; ++r) w2[r] = pf_mul(w2[r], wp[r]);
+        } else {
+#pragma unroll
+            for (int r = 1; r < R2; ++r) w2[r] = pf_mul(w2[r], ff_tw<INV>(tw, r * k * (K / NS3)));
+        }
         ff_small<INV, R2>(w2);
         // stores: elements o0 + 8 r with o0 = (t >> 3) NS3 + k, k < 8, NS3 a multiple of 2^PS:
         //   PS == 3: (o0 + 8 r) >> 3 == (o0 >> 3) + r        => position = pos(o0) + 9 r
@@ -187,8 +203,15 @@ __device__ __forceinline__ void ff_transform(float2* __restrict__ buf, const flo
                 const float2* p3 = buf + (j + (j >> PS));
 #pragma unroll
                 for (int r = 0; r < R3; ++r) u[r] = p3[r * S3];
+                if (TWREC) {
+                    float2 wp[R3];
+                    ff_tw_powers<R3>(ff_tw<INV>(tw, j), wp);
 #pragma unroll
-                for (int r = 1; r < R3; ++r) u[r] = pf_mul(u[r], ff_tw<INV>(tw, r * j));
+                    for (int r = 1; r < R3; ++r) u[r] = pf_mul(u[r], wp[r]);
+                } else {
+#pragma unroll
+                    for (int r = 1; r < R3; ++r) u[r] = pf_mul(u[r], ff_tw<INV>(tw, r * j));
+                }
                 ff_small<INV, R3>(u);
 #pragma unroll
                 for (int r = 0; r < R3; ++r)
@@ -211,8 +234,15 @@ __device__ __forceinline__ void ff_transform(float2* __restrict__ buf, const flo
         for (int i = 0; i < PER; ++i) {
             const int j = t + i * TPS;
             if (j < NS3) {
+                if (TWREC) {
+                    float2 wp[R3];
+                    ff_tw_powers<R3>(ff_tw<INV>(tw, j), wp);
 #pragma unroll
-                for (int r = 1; r < R3; ++r) u[i][r] = pf_mul(u[i][r], ff_tw<INV>(tw, r * j));
+                    for (int r = 1; r < R3; ++r) u[i][r] = pf_mul(u[i][r], wp[r]);
+                } else {
+#pragma unroll
+                    for (int r = 1; r < R3; ++r) u[i][r] = pf_mul(u[i][r], ff_tw<INV>(tw, r * j));
+                }
                 ff_small<INV, R3>(u[i]);
 #pragma unroll
                 for (int r = 0; r < R3; ++r)
