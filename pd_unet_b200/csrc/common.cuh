@@ -108,8 +108,10 @@ __device__ __forceinline__ bool mbar_try_wait_hint(uint32_t bar_smem, uint32_t p
 __device__ __forceinline__ bool mbar_wait_bounded(uint32_t bar_smem, uint32_t parity, unsigned long long timeout_ns) {
     if (mbar_try_wait_hint(bar_smem, parity, 20000u)) return true;
     const unsigned long long t0 = global_timer_ns();
-    do {
-        if (mbar_try_wait_hint(bar_smem, parity, 20000u)) return true;
+    do {                                       // the clock is read once per 16 polls: a poll is 4 instructions, the
+#pragma unroll 1                               // 64-bit time comparison 7, and waiting warps share the issue slots
+        for (int i = 0; i < 16; ++i)           // with the warps that are sampling
+            if (mbar_try_wait_hint(bar_smem, parity, 20000u)) return true;
     } while (global_timer_ns() - t0 < timeout_ns);
     return false;
 }
