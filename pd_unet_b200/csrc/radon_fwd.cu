@@ -429,11 +429,121 @@ struct QuadCfg {
     static_assert(W <= 128, "one TMA box of 2 W doubles");
 };
 
+// the per-ray quantities of the cell-tile kernels: cell coordinates (pixel-centre coordinate + 1), (u, w) = (column, row)
+// of the source the CTA reads, walked in the direction of increasing w
+struct QuadRay {
+    float u0, w0, vu, vw, jf, dj, step;
+    int n;
+    bool rev;
+};
+__device__ __forceinline__ QuadRay quad_ray(const pdu_radon_geom_t& g, const float* __restrict__ trig, int a, int d, bool valid, bool use_t) {
+    Ray r;
+    r.n_steps = -1;
+    r.xc0 = r.yc0 = r.vx = r.vy = r.step = 0.f;
+    if (valid) r = ray_setup(g, __ldg(trig + 2 * a), __ldg(trig + 2 * a + 1), d);
+    QuadRay q;
+    q.u0 = (use_t ? r.yc0 : r.xc0) + 1.f;
+    q.w0 = (use_t ? r.xc0 : r.yc0) + 1.f;
+    q.vu = use_t ? r.vy : r.vx;
+    q.vw = use_t ? r.vx : r.vy;
+    q.n = r.n_steps;
+    q.rev = q.vw < 0.f;
+    q.dj = q.rev ? -1.f : 1.f;
+    q.jf = q.rev ? (float)q.n : 0.f;
+    q.step = r.step;
+    return q;
+}
+constexpr float QUAD_EPS = 1e-3f;
+// first strip a ray takes samples from (INT_MAX: the ray misses the slice)
+template <int TH>
+__device__ __forceinline__ int quad_first_strip(const QuadRay& q) {
+    const float wa = fmaf(q.jf, q.vw, q.w0);
+    return q.n >= 0 ? max((int)floorf(wa - QUAD_EPS), 0) / TH : INT_MAX;
+}
+
+// Strip boxes of one CTA (DB detectors x AG views): for every TH-row strip the range of cell columns its rays touch.
+// They depend on the geometry only, not on the slice: quad_boxes_kernel computes them once per call for the
+// (detector block, view group) grid and every slice's CTA reads its row of the table (r01 / early r02: every CTA
+// registered its own boxes -- 9.5 % of the kernel's instructions and two more CTA barriers, repeated for each slice).
+// Warp-reduced extents, one lane per warp touches the shared box.  u is monotone along the ray, so its range inside
+// strip k is [U_k, U_k+1] clamped to the ray's own range, with U_k = u at the strip boundary: one FMA, one clamp and
+// one floor per boundary, shared by the two strips it separates.
+template <int TH>
+__device__ __forceinline__ void quad_register_boxes(const QuadRay& q, int n_strips, int lane, int* s_umin, int* s_umax) {
+    const int n = q.n;
+    const float wa = fmaf(q.jf, q.vw, q.w0), ua = fmaf(q.jf, q.vu, q.u0);
+    const float jend = q.rev ? 0.f : (float)n;
+    const float wb = fmaf(jend, q.vw, q.w0), ub = fmaf(jend, q.vu, q.u0);
+    const int kA = quad_first_strip<TH>(q);
+    const int kB = n >= 0 ? min(max((int)floorf(wb + QUAD_EPS), 0) / TH, n_strips - 1) : -1;
+    const float dw = wb - wa;
+    const bool lin = dw > 0.f;
+    const float slope = lin ? (ub - ua) / dw : 0.f;
+    const float umin = fminf(ua, ub), umax = fmaxf(ua, ub);
+    const int kA_w = __reduce_min_sync(0xffffffffu, kA), kB_w = __reduce_max_sync(0xffffffffu, kB);
+    // a strip takes this ray's samples with row coordinate in [k TH - 1/2, (k + 1) TH + 1/2) (slack row, see QuadCfg):
+    // Us = u at k TH - 1/2, Ue = u at (k + 1) TH + 1/2 = (next strip's Us) + slope
+    auto u_at = [&](float w) { return lin ? fminf(fmaxf(fmaf(w - wa, slope, ua), umin), umax) : umin; };
+    float wk = (float)((kA_w <= kB_w ? kA_w : 0) * TH) - 0.5f;      // (no valid ray in the warp: kA_w == INT_MAX, loop empty)
+    int Fs = (int)floorf(u_at(wk));
+    for (int k = kA_w; k <= kB_w; ++k) {
+        wk += (float)TH;
+        const int Fs1 = (int)floorf(u_at(wk));
+        const int Fe = (int)floorf(lin ? u_at(wk + 1.f) : umax);
+        int lo_k = INT_MAX, hi_k = INT_MIN;
+        if (k >= kA && k <= kB) {
+            lo_k = min(Fs, Fe) - 1;
+            hi_k = max(Fs, Fe) + 1;
+        }
+        lo_k = __reduce_min_sync(0xffffffffu, lo_k);
+        hi_k = __reduce_max_sync(0xffffffffu, hi_k);
+        if (lane == 0 && lo_k <= hi_k) {
+            atomicMin(&s_umin[k], lo_k);
+            atomicMax(&s_umax[k], hi_k);
+        }
+        Fs = Fs1;
+    }
+}
+
+// thread -> (detector, view) of a DB x AG CTA whose warps are LD detectors x 32 / LD views
+template <int DB, int AG, int LD>
+__device__ __forceinline__ void quad_thread_ray(int tid, int& dl, int& al) {
+    static_assert(32 % LD == 0 && DB % LD == 0 && AG % (32 / LD) == 0, "warp shape must tile the CTA");
+    constexpr int AGW = 32 / LD;
+    const int lane = tid & 31, warp = tid >> 5;
+    dl = (warp % (DB / LD)) * LD + lane % LD;
+    al = (warp / (DB / LD)) * AGW + lane / LD;
+}
+
+template <int DB, int AG, int TH, int LD>
+__global__ void __launch_bounds__(DB* AG)
+    quad_boxes_kernel(const float* __restrict__ trig, const pdu_radon_geom_t g, int2* __restrict__ boxes) {
+    __shared__ int s_umin[MAX_STRIPS], s_umax[MAX_STRIPS];
+    const int tid = threadIdx.x;
+    int dl, al;
+    quad_thread_ray<DB, AG, LD>(tid, dl, al);
+    const int d = blockIdx.x * DB + dl, a = blockIdx.y * AG + al;
+    const int n_strips = (g.n + 1 + TH - 1) / TH;
+    for (int k = tid; k < n_strips; k += DB * AG) {
+        s_umin[k] = INT_MAX;
+        s_umax[k] = INT_MIN;
+    }
+    const int a_ref = min(blockIdx.y * AG, g.n_angles - 1);
+    const bool use_t = fabsf(__ldg(trig + 2 * a_ref + 1)) > fabsf(__ldg(trig + 2 * a_ref));
+    const QuadRay q = quad_ray(g, trig, a, d, d < g.det_count && a < g.n_angles, use_t);
+    __syncthreads();
+    quad_register_boxes<TH>(q, n_strips, tid & 31, s_umin, s_umax);
+    __syncthreads();
+    int2* dst = boxes + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * n_strips;
+    for (int k = tid; k < n_strips; k += DB * AG) dst[k] = make_int2(s_umin[k], s_umax[k]);
+}
+
 template <int DB, int AG, int TH, int W, int NBUF, int LD, bool TEXQ>
 __global__ void __launch_bounds__(DB* AG + 32, 5)      // 5: ptxas settles at 40 registers without a spill (4: 56 registers WITH one)
     radon_fwd_quad_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_qt,
                           const float4* __restrict__ q, const float4* __restrict__ qt, float* __restrict__ sino,
-                          const float* __restrict__ trig, const pdu_radon_geom_t g, const FaultCtl fc) {
+                          const float* __restrict__ trig, const int2* __restrict__ boxes, const pdu_radon_geom_t g,
+                          const FaultCtl fc) {
     using C = QuadCfg<DB, AG, TH, W, NBUF>;
     extern __shared__ __align__(1024) unsigned char smem_dyn[];
     uint64_t* full = (uint64_t*)(smem_dyn + NBUF * C::TILE_STRIDE);
@@ -442,14 +552,12 @@ __global__ void __launch_bounds__(DB* AG + 32, 5)      // 5: ptxas settles at 40
     int* s_umax = s_umin + MAX_STRIPS;
 
     const int tid = threadIdx.x;
-    static_assert(32 % LD == 0 && DB % LD == 0 && AG % (32 / LD) == 0, "warp shape must tile the CTA");
-    constexpr int AGW = 32 / LD;
     const int lane = tid & 31, warp = tid >> 5;
     // warp THREADS/32 is the TMA producer: it owns no rays, so no compute warp ever waits for the other
     // warps of the CTA (the `empty` barriers) before starting its own strip
     const bool producer = warp == C::THREADS / 32;
-    const int dl = (warp % (DB / LD)) * LD + lane % LD;
-    const int al = (warp / (DB / LD)) * AGW + lane / LD;
+    int dl, al;
+    quad_thread_ray<DB, AG, LD>(tid, dl, al);
     const int d = blockIdx.x * DB + dl;
     const int a = blockIdx.y * AG + al;
     const int b = blockIdx.z;
@@ -459,9 +567,13 @@ __global__ void __launch_bounds__(DB* AG + 32, 5)      // 5: ptxas settles at 40
     const uint32_t smem_base = smem_u32(smem_dyn);
     const bool tma_ok = (smem_base & 127u) == 0;
 
-    for (int k = tid; k < n_strips; k += C::THREADS + 32) {
-        s_umin[k] = INT_MAX;
-        s_umax[k] = INT_MIN;
+    {   // this CTA's strip boxes (quad_boxes_kernel)
+        const int2* bx = boxes + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * n_strips;
+        for (int k = tid; k < n_strips; k += C::THREADS + 32) {
+            const int2 v = __ldg(bx + k);
+            s_umin[k] = v.x;
+            s_umax[k] = v.y;
+        }
     }
     if (tid == 0) {
         for (int i = 0; i < NBUF; ++i) {
@@ -474,63 +586,13 @@ __global__ void __launch_bounds__(DB* AG + 32, 5)      // 5: ptxas settles at 40
     const int a_ref = min(blockIdx.y * AG, g.n_angles - 1);
     const bool use_t = fabsf(__ldg(trig + 2 * a_ref + 1)) > fabsf(__ldg(trig + 2 * a_ref));
 
-    Ray r;
-    r.n_steps = -1;
-    r.xc0 = r.yc0 = r.vx = r.vy = r.step = 0.f;
-    if (valid) r = ray_setup(g, __ldg(trig + 2 * a), __ldg(trig + 2 * a + 1), d);
-    // cell coordinates (pixel-centre coordinate + 1): (u, w) = (column, row) of the source the CTA reads
-    const float u0 = (use_t ? r.yc0 : r.xc0) + 1.f, w0 = (use_t ? r.xc0 : r.yc0) + 1.f;
-    const float vu = use_t ? r.vy : r.vx, vw = use_t ? r.vx : r.vy;
-    const int n = r.n_steps;
-    const bool rev = vw < 0.f;
-    const float dj = rev ? -1.f : 1.f;
-    float jf = rev ? (float)n : 0.f;
+    const QuadRay qr = quad_ray(g, trig, a, d, valid, use_t);
+    const float u0 = qr.u0, w0 = qr.w0, vu = qr.vu, vw = qr.vw, dj = qr.dj;
+    const int n = qr.n;
+    float jf = qr.jf;
     const float aw = fabsf(vw);
     const float inv_aw = aw > 1e-3f ? __fdividef(1.f, aw) : 0.f;
-
-    __syncthreads();
-    int k_first = INT_MAX;            // the first strip this ray registered in: it takes no sample from an earlier one
-    {
-        // strip boxes: warp-reduced extents, one lane per warp touches the shared box (see the float-tile kernel).
-        // u is monotone along the ray, so its range inside strip k is [U_k, U_k+1] clamped to the ray's own range,
-        // with U_k = u at the strip boundary w = k TH: one FMA, one clamp and one floor per boundary, shared by the
-        // two strips it separates (the first version clamped in w and evaluated both ends per strip: 47 instructions
-        // per strip and warp, 10 % of the kernel's instructions; now ~18).
-        const float wa = fmaf(jf, vw, w0), ua = fmaf(jf, vu, u0);
-        const float jend = rev ? 0.f : (float)n;
-        const float wb = fmaf(jend, vw, w0), ub = fmaf(jend, vu, u0);
-        constexpr float EPS = 1e-3f;
-        const int kA = n >= 0 ? max((int)floorf(wa - EPS), 0) / TH : INT_MAX;
-        const int kB = n >= 0 ? min(max((int)floorf(wb + EPS), 0) / TH, n_strips - 1) : -1;
-        k_first = kA;
-        const float dw = wb - wa;
-        const bool lin = dw > 0.f;
-        const float slope = lin ? (ub - ua) / dw : 0.f;
-        const float umin = fminf(ua, ub), umax = fmaxf(ua, ub);
-        const int kA_w = __reduce_min_sync(0xffffffffu, kA), kB_w = __reduce_max_sync(0xffffffffu, kB);
-        // a strip takes this ray's samples with row coordinate in [k TH - 1/2, (k + 1) TH + 1/2) (slack row, see QuadCfg):
-        // Us = u at k TH - 1/2, Ue = u at (k + 1) TH + 1/2 = (next strip's Us) + slope
-        auto u_at = [&](float w) { return lin ? fminf(fmaxf(fmaf(w - wa, slope, ua), umin), umax) : umin; };
-        float wk = (float)((kA_w <= kB_w ? kA_w : 0) * TH) - 0.5f;      // (no valid ray in the warp: kA_w == INT_MAX, loop empty)
-        int Fs = (int)floorf(u_at(wk));
-        for (int k = kA_w; k <= kB_w; ++k) {
-            wk += (float)TH;
-            const int Fs1 = (int)floorf(u_at(wk));
-            const int Fe = (int)floorf(lin ? u_at(wk + 1.f) : umax);
-            int lo_k = INT_MAX, hi_k = INT_MIN;
-            if (k >= kA && k <= kB) {
-                lo_k = min(Fs, Fe) - 1;
-                hi_k = max(Fs, Fe) + 1;
-            }
-            lo_k = __reduce_min_sync(0xffffffffu, lo_k);
-            hi_k = __reduce_max_sync(0xffffffffu, hi_k);
-            if (lane == 0 && lo_k <= hi_k) {
-                atomicMin(&s_umin[k], lo_k);
-                atomicMax(&s_umax[k], hi_k);
-            }
-            Fs = Fs1;
-        }
-    }
+    const int k_first = quad_first_strip<TH>(qr);     // the first strip this ray registered in: it takes no sample from an earlier one
     __syncthreads();
 
     const CUtensorMap* tm = use_t ? &tm_qt : &tm_q;
@@ -621,7 +683,7 @@ __global__ void __launch_bounds__(DB* AG + 32, 5)      // 5: ptxas settles at 40
         if ((tid & 31) == 0) mbar_arrive(empty + buf);
         ++seq;
     }
-    if (valid) sino[((long)b * g.n_angles + a) * g.det_count + d] = (acc0 + acc1) * r.step;
+    if (valid) sino[((long)b * g.n_angles + a) * g.det_count + d] = (acc0 + acc1) * qr.step;
 }
 
 // ------------------------------------------------------------------ host side
@@ -716,10 +778,17 @@ static int make_quad_map(CUtensorMap* tm, const float4* ptr, int batch, int n1, 
 
 static size_t quad_bytes(int n, int batch) { return (size_t)2 * batch * (n + 1) * (n + 1) * sizeof(float4); }
 
+// strip-box table of the cell-tile kernels: one row of n_strips (lo, hi) pairs per (detector block, view group);
+// sized for the smallest CTA shape the dispatcher uses (32 detectors x 4 views, 16-row strips)
+static size_t quad_boxes_bytes(const pdu_radon_geom_t& g) {
+    return (size_t)cdiv(g.det_count, 32) * cdiv(g.n_angles, 4) * ((g.n + 1 + 15) / 16) * sizeof(int2);
+}
+
 template <int DB, int AG, int TH, int W, int NBUF, int LD>
-static int launch_quad(const float4* q, const float4* qt, float* sino, const float* trig, int batch,
+static int launch_quad(const float4* q, const float4* qt, float* sino, const float* trig, int2* boxes, int batch,
                        const pdu_radon_geom_t& g, cudaStream_t st) {
     using C = QuadCfg<DB, AG, TH, W, NBUF>;
+    static_assert(DB >= 32 && AG >= 4 && TH >= 16, "quad_boxes_bytes assumes no smaller CTA shape");
     CUtensorMap tm, tmT;
     int rc = make_quad_map(&tm, q, batch, g.n + 1, W, C::ROWS);
     if (rc) return rc;
@@ -727,15 +796,17 @@ static int launch_quad(const float4* q, const float4* qt, float* sino, const flo
     if (rc) return rc;
     const FaultCtl fc = fault_ctl();
     dim3 grid((unsigned)cdiv(g.det_count, DB), (unsigned)cdiv(g.n_angles, AG), (unsigned)batch);
+    quad_boxes_kernel<DB, AG, TH, LD><<<dim3(grid.x, grid.y), C::THREADS, 0, st>>>(trig, g, boxes);
+    PDU_LAUNCHED();
     if (fc.texq) {
         PDU_CUDA((ensure_dyn_smem<radon_fwd_quad_kernel<DB, AG, TH, W, NBUF, LD, true>>(C::SMEM)));
-        radon_fwd_quad_kernel<DB, AG, TH, W, NBUF, LD, true><<<grid, C::THREADS + 32, C::SMEM, st>>>(tm, tmT, q, qt, sino, trig, g, fc);
+        radon_fwd_quad_kernel<DB, AG, TH, W, NBUF, LD, true><<<grid, C::THREADS + 32, C::SMEM, st>>>(tm, tmT, q, qt, sino, trig, boxes, g, fc);
     } else {
         PDU_CUDA((ensure_dyn_smem<radon_fwd_quad_kernel<DB, AG, TH, W, NBUF, LD, false>>(C::SMEM)));
-        radon_fwd_quad_kernel<DB, AG, TH, W, NBUF, LD, false><<<grid, C::THREADS + 32, C::SMEM, st>>>(tm, tmT, q, qt, sino, trig, g, fc);
+        radon_fwd_quad_kernel<DB, AG, TH, W, NBUF, LD, false><<<grid, C::THREADS + 32, C::SMEM, st>>>(tm, tmT, q, qt, sino, trig, boxes, g, fc);
     }
     PDU_LAUNCHED();
-    note_kernel(OP_RADON_FWD, "quad_build_kernel + radon_fwd_quad_kernel<%d,%d,%d,%d,%d,%d> grid %ux%ux%u (bilinear-cell tiles, TMA ring)",
+    note_kernel(OP_RADON_FWD, "quad_build_kernel + quad_boxes_kernel + radon_fwd_quad_kernel<%d,%d,%d,%d,%d,%d> grid %ux%ux%u (bilinear-cell tiles, TMA ring)",
                 DB, AG, TH, W, NBUF, LD, grid.x, grid.y, grid.z);
     return PDU_OK;
 }
@@ -770,7 +841,7 @@ size_t pdu_radon_workspace_bytes(const pdu_radon_geom_t* g, int batch) {
     if (!g || g->n <= 0 || batch <= 0) return 0;
     // cell tensors of the slice and of its transpose (quad variants); the float-tile variants use the
     // first batch * n * n floats of the same scratch for the transposed copy
-    return quad_bytes(g->n, batch);
+    return quad_bytes(g->n, batch) + quad_boxes_bytes(*g);
 }
 
 int pdu_radon_fwd_f32(const float* img, float* sino, const float* trig, int batch, const pdu_radon_geom_t* g,
@@ -819,7 +890,7 @@ int pdu_radon_fwd_f32(const float* img, float* sino, const float* trig, int batc
         note_kernel(OP_RADON_FWD, "radon_fwd_gather_kernel grid %ux%ux%u (one thread per ray, L1 gather)", grid.x, grid.y, grid.z);
         return PDU_OK;
     }
-    const size_t need = variant >= 7 ? quad_bytes(g->n, batch) : (size_t)batch * g->n * g->n * sizeof(float);
+    const size_t need = variant >= 7 ? quad_bytes(g->n, batch) + quad_boxes_bytes(*g) : (size_t)batch * g->n * g->n * sizeof(float);
     if (!workspace || workspace_bytes < need || ((uintptr_t)workspace & 15)) {
         set_error("pdu_radon_fwd_f32: workspace of %zu bytes (16-byte aligned) required, got %zu", need,
                   workspace ? workspace_bytes : (size_t)0);
@@ -829,6 +900,7 @@ int pdu_radon_fwd_f32(const float* img, float* sino, const float* trig, int batc
         const int n1 = g->n + 1;
         float4* q = (float4*)workspace;
         float4* qt = q + (size_t)batch * n1 * n1;
+        int2* boxes = (int2*)(qt + (size_t)batch * n1 * n1);
         {
             dim3 block(32, 8);
             dim3 grid((unsigned)cdiv(n1, 32), (unsigned)cdiv(n1, 32), (unsigned)batch);
@@ -841,9 +913,9 @@ int pdu_radon_fwd_f32(const float* img, float* sino, const float* trig, int batc
         // four samples from per-strip origins (one FMA2 per sample, no per-sample counter): 454 us at 56 registers --
         // the loop is paced by the LDS.128 wavefronts, not by those two instructions)
         switch (variant) {
-            case 9: return launch_quad<32, 4, 16, 120, 2, 8>(q, qt, sino, trig, batch, *g, st);    // 4 views / CTA (sparser views)
-            case 11: return launch_quad<32, 8, 16, 128, 2, 8>(q, qt, sino, trig, batch, *g, st);   // widest cell box (sparser views)
-            default: return launch_quad<32, 8, 16, 92, 2, 4>(q, qt, sino, trig, batch, *g, st);    // 13: quarter-warp = 4 detectors x 2 views
+            case 9: return launch_quad<32, 4, 16, 120, 2, 8>(q, qt, sino, trig, boxes, batch, *g, st);    // 4 views / CTA (sparser views)
+            case 11: return launch_quad<32, 8, 16, 128, 2, 8>(q, qt, sino, trig, boxes, batch, *g, st);   // widest cell box (sparser views)
+            default: return launch_quad<32, 8, 16, 92, 2, 4>(q, qt, sino, trig, boxes, batch, *g, st);    // 13: quarter-warp = 4 detectors x 2 views
         }
     }
     float* imgT = (float*)workspace;
