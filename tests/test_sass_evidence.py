@@ -34,7 +34,8 @@ def _mnemonics(text):
 
 
 @pytest.mark.parametrize("kernel,needles", [
-    ("radon_fwd_quad_kernel", ["UTMALDG.3D", "LDS.128", "FFMA2", "FADD2.RM", "SYNCS.PHASECHK.TRANS64.TRYWAIT", "CREDUX.MIN.S32"]),
+    ("radon_fwd_quad_kernel", ["UTMALDG.3D", "LDS.128", "FFMA2", "FADD2.RM", "SYNCS.PHASECHK.TRANS64.TRYWAIT"]),
+    ("quad_boxes_kernel", ["CREDUX.MIN.S32", "ATOMS.MIN"]),
     ("radon_fwd_strip_kernel", ["UTMALDG.3D", "FFMA2", "SYNCS.PHASECHK.TRANS64.TRYWAIT", "CREDUX.MIN.S32"]),
     ("radon_adj_tile_kernel", ["LDS.64", "FFMA2", "FADD2.RM"]),
     ("filter_tc_kernel", ["UTMALDG.2D", "UTCHMMA", "LDTM", "UTCBAR"]),
