@@ -8,7 +8,7 @@ sys.path.insert(0, ROOT)
 import numpy as np, torch
 import pd_unet_b200 as pdu
 
-out_path = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "profiles", "r01_sweep.md")
+out_path = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "profiles", "r02_sweep.md")
 reps = 5
 dev = "cuda:0"
 peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
@@ -26,7 +26,7 @@ def timed(fn):
     return statistics.median(ts)
 
 
-lines = ["# r01 operator sweep (BASELINE.json configs[4]) on one B200\n",
+lines = ["# r02 operator sweep (BASELINE.json configs[4]) on one B200\n",
          f"median of {reps} CUDA-event timings, 256 MiB L2 flush between; HBM roof {peak:.0f} GB/s (measured).\n",
          "\n## Radon, parallel beam, batch 8, det_count = N\n",
          "| N | views | fwd us | fwd GSamples/s | fwd HBM frac | adj us | adj GSamples/s | adj HBM frac |",
