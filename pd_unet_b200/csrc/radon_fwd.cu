@@ -181,6 +181,8 @@ __global__ void __launch_bounds__(DB* AG)
 
     __syncthreads();
     {
+        // (moving this registration into a once-per-call kernel, as quad_boxes_kernel does for the cell kernels, was
+        //  measured here too: 529 -> 531 us at configs[1], so the float-tile kernel keeps it in place)
         // every ray registers its column extent in every strip it crosses.  The lanes of a warp mostly
         // cross the same strips, so the extents are first reduced across the warp (REDUX) and one lane
         // updates the shared box: per-lane atomics on one address serialise 32-way (ncu r02: a third of
