@@ -44,7 +44,8 @@ static_assert(sizeof(BinRec) == 64, "entry record is one 64-byte line half");
 struct BinsView {
     int* hdr;            // [16]: magic, M (lo, hi), K0, K1, J, n_entries
     int* key_ptr;        // [K0 K1 + 1]: first sorted entry whose (row K1 + column) key is >= i
-    int* row_order;      // [K0]: grid rows by decreasing entry count (heavy rows are scheduled first)
+    int4* row_order;     // [K0]: (row, first entry, end entry, 0) by decreasing entry count -- heavy rows are scheduled
+                         // first, and a CTA finds its row and entry range with one 16-byte load
     unsigned short* cell_order;   // [K0][K1]: the cells of every row by decreasing contributor count (adjoint gather)
     BinRec* rec;         // [M J]
     float2* w0;          // [J][M]: phase[m] * c0[m][a], the forward's row weights
@@ -67,7 +68,7 @@ static BinsView bins_layout(const pdu_nufft_plan* p, long M, void* base, bool wi
     auto take = [&](size_t bytes) { size_t o = off; off += align256(bytes); return (char*)base + o; };
     v.hdr = (int*)take(64);
     v.key_ptr = (int*)take((cells + 1) * 4);
-    v.row_order = (int*)take((size_t)p->k0 * 4);
+    v.row_order = (int4*)take((size_t)p->k0 * 16);
     v.cell_order = (unsigned short*)take(cells * 2);
     v.rec = (BinRec*)take(n * sizeof(BinRec));
     v.w0 = (float2*)take(n * 8);
@@ -143,7 +144,7 @@ __global__ void __launch_bounds__(256)
 }
 
 // rows by decreasing entry count (ties by row index): one CTA, K0 <= 2048 rows, an O(K0^2) rank is nothing
-__global__ void __launch_bounds__(1024) bin_row_order_kernel(const int* __restrict__ key_ptr, int* __restrict__ row_order, int K0, int K1) {
+__global__ void __launch_bounds__(1024) bin_row_order_kernel(const int* __restrict__ key_ptr, int4* __restrict__ row_order, int K0, int K1) {
     __shared__ int cnt[2048];
     for (int r = threadIdx.x; r < K0; r += blockDim.x) cnt[r] = key_ptr[(long)(r + 1) * K1] - key_ptr[(long)r * K1];
     __syncthreads();
@@ -151,7 +152,7 @@ __global__ void __launch_bounds__(1024) bin_row_order_kernel(const int* __restri
         const int c = cnt[r];
         int rank = 0;
         for (int q = 0; q < K0; ++q) rank += (cnt[q] > c || (cnt[q] == c && q < r)) ? 1 : 0;
-        row_order[rank] = r;
+        row_order[rank] = make_int4(r, key_ptr[(long)r * K1], key_ptr[(long)(r + 1) * K1], 0);
     }
 }
 
@@ -285,16 +286,16 @@ __global__ void __launch_bounds__(SEQ* FastFft<K>::TPS)
 struct FzItem {
     int R, p0, beg, end;
 };
-__device__ __forceinline__ FzItem fz_item(int item, int n_items, int groups, int PG, int K, const int* __restrict__ row_order,
-                                          const int* __restrict__ key_ptr) {
+__device__ __forceinline__ FzItem fz_item(int item, int n_items, int groups, int PG, const int4* __restrict__ row_order) {
     FzItem it;
     it.R = -1;
     it.p0 = it.beg = it.end = 0;
     if (item < n_items) {
-        it.R = __ldg(row_order + item / groups);
+        const int4 ro = __ldg(row_order + item / groups);
+        it.R = ro.x;
         it.p0 = (item % groups) * PG;
-        it.beg = __ldg(key_ptr + (long)it.R * K);
-        it.end = __ldg(key_ptr + (long)(it.R + 1) * K);
+        it.beg = ro.y;
+        it.end = ro.z;
     }
     return it;
 }
@@ -302,7 +303,7 @@ __device__ __forceinline__ FzItem fz_item(int item, int n_items, int groups, int
 template <int K, int PG>
 __global__ void __launch_bounds__(PG* FastFft<K>::TPS, (1536 / (PG * FastFft<K>::TPS)) > 0 ? (1536 / (PG * FastFft<K>::TPS)) : 1)
     fz_rows_fwd_kernel(const float2* __restrict__ T, float2* __restrict__ P, const int* __restrict__ key_ptr,
-                       const int* __restrict__ row_order, const BinRec* __restrict__ rec, const float2* __restrict__ tw_g, NufftDims d,
+                       const int4* __restrict__ row_order, const BinRec* __restrict__ rec, const float2* __restrict__ tw_g, NufftDims d,
                        int planes, long M, int groups) {
     using F = FastFft<K>;
     constexpr int PITCH = F::template pitch<4>();
@@ -310,7 +311,7 @@ __global__ void __launch_bounds__(PG* FastFft<K>::TPS, (1536 / (PG * FastFft<K>:
     float2* buf = fz_smem<float2>();
     float2* tw = buf + PG * PITCH;
     const int tid = threadIdx.x, s = tid / F::TPS, t = tid - s * F::TPS;
-    const FzItem cur = fz_item(blockIdx.x, K * groups, groups, PG, K, row_order, key_ptr);
+    const FzItem cur = fz_item(blockIdx.x, K * groups, groups, PG, row_order);
     if (cur.beg == cur.end) return;                                // no sample touches this row: its transform is not needed
     for (int i = tid; i < K; i += NT) tw[i] = __ldg(tw_g + i);
     {
@@ -407,7 +408,7 @@ __global__ void __launch_bounds__(128)
 template <int K, int PG, int EC>
 __global__ void __launch_bounds__(PG* FastFft<K>::TPS, (1024 / (PG * FastFft<K>::TPS)) > 0 ? (1024 / (PG * FastFft<K>::TPS)) : 1)
     fz_rows_adj_kernel(const float* __restrict__ kdata, const float* __restrict__ kweight, float2* __restrict__ T,
-                       const int* __restrict__ key_ptr, const int* __restrict__ row_order,
+                       const int* __restrict__ key_ptr, const int4* __restrict__ row_order,
                        const unsigned short* __restrict__ cell_order, const BinRec* __restrict__ rec,
                        const float2* __restrict__ tw_g, NufftDims d, int planes, long M, int split, int groups) {
     using F = FastFft<K>;
@@ -422,7 +423,7 @@ __global__ void __launch_bounds__(PG* FastFft<K>::TPS, (1024 / (PG * FastFft<K>:
     int* us = reinterpret_cast<int*>(cs + EC * FZ_J); // [EC]
     int* kp = us + EC;                                // [K + 1]
     const int tid = threadIdx.x, s = tid / F::TPS, t = tid - s * F::TPS;
-    const FzItem cur = fz_item(blockIdx.x, K * groups, groups, PG, K, row_order, key_ptr);
+    const FzItem cur = fz_item(blockIdx.x, K * groups, groups, PG, row_order);
     {
         const int R = cur.R, p0 = cur.p0, beg = cur.beg, end = cur.end;
         const int p = p0 + s;
