@@ -135,7 +135,10 @@ __device__ __forceinline__ float rcp_approx(float d) {
     return r;
 }
 
-template <int PY, int SEG, bool SAFE, bool TQ>
+// FBP (fan-beam FBP's second 1 / den, Kak & Slaney 3.4.2) is a template parameter: as a run-time uniform branch it was
+// compiled to 16 predicated instructions per view and thread that the plain adjoint issued for nothing (19 % of its
+// tap loop, ncu r02)
+template <int PY, int SEG, bool SAFE, bool TQ, bool FBP>
 __device__ __forceinline__ void fan_taps_line(const float* __restrict__ view, uint32_t cbase, float lx,
                                               const ull* __restrict__ ly_pk, float kk, float sfbp, float* __restrict__ acc) {
     constexpr float MAGIC = 8388608.f;
@@ -165,7 +168,7 @@ __device__ __forceinline__ void fan_taps_line(const float* __restrict__ view, ui
         float t0, t1, w0, w1;
         upk2(add2_rm(p_c, p_m), t0, t1);
         ull p_w = mul2(p_k, p_r);
-        if (sfbp != 0.f) p_w = mul2(p_w, mul2(pk2(sfbp, sfbp), p_r));     // fan-beam FBP: k s / den^2 (uniform branch)
+        if (FBP) p_w = mul2(p_w, mul2(pk2(sfbp, sfbp), p_r));             // fan-beam FBP: k s / den^2
         upk2(p_w, w0, w1);
         const float2 s0 = lds64((uint32_t)__float_as_int(t0) * 8u + cbase);
         const float2 s1 = lds64((uint32_t)__float_as_int(t1) * 8u + cbase);
@@ -174,7 +177,7 @@ __device__ __forceinline__ void fan_taps_line(const float* __restrict__ view, ui
     }
 }
 
-template <int TX, int TY, int PY, int AC, int SEG, bool FAN, bool TQ>
+template <int TX, int TY, int PY, int AC, int SEG, bool FAN, bool TQ, bool FBP>
 __global__ void __launch_bounds__(TX*(TY / PY), FAN ? (PY == 8 ? 5 : 2) : (PY == 8 ? 7 : 3))
     radon_adj_tile_kernel(const float* __restrict__ sino, float* __restrict__ img, const float* __restrict__ trig,
                           const AdjGeom g) {
@@ -267,13 +270,15 @@ __global__ void __launch_bounds__(TX*(TY / PY), FAN ? (PY == 8 ? 5 : 2) : (PY ==
                 constexpr int NB = SEG / 32;
                 const int lane = tid & 31;
                 for (int al = tid >> 5; al < na; al += THREADS / 32) {
-                    const int lo = s_lo[al];
-                    const float* row = sb + (long)(a0 + al) * g.det_count;
+                    const int d0 = s_lo[al] + lane;
+                    // one 64-bit address per view; the NB + 1 loads are that address + i * 128 bytes (never dereferenced
+                    // outside the row: the bounds predicate guards each load)
+                    const float* rp = sb + ((long)(a0 + al) * g.det_count + d0);
                     float v[NB + 1];
 #pragma unroll
                     for (int i = 0; i <= NB; ++i) {
-                        const int d = lo + i * 32 + lane;
-                        v[i] = ((unsigned)d < (unsigned)g.det_count && (i < NB || lane == 0)) ? __ldg(row + d) : 0.f;
+                        const int d = d0 + i * 32;
+                        v[i] = ((unsigned)d < (unsigned)g.det_count && (i < NB || lane == 0)) ? __ldg(rp + i * 32) : 0.f;
                     }
 #pragma unroll
                     for (int i = 0; i < NB; ++i) {
@@ -316,9 +321,8 @@ __global__ void __launch_bounds__(TX*(TY / PY), FAN ? (PY == 8 ? 5 : 2) : (PY ==
                         }
                     } else {
                         const uint32_t cbase = (uint32_t)__cvta_generic_to_shared(seg) - g.koff;
-                        const float sfbp = g.fbp ? g.s_dist : 0.f;
-                        if (close) fan_taps_line<PY, SEG, false, TQ>(s_view[al], cbase, lx, ly_pk, g.k, sfbp, acc);
-                        else fan_taps_line<PY, SEG, true, TQ>(s_view[al], cbase, lx, ly_pk, g.k, sfbp, acc);
+                        if (close) fan_taps_line<PY, SEG, false, TQ, FBP>(s_view[al], cbase, lx, ly_pk, g.k, g.s_dist, acc);
+                        else fan_taps_line<PY, SEG, true, TQ, FBP>(s_view[al], cbase, lx, ly_pk, g.k, g.s_dist, acc);
                     }
                 }
             }
@@ -419,15 +423,20 @@ extern "C" int pdu_radon_adj_weighted_f32(const float* sino, float* img, const f
         // parallel beams with det_spacing >= 0.8 (a third less staging work)
         const bool seg64 = !ag.fan && 46.f * ag.ids + 5.f <= 64.f;
         const dim3 blk(TX, TY / 8);
+#define PDU_ADJ_LAUNCH(SEG_, FAN_, TQ_, FBP_) \
+    radon_adj_tile_kernel<TX, TY, 8, 32, SEG_, FAN_, TQ_, FBP_><<<grid, blk, 0, st>>>(sino, img, trig, ag)
         if (ag.texq) {
-            if (ag.fan) radon_adj_tile_kernel<TX, TY, 8, 32, 96, true, true><<<grid, blk, 0, st>>>(sino, img, trig, ag);
-            else if (seg64) radon_adj_tile_kernel<TX, TY, 8, 32, 64, false, true><<<grid, blk, 0, st>>>(sino, img, trig, ag);
-            else radon_adj_tile_kernel<TX, TY, 8, 32, 96, false, true><<<grid, blk, 0, st>>>(sino, img, trig, ag);
+            if (ag.fan && ag.fbp) PDU_ADJ_LAUNCH(96, true, true, true);
+            else if (ag.fan) PDU_ADJ_LAUNCH(96, true, true, false);
+            else if (seg64) PDU_ADJ_LAUNCH(64, false, true, false);
+            else PDU_ADJ_LAUNCH(96, false, true, false);
         } else {
-            if (ag.fan) radon_adj_tile_kernel<TX, TY, 8, 32, 96, true, false><<<grid, blk, 0, st>>>(sino, img, trig, ag);
-            else if (seg64) radon_adj_tile_kernel<TX, TY, 8, 32, 64, false, false><<<grid, blk, 0, st>>>(sino, img, trig, ag);
-            else radon_adj_tile_kernel<TX, TY, 8, 32, 96, false, false><<<grid, blk, 0, st>>>(sino, img, trig, ag);
+            if (ag.fan && ag.fbp) PDU_ADJ_LAUNCH(96, true, false, true);
+            else if (ag.fan) PDU_ADJ_LAUNCH(96, true, false, false);
+            else if (seg64) PDU_ADJ_LAUNCH(64, false, false, false);
+            else PDU_ADJ_LAUNCH(96, false, false, false);
         }
+#undef PDU_ADJ_LAUNCH
         note_kernel(OP_RADON_ADJ, "radon_adj_tile_kernel<32,32,8,32,%d,%s> grid %ux%ux%u (line-form taps in shared memory, packed FP32)",
                     ag.fan ? 96 : (seg64 ? 64 : 96), ag.fan ? "fan" : "parallel", grid.x, grid.y, grid.z);
     }

@@ -57,6 +57,6 @@ def test_no_local_memory_traffic_in_the_projectors(sass):
     backprojector passes its geometry struct to the out-of-line fallback through a 56-byte stack frame -- parameter
     passing, not a spill (ptxas -v: 0 bytes spill stores) -- so it is not checked here."""
     for name, text in _functions(sass).items():
-        if "radon_fwd_quad_kernel" in name or ("radon_adj_tile_kernel" in name and re.search(r"ELi(64|96)ELb0ELb[01]E", name)):   # FAN = false
+        if "radon_fwd_quad_kernel" in name or ("radon_adj_tile_kernel" in name and re.search(r"ELi(64|96)ELb0ELb[01]ELb0E", name)):   # FAN = false
             body = _mnemonics(text)
             assert not any(m.startswith("STL") or m.startswith("LDL") for m in body), f"local-memory traffic in {name[:90]}"
