@@ -48,7 +48,7 @@ WORKLOAD = ("configs[1]: parallel-beam CT PD-UNet 256x256, 64->512 views sinogra
 
 
 # ncu --set full numbers that bench.py does not measure itself (labelled as such in the JSON line)
-STATIC_TRAFFIC = {"cold": 33847552 + 18432, "in_step": 7936 + 3614976,
+STATIC_TRAFFIC = {"cold": 33912064 + 37888, "in_step": 52992 + 3401984,
                   "source": "profiles/r02_ncu_full_summary_fwd.md (cold: ncu flushes the caches, the kernel re-reads the two 16.9 MB "
                             "cell tensors) + profiles/r02_traffic_in_step.csv (--cache-control none: cells still in L2); ncu captures "
                             "of radon_fwd_quad_kernel<32,8,16,92,2,4,0>, dram read + write per launch; not re-measured by this run"}
@@ -271,8 +271,8 @@ def run_ours(args):
                      "smem_roof_frac": (BATCH * A_FULL * N * N / (fwd_avg_ms * 1e-3)) / (148 * 8 * 1.965e9),
                      "note": "bound on-chip, not by HBM (43 samples per algorithmic byte): smem_roof_frac is samples/s "
                              "against the shared-memory roof of 8 bilinear samples/clk/SM (16 B/sample at 128 B/clk); "
-                             "ncu (r02): L1/shared pipe 68 % busy (15 % of the wavefronts are bank conflicts of the 16-byte "
-                             "cell loads), issue slots 75 % busy. DESIGN.md section 3"},
+                             "ncu (r02): L1/shared pipe 73 % busy (16 % of the wavefronts are bank conflicts of the 16-byte "
+                             "cell loads), issue slots 71 % busy. DESIGN.md section 3"},
         "operators": ops,
         "extras": extras,
     }

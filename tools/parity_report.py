@@ -1,5 +1,5 @@
 """Parity table: rel-L2 of every hot-path operator (through the C ABI) against the float64 oracle at the
-BASELINE.json shapes, written as markdown (default profiles/r01_parity.md).  Runs on the GPU box."""
+BASELINE.json shapes, written as markdown (default profiles/r02_parity.md).  Runs on the GPU box."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -10,7 +10,7 @@ from oracle.radon import FAN
 import pd_unet_b200 as pdu
 from pd_unet_b200.phantoms import phantom_batch, coil_maps
 
-out_path = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "profiles", "r01_parity.md")
+out_path = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "profiles", "r02_parity.md")
 dev = "cuda:0"
 
 
@@ -69,7 +69,7 @@ o, s = pdu.updates.residual_slice(h.to(dev), d.to(dev), 0)
 rows.append(("updates", "residual + slice", max(rel(o, ou.dual_update(h, d, 0)[0]), rel(s[:, 0], ou.dual_update(h, d, 0)[1]))))
 sp = seeded((4, 64, 256), 13)
 rows.append(("updates", "angular upsample 64 -> 512 views", rel(pdu.updates.angular_upsample(sp.to(dev), 8, "flip"), ou.angular_upsample(sp, 8, "flip"))))
-lines = ["# r01 parity: CUDA path (through the C ABI) vs the float64 oracle\n",
+lines = ["# r02 parity: CUDA path (through the C ABI) vs the float64 oracle\n",
          "rel-L2 = ||cuda - oracle|| / ||oracle||; budget 1e-5 (BASELINE.json north_star). The oracle is this repo's own",
          "restatement (parity unpinned, DESIGN.md section 0).\n", "| configuration | operator | rel-L2 |", "|---|---|---:|"]
 lines += [f"| {a} | {b} | {c:.2e} |" for a, b, c in rows]
