@@ -111,7 +111,10 @@ __global__ void __launch_bounds__(TX*(TY / PY))
 //   fan:       t - lo = (n0 + nx lx + ny ly) / den,   den = d0 + sn lx - cs ly,   weight = k / den
 // (lx, ly) = pixel offset inside the tile, lo = first detector bin of the staged segment.
 // parallel beam: cap the registers so that 7 (PY = 8) / 3 (PY = 4) CTAs fit an SM -- B N^2 / PY threads then
-// make one balanced wave; the rarely taken float64 fallback is what would otherwise raise the count
+// make one balanced wave; the rarely taken float64 fallback is what would otherwise raise the count.
+// fan beam: also 7 CTAs (72 registers; ptxas spills 40 bytes in the per-chunk float64 set-up, none in the tap loop).
+// At the 96 registers of 5 CTAs the kernel ran at 28 % warps active and 66 % issue: measured on the configs[2] share
+// (2048 CTAs), 5 / 6 / 7 / 8 CTAs per SM: 1033 / 985 / 955 / 969 us -- 7 also makes it two even waves
 // The segment holds the line through the two samples in the segment's own coordinate, (A, B) with
 //   tap(t) = A + t B, A = value - c B for entry c.  No fraction is needed, only floor(t) for the index, and the byte
 //   address comes from the magic-number bit pattern with one IMAD (the constant exponent part is folded into the
@@ -178,7 +181,7 @@ __device__ __forceinline__ void fan_taps_line(const float* __restrict__ view, ui
 }
 
 template <int TX, int TY, int PY, int AC, int SEG, bool FAN, bool TQ, bool FBP>
-__global__ void __launch_bounds__(TX*(TY / PY), FAN ? (PY == 8 ? 5 : 2) : (PY == 8 ? 7 : 3))
+__global__ void __launch_bounds__(TX*(TY / PY), FAN ? (PY == 8 ? 7 : 2) : (PY == 8 ? 7 : 3))
     radon_adj_tile_kernel(const float* __restrict__ sino, float* __restrict__ img, const float* __restrict__ trig,
                           const AdjGeom g) {
     constexpr int THREADS = TX * (TY / PY);
