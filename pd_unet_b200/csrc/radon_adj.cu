@@ -29,6 +29,9 @@ struct AdjGeom {
     float half;     // n / 2 - 0.5
     uint32_t koff;  // 0x4B000000 * 8 mod 2^32, passed at run time so that ptxas keeps `base - koff` in one register
     int texq;       // tex_weights option: the interpolation fraction rounded to 8 bits (radon_common.cuh)
+    float out_scale;  // tile kernel: what the accumulators are multiplied by on the way out -- 1 / det_spacing, and for fan
+                      // beams the constant factor of the tap weights (k, or k s with fbp), which the taps leave out
+    float inv_w;      // tile kernel, fan beam: 1 / that constant factor (the float64 fallback tap returns full weights)
     int fbp;        // fan beam only: weight every tap by (s / den) once more -- the 1 / U^2 of fan-beam FBP (Kak & Slaney 3.4.2)
 };
 
@@ -143,14 +146,14 @@ __device__ __forceinline__ float rcp_approx(float d) {
 // tap loop, ncu r02)
 template <int PY, int SEG, bool SAFE, bool TQ, bool FBP>
 __device__ __forceinline__ void fan_taps_line(const float* __restrict__ view, uint32_t cbase, float lx,
-                                              const ull* __restrict__ ly_pk, float kk, float sfbp, float* __restrict__ acc) {
+                                              const ull* __restrict__ ly_pk, float* __restrict__ acc) {
     constexpr float MAGIC = 8388608.f;
     const float4 v = *reinterpret_cast<const float4*>(view);
     const float2 tr = *reinterpret_cast<const float2*>(view + 4);
     const float nx_ = fmaf(v.y, lx, v.x), dx_ = fmaf(tr.x, lx, v.w);
     const ull p_nx = pk2(nx_, nx_), p_dx = pk2(dx_, dx_);
     const ull p_ny = pk2(v.z, v.z), p_dy = pk2(-tr.y, -tr.y);
-    const ull p_one = pk2(1.f, 1.f), p_k = pk2(kk, kk), p_m = pk2(MAGIC, MAGIC);
+    const ull p_one = pk2(1.f, 1.f), p_m = pk2(MAGIC, MAGIC);
 #pragma unroll
     for (int k = 0; k < PY; k += 2) {
         const ull p_num = fma2(p_ny, ly_pk[k / 2], p_nx);
@@ -170,8 +173,9 @@ __device__ __forceinline__ void fan_taps_line(const float* __restrict__ view, ui
         }
         float t0, t1, w0, w1;
         upk2(add2_rm(p_c, p_m), t0, t1);
-        ull p_w = mul2(p_k, p_r);
-        if (FBP) p_w = mul2(p_w, mul2(pk2(sfbp, sfbp), p_r));             // fan-beam FBP: k s / den^2
+        // tap weight k / den (fan-beam FBP: k s / den^2) without its constant factor: the kernel multiplies the
+        // accumulators by it once on the way out (AdjGeom::out_scale) instead of once (twice) per pixel pair and view
+        const ull p_w = FBP ? mul2(p_r, p_r) : p_r;
         upk2(p_w, w0, w1);
         const float2 s0 = lds64((uint32_t)__float_as_int(t0) * 8u + cbase);
         const float2 s1 = lds64((uint32_t)__float_as_int(t1) * 8u + cbase);
@@ -324,8 +328,8 @@ __global__ void __launch_bounds__(TX*(TY / PY), FAN ? (PY == 8 ? 7 : 2) : (PY ==
                         }
                     } else {
                         const uint32_t cbase = (uint32_t)__cvta_generic_to_shared(seg) - g.koff;
-                        if (close) fan_taps_line<PY, SEG, false, TQ, FBP>(s_view[al], cbase, lx, ly_pk, g.k, g.s_dist, acc);
-                        else fan_taps_line<PY, SEG, true, TQ, FBP>(s_view[al], cbase, lx, ly_pk, g.k, g.s_dist, acc);
+                        if (close) fan_taps_line<PY, SEG, false, TQ, FBP>(s_view[al], cbase, lx, ly_pk, acc);
+                        else fan_taps_line<PY, SEG, true, TQ, FBP>(s_view[al], cbase, lx, ly_pk, acc);
                     }
                 }
             }
@@ -337,7 +341,7 @@ __global__ void __launch_bounds__(TX*(TY / PY), FAN ? (PY == 8 ? 7 : 2) : (PY ==
 #pragma unroll
                 for (int k = 0; k < PY; ++k) {
                     const float dy = (float)(y0 + k * RY) - g.half;
-                    acc[k] += tap_global<FAN>(g, row, cs, sn, dx, dy);
+                    acc[k] += FAN ? tap_global<FAN>(g, row, cs, sn, dx, dy) * g.inv_w : tap_global<FAN>(g, row, cs, sn, dx, dy);
                 }
             }
         }
@@ -358,7 +362,7 @@ __global__ void __launch_bounds__(TX*(TY / PY), FAN ? (PY == 8 ? 7 : 2) : (PY ==
         if (x < g.n && y < g.n) {
             const float dy = (float)y - g.half;
             const float r2 = dx * dx + dy * dy, lim = 0.25f * (float)g.n * (float)g.n;
-            const float v = (g.clip && r2 > lim) ? 0.f : acc[k] * g.ids;
+            const float v = (g.clip && r2 > lim) ? 0.f : acc[k] * g.out_scale;
             img[((long)b * g.n + y) * g.n + x] = v;
         }
     }
@@ -410,6 +414,11 @@ extern "C" int pdu_radon_adj_weighted_f32(const float* sino, float* img, const f
     ag.half = 0.5f * (float)g->n - 0.5f;
     ag.koff = 0x4B000000u * 8u;
     ag.fbp = (fbp_weight && ag.fan) ? 1 : 0;
+    {
+        const double wc = ag.fan ? (double)ag.k * (ag.fbp ? (double)ag.s_dist : 1.0) : 1.0;
+        ag.out_scale = (float)((double)ag.ids * wc);
+        ag.inv_w = (float)(1.0 / wc);
+    }
     ag.texq = option(OPT_TEX_WEIGHTS) > 0 ? 1 : 0;
 
     cudaStream_t st = (cudaStream_t)stream;
