@@ -421,7 +421,7 @@ __global__ void __launch_bounds__(SEQ* FastFft<K>::TPS)
     auto st = [&](int j, int r, float2 v) {
         if (live) dst[j + r * NS3] = v;
     };
-    ff_transform<K, 4, false, true, false>(buf + s * F::template pitch<4>(), tw, t, ld, st);
+    ff_transform<K, 4, false, true, false, false, false, true>(buf + s * F::template pitch<4>(), tw, t, ld, st);
 }
 
 template <int K, int SEQ>
@@ -463,7 +463,7 @@ __global__ void __launch_bounds__(SEQ* FastFft<K>::TPS)
     auto st = [&](int j, int r, float2 v) {
         if (live) __stcs(dst + j + r * NS3, v);
     };
-    ff_transform<K, 4, true, false, true>(buf + s * F::template pitch<4>(), tw, t, ld, st);
+    ff_transform<K, 4, true, false, true, false, false, true>(buf + s * F::template pitch<4>(), tw, t, ld, st);
 }
 
 template <int K, int SEQ>
