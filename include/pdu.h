@@ -97,7 +97,8 @@ PDU_API int pdu_radon_trig_f32(const float* angles, float* trig, int n_angles, p
 
 /* Bytes of scratch the forward projector wants: the bilinear-cell tensors of the batch and of its
  * transpose, 2 * batch * (n+1)^2 * 16 bytes (the float-tile variants use the head of it for a
- * transposed copy).  0 is a valid answer. */
+ * transposed copy), followed by the strip-box table of the call's geometry (8 bytes per strip and
+ * (detector block, view group)).  0 is a valid answer. */
 PDU_API size_t pdu_radon_workspace_bytes(const pdu_radon_geom_t* g, int batch);
 
 /* img [batch, n, n] -> sino [batch, n_angles, det_count].
