@@ -30,7 +30,9 @@ struct FastFft {
     //    passes 2 and 3 then never straddle a padding slot (PS = 3 made 16 lanes span 18 slots: a 2-way conflict on
     //    every load), the stride-8 stores of pass 1 stay conflict free, only the pass-2 stores keep a 2-way conflict.
     template <int PS>
-    __host__ __device__ static constexpr int pitch() { return (K + (K >> PS) + 13) / 16 * 16 + 2; }
+    __host__ __device__ static constexpr int pitch() {      // PS == 4: room for the second exchange's 4 slots per 64 elements
+        return (K + (K >> PS) + (PS == 4 ? 4 * (K / 64) : 0) + 13) / 16 * 16 + 2;
+    }
 };
 static inline bool fast_fft_size(int K) { return K == 256 || K == 512 || K == 640 || K == 1024 || K == 2048; }
 template <int PS>
@@ -183,24 +185,28 @@ __device__ __forceinline__ void ff_transform(float2* __restrict__ buf, const flo
         ff_small<INV, R2>(w2);
         // stores: elements o0 + 8 r with o0 = (t >> 3) NS3 + k, k < 8, NS3 a multiple of 2^PS:
         //   PS == 3: (o0 + 8 r) >> 3 == (o0 >> 3) + r        => position = pos(o0) + 9 r
-        //   PS == 4: (o0 + 8 r) >> 4 == (o0 >> 4) + (r >> 1) => position = pos(o0) + 8 r + (r >> 1)
+        //   PS == 4: this exchange (pass 2 -> pass 3) has its own layout, position = e + (e >> 4) + 4 (e >> 6).  With
+        //     e + (e >> 4) alone the two octets of butterflies a half-warp holds store 64 elements = 68 slots apart,
+        //     i.e. 4 (mod 16) float2: a 2-way bank conflict on every pass-2 store (ncu r02: 9 % of the shared-memory
+        //     wavefronts of fz_rows_fwd_kernel); 4 more slots per 64 elements make it 72 = 8 (mod 16).  The first
+        //     exchange keeps e + (e >> 4): its stride-8 stores need exactly that.
         const int o0 = (t >> 3) * NS3 + k;
-        float2* p2s = buf + (o0 + (o0 >> PS));
+        float2* p2s = buf + (PS == 3 ? o0 + (o0 >> 3) : (t >> 3) * (NS3 + NS3 / 16 + 4 * (NS3 / 64)) + k);
 #pragma unroll
-        for (int r = 0; r < R2; ++r) p2s[PS == 3 ? 9 * r : 8 * r + (r >> 1)] = w2[r];
+        for (int r = 0; r < R2; ++r) p2s[PS == 3 ? 9 * r : 8 * r + (r >> 1) + 4 * (r >> 3)] = w2[r];
     }
     __syncthreads();
     // pass 3: radix R3, Ns = 8 R2; NS3 butterflies (TPS = 32: two per thread).  loads: elements j + r NS3
-    //   => position = pos(j) + r (NS3 + NS3 / 2^PS)
+    //   => position = pos(j) + r (NS3 + NS3 / 2^PS)   (PS == 4: the second exchange's layout, see above)
     constexpr int PER = TPS >= NS3 ? 1 : NS3 / TPS;
-    constexpr int S3 = NS3 + NS3 / PADM;
+    constexpr int S3 = PS == 3 ? NS3 + NS3 / PADM : NS3 + NS3 / 16 + 4 * (NS3 / 64);
     if (!ST_BUF) {
 #pragma unroll
         for (int i = 0; i < PER; ++i) {
             const int j = t + i * TPS;
             if (j < NS3) {
                 float2 u[R3];
-                const float2* p3 = buf + (j + (j >> PS));
+                const float2* p3 = buf + (PS == 3 ? j + (j >> 3) : j + (j >> 4) + 4 * (j >> 6));
 #pragma unroll
                 for (int r = 0; r < R3; ++r) u[r] = p3[r * S3];
                 if (TWREC) {
@@ -224,7 +230,7 @@ __device__ __forceinline__ void ff_transform(float2* __restrict__ buf, const flo
         for (int i = 0; i < PER; ++i) {
             const int j = t + i * TPS;
             if (j < NS3) {
-                const float2* p3 = buf + (j + (j >> PS));
+                const float2* p3 = buf + (PS == 3 ? j + (j >> 3) : j + (j >> 4) + 4 * (j >> 6));
 #pragma unroll
                 for (int r = 0; r < R3; ++r) u[i][r] = p3[r * S3];
             }
