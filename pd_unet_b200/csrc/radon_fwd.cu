@@ -875,8 +875,14 @@ int pdu_radon_fwd_f32(const float* img, float* sino, const float* trig, int batc
     // measured on the sweep's sparse shapes (tools/prof_fwd_shapes.py): tile kernel 1.2 - 1.4x faster there,
     // cell kernel 1.03 - 1.15x faster at drift <= 3.3.  Shape 13 (a quarter-warp = 4 detectors x 2 neighbouring views:
     // the 8 lanes of one LDS.128 phase then span < 8 cell columns) is 2-3 % faster than shape 7 (8 detectors of one view)
+    // r02 re-tuning after the strip-box table (tools/prof_fwd_shapes.py, batch 8): from 512^2 up the cell kernels also win
+    // on sparser view sets -- drift 4.4: 462 vs 534 us (512^2 x 256 views), 3073 vs 3826 (1024^2 x 512); drift 8.9:
+    // the 128-cell box 1799 vs 2014 us (1024^2 x 256); drift 17.8: four views per CTA 179 vs 218 us (512^2 x 64);
+    // below 512^2 the float-tile kernel stays equal or better on those view sets
     if (variant < 0) {
-        if (quad_ok && 7.f * drift <= 27.f) variant = 13;
+        const bool large = g->n >= 512;
+        if (quad_ok && (7.f * drift <= 27.f || (large && 7.f * drift <= 35.f))) variant = 13;
+        else if (quad_ok && large) variant = 7.f * drift <= 84.f ? 11 : 9;
         else if (tile_ok) variant = 1;
         else if (quad_ok) variant = 7.f * drift <= 63.f ? 11 : 9;
         else variant = 0;
