@@ -134,7 +134,13 @@ class _Plan:
         if not self.use_fused or not L.pdu_nufft_has_fused_path(h):
             return None
         if self.use_fused == "auto":
-            if planes < 8 or (adjoint and planes > 32 and self.grid_size[0] in (512, 640)):
+            # measured policy (profiles/r02_nufft_timings.txt, profiles/r02_nufft_policy.txt): the row-binned kernels pay
+            # per (sample, row) entry, so they win for sparse trajectories -- samples per grid cell rho <= 0.15
+            # (configs[3]: 0.075) -- and lose by 2 - 8 x for dense ones (rho >= 0.5); below 16 planes the generic
+            # adjoint scatters with atomics, which the fused gather still beats up to rho = 0.3
+            rho = omega.shape[1] / float(self.grid_size[0] * self.grid_size[1])
+            sparse = rho <= 0.15 or (adjoint and planes < 16 and rho <= 0.3)
+            if planes < 8 or not sparse or (adjoint and planes > 32 and self.grid_size[0] in (512, 640)):
                 return None
         ent = self._entry(omega)
         if ent["bins"] is None:
