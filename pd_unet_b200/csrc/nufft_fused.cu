@@ -42,7 +42,7 @@ struct __align__(16) BinRec {
 static_assert(sizeof(BinRec) == 64, "entry record is one 64-byte line half");
 
 struct BinsView {
-    int* hdr;            // [16]: magic, M (lo, hi), K0, K1, J, n_entries
+    int* hdr;            // [16]: magic, M (lo, hi), K0, K1, J, n_entries, entries of the heaviest row
     int* key_ptr;        // [K0 K1 + 1]: first sorted entry whose (row K1 + column) key is >= i
     int4* row_order;     // [K0]: (row, first entry, end entry, 0) by decreasing entry count -- heavy rows are scheduled
                          // first, and a CTA finds its row and entry range with one 16-byte load
@@ -191,7 +191,8 @@ __global__ void __launch_bounds__(512) bin_cell_order_kernel(const int* __restri
     for (int i = threadIdx.x; i < K; i += blockDim.x) cell_order[(long)R * K + i] = (unsigned short)(4095 - (keys[i] & 4095u));
 }
 
-__global__ void bin_header_kernel(int* hdr, long M, int K0, int K1, long n) {
+__global__ void bin_header_kernel(int* hdr, const int4* __restrict__ row_order, long M, int K0, int K1, long n) {
+    hdr[7] = row_order[0].z - row_order[0].y;      // entries of the heaviest row (the host's path policy reads it)
     hdr[0] = (int)FZ_MAGIC;
     hdr[1] = (int)(M & 0xffffffffL);
     hdr[2] = (int)(M >> 32);
@@ -223,7 +224,7 @@ static int bins_build(pdu_nufft_plan* p, const float* omega, long M, void* buf, 
     PDU_LAUNCHED();
     bin_cell_order_kernel<<<(unsigned)p->k0, 512, 0, st>>>(v.key_ptr, v.cell_order, p->k1);
     PDU_LAUNCHED();
-    bin_header_kernel<<<1, 1, 0, st>>>(v.hdr, M, p->k0, p->k1, n);
+    bin_header_kernel<<<1, 1, 0, st>>>(v.hdr, v.row_order, M, p->k0, p->k1, n);
     PDU_LAUNCHED();
     return PDU_OK;
 }

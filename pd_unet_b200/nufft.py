@@ -89,6 +89,7 @@ class _Plan:
         # at 256^2 x 1 plane), and for the adjoint of the 512 / 640 grids only up to 32 planes (64 planes of 640^2:
         # fused 326 us, generic sorted gather + register FFT 308 us; forward 226 vs 263 us)
         self.use_fused = "auto"
+        self.fused_max_row = 4096     # "auto": no fused path for a trajectory whose heaviest grid row has more entries
 
     # -------------------------------------------------------------- per-trajectory cache
     def _entry(self, omega: torch.Tensor) -> dict:
@@ -152,8 +153,13 @@ class _Plan:
             ent["bins"] = self._keep_prefix(buf, persist.value)
             self._built(ent)
             self._trim()
+            # entries of the heaviest grid row (header word 7): one small read-back per trajectory, at build time
+            ent["max_row"] = (int(ent["bins"][:64].cpu().view(torch.int32)[7])
+                              if not torch.cuda.is_current_stream_capturing() else 0)
         else:
             self._wait(ent)
+        if self.use_fused == "auto" and ent.get("max_row", 0) > self.fused_max_row:
+            return None       # a few very heavy rows (dense or concentrated trajectory) serialise the row kernels
         return ent["bins"]
 
     def _csr_for(self, omega: torch.Tensor, planes: int = 1 << 30):

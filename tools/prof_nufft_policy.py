@@ -1,5 +1,5 @@
 import sys, os, statistics
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import pd_unet_b200 as pdu
 dev = "cuda:0"
