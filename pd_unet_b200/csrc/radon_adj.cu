@@ -141,13 +141,21 @@ __device__ __forceinline__ float rcp_approx(float d) {
     return r;
 }
 
+// Segments wider than 96 entries (fine detectors) hold the lines in a coordinate CENTRED on the segment, t' = t - SEG / 2:
+// A = value - (c - SEG / 2) B is then rounded at the magnitude of 96 |B| as in the 96-entry segment, not of 192 |B|
+// (uncentred, a 16-view white-noise backprojection at det_spacing 0.25 measured 1.003e-5 against the 1e-5 budget).  The
+// shift is folded into the per-view constants (float64 set-up) and into the address constant; the floor trick uses
+// 1.5 x 2^23 so that negative coordinates stay in the binade with ulp 1.
+__host__ __device__ constexpr int adj_seg_centre(int seg) { return seg > 96 ? seg / 2 : 0; }
+
 // FBP (fan-beam FBP's second 1 / den, Kak & Slaney 3.4.2) is a template parameter: as a run-time uniform branch it was
 // compiled to 16 predicated instructions per view and thread that the plain adjoint issued for nothing (19 % of its
 // tap loop, ncu r02)
 template <int PY, int SEG, bool SAFE, bool TQ, bool FBP>
 __device__ __forceinline__ void fan_taps_line(const float* __restrict__ view, uint32_t cbase, float lx,
                                               const ull* __restrict__ ly_pk, float* __restrict__ acc) {
-    constexpr float MAGIC = 8388608.f;
+    constexpr int CEN = adj_seg_centre(SEG);
+    constexpr float MAGIC = CEN ? 12582912.f : 8388608.f;       // 1.5 x 2^23 when the coordinate can be negative (centred)
     const float4 v = *reinterpret_cast<const float4*>(view);
     const float2 tr = *reinterpret_cast<const float2*>(view + 4);
     const float nx_ = fmaf(v.y, lx, v.x), dx_ = fmaf(tr.x, lx, v.w);
@@ -167,8 +175,8 @@ __device__ __forceinline__ void fan_taps_line(const float* __restrict__ view, ui
         float c0, c1;
         upk2(p_c, c0, c1);
         if (!SAFE) {
-            c0 = fminf(fmaxf(c0, 0.f), (float)(SEG - 1));
-            c1 = fminf(fmaxf(c1, 0.f), (float)(SEG - 1));
+            c0 = fminf(fmaxf(c0, (float)-CEN), (float)(SEG - 1 - CEN));
+            c1 = fminf(fmaxf(c1, (float)-CEN), (float)(SEG - 1 - CEN));
             p_c = pk2(c0, c1);
         }
         float t0, t1, w0, w1;
@@ -215,7 +223,8 @@ __global__ void __launch_bounds__(TX*(TY / PY), FAN ? (PY == 8 ? 7 : 2) : (PY ==
     ull acc2[PY / 2];        // parallel beam: packed accumulators of the pixel pairs
 #pragma unroll
     for (int k = 0; k < PY / 2; ++k) acc2[k] = pk2(0.f, 0.f);
-    constexpr float MAGIC = 8388608.f;
+    constexpr int CEN = adj_seg_centre(SEG);
+    constexpr float MAGIC = CEN ? 12582912.f : 8388608.f;
     static_assert(PY % 2 == 0, "pixels are processed in packed pairs");
     ull ly_pk[PY / 2];      // row offsets inside the tile of this thread's pixel pairs, clamped to the image
 #pragma unroll
@@ -240,7 +249,7 @@ __global__ void __launch_bounds__(TX*(TY / PY), FAN ? (PY == 8 ? 7 : 2) : (PY ==
                 const int lo = (int)floor(tmin) - 1;
                 s_lo[tid] = lo;
                 float* v = s_view[tid];
-                v[0] = (float)a; v[1] = (float)bb; v[2] = (float)(t00 - (double)lo); v[3] = 0.f;
+                v[0] = (float)a; v[1] = (float)bb; v[2] = (float)(t00 - (double)(lo + CEN)); v[3] = 0.f;
             } else {
                 const double K = ids * ((double)g.s_dist + (double)g.d_dist);
                 const double p0 = cs * ox + sn * oy, d0 = (double)g.s_dist + sn * ox - cs * oy;
@@ -258,7 +267,7 @@ __global__ void __launch_bounds__(TX*(TY / PY), FAN ? (PY == 8 ? 7 : 2) : (PY ==
                 const bool sane = tmin > -1e8 && tmax < 1e8;
                 const int lo = sane ? (int)floor(tmin) - 1 : 0;
                 s_lo[tid] = lo;
-                const double L = (double)lo - cr;
+                const double L = (double)(lo + CEN) - cr;
                 float* v = s_view[tid];
                 v[0] = (float)(K * p0 - L * d0); v[1] = (float)(K * cs - L * sn); v[2] = (float)(K * sn + L * cs);
                 v[3] = (float)d0; v[4] = (float)sn; v[5] = (float)cs; v[6] = v[7] = 0.f;
@@ -293,7 +302,7 @@ __global__ void __launch_bounds__(TX*(TY / PY), FAN ? (PY == 8 ? 7 : 2) : (PY ==
                         const float dn = __shfl_down_sync(0xffffffffu, v[i], 1);
                         const float dv = (lane == 31 ? nxt : dn) - v[i];
                         const int c = i * 32 + lane;
-                        s_seg[al][c] = make_float2(fmaf(-(float)c, dv, v[i]), dv);
+                        s_seg[al][c] = make_float2(fmaf(-(float)(c - CEN), dv, v[i]), dv);
                     }
                 }
             }
@@ -434,23 +443,35 @@ extern "C" int pdu_radon_adj_weighted_f32(const float* sino, float* img, const f
         // a 32 x 32 tile projects onto at most 32 sqrt(2) / det_spacing bins: a 64-entry segment is enough for
         // parallel beams with det_spacing >= 0.8 (a third less staging work)
         const bool seg64 = !ag.fan && 46.f * ag.ids + 5.f <= 64.f;
+        // fine detectors (det_spacing < 0.5, or a fan beam's magnification): the tile projects onto more than 96 bins and
+        // every chunk would take the float64 global-load path (measured, 16 x 256^2 x 512 views: det_spacing 0.4 839 us,
+        // 0.25 1106 us against 180 us at 1.0).  A 192-entry segment with 16 views per chunk (same shared memory) keeps
+        // those geometries on the shared-memory taps.
+        const float mag = ag.fan ? ag.k / fmaxf(ag.s_dist - 0.7072f * (float)ag.n, 1.f) : 1.f;
+        const bool seg192 = 45.3f * ag.ids * mag + 4.f > 96.f;     // (32 sqrt 2 bins per unit spacing + the two slack taps and rounding)
         const dim3 blk(TX, TY / 8);
-#define PDU_ADJ_LAUNCH(SEG_, FAN_, TQ_, FBP_) \
-    radon_adj_tile_kernel<TX, TY, 8, 32, SEG_, FAN_, TQ_, FBP_><<<grid, blk, 0, st>>>(sino, img, trig, ag)
-        if (ag.texq) {
-            if (ag.fan && ag.fbp) PDU_ADJ_LAUNCH(96, true, true, true);
-            else if (ag.fan) PDU_ADJ_LAUNCH(96, true, true, false);
-            else if (seg64) PDU_ADJ_LAUNCH(64, false, true, false);
-            else PDU_ADJ_LAUNCH(96, false, true, false);
-        } else {
-            if (ag.fan && ag.fbp) PDU_ADJ_LAUNCH(96, true, false, true);
-            else if (ag.fan) PDU_ADJ_LAUNCH(96, true, false, false);
-            else if (seg64) PDU_ADJ_LAUNCH(64, false, false, false);
-            else PDU_ADJ_LAUNCH(96, false, false, false);
-        }
+#define PDU_ADJ_LAUNCH(AC_, SEG_, FAN_, TQ_, FBP_) \
+    radon_adj_tile_kernel<TX, TY, 8, AC_, SEG_, FAN_, TQ_, FBP_><<<grid, blk, 0, st>>>(sino, img, trig, ag)
+#define PDU_ADJ_DISPATCH(TQ_)                                                   \
+    do {                                                                        \
+        if (ag.fan && ag.fbp) {                                                 \
+            if (seg192) PDU_ADJ_LAUNCH(16, 192, true, TQ_, true);               \
+            else PDU_ADJ_LAUNCH(32, 96, true, TQ_, true);                       \
+        } else if (ag.fan) {                                                    \
+            if (seg192) PDU_ADJ_LAUNCH(16, 192, true, TQ_, false);              \
+            else PDU_ADJ_LAUNCH(32, 96, true, TQ_, false);                      \
+        } else if (seg64) PDU_ADJ_LAUNCH(32, 64, false, TQ_, false);            \
+        else if (seg192) PDU_ADJ_LAUNCH(16, 192, false, TQ_, false);            \
+        else PDU_ADJ_LAUNCH(32, 96, false, TQ_, false);                         \
+    } while (0)
+        if (seg192 && !seg64)      // centred coordinate: bits(t' + 1.5 x 2^23) * 8 + base - koff = base + 8 (floor(t') + 96)
+            ag.koff = 0x4B400000u * 8u - 8u * (uint32_t)adj_seg_centre(192);
+        if (ag.texq) PDU_ADJ_DISPATCH(true);
+        else PDU_ADJ_DISPATCH(false);
+#undef PDU_ADJ_DISPATCH
 #undef PDU_ADJ_LAUNCH
-        note_kernel(OP_RADON_ADJ, "radon_adj_tile_kernel<32,32,8,32,%d,%s> grid %ux%ux%u (line-form taps in shared memory, packed FP32)",
-                    ag.fan ? 96 : (seg64 ? 64 : 96), ag.fan ? "fan" : "parallel", grid.x, grid.y, grid.z);
+        note_kernel(OP_RADON_ADJ, "radon_adj_tile_kernel<32,32,8,%d,%d,%s> grid %ux%ux%u (line-form taps in shared memory, packed FP32)",
+                    seg192 && !seg64 ? 16 : 32, seg64 ? 64 : (seg192 ? 192 : 96), ag.fan ? "fan" : "parallel", grid.x, grid.y, grid.z);
     }
     PDU_LAUNCHED();
     return PDU_OK;
