@@ -4,7 +4,8 @@
 // so it is done directly as a Toeplitz contraction and the sinogram makes one round trip through HBM
 // instead of the FFT route's three.
 //
-// variant 1 (default when det_count % 128 == 0) -- exact split-TF32 GEMM on tcgen05 tensor cores: filter_tc.cu.
+// variant 1 (default when det_count % 4 == 0 and >= 128; the contraction is zero-padded to the 128-wide tile) -- exact
+//   split-TF32 GEMM on tcgen05 tensor cores: filter_tc.cu.
 //   Measured on B200 (8192 x 256 rows): 20.5 us against 47.1 us for variant 0.
 // variant 0 -- register-tiled FP32 contraction on the CUDA cores.  A CTA owns RB rows; the rows
 //   and the 2D-1 taps sit in shared memory; a thread produces a 4 (rows) x 4 (adjacent outputs)
@@ -121,7 +122,7 @@ int pdu_filter_sinogram_weighted_f32(const float* sino, float* out, const float*
     PDU_REQUIRE(blocks <= 2147483647L, "pdu_filter_sinogram_f32: too many rows");
     filter_direct_kernel<<<(unsigned)blocks, 256, smem, (cudaStream_t)stream>>>(sino, out, taps, col_weight, rows, D);
     PDU_LAUNCHED();
-    note_kernel(OP_FILTER, "filter_direct_kernel grid %ld (CUDA-core Toeplitz contraction, det_count %% 128 != 0)%s", blocks,
+    note_kernel(OP_FILTER, "filter_direct_kernel grid %ld (CUDA-core Toeplitz contraction: det_count %% 4 != 0 or < 128)%s", blocks,
                 col_weight ? " + fused detector weight" : "");
     return PDU_OK;
 }

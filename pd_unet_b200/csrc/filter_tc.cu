@@ -107,7 +107,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.x * TC_BM, n0 = blockIdx.y * TC_BN;
-    const int n_kb = D / TC_BK;
+    const int Dp = (D + TC_BN - 1) / TC_BN * TC_BN;         // the contraction runs on D rounded up to the tile: TMA zero-fills
+    const int n_kb = Dp / TC_BK;                              // the columns of X beyond D, H is built zero-padded
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < TC_STAGES; ++s) {
@@ -143,7 +144,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                 tc_tma_2d(st, &tm_x, kb * TC_BK, m0, full(s));                         // raw X -> split in place into X1
 #pragma unroll
                 for (int p = 0; p < TC_SPLIT; ++p)                                     // pre-split H pieces, stacked by rows
-                    tc_tma_2d(st + (TC_SPLIT + p) * TC_TILE_BYTES, &tm_h, kb * TC_BK, p * D + n0, full(s));
+                    tc_tma_2d(st + (TC_SPLIT + p) * TC_TILE_BYTES, &tm_h, kb * TC_BK, p * Dp + n0, full(s));
             }
         }
     } else if (warp == 1) {
@@ -192,7 +193,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                 if (col_weight) {
                     // SWIZZLE_128B: physical chunk = logical chunk ^ (row & 7)
                     const int n = idx / CHUNKS, c = (idx % CHUNKS) ^ (n & 7);
-                    const float4 w = __ldg((const float4*)(col_weight + kb * TC_BK) + c);
+                    const float4 w = kb * TC_BK + 4 * c < D ? __ldg((const float4*)(col_weight + kb * TC_BK) + c)
+                                                             : make_float4(0.f, 0.f, 0.f, 0.f);   // (D % 4 == 0)
                     v.x *= w.x; v.y *= w.y; v.z *= w.z; v.w *= w.w;
                 }
                 float4 a, b, c, d;
@@ -236,8 +238,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                     float4* dst = (float4*)(out + row * D + n0 + c);
 #pragma unroll
                     for (int i = 0; i < 8; ++i)
-                        dst[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
-                                             __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+                        if (n0 + c + 4 * i < D)            // the last column tile of a padded width is partly outside
+                            dst[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                                                 __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
                 }
             }
         }
@@ -252,11 +255,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 
 // workspace layout: [H1 | H2 | H3] each D*D floats (three 11-bit pieces, H1 + H2 + H3 == H exactly),
 // K-major: B[n][k] = taps[(n - k) + D - 1].
-__global__ void __launch_bounds__(256) filter_tc_prepare_kernel(const float* __restrict__ taps, float* __restrict__ ws, int D) {
-    const long total = (long)D * D;
+__global__ void __launch_bounds__(256) filter_tc_prepare_kernel(const float* __restrict__ taps, float* __restrict__ ws, int D, int Dp) {
+    const long total = (long)Dp * Dp;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-        const int n = (int)(i / D), k = (int)(i - (long)n * D);
-        const float v = __ldg(taps + (n - k) + D - 1);
+        const int n = (int)(i / Dp), k = (int)(i - (long)n * Dp);
+        const float v = (n < D && k < D) ? __ldg(taps + (n - k) + D - 1) : 0.f;
         const float h1 = tf32_head(v), r = v - h1;
         const float h2 = tf32_head(r);
         ws[i] = h1;
@@ -301,10 +304,12 @@ static int tc_make_map(CUtensorMap* tm, const float* ptr, long n_rows, int D) {
     return PDU_OK;
 }
 
-bool filter_tc_supported(int D) { return D % TC_BN == 0 && D >= TC_BN && D <= 4096; }
+// any detector count whose rows are 16-byte multiples (the TMA row pitch); the contraction is padded to the 128-wide tile
+bool filter_tc_supported(int D) { return D % 4 == 0 && D >= TC_BN && D <= 4096; }
+static int tc_padded(int D) { return (D + TC_BN - 1) / TC_BN * TC_BN; }
 
 size_t filter_tc_workspace_bytes(int D) {
-    return filter_tc_supported(D) ? (size_t)3 * D * D * sizeof(float) : 0;
+    return filter_tc_supported(D) ? (size_t)3 * tc_padded(D) * tc_padded(D) * sizeof(float) : 0;
 }
 
 int filter_tc_prepare(const float* taps, void* ws, size_t ws_bytes, int D, cudaStream_t st) {
@@ -313,8 +318,9 @@ int filter_tc_prepare(const float* taps, void* ws, size_t ws_bytes, int D, cudaS
         set_error("pdu_filter_prepare_f32: workspace of %zu bytes (16-byte aligned) required", filter_tc_workspace_bytes(D));
         return PDU_ENOMEM;
     }
-    const long total = (long)D * D;
-    filter_tc_prepare_kernel<<<(unsigned)std::min<long>(cdiv(total, 256), 148L * 8), 256, 0, st>>>(taps, (float*)ws, D);
+    const int Dp = tc_padded(D);
+    const long total = (long)Dp * Dp;
+    filter_tc_prepare_kernel<<<(unsigned)std::min<long>(cdiv(total, 256), 148L * 8), 256, 0, st>>>(taps, (float*)ws, D, Dp);
     PDU_LAUNCHED();
     return PDU_OK;
 }
@@ -323,10 +329,11 @@ int filter_tc_launch(const float* sino, float* out, const void* ws, const float*
     CUtensorMap tx, th;
     int rc = tc_make_map(&tx, sino, rows, D);
     if (rc) return rc;
-    rc = tc_make_map(&th, (const float*)ws, 3L * D, D);     // the three pieces stacked by rows
+    const int Dp = tc_padded(D);
+    rc = tc_make_map(&th, (const float*)ws, 3L * Dp, Dp);   // the three pieces stacked by rows
     if (rc) return rc;
     PDU_CUDA((ensure_dyn_smem<filter_tc_kernel>(TC_SMEM)));
-    dim3 grid((unsigned)cdiv(rows, TC_BM), (unsigned)(D / TC_BN));
+    dim3 grid((unsigned)cdiv(rows, TC_BM), (unsigned)(Dp / TC_BN));
     const int fault = option(OPT_DEBUG_FAULT) == 1 ? 1 : 0;
     filter_tc_kernel<<<grid, TC_THREADS, TC_SMEM, st>>>(tx, th, col_weight, out, rows, D, device_error_word(),
                                                         fault ? MBAR_TIMEOUT_FAULT_NS : MBAR_TIMEOUT_NS, fault);

@@ -193,12 +193,14 @@ def test_full_size_properties(name):
         assert abs(lhs - rhs) / abs(lhs) < 2e-2
 
 
-@pytest.mark.parametrize("D,A,B", [(128, 24, 2), (256, 64, 2), (512, 50, 3), (384, 7, 1)])
+@pytest.mark.parametrize("D,A,B", [(128, 24, 2), (256, 64, 2), (512, 50, 3), (384, 7, 1), (320, 40, 2), (500, 33, 1), (132, 9, 2)])
 def test_filter_tensor_core_variant(D, A, B):
-    """The tcgen05 split-TF32 Toeplitz GEMM (filter_variant 1, the default when D % 128 == 0) against the
+    """The tcgen05 split-TF32 Toeplitz GEMM (filter_variant 1, the default when D % 4 == 0 and D >= 128; widths that
+    are not a multiple of the 128-column tile are zero-padded by TMA and by the prepared filter matrix) against the
     float64 oracle and the CUDA-core kernel.  rows = B*A is deliberately not always a multiple of the
     128-row tile.  The object sinogram is the hard input: its ramp-filtered output is ~50x smaller than
     sum |x||h|, which is what the rounding error scales with."""
+    from pd_unet_b200 import _lib
     op = pdu.Radon(D, user_angles(A), det_count=D)
     noise = seeded((B, A, D), 17)
     obj = op.forward(phantom_batch(B, D, seed=5).to(DEV)).cpu()
@@ -211,6 +213,7 @@ def test_filter_tensor_core_variant(D, A, B):
                 torch.cuda.synchronize()
             finally:
                 pdu.set_option("filter_variant", -1)
+            assert ("filter_tc_kernel" in _lib.last_kernel("filter")) == (variant == 1)
             assert rel_l2(got, want) <= TOL, f"variant {variant}"
     try:
         pdu.set_option("filter_variant", 1)
