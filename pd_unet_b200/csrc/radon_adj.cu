@@ -146,6 +146,11 @@ __device__ __forceinline__ float rcp_approx(float d) {
 // (uncentred, a 16-view white-noise backprojection at det_spacing 0.25 measured 1.003e-5 against the 1e-5 budget).  The
 // shift is folded into the per-view constants (float64 set-up) and into the address constant; the floor trick uses
 // 1.5 x 2^23 so that negative coordinates stay in the binade with ulp 1.
+// (r02 random sweep, tools/fuzz_parity.py: fan beams through the 192-entry segment sit at 7e-6 median / 1.7e-5 worst on
+//  few-view white-noise sinograms.  Keeping (value, difference) pairs and taking the fraction from the fused residual
+//  (num - floor(c) den) / den removes the line offset's and the quotient's rounding: 7.3e-6 -> 5.9e-6 median,
+//  1.3e-5 -> 1.2e-5 worst, for 293 -> 367 us at s_dist = n -- not kept: what remains is float32 evaluating num and den
+//  themselves at the magnitude |c| den, which only float64 coordinates (radon_adj_variant 0) remove.)
 __host__ __device__ constexpr int adj_seg_centre(int seg) { return seg > 96 ? seg / 2 : 0; }
 
 // FBP (fan-beam FBP's second 1 / den, Kak & Slaney 3.4.2) is a template parameter: as a run-time uniform branch it was
