@@ -707,38 +707,99 @@ __global__ void __launch_bounds__(256)
     }
 }
 
-template <int PG>
+// Sorted gather on the plane-interleaved samples.  LPC neighbouring lanes share a cell; a lane owns two planes in each of
+// G plane groups 2 LPC apart, i.e. one 16-byte load per entry and group, and the LPC lanes of a cell read LPC * 16
+// contiguous bytes: a warp instruction touches 32 / LPC cache lines, only 32 / LPC cells share a warp's trip count, per
+// plane a warp writes 32 / LPC neighbouring cells, and an entry's index and weight are loaded once for 2 LPC G planes
+// with G independent sample loads in flight.  r01's form -- one thread = one cell x 8 planes = four 16-byte loads, every
+// one of them from 32 different lines (ncu: L1 74 % busy at 18 % of the DRAM rate, 40 % warps active) -- against
+// (LPC, G), whole adjoint at 64 planes of 640^2, one box: (4, 1) 280, (4, 2) 253, (4, 4) 259, (4, 8) 290, (8, 1) 284,
+// (8, 2) 259, (8, 4) 263, (2, 4) 266, (2, 8) 296 us, r01's form with the long rows as a kernel of their own ~ 300;
+// two or four neighbouring cells per thread with 16-byte stores lost to the merged loop's divergence (310 / 361 us).
+// Entries are summed in the same order per (cell, plane) whatever the shape: bit-identical results.
+// The first long_blocks CTAs of every plane group take the long rows (the k-space centre: more than CSR_LONG entries),
+// one warp per row, lanes striding the entries and a fixed-order shuffle tree adding them up, exactly as
+// interp_adj_csr_long_kernel does from the planar samples -- inside this launch, and scheduled first, the serial walk
+// over a centre cell's ~1700 entries (18 us as a kernel of its own) is hidden behind the short cells.
+template <int LPC, int G>
 __global__ void __launch_bounds__(256)
     interp_adj_csrT_kernel(const float2* __restrict__ kT, float2* __restrict__ grid, const int* __restrict__ row_ptr,
-                           const int* __restrict__ samp, const float2* __restrict__ w, long cells, int planes, int planes4) {
-    static_assert(PG % 2 == 0, "planes are read in pairs");
-    const long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= cells) return;
-    const int p0 = blockIdx.y * PG;
-    float2 acc[PG];
+                           const int* __restrict__ samp, const float2* __restrict__ w, const int* __restrict__ n_long,
+                           const int* __restrict__ long_rows, long cells, int planes, int planes4, int long_blocks) {
+    constexpr int CPB = 256 / LPC;
+    if ((int)blockIdx.x < long_blocks) {
+        constexpr int PG = 2 * LPC * G;                   // planes of this plane group
+        const int lane = threadIdx.x & 31, p0 = blockIdx.y * PG;
+        const int nl = __ldg(n_long);
+        for (int r = blockIdx.x * 8 + (threadIdx.x >> 5); r < nl; r += long_blocks * 8) {
+            const long c = __ldg(long_rows + r);
+            const int beg = __ldg(row_ptr + c), end = __ldg(row_ptr + c + 1);
+            // four planes at a time: eight accumulators, so that this rare path does not set the kernel's register count
+#pragma unroll 1
+            for (int h = 0; h < PG && p0 + h < planes4; h += 4) {
+                float2 acc[4];
 #pragma unroll
-    for (int q = 0; q < PG; ++q) acc[q] = make_float2(0.f, 0.f);
+                for (int q = 0; q < 4; ++q) acc[q] = make_float2(0.f, 0.f);
+                for (int i = beg + lane; i < end; i += 32) {
+                    const long m = __ldg(samp + i);
+                    const float2 wi = __ldg(w + i);
+                    const float4* src = reinterpret_cast<const float4*>(kT + m * planes4 + p0 + h);
+#pragma unroll
+                    for (int q = 0; q < 4; q += 2) {
+                        const float4 v = __ldg(src + q / 2);
+                        const float2 z0 = cmul(make_float2(v.x, v.y), wi), z1 = cmul(make_float2(v.z, v.w), wi);
+                        acc[q].x += z0.x;
+                        acc[q].y += z0.y;
+                        acc[q + 1].x += z1.x;
+                        acc[q + 1].y += z1.y;
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        acc[q].x += __shfl_xor_sync(0xffffffffu, acc[q].x, o);
+                        acc[q].y += __shfl_xor_sync(0xffffffffu, acc[q].y, o);
+                    }
+                    if (lane == 0 && p0 + h + q < planes) grid[(long)(p0 + h + q) * cells + c] = acc[q];
+                }
+            }
+        }
+        return;
+    }
+    const int sub = threadIdx.x % LPC;
+    const long c = (long)(blockIdx.x - long_blocks) * CPB + threadIdx.x / LPC;
+    const int p = blockIdx.y * (2 * LPC * G) + 2 * sub;   // first of this lane's planes; the others follow 2 LPC apart
+    if (c >= cells || p >= planes4) return;
     const int beg = __ldg(row_ptr + c), end = __ldg(row_ptr + c + 1);
-    if (end - beg > CSR_LONG) return;                     // interp_adj_csr_long_kernel owns this cell
+    if (end - beg > CSR_LONG) return;                     // the long-row CTAs own this cell
+    float2 a0[G], a1[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) a0[g] = a1[g] = make_float2(0.f, 0.f);
+    const float2* src = kT + p;
     for (int i = beg; i < end; ++i) {
         const long m = __ldg(samp + i);
         const float2 wi = __ldg(w + i);
-        const float4* src = reinterpret_cast<const float4*>(kT + m * planes4 + p0);
+        const float4* sp = reinterpret_cast<const float4*>(src + m * planes4);
+        float4 v[G];
 #pragma unroll
-        for (int q = 0; q < PG; q += 2) {
-            if (p0 + q < planes4) {
-                const float4 v = __ldg(src + q / 2);
-                const float2 z0 = cmul(make_float2(v.x, v.y), wi), z1 = cmul(make_float2(v.z, v.w), wi);
-                acc[q].x += z0.x;
-                acc[q].y += z0.y;
-                acc[q + 1].x += z1.x;
-                acc[q + 1].y += z1.y;
-            }
+        for (int g = 0; g < G; ++g)
+            v[g] = p + g * 2 * LPC < planes4 ? __ldg(sp + g * LPC) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            const float2 z0 = cmul(make_float2(v[g].x, v[g].y), wi), z1 = cmul(make_float2(v[g].z, v[g].w), wi);
+            a0[g].x += z0.x;
+            a0[g].y += z0.y;
+            a1[g].x += z1.x;
+            a1[g].y += z1.y;
         }
     }
 #pragma unroll
-    for (int q = 0; q < PG; ++q)
-        if (p0 + q < planes) grid[(long)(p0 + q) * cells + c] = acc[q];
+    for (int g = 0; g < G; ++g) {
+        const int pg = p + g * 2 * LPC;
+        if (pg < planes) grid[(long)pg * cells + c] = a0[g];
+        if (pg + 1 < planes) grid[(long)(pg + 1) * cells + c] = a1[g];
+    }
 }
 
 // one warp per long row; lanes stride the entries, a fixed-order shuffle tree adds them up (reproducible)
@@ -818,12 +879,15 @@ static int launch_interp_adj_csr(pdu_nufft_plan* p, const float2* kdata, float2*
         transpose_kdata_kernel<<<dim3((unsigned)cdiv(M, 32), (unsigned)cdiv(planes4, 32)), dim3(32, 8), 0, st>>>(
             kdata, kT_scratch, M, planes, planes4);
         PDU_LAUNCHED();
-        constexpr int PGT = 8;
-        dim3 gt((unsigned)cdiv(cells, 256), (unsigned)cdiv(planes, PGT));
-        interp_adj_csrT_kernel<PGT><<<gt, 256, 0, st>>>(kT_scratch, grid, v.row_ptr, v.samp, v.w, cells, planes, planes4);
-    } else {
-        interp_adj_csr_kernel<PG><<<g, 256, 0, st>>>(kdata, grid, v.row_ptr, v.samp, v.w, cells, M, planes);
+        const int long_blocks = sm_count();               // 8 warps each, grid-stride over the long rows
+        constexpr int LPC = 4, G = 2;                     // 16 planes per plane group
+        dim3 gt((unsigned)(long_blocks + cdiv(cells, 256 / LPC)), (unsigned)cdiv(planes4, 2 * LPC * G));
+        interp_adj_csrT_kernel<LPC, G><<<gt, 256, 0, st>>>(kT_scratch, grid, v.row_ptr, v.samp, v.w, v.n_long, v.long_rows, cells,
+                                                           planes, planes4, long_blocks);
+        PDU_LAUNCHED();
+        return PDU_OK;
     }
+    interp_adj_csr_kernel<PG><<<g, 256, 0, st>>>(kdata, grid, v.row_ptr, v.samp, v.w, cells, M, planes);
     PDU_LAUNCHED();
     dim3 gl((unsigned)(2 * sm_count()), (unsigned)cdiv(planes, PG));      // 8 warps per CTA, grid-stride over the long rows
     interp_adj_csr_long_kernel<PG><<<gl, 256, 0, st>>>(kdata, grid, v.row_ptr, v.n_long, v.long_rows, v.samp, v.w, cells, M,
@@ -1051,7 +1115,7 @@ static int nufft_adj_chunk(pdu_nufft_plan_t* p, const float2* kdata, float2* ima
     if (variant < 0) variant = ff_supported(p) ? 2 : (p->pfft_ok ? 1 : 0);      // see nufft_fwd_chunk
     if (variant == 2 && !ff_supported(p)) variant = 0;
     note_kernel(OP_NUFFT_ADJ, "%s + %s + crop_apod_kernel (%d planes of %dx%d, M=%ld)",
-                csr ? "transpose_kdata_kernel + interp_adj_csrT_kernel + interp_adj_csr_long_kernel (sorted gather)"
+                csr ? "transpose_kdata_kernel + interp_adj_csrT_kernel (sorted gather: 4 lanes per cell x 16 planes, long rows by warps)"
                     : "interp_adj_kernel (float2 atomics)",
                 variant == 2 ? "ff_rows_adj_kernel + ff_cols_adj_kernel (register-resident pruned FFT)"
                              : (variant == 1 && p->pfft_ok ? "pfft_rows_adj_kernel + pfft_cols_adj_kernel (generic pruned FFT)"

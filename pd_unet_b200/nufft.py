@@ -141,7 +141,14 @@ class _Plan:
             # adjoint scatters with atomics, which the fused gather still beats up to rho = 0.3
             rho = omega.shape[1] / float(self.grid_size[0] * self.grid_size[1])
             sparse = rho <= 0.15 or (adjoint and planes < 16 and rho <= 0.3)
-            if planes < 8 or not sparse or (adjoint and planes > 32 and self.grid_size[0] in (512, 640)):
+            # adjoint with many planes: the sorted gather (4 lanes per cell x 16 planes since r02) + FFT passes overtake the
+            # row-binned kernel -- from 64 planes everywhere, from 32 on the 512 and 1024 grids
+            # (tools/prof_nufft_adj_policy.py, generic / fused us: 256^2 x 32 / 48 / 64 planes 105 / 149 / 185 against
+            # 114 / 161 / 208; 512^2 413 / 609 / 794 against 484 / 689 / 949; 320^2 151 / 212 / 269 against 147 / 210 / 273;
+            # with coil maps at the configs[3] share, 64 planes of 640^2: 253 against 294)
+            g0 = self.grid_size[0]
+            many = adjoint and (planes >= 64 or (planes >= 32 and (g0 == 512 or g0 >= 1024)))
+            if planes < 8 or not sparse or many:
                 return None
         ent = self._entry(omega)
         if ent["bins"] is None:
