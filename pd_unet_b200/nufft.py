@@ -78,16 +78,15 @@ class _Plan:
         # the trajectory tensor's identity; a fixed trajectory is reused by every unrolled iteration / training step
         self._traj: "OrderedDict[tuple, dict]" = OrderedDict()
         self.traj_cache_bytes = 512 << 20
-        # "auto": the gather where it is faster (measured on B200: >= 16 planes per call; with fewer planes
-        # the atomic scatter wins -- 54 vs 138 us at 256 spokes x 1 plane, 165 vs 157 us at 16 planes, 597 vs
-        # 437 us at 64 planes); True: always (bit-reproducible adjoint); False: never.  Only the generic path
-        # (grids without a fused path, KbInterpAdjoint) looks at it.
+        # "auto": the gather where it is faster (measured on B200: >= 8 planes per call, see _csr_for; with fewer
+        # planes the atomic scatter wins -- 67 vs 180 us at 256 spokes x 1 plane); True: always (bit-reproducible
+        # adjoint); False: never.  Only the generic path (grids without a fused path, KbInterpAdjoint) looks at it.
         self.use_csr = "auto"
         # the fused path (csrc/nufft_fused.cu): True -- wherever the library has one for the grid; False -- never;
         # "auto" -- where it measured faster on B200 (tools/prof_nufft.py, profiles/r02_nufft_timings.txt): from 8 planes
         # per call up (below that a call is ~700 short-lived CTAs and the generic path's wide gathers win: 24 vs 36 us
-        # at 256^2 x 1 plane), and for the adjoint of the 512 / 640 grids only up to 32 planes (64 planes of 640^2:
-        # fused 326 us, generic sorted gather + register FFT 308 us; forward 226 vs 263 us)
+        # at 256^2 x 1 plane), and for the adjoint only while the plane count is moderate (_bins_for: 64 planes of
+        # 640^2 with coil maps: fused 294 us, generic sorted gather + register FFT 253 us; forward 206 vs 261 us)
         self.use_fused = "auto"
         self.fused_max_row = 4096     # "auto": no fused path for a trajectory whose heaviest grid row has more entries
 
@@ -171,7 +170,9 @@ class _Plan:
 
     def _csr_for(self, omega: torch.Tensor, planes: int = 1 << 30):
         """The sorted-gather form of the adjoint interpolator for this trajectory, built on first use."""
-        if self.use_csr is False or (self.use_csr == "auto" and planes < 16):
+        # from 8 planes (16 before the gather went to 4 lanes per cell; tools/prof_nufft_csr_policy.py, atomics / sorted us:
+        # 8 planes of 512^2 x 256 spokes 406 / 282, of 320^2 x 48 83 / 73, of 256^2 x 256 251 / 266; 4 planes 134 / 175)
+        if self.use_csr is False or (self.use_csr == "auto" and planes < 8):
             return None
         ent = self._entry(omega)
         if ent["csr"] is None:
