@@ -136,10 +136,12 @@ class _Plan:
         if self.use_fused == "auto":
             # measured policy (profiles/r02_nufft_timings.txt, profiles/r02_nufft_policy.txt): the row-binned kernels pay
             # per (sample, row) entry, so they win for sparse trajectories -- samples per grid cell rho <= 0.15
-            # (configs[3]: 0.075) -- and lose by 2 - 8 x for dense ones (rho >= 0.5); below 16 planes the generic
-            # adjoint scatters with atomics, which the fused gather still beats up to rho = 0.3
+            # (configs[3]: 0.075) -- and lose by 2 - 8 x for dense ones (rho >= 0.5).  (While the generic adjoint still
+            # scattered with atomics below 16 planes the fused one was also used up to rho = 0.3 there; against the
+            # sorted gather from 8 planes it no longer pays: rho = 0.25, 8 / 12 planes, generic / fused us: 128^2
+            # 48 / 60, 48 / 61; 256^2 91 / 110, 118 / 118; 512^2 294 / 253, 339 / 521.)
             rho = omega.shape[1] / float(self.grid_size[0] * self.grid_size[1])
-            sparse = rho <= 0.15 or (adjoint and planes < 16 and rho <= 0.3)
+            sparse = rho <= 0.15
             # adjoint with many planes: the sorted gather (4 lanes per cell x 16 planes since r02) + FFT passes overtake the
             # row-binned kernel -- from 64 planes everywhere, from 32 on the 512 and 1024 grids
             # (tools/prof_nufft_adj_policy.py, generic / fused us: 256^2 x 32 / 48 / 64 planes 105 / 149 / 185 against
