@@ -136,6 +136,32 @@ def test_sorted_gather_adjoint_matches_scatter_and_is_reproducible():
     assert rel_l2(xa, oracle.nufft_adjoint(k, 0.5 * om, spec, smaps=sm, norm="ortho")) <= TOL
 
 
+@pytest.mark.parametrize("planes", [(1, 4), (1, 5), (1, 7), (2, 4), (3, 4), (1, 16), (3, 7), (2, 16), (1, 33), (4, 16)])
+@pytest.mark.parametrize("dense", [False, True])
+def test_sorted_gather_shapes_over_plane_counts(planes, dense):
+    """Every instantiation of the sorted gather -- 2 lanes per cell (4 - 7 planes), 4 lanes x 8 planes (8 - 15, and dense
+    trajectories), 4 lanes x 16 planes (sparse trajectories from 16 planes, everything from 64), plane counts that are
+    not a multiple of the group size, and the long rows (k-space centre) inside the same launch -- against the oracle,
+    against the atomic scatter, and bit-reproducible."""
+    from pd_unet_b200 import _lib
+    B, Cc = planes
+    im = (40, 36)
+    spec = oracle.NufftSpec(im)
+    om = _traj(36 if dense else 7, 80)                # dense: 18 entries per cell and centre cells far above 32 entries
+    omd = torch.from_numpy(om).to(DEV)
+    k = seeded((B, Cc, om.shape[1]), 100 + B * Cc, complex_=True)
+    adj = pdu.KbNufftAdjoint(im)
+    adj._plan.use_csr, adj._plan.use_fused = True, False
+    a1 = adj(k.to(DEV), omd)
+    assert "interp_adj_csrT_kernel" in _lib.last_kernel("nufft_adj")
+    assert torch.equal(a1, adj(k.to(DEV), omd))
+    pick = [(0, 0), (B - 1, Cc - 1), (B // 2, Cc // 2)]
+    for b, c in pick:
+        assert rel_l2(a1[b:b + 1, c:c + 1], oracle.nufft_adjoint(k[b:b + 1, c:c + 1], om, spec)) <= TOL
+    adj._plan.use_csr = False
+    assert rel_l2(adj(k.to(DEV), omd), a1) <= 2e-6    # every plane agrees with the scatter
+
+
 @pytest.mark.parametrize("im", [(32, 32), (48, 40), (320, 320), (256, 256), (250, 250)])
 def test_pruned_fft_and_cufft_paths_agree(im):
     """variant 1: the own pruned shared-memory FFT; variant 0 (default, currently faster): pad + cuFFT.  Same
