@@ -14,6 +14,7 @@
 // Grid offsets and table indices are computed with explicitly rounded float32 operations, the same
 // sequence oracle/nufft.py::_tap_indices_f32 performs, so both read the same table entries.
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 #include <math.h>
 
@@ -466,6 +467,58 @@ __global__ void __launch_bounds__(SEQ* FastFft<K>::TPS)
     ff_transform<K, 4, true, false, true, false, false, true>(buf + s * F::template pitch<4>(), tw, t, ld, st);
 }
 
+// The row pass on the COMPACT gridded samples (interp_adj_csrT_kernel<.., true>): a thread finds each of its eight inputs
+// through the occupancy word of the cell and the compact index at the word's start (two cached loads + a population
+// count) and loads the value only where the cell is non-empty.  Against the dense form the gather writes and this pass
+// reads one value per non-empty cell instead of K per row.  (First version: non-empty cells spread over a zeroed
+// shared-memory row and the transform started from there -- three more CTA barriers and the extra shared-memory round
+// trip made the pass slower than the dense one, 86 against 72 us at 64 planes of 640^2 in spite of 94 instead of 210 MB.)
+template <int K, int SEQ>
+__global__ void __launch_bounds__(SEQ* FastFft<K>::TPS)
+    ff_rows_adj_compact_kernel(const float2* __restrict__ gridc, float2* __restrict__ T, const float2* __restrict__ tw_g,
+                               const unsigned* __restrict__ nz_mask, const int* __restrict__ nz_wrank, NufftDims d) {
+    using F = FastFft<K>;
+    constexpr int N = K / 2, TPS = F::TPS, NS3 = F::NS3;
+    static_assert(K % 32 == 0, "a row is whole occupancy words");
+    float2* buf = pf_smem<float2>();
+    float2* tw = buf + SEQ * F::template pitch<4>();
+    const int tid = threadIdx.x, s = tid / TPS, t = tid - s * TPS;
+    const int p = blockIdx.y;
+    const int row = blockIdx.x * SEQ + s;
+    for (int i = tid; i < K; i += SEQ * TPS) tw[i] = __ldg(tw_g + i);
+    const bool live = row < K;
+    const float2* src = gridc + (long)p * K * K;
+    const unsigned* mrow = nz_mask + row * (K / 32);
+    const int* wrow = nz_wrank + row * (K / 32);
+    float2* dst = T + ((long)p * K + row) * N;
+    // branch-free: an empty cell reads the row's first value (one shared sector) and discards it, so that the eight index
+    // pairs and then the eight values are in flight together (with a branch per input the loads went out one at a time)
+    float2 val[8];
+    {
+        unsigned m[8];
+        int wr[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const int wd = (t + r * TPS) >> 5;
+            m[r] = live ? __ldg(mrow + wd) : 0u;
+            wr[r] = live ? __ldg(wrow + wd) : 0;
+        }
+        const int first = live ? __ldg(wrow) : 0;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const unsigned bit = 1u << ((t + r * TPS) & 31);
+            const bool on = (m[r] & bit) != 0;
+            const float2 x = __ldcs(src + (on ? wr[r] + __popc(m[r] & (bit - 1)) : first));
+            val[r] = on ? x : make_float2(0.f, 0.f);
+        }
+    }
+    auto ld = [&](int r) { return val[r]; };
+    auto st = [&](int j, int r, float2 v) {
+        if (live) __stcs(dst + j + r * NS3, v);
+    };
+    ff_transform<K, 4, true, false, true, false, false, true>(buf + s * F::template pitch<4>(), tw, t, ld, st);
+}
+
 template <int K, int SEQ>
 __global__ void __launch_bounds__(SEQ* FastFft<K>::TPS, K <= 640 ? 3 : 1)
     ff_cols_adj_kernel(const float2* __restrict__ T, float2* __restrict__ U, const float2* __restrict__ tw_g, NufftDims d) {
@@ -515,16 +568,21 @@ static int ff_forward(pdu_nufft_plan* p, const float2* image, const float2* smap
     return PDU_OK;
 }
 
+// nz_mask / nz_wrank: the compact form of the gridded samples (CsrView), nullptr for dense K x K planes
 template <int K>
-static int ff_adjoint(pdu_nufft_plan* p, const float2* grid, float2* T, float2* U, int planes, cudaStream_t st) {
+static int ff_adjoint(pdu_nufft_plan* p, const float2* grid, float2* T, float2* U, int planes, cudaStream_t st,
+                      const unsigned* nz_mask = nullptr, const int* nz_wrank = nullptr) {
     const NufftDims d = dims_of(p);
     constexpr int FF_SEQ_COLS = ff_seq_cols<K>();
     auto rows = ff_rows_adj_kernel<K, FF_SEQ_ROWS>;
+    auto rows_c = ff_rows_adj_compact_kernel<K, FF_SEQ_ROWS>;
     auto cols = ff_cols_adj_kernel<K, FF_SEQ_COLS>;
     PDU_CUDA((ensure_dyn_smem<ff_rows_adj_kernel<K, FF_SEQ_ROWS>>((int)ff_smem_bytes<K>(FF_SEQ_ROWS))));
+    PDU_CUDA((ensure_dyn_smem<ff_rows_adj_compact_kernel<K, FF_SEQ_ROWS>>((int)ff_smem_bytes<K>(FF_SEQ_ROWS))));
     PDU_CUDA((ensure_dyn_smem<ff_cols_adj_kernel<K, FF_SEQ_COLS>>((int)ff_smem_bytes<K>(FF_SEQ_COLS))));
-    rows<<<dim3((unsigned)cdiv(p->k0, FF_SEQ_ROWS), (unsigned)planes), FF_SEQ_ROWS * FastFft<K>::TPS, ff_smem_bytes<K>(FF_SEQ_ROWS), st>>>(
-        grid, T, p->d_w1, d);
+    const dim3 gr((unsigned)cdiv(p->k0, FF_SEQ_ROWS), (unsigned)planes);
+    if (nz_mask) rows_c<<<gr, FF_SEQ_ROWS * FastFft<K>::TPS, ff_smem_bytes<K>(FF_SEQ_ROWS), st>>>(grid, T, p->d_w1, nz_mask, nz_wrank, d);
+    else rows<<<gr, FF_SEQ_ROWS * FastFft<K>::TPS, ff_smem_bytes<K>(FF_SEQ_ROWS), st>>>(grid, T, p->d_w1, d);
     PDU_LAUNCHED();
     cols<<<dim3((unsigned)cdiv(p->n1, FF_SEQ_COLS), (unsigned)planes), FF_SEQ_COLS * FastFft<K>::TPS, ff_smem_bytes<K>(FF_SEQ_COLS), st>>>(
         T, U, p->d_w0, d);
@@ -556,7 +614,11 @@ constexpr int CSR_LONG = 32;      // rows with more entries than this are summed
 struct CsrView {
     int* row_ptr;
     int* n_long;       // [1] number of long rows
-    int* long_rows;    // [cells] their cell indices (first n_long valid)
+    int* long_rows;    // [cells] their indices in nz_cell (first n_long valid)
+    int* nz_cell;      // [cells] the non-empty cells in increasing order (first nz_ptr[k0] valid)
+    int* nz_ptr;       // [k0 + 1] grid row r owns nz_cell[nz_ptr[r] .. nz_ptr[r + 1])
+    unsigned* nz_mask; // [ceil(cells / 32)] bit c % 32 of word c / 32: cell c is non-empty
+    int* nz_wrank;     // [ceil(cells / 32)] compact index of the first non-empty cell at or after cell 32 w
     int* samp;
     float2* w;
     // build scratch
@@ -565,6 +627,7 @@ struct CsrView {
     unsigned* key_out;
     unsigned* id_out;
     float2* w_unsorted;
+    int* rank;         // [cells + 1] number of non-empty cells before cell c
     void* cub_tmp;
     size_t cub_bytes;
     size_t total;
@@ -578,6 +641,10 @@ static CsrView csr_layout(const pdu_nufft_plan* p, long M, void* base, bool with
     v.row_ptr = (int*)take((cells + 1) * 4);
     v.n_long = (int*)take(4);
     v.long_rows = (int*)take(cells * 4);
+    v.nz_cell = (int*)take(cells * 4);
+    v.nz_ptr = (int*)take(((size_t)p->k0 + 1) * 4);
+    v.nz_mask = (unsigned*)take((cells + 31) / 32 * 4);
+    v.nz_wrank = (int*)take((cells + 31) / 32 * 4);
     v.samp = (int*)take(n * 4);
     v.w = (float2*)take(n * 8);
     v.key_in = (unsigned*)take(n * 4);
@@ -585,12 +652,16 @@ static CsrView csr_layout(const pdu_nufft_plan* p, long M, void* base, bool with
     v.key_out = (unsigned*)take(n * 4);
     v.id_out = (unsigned*)take(n * 4);
     v.w_unsorted = (float2*)take(n * 8);
+    v.rank = (int*)take((cells + 1) * 4);
     v.cub_bytes = 0;
     v.cub_tmp = nullptr;
     v.total = off;
-    if (!with_scratch) return v;      // applying the matrix only needs the three arrays above
+    if (!with_scratch) return v;      // applying the matrix only needs the arrays before key_in
     cub::DeviceRadixSort::SortPairs(nullptr, v.cub_bytes, (const unsigned*)nullptr, (unsigned*)nullptr, (const unsigned*)nullptr,
                                     (unsigned*)nullptr, (int)n);
+    size_t scan_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (const int*)nullptr, (int*)nullptr, (int)(cells + 1));
+    if (scan_bytes > v.cub_bytes) v.cub_bytes = scan_bytes;
     v.cub_tmp = take(v.cub_bytes);
     v.total = off;
     return v;
@@ -648,12 +719,38 @@ __global__ void __launch_bounds__(256)
     }
 }
 
-// rows too long for one thread (the k-space centre of a radial trajectory collects every spoke)
-__global__ void __launch_bounds__(256)
-    csr_long_rows_kernel(const int* __restrict__ row_ptr, int* __restrict__ n_long, int* __restrict__ long_rows, long cells) {
+// A sparse trajectory leaves most of the oversampled grid empty (48 radial spokes on 640^2: 61 % of the cells), so the
+// NUFFT adjoint keeps the gridded samples COMPACT between the gather and the row pass: one value per non-empty cell, in
+// cell order.  flag[c] = 1 for a non-empty cell (c < cells), 0 for c == cells; its exclusive sum is the compact index.
+__global__ void __launch_bounds__(256) csr_flag_kernel(const int* __restrict__ row_ptr, int* __restrict__ flag, long cells) {
     const long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= cells) return;
-    if (row_ptr[c + 1] - row_ptr[c] > CSR_LONG) long_rows[atomicAdd(n_long, 1)] = (int)c;
+    if (c <= cells) flag[c] = (c < cells && row_ptr[c + 1] > row_ptr[c]) ? 1 : 0;
+}
+// the compact list itself, the first compact index of every grid row, and the rows too long for one thread (the k-space
+// centre of a radial trajectory collects every spoke) by their compact index
+// 32 cells per word: the occupancy bits and the compact index at the word's start -- the row pass finds a cell's value
+// with two cached loads and a population count
+__global__ void __launch_bounds__(256)
+    csr_mask_kernel(const int* __restrict__ row_ptr, const int* __restrict__ rank, unsigned* __restrict__ mask,
+                    int* __restrict__ wrank, long cells) {
+    const long wd = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (wd * 32 >= cells) return;
+    unsigned m = 0;
+    for (int b = 0; b < 32 && wd * 32 + b < cells; ++b)
+        if (row_ptr[wd * 32 + b + 1] > row_ptr[wd * 32 + b]) m |= 1u << b;
+    mask[wd] = m;
+    wrank[wd] = rank[wd * 32];
+}
+__global__ void __launch_bounds__(256)
+    csr_compact_kernel(const int* __restrict__ row_ptr, const int* __restrict__ rank, int* __restrict__ nz_cell,
+                       int* __restrict__ nz_ptr, int* __restrict__ n_long, int* __restrict__ long_rows, long cells, int k0, int k1) {
+    const long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c > cells) return;
+    if (c % k1 == 0) nz_ptr[c / k1] = rank[c];          // c == cells: nz_ptr[k0] = the number of non-empty cells
+    if (c == cells) return;
+    const int len = row_ptr[c + 1] - row_ptr[c];
+    if (len > 0) nz_cell[rank[c]] = (int)c;
+    if (len > CSR_LONG) long_rows[atomicAdd(n_long, 1)] = rank[c];
 }
 
 // one thread per grid cell, PG planes per thread (an entry is loaded once for all of them)
@@ -721,18 +818,23 @@ __global__ void __launch_bounds__(256)
 // one warp per row, lanes striding the entries and a fixed-order shuffle tree adding them up, exactly as
 // interp_adj_csr_long_kernel does from the planar samples -- inside this launch, and scheduled first, the serial walk
 // over a centre cell's ~1700 entries (18 us as a kernel of its own) is hidden behind the short cells.
-template <int LPC, int G>
+// COMPACT: one value per NON-EMPTY cell (nz_cell, csr_compact_kernel) at grid[plane * cells + compact index] -- the row
+// pass (ff_rows_adj_compact_kernel) spreads them over its shared-memory row; otherwise the dense K x K planes.
+template <int LPC, int G, bool COMPACT>
 __global__ void __launch_bounds__(256)
     interp_adj_csrT_kernel(const float2* __restrict__ kT, float2* __restrict__ grid, const int* __restrict__ row_ptr,
                            const int* __restrict__ samp, const float2* __restrict__ w, const int* __restrict__ n_long,
-                           const int* __restrict__ long_rows, long cells, int planes, int planes4, int long_blocks) {
+                           const int* __restrict__ long_rows, const int* __restrict__ nz_cell, const int* __restrict__ n_nz,
+                           long cells, int planes, int planes4, int long_blocks) {
     constexpr int CPB = 256 / LPC;
     if ((int)blockIdx.x < long_blocks) {
         constexpr int PG = 2 * LPC * G;                   // planes of this plane group
         const int lane = threadIdx.x & 31, p0 = blockIdx.y * PG;
         const int nl = __ldg(n_long);
         for (int r = blockIdx.x * 8 + (threadIdx.x >> 5); r < nl; r += long_blocks * 8) {
-            const long c = __ldg(long_rows + r);
+            const int ci = __ldg(long_rows + r);
+            const long c = __ldg(nz_cell + ci);
+            const long slot = COMPACT ? (long)ci : c;     // where the cell's value goes inside a plane
             const int beg = __ldg(row_ptr + c), end = __ldg(row_ptr + c + 1);
             // four planes at a time: eight accumulators, so that this rare path does not set the kernel's register count
 #pragma unroll 1
@@ -761,16 +863,17 @@ __global__ void __launch_bounds__(256)
                         acc[q].x += __shfl_xor_sync(0xffffffffu, acc[q].x, o);
                         acc[q].y += __shfl_xor_sync(0xffffffffu, acc[q].y, o);
                     }
-                    if (lane == 0 && p0 + h + q < planes) grid[(long)(p0 + h + q) * cells + c] = acc[q];
+                    if (lane == 0 && p0 + h + q < planes) grid[(long)(p0 + h + q) * cells + slot] = acc[q];
                 }
             }
         }
         return;
     }
     const int sub = threadIdx.x % LPC;
-    const long c = (long)(blockIdx.x - long_blocks) * CPB + threadIdx.x / LPC;
+    const long o = (long)(blockIdx.x - long_blocks) * CPB + threadIdx.x / LPC;
     const int p = blockIdx.y * (2 * LPC * G) + 2 * sub;   // first of this lane's planes; the others follow 2 LPC apart
-    if (c >= cells || p >= planes4) return;
+    if (o >= (COMPACT ? (long)__ldg(n_nz) : cells) || p >= planes4) return;
+    const long c = COMPACT ? (long)__ldg(nz_cell + o) : o;
     const int beg = __ldg(row_ptr + c), end = __ldg(row_ptr + c + 1);
     if (end - beg > CSR_LONG) return;                     // the long-row CTAs own this cell
     float2 a0[G], a1[G];
@@ -797,8 +900,8 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
     for (int g = 0; g < G; ++g) {
         const int pg = p + g * 2 * LPC;
-        if (pg < planes) grid[(long)pg * cells + c] = a0[g];
-        if (pg + 1 < planes) grid[(long)(pg + 1) * cells + c] = a1[g];
+        if (pg < planes) grid[(long)pg * cells + o] = a0[g];
+        if (pg + 1 < planes) grid[(long)(pg + 1) * cells + o] = a1[g];
     }
 }
 
@@ -806,14 +909,14 @@ __global__ void __launch_bounds__(256)
 template <int PG>
 __global__ void __launch_bounds__(256)
     interp_adj_csr_long_kernel(const float2* __restrict__ kdata, float2* __restrict__ grid, const int* __restrict__ row_ptr,
-                               const int* __restrict__ n_long, const int* __restrict__ long_rows,
+                               const int* __restrict__ n_long, const int* __restrict__ long_rows, const int* __restrict__ nz_cell,
                                const int* __restrict__ samp, const float2* __restrict__ w, long cells, long M, int planes) {
     const int lane = threadIdx.x & 31;
     const int warps = (gridDim.x * blockDim.x) >> 5;
     const int p0 = blockIdx.y * PG;
     const int nl = __ldg(n_long);
     for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < nl; r += warps) {
-        const long c = __ldg(long_rows + r);
+        const long c = __ldg(nz_cell + __ldg(long_rows + r));
         const int beg = __ldg(row_ptr + c), end = __ldg(row_ptr + c + 1);
         float2 acc[PG];
 #pragma unroll
@@ -862,14 +965,24 @@ static int csr_build(pdu_nufft_plan* p, const float* omega, long M, void* buf, s
                                                                  cells, p->J * p->J);
     PDU_LAUNCHED();
     PDU_CUDA(cudaMemsetAsync(v.n_long, 0, 4, st));
-    csr_long_rows_kernel<<<(unsigned)cdiv(cells, 256), 256, 0, st>>>(v.row_ptr, v.n_long, v.long_rows, cells);
+    int* flag = (int*)v.key_out;                        // the sorted keys have been consumed by csr_finish_kernel
+    int* flag_buf = n >= cells + 1 ? flag : v.rank;     // (a trajectory with fewer entries than cells: scan in place)
+    csr_flag_kernel<<<(unsigned)cdiv(cells + 1, 256), 256, 0, st>>>(v.row_ptr, flag_buf, cells);
+    PDU_LAUNCHED();
+    PDU_CUDA(cub::DeviceScan::ExclusiveSum(v.cub_tmp, v.cub_bytes, flag_buf, v.rank, (int)(cells + 1), st));
+    count_launch(2);
+    csr_compact_kernel<<<(unsigned)cdiv(cells + 1, 256), 256, 0, st>>>(v.row_ptr, v.rank, v.nz_cell, v.nz_ptr, v.n_long, v.long_rows,
+                                                                      cells, p->k0, p->k1);
+    PDU_LAUNCHED();
+    csr_mask_kernel<<<(unsigned)cdiv(cdiv(cells, 32), 256), 256, 0, st>>>(v.row_ptr, v.rank, v.nz_mask, v.nz_wrank, cells);
     PDU_LAUNCHED();
     return PDU_OK;
 }
 
 // kT_scratch (optional): room for M * round_up(planes, 4) float2 -- the plane-interleaved copy of kdata
+// compact (with kT_scratch only): see interp_adj_csrT_kernel; *compact is cleared when the dense form was written
 static int launch_interp_adj_csr(pdu_nufft_plan* p, const float2* kdata, float2* grid, const void* csr, int planes, long M,
-                                 cudaStream_t st, float2* kT_scratch = nullptr) {
+                                 cudaStream_t st, float2* kT_scratch = nullptr, bool* compact = nullptr) {
     const CsrView v = csr_layout(p, M, const_cast<void*>(csr), false);
     const long cells = (long)p->k0 * p->k1;
     constexpr int PG = 4;
@@ -880,8 +993,22 @@ static int launch_interp_adj_csr(pdu_nufft_plan* p, const float2* kdata, float2*
             kdata, kT_scratch, M, planes, planes4);
         PDU_LAUNCHED();
         const int long_blocks = sm_count();               // 8 warps each, grid-stride over the long rows
-#define PDU_CSRT(L, G_) interp_adj_csrT_kernel<L, G_><<<dim3((unsigned)(long_blocks + cdiv(cells, 256 / L)), (unsigned)cdiv(planes4, 2 * L * G_)), 256, 0, st>>>( \
-        kT_scratch, grid, v.row_ptr, v.samp, v.w, v.n_long, v.long_rows, cells, planes, planes4, long_blocks)
+        const bool cpt = compact && *compact;
+        // compact: the grid is sized for the non-empty cells the trajectory can have at most (min(cells, entries)); threads
+        // past the actual count (nz_ptr[k0], on the device) leave at once
+        const long slots = cpt ? std::min(cells, M * p->J * p->J) : cells;
+#define PDU_CSRT(L, G_)                                                                                                     \
+    do {                                                                                                                    \
+        dim3 gt_((unsigned)(long_blocks + cdiv(slots, 256 / L)), (unsigned)cdiv(planes4, 2 * L * G_));                       \
+        if (cpt)                                                                                                            \
+            interp_adj_csrT_kernel<L, G_, true><<<gt_, 256, 0, st>>>(kT_scratch, grid, v.row_ptr, v.samp, v.w, v.n_long,      \
+                                                                    v.long_rows, v.nz_cell, v.nz_ptr + p->k0, cells, planes, \
+                                                                    planes4, long_blocks);                                  \
+        else                                                                                                                \
+            interp_adj_csrT_kernel<L, G_, false><<<gt_, 256, 0, st>>>(kT_scratch, grid, v.row_ptr, v.samp, v.w, v.n_long,     \
+                                                                     v.long_rows, v.nz_cell, v.nz_ptr + p->k0, cells, planes,\
+                                                                     planes4, long_blocks);                                 \
+    } while (0)
         // 16 planes per plane group for sparse trajectories (few entries per cell: the index loads are a large part of the
         // loop) and from 64 planes on; 8 otherwise (measured, 16 / 32 planes: 320^2 x 48 spokes 91 / 151 against 97 / 165 us,
         // 512^2 x 96 226 / 425 against 253 / 485; but 320^2 x 160 spokes 228 / 325 against 184 / 312)
@@ -893,11 +1020,12 @@ static int launch_interp_adj_csr(pdu_nufft_plan* p, const float2* kdata, float2*
         PDU_LAUNCHED();
         return PDU_OK;
     }
+    if (compact) *compact = false;
     interp_adj_csr_kernel<PG><<<g, 256, 0, st>>>(kdata, grid, v.row_ptr, v.samp, v.w, cells, M, planes);
     PDU_LAUNCHED();
     dim3 gl((unsigned)(2 * sm_count()), (unsigned)cdiv(planes, PG));      // 8 warps per CTA, grid-stride over the long rows
-    interp_adj_csr_long_kernel<PG><<<gl, 256, 0, st>>>(kdata, grid, v.row_ptr, v.n_long, v.long_rows, v.samp, v.w, cells, M,
-                                                       planes);
+    interp_adj_csr_long_kernel<PG><<<gl, 256, 0, st>>>(kdata, grid, v.row_ptr, v.n_long, v.long_rows, v.nz_cell, v.samp, v.w,
+                                                       cells, M, planes);
     PDU_LAUNCHED();
     return PDU_OK;
 }
@@ -1104,12 +1232,19 @@ static int nufft_adj_chunk(pdu_nufft_plan_t* p, const float2* kdata, float2* ima
                            cudaStream_t st) {
     const int planes = batch * coils;
     int rc;
+    int variant = option(OPT_NUFFT_ADJ);
+    if (variant < 0) variant = ff_supported(p) ? 2 : (p->pfft_ok ? 1 : 0);      // see nufft_fwd_chunk
+    if (variant == 2 && !ff_supported(p)) variant = 0;
+    // the gridded samples stay compact (non-empty cells only) between the sorted gather and the register FFT's row pass
+    // (only for sparse trajectories, at most 8 interpolation entries per cell on average: 48 radial spokes on 640^2 have
+    //  2.7 and leave 61 % of the cells empty; a dense trajectory fills the grid and would only pay for the indirection)
+    bool compact = csr && variant == 2 && (double)m * p->J * p->J <= 8.0 * (double)p->k0 * p->k1;
     if (csr) {
         // the FFT's intermediate buffer is free until the transform starts: it holds the plane-interleaved kdata
         float2* mid = grid + (long)planes * p->k0 * p->k1;
         const long mid_elems = (long)planes * std::max((long)p->n0 * p->k1, (long)p->k0 * p->n1);
         const bool fits = m * (long)((planes + 3) & ~3) <= mid_elems;
-        rc = launch_interp_adj_csr(p, kdata, grid, csr, planes, m, st, fits ? mid : nullptr);   // writes every cell: no memset
+        rc = launch_interp_adj_csr(p, kdata, grid, csr, planes, m, st, fits ? mid : nullptr, &compact);   // writes every cell: no memset
     } else {
         PDU_CUDA(cudaMemsetAsync(grid, 0, (size_t)planes * p->k0 * p->k1 * sizeof(float2), st));
         rc = launch_interp_adj(p, kdata, grid, omega, planes, m, st);
@@ -1117,25 +1252,27 @@ static int nufft_adj_chunk(pdu_nufft_plan_t* p, const float2* kdata, float2* ima
     if (rc) return rc;
     const int out_planes = smaps ? batch : planes;
     const long total = (long)out_planes * p->n0 * p->n1;
-    int variant = option(OPT_NUFFT_ADJ);
-    if (variant < 0) variant = ff_supported(p) ? 2 : (p->pfft_ok ? 1 : 0);      // see nufft_fwd_chunk
-    if (variant == 2 && !ff_supported(p)) variant = 0;
     note_kernel(OP_NUFFT_ADJ, "%s + %s + crop_apod_kernel (%d planes of %dx%d, M=%ld)",
-                csr ? "transpose_kdata_kernel + interp_adj_csrT_kernel (sorted gather: 4 lanes per cell x 16 planes, long rows by warps)"
+                csr ? (compact ? "transpose_kdata_kernel + interp_adj_csrT_kernel (sorted gather: 4 lanes per cell x 16 planes, long rows by warps, non-empty cells only)"
+                               : "transpose_kdata_kernel + interp_adj_csrT_kernel (sorted gather: 4 lanes per cell x 16 planes, long rows by warps)")
                     : "interp_adj_kernel (float2 atomics)",
-                variant == 2 ? "ff_rows_adj_kernel + ff_cols_adj_kernel (register-resident pruned FFT)"
+                variant == 2 ? (compact ? "ff_rows_adj_compact_kernel + ff_cols_adj_kernel (register-resident pruned FFT)"
+                                        : "ff_rows_adj_kernel + ff_cols_adj_kernel (register-resident pruned FFT)")
                              : (variant == 1 && p->pfft_ok ? "pfft_rows_adj_kernel + pfft_cols_adj_kernel (generic pruned FFT)"
                                                            : "cuFFT C2C"),
                 planes, p->k0, p->k1, m);
     if (variant == 2) {
         float2* T = grid + (long)planes * p->k0 * p->k1;
         float2* U = T + (long)planes * std::max((long)p->n0 * p->k1, (long)p->k0 * p->n1);
+        const CsrView cv = compact ? csr_layout(p, m, const_cast<void*>(csr), false) : CsrView{};
+        const unsigned* nzc = compact ? cv.nz_mask : nullptr;
+        const int* nzp = compact ? cv.nz_wrank : nullptr;
         switch (p->k0) {
-            case 256: rc = ff_adjoint<256>(p, grid, T, U, planes, st); break;
-            case 512: rc = ff_adjoint<512>(p, grid, T, U, planes, st); break;
-            case 640: rc = ff_adjoint<640>(p, grid, T, U, planes, st); break;
-            case 1024: rc = ff_adjoint<1024>(p, grid, T, U, planes, st); break;
-            default: rc = ff_adjoint<2048>(p, grid, T, U, planes, st); break;
+            case 256: rc = ff_adjoint<256>(p, grid, T, U, planes, st, nzc, nzp); break;
+            case 512: rc = ff_adjoint<512>(p, grid, T, U, planes, st, nzc, nzp); break;
+            case 640: rc = ff_adjoint<640>(p, grid, T, U, planes, st, nzc, nzp); break;
+            case 1024: rc = ff_adjoint<1024>(p, grid, T, U, planes, st, nzc, nzp); break;
+            default: rc = ff_adjoint<2048>(p, grid, T, U, planes, st, nzc, nzp); break;
         }
         if (rc) return rc;
         NufftDims dc = dims_of(p);          // the cropped result is a dense [n0][n1] "grid"
