@@ -18,3 +18,6 @@ timeout 600 python tools/prof_ops.py 5 > gpurun_out/ops.log 2>&1
 timeout 600 python tools/prof_nufft.py 7 all --variants > gpurun_out/nufft_variants.log 2>&1; grep -c . gpurun_out/nufft_variants.log
 timeout 900 python tools/sweep.py gpurun_out/r02_sweep.md > gpurun_out/sweep.log 2>&1; echo "sweep rc=$?"
 timeout 600 python tools/parity_report.py gpurun_out/r02_parity.md > gpurun_out/parity.log 2>&1; echo "parity rc=$?"; tail -12 gpurun_out/r02_parity.md
+timeout 300 python tools/prof_nufft.py 1 "cfg4 320^2 c8 b8" > gpurun_out/plain_nufft.log 2>&1 && \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"ff_rows_adj|ff_cols_adj|interp_adj_csrT|crop_apod|transpose_kdata" -s 5 -c 5 -f -o gpurun_out/r02_nufft_adj2 python tools/prof_nufft.py 1 "cfg4 320^2 c8 b8" > gpurun_out/ncu_r02_nufft_adj2.log 2>&1
+ls -la gpurun_out/r02_nufft_adj2.ncu-rep
