@@ -610,7 +610,11 @@ static int pf_set_smem(Kern kern, size_t bytes) {
 // that touch it and their conjugated Kaiser-Bessel weights, phase included), sorted by cell with a
 // stable radix sort, and applied as a gather: no atomics, no memset, bit-reproducible.
 //   csr buffer:  row_ptr int32[cells + 1] | samp int32[n] | w float2[n] | build scratch      (n = M J^2)
-constexpr int CSR_LONG = 32;      // rows with more entries than this are summed by a whole warp
+// Rows with more entries than this are summed by a whole warp (lanes stride the entries: coalesced index and weight
+// loads).  A bound that follows the trajectory's average, 4 x entries per cell, so that dense trajectories keep their
+// cells on the lane-group loop, was measured and lost (128^2 x 256 spokes, 8 planes: 218 against 159 us): the warp form
+// is the better one for every row of 32 entries or more; what dense trajectories need is enough warp-per-row CTAs.
+static int csr_long_threshold(const pdu_nufft_plan*, long) { return 32; }
 
 struct CsrView {
     int* row_ptr;
@@ -744,21 +748,23 @@ __global__ void __launch_bounds__(256)
 }
 __global__ void __launch_bounds__(256)
     csr_compact_kernel(const int* __restrict__ row_ptr, const int* __restrict__ rank, int* __restrict__ nz_cell,
-                       int* __restrict__ nz_ptr, int* __restrict__ n_long, int* __restrict__ long_rows, long cells, int k0, int k1) {
+                       int* __restrict__ nz_ptr, int* __restrict__ n_long, int* __restrict__ long_rows, long cells, int k0, int k1,
+                       int long_thresh) {
     const long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (c > cells) return;
     if (c % k1 == 0) nz_ptr[c / k1] = rank[c];          // c == cells: nz_ptr[k0] = the number of non-empty cells
     if (c == cells) return;
     const int len = row_ptr[c + 1] - row_ptr[c];
     if (len > 0) nz_cell[rank[c]] = (int)c;
-    if (len > CSR_LONG) long_rows[atomicAdd(n_long, 1)] = rank[c];
+    if (len > long_thresh) long_rows[atomicAdd(n_long, 1)] = rank[c];
 }
 
 // one thread per grid cell, PG planes per thread (an entry is loaded once for all of them)
 template <int PG>
 __global__ void __launch_bounds__(256)
     interp_adj_csr_kernel(const float2* __restrict__ kdata, float2* __restrict__ grid, const int* __restrict__ row_ptr,
-                          const int* __restrict__ samp, const float2* __restrict__ w, long cells, long M, int planes) {
+                          const int* __restrict__ samp, const float2* __restrict__ w, long cells, long M, int planes,
+                          int long_thresh) {
     const long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= cells) return;
     const int p0 = blockIdx.y * PG;
@@ -766,7 +772,7 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
     for (int q = 0; q < PG; ++q) acc[q] = make_float2(0.f, 0.f);
     const int beg = __ldg(row_ptr + c), end = __ldg(row_ptr + c + 1);
-    if (end - beg > CSR_LONG) return;                     // interp_adj_csr_long_kernel owns this cell
+    if (end - beg > long_thresh) return;                  // interp_adj_csr_long_kernel owns this cell
     for (int i = beg; i < end; ++i) {
         const long m = __ldg(samp + i);
         const float2 wi = __ldg(w + i);
@@ -815,7 +821,7 @@ __global__ void __launch_bounds__(256)
 // (8, 2) 259, (8, 4) 263, (2, 4) 266, (2, 8) 296 us, r01's form with the long rows as a kernel of their own ~ 300;
 // two or four neighbouring cells per thread with 16-byte stores lost to the merged loop's divergence (310 / 361 us).
 // Entries are summed in the same order per (cell, plane) whatever the shape: bit-identical results.
-// The first long_blocks CTAs of every plane group take the long rows (the k-space centre: more than CSR_LONG entries),
+// The first long_blocks CTAs of every plane group take the long rows (the k-space centre: more than csr_long_threshold entries),
 // one warp per row, lanes striding the entries and a fixed-order shuffle tree adding them up, exactly as
 // interp_adj_csr_long_kernel does from the planar samples -- inside this launch, and scheduled first, the serial walk
 // over a centre cell's ~1700 entries (18 us as a kernel of its own) is hidden behind the short cells.
@@ -826,7 +832,7 @@ __global__ void __launch_bounds__(256)
     interp_adj_csrT_kernel(const float2* __restrict__ kT, float2* __restrict__ grid, const int* __restrict__ row_ptr,
                            const int* __restrict__ samp, const float2* __restrict__ w, const int* __restrict__ n_long,
                            const int* __restrict__ long_rows, const int* __restrict__ nz_cell, const int* __restrict__ n_nz,
-                           long cells, int planes, int planes4, int long_blocks) {
+                           long cells, int planes, int planes4, int long_blocks, int long_thresh) {
     constexpr int CPB = 256 / LPC;
     if ((int)blockIdx.x < long_blocks) {
         constexpr int PG = 2 * LPC * G;                   // planes of this plane group
@@ -876,7 +882,7 @@ __global__ void __launch_bounds__(256)
     if (o >= (COMPACT ? (long)__ldg(n_nz) : cells) || p >= planes4) return;
     const long c = COMPACT ? (long)__ldg(nz_cell + o) : o;
     const int beg = __ldg(row_ptr + c), end = __ldg(row_ptr + c + 1);
-    if (end - beg > CSR_LONG) return;                     // the long-row CTAs own this cell
+    if (end - beg > long_thresh) return;                  // the long-row CTAs own this cell
     float2 a0[G], a1[G];
 #pragma unroll
     for (int g = 0; g < G; ++g) a0[g] = a1[g] = make_float2(0.f, 0.f);
@@ -973,7 +979,7 @@ static int csr_build(pdu_nufft_plan* p, const float* omega, long M, void* buf, s
     PDU_CUDA(cub::DeviceScan::ExclusiveSum(v.cub_tmp, v.cub_bytes, flag_buf, v.rank, (int)(cells + 1), st));
     count_launch(2);
     csr_compact_kernel<<<(unsigned)cdiv(cells + 1, 256), 256, 0, st>>>(v.row_ptr, v.rank, v.nz_cell, v.nz_ptr, v.n_long, v.long_rows,
-                                                                      cells, p->k0, p->k1);
+                                                                      cells, p->k0, p->k1, csr_long_threshold(p, M));
     PDU_LAUNCHED();
     csr_mask_kernel<<<(unsigned)cdiv(cdiv(cells, 32), 256), 256, 0, st>>>(v.row_ptr, v.rank, v.nz_mask, v.nz_wrank, cells);
     PDU_LAUNCHED();
@@ -1000,15 +1006,16 @@ static int launch_interp_adj_csr(pdu_nufft_plan* p, const float2* kdata, float2*
         const long slots = cpt ? std::min(cells, M * p->J * p->J) : cells;
 #define PDU_CSRT(L, G_)                                                                                                     \
     do {                                                                                                                    \
+        const int lt_ = csr_long_threshold(p, M);                                                                           \
         dim3 gt_((unsigned)(long_blocks + cdiv(slots, 256 / L)), (unsigned)cdiv(planes4, 2 * L * G_));                       \
         if (cpt)                                                                                                            \
             interp_adj_csrT_kernel<L, G_, true><<<gt_, 256, 0, st>>>(kT_scratch, grid, v.row_ptr, v.samp, v.w, v.n_long,      \
                                                                     v.long_rows, v.nz_cell, v.nz_ptr + p->k0, cells, planes, \
-                                                                    planes4, long_blocks);                                  \
+                                                                    planes4, long_blocks, lt_);                             \
         else                                                                                                                \
             interp_adj_csrT_kernel<L, G_, false><<<gt_, 256, 0, st>>>(kT_scratch, grid, v.row_ptr, v.samp, v.w, v.n_long,     \
                                                                      v.long_rows, v.nz_cell, v.nz_ptr + p->k0, cells, planes,\
-                                                                     planes4, long_blocks);                                 \
+                                                                     planes4, long_blocks, lt_);                            \
     } while (0)
         // 16 planes per plane group for sparse trajectories (few entries per cell: the index loads are a large part of the
         // loop) and from 64 planes on; 8 otherwise (measured, 16 / 32 planes: 320^2 x 48 spokes 91 / 151 against 97 / 165 us,
@@ -1022,7 +1029,7 @@ static int launch_interp_adj_csr(pdu_nufft_plan* p, const float2* kdata, float2*
         return PDU_OK;
     }
     if (compact) *compact = false;
-    interp_adj_csr_kernel<PG><<<g, 256, 0, st>>>(kdata, grid, v.row_ptr, v.samp, v.w, cells, M, planes);
+    interp_adj_csr_kernel<PG><<<g, 256, 0, st>>>(kdata, grid, v.row_ptr, v.samp, v.w, cells, M, planes, csr_long_threshold(p, M));
     PDU_LAUNCHED();
     dim3 gl((unsigned)(2 * sm_count()), (unsigned)cdiv(planes, PG));      // 8 warps per CTA, grid-stride over the long rows
     interp_adj_csr_long_kernel<PG><<<gl, 256, 0, st>>>(kdata, grid, v.row_ptr, v.n_long, v.long_rows, v.nz_cell, v.samp, v.w,
