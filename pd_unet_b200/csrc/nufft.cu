@@ -1248,9 +1248,10 @@ static int nufft_adj_chunk(pdu_nufft_plan_t* p, const float2* kdata, float2* ima
     //  2.7 and leave 61 % of the cells empty; a dense trajectory fills the grid and would only pay for the indirection)
     bool compact = csr && variant == 2 && (double)m * p->J * p->J <= 8.0 * (double)p->k0 * p->k1;
     if (csr) {
-        // the FFT's intermediate buffer is free until the transform starts: it holds the plane-interleaved kdata
+        // the FFT's intermediate buffer and the cropped result behind it are free until the transform starts: they hold the
+        // plane-interleaved kdata
         float2* mid = grid + (long)planes * p->k0 * p->k1;
-        const long mid_elems = (long)planes * std::max((long)p->n0 * p->k1, (long)p->k0 * p->n1);
+        const long mid_elems = (long)planes * (std::max((long)p->n0 * p->k1, (long)p->k0 * p->n1) + (long)p->n0 * p->n1);
         const bool fits = m * (long)((planes + 3) & ~3) <= mid_elems;
         rc = launch_interp_adj_csr(p, kdata, grid, csr, planes, m, st, fits ? mid : nullptr, &compact);   // writes every cell: no memset
     } else {

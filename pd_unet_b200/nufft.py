@@ -174,13 +174,13 @@ class _Plan:
         """The sorted-gather form of the adjoint interpolator for this trajectory, built on first use."""
         # from 8 planes (16 before the gather went to 4 lanes per cell; tools/prof_nufft_csr_policy.py, atomics / sorted us:
         # 8 planes of 512^2 x 256 spokes 406 / 282, of 320^2 x 48 83 / 73, of 256^2 x 256 251 / 266; 4 planes 134 / 175)
-        # -- where the plane-interleaved copy of the samples fits the call's scratch (M <= about half the grid cells); a denser
+        # -- where the plane-interleaved copy of the samples fits the call's scratch (M <= about three quarters of the grid cells); a denser
         # trajectory runs the planar form of the gather, which only pays from 16 planes (256^2 x 512 spokes, 8 planes:
         # 396 against 374 us for the scatter; 16 planes: 527 against 722)
         if self.use_csr == "auto":
             n0, n1 = self.im_size
             k0, k1 = self.grid_size
-            fits = omega.shape[1] * ((planes + 3) & ~3) <= planes * max(n0 * k1, k0 * n1)
+            fits = omega.shape[1] * ((planes + 3) & ~3) <= planes * (max(n0 * k1, k0 * n1) + n0 * n1)
             if planes < (8 if fits else 16):
                 return None
         if self.use_csr is False:
