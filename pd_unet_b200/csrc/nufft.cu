@@ -477,7 +477,7 @@ __global__ void __launch_bounds__(SEQ* FastFft<K>::TPS)
 template <int K, int SEQ>
 __global__ void __launch_bounds__(SEQ* FastFft<K>::TPS)
     ff_rows_adj_compact_kernel(const float2* __restrict__ gridc, float2* __restrict__ T, const float2* __restrict__ tw_g,
-                               const unsigned* __restrict__ nz_mask, const int* __restrict__ nz_wrank, NufftDims d) {
+                               const uint2* __restrict__ nz_mw, NufftDims d) {
     using F = FastFft<K>;
     constexpr int N = K / 2, TPS = F::TPS, NS3 = F::NS3;
     static_assert(K % 32 == 0, "a row is whole occupancy words");
@@ -489,8 +489,7 @@ __global__ void __launch_bounds__(SEQ* FastFft<K>::TPS)
     for (int i = tid; i < K; i += SEQ * TPS) tw[i] = __ldg(tw_g + i);
     const bool live = row < K;
     const float2* src = gridc + (long)p * K * K;
-    const unsigned* mrow = nz_mask + row * (K / 32);
-    const int* wrow = nz_wrank + row * (K / 32);
+    const uint2* mwrow = nz_mw + row * (K / 32);
     float2* dst = T + ((long)p * K + row) * N;
     // branch-free: an empty cell reads the row's first value (one shared sector) and discards it, so that the eight index
     // pairs and then the eight values are in flight together (with a branch per input the loads went out one at a time)
@@ -500,11 +499,11 @@ __global__ void __launch_bounds__(SEQ* FastFft<K>::TPS)
         int wr[8];
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
-            const int wd = (t + r * TPS) >> 5;
-            m[r] = live ? __ldg(mrow + wd) : 0u;
-            wr[r] = live ? __ldg(wrow + wd) : 0;
+            const uint2 mw = live ? __ldg(mwrow + ((t + r * TPS) >> 5)) : make_uint2(0u, 0u);
+            m[r] = mw.x;
+            wr[r] = (int)mw.y;
         }
-        const int first = live ? __ldg(wrow) : 0;
+        const int first = live ? (int)__ldg(mwrow).y : 0;
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
             const unsigned bit = 1u << ((t + r * TPS) & 31);
@@ -569,10 +568,10 @@ static int ff_forward(pdu_nufft_plan* p, const float2* image, const float2* smap
     return PDU_OK;
 }
 
-// nz_mask / nz_wrank: the compact form of the gridded samples (CsrView), nullptr for dense K x K planes
+// nz_mw: the compact form of the gridded samples (CsrView), nullptr for dense K x K planes
 template <int K>
 static int ff_adjoint(pdu_nufft_plan* p, const float2* grid, float2* T, float2* U, int planes, cudaStream_t st,
-                      const unsigned* nz_mask = nullptr, const int* nz_wrank = nullptr) {
+                      const uint2* nz_mw = nullptr) {
     const NufftDims d = dims_of(p);
     constexpr int FF_SEQ_COLS = ff_seq_cols<K>();
     auto rows = ff_rows_adj_kernel<K, FF_SEQ_ROWS>;
@@ -582,7 +581,7 @@ static int ff_adjoint(pdu_nufft_plan* p, const float2* grid, float2* T, float2* 
     PDU_CUDA((ensure_dyn_smem<ff_rows_adj_compact_kernel<K, FF_SEQ_ROWS>>((int)ff_smem_bytes<K>(FF_SEQ_ROWS))));
     PDU_CUDA((ensure_dyn_smem<ff_cols_adj_kernel<K, FF_SEQ_COLS>>((int)ff_smem_bytes<K>(FF_SEQ_COLS))));
     const dim3 gr((unsigned)cdiv(p->k0, FF_SEQ_ROWS), (unsigned)planes);
-    if (nz_mask) rows_c<<<gr, FF_SEQ_ROWS * FastFft<K>::TPS, ff_smem_bytes<K>(FF_SEQ_ROWS), st>>>(grid, T, p->d_w1, nz_mask, nz_wrank, d);
+    if (nz_mw) rows_c<<<gr, FF_SEQ_ROWS * FastFft<K>::TPS, ff_smem_bytes<K>(FF_SEQ_ROWS), st>>>(grid, T, p->d_w1, nz_mw, d);
     else rows<<<gr, FF_SEQ_ROWS * FastFft<K>::TPS, ff_smem_bytes<K>(FF_SEQ_ROWS), st>>>(grid, T, p->d_w1, d);
     PDU_LAUNCHED();
     cols<<<dim3((unsigned)cdiv(p->n1, FF_SEQ_COLS), (unsigned)planes), FF_SEQ_COLS * FastFft<K>::TPS, ff_smem_bytes<K>(FF_SEQ_COLS), st>>>(
@@ -622,8 +621,8 @@ struct CsrView {
     int* long_rows;    // [cells] their indices in nz_cell (first n_long valid)
     int* nz_cell;      // [cells] the non-empty cells in increasing order (first nz_ptr[k0] valid)
     int* nz_ptr;       // [k0 + 1] grid row r owns nz_cell[nz_ptr[r] .. nz_ptr[r + 1])
-    unsigned* nz_mask; // [ceil(cells / 32)] bit c % 32 of word c / 32: cell c is non-empty
-    int* nz_wrank;     // [ceil(cells / 32)] compact index of the first non-empty cell at or after cell 32 w
+    uint2* nz_mw;      // [ceil(cells / 32)] .x: bit c % 32 of word c / 32 = cell c is non-empty; .y: compact index of the
+                       //                     first non-empty cell at or after cell 32 w
     int* samp;
     float2* w;
     // build scratch
@@ -648,8 +647,7 @@ static CsrView csr_layout(const pdu_nufft_plan* p, long M, void* base, bool with
     v.long_rows = (int*)take(cells * 4);
     v.nz_cell = (int*)take(cells * 4);
     v.nz_ptr = (int*)take(((size_t)p->k0 + 1) * 4);
-    v.nz_mask = (unsigned*)take((cells + 31) / 32 * 4);
-    v.nz_wrank = (int*)take((cells + 31) / 32 * 4);
+    v.nz_mw = (uint2*)take((cells + 31) / 32 * 8);
     v.samp = (int*)take(n * 4);
     v.w = (float2*)take(n * 8);
     v.key_in = (unsigned*)take(n * 4);
@@ -736,15 +734,13 @@ __global__ void __launch_bounds__(256) csr_flag_kernel(const int* __restrict__ r
 // 32 cells per word: the occupancy bits and the compact index at the word's start -- the row pass finds a cell's value
 // with two cached loads and a population count
 __global__ void __launch_bounds__(256)
-    csr_mask_kernel(const int* __restrict__ row_ptr, const int* __restrict__ rank, unsigned* __restrict__ mask,
-                    int* __restrict__ wrank, long cells) {
+    csr_mask_kernel(const int* __restrict__ row_ptr, const int* __restrict__ rank, uint2* __restrict__ mw, long cells) {
     const long wd = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (wd * 32 >= cells) return;
     unsigned m = 0;
     for (int b = 0; b < 32 && wd * 32 + b < cells; ++b)
         if (row_ptr[wd * 32 + b + 1] > row_ptr[wd * 32 + b]) m |= 1u << b;
-    mask[wd] = m;
-    wrank[wd] = rank[wd * 32];
+    mw[wd] = make_uint2(m, (unsigned)rank[wd * 32]);
 }
 __global__ void __launch_bounds__(256)
     csr_compact_kernel(const int* __restrict__ row_ptr, const int* __restrict__ rank, int* __restrict__ nz_cell,
@@ -981,7 +977,7 @@ static int csr_build(pdu_nufft_plan* p, const float* omega, long M, void* buf, s
     csr_compact_kernel<<<(unsigned)cdiv(cells + 1, 256), 256, 0, st>>>(v.row_ptr, v.rank, v.nz_cell, v.nz_ptr, v.n_long, v.long_rows,
                                                                       cells, p->k0, p->k1, csr_long_threshold(p, M));
     PDU_LAUNCHED();
-    csr_mask_kernel<<<(unsigned)cdiv(cdiv(cells, 32), 256), 256, 0, st>>>(v.row_ptr, v.rank, v.nz_mask, v.nz_wrank, cells);
+    csr_mask_kernel<<<(unsigned)cdiv(cdiv(cells, 32), 256), 256, 0, st>>>(v.row_ptr, v.rank, v.nz_mw, cells);
     PDU_LAUNCHED();
     return PDU_OK;
 }
@@ -1274,14 +1270,13 @@ static int nufft_adj_chunk(pdu_nufft_plan_t* p, const float2* kdata, float2* ima
         float2* T = grid + (long)planes * p->k0 * p->k1;
         float2* U = T + (long)planes * std::max((long)p->n0 * p->k1, (long)p->k0 * p->n1);
         const CsrView cv = compact ? csr_layout(p, m, const_cast<void*>(csr), false) : CsrView{};
-        const unsigned* nzc = compact ? cv.nz_mask : nullptr;
-        const int* nzp = compact ? cv.nz_wrank : nullptr;
+        const uint2* nzc = compact ? cv.nz_mw : nullptr;
         switch (p->k0) {
-            case 256: rc = ff_adjoint<256>(p, grid, T, U, planes, st, nzc, nzp); break;
-            case 512: rc = ff_adjoint<512>(p, grid, T, U, planes, st, nzc, nzp); break;
-            case 640: rc = ff_adjoint<640>(p, grid, T, U, planes, st, nzc, nzp); break;
-            case 1024: rc = ff_adjoint<1024>(p, grid, T, U, planes, st, nzc, nzp); break;
-            default: rc = ff_adjoint<2048>(p, grid, T, U, planes, st, nzc, nzp); break;
+            case 256: rc = ff_adjoint<256>(p, grid, T, U, planes, st, nzc); break;
+            case 512: rc = ff_adjoint<512>(p, grid, T, U, planes, st, nzc); break;
+            case 640: rc = ff_adjoint<640>(p, grid, T, U, planes, st, nzc); break;
+            case 1024: rc = ff_adjoint<1024>(p, grid, T, U, planes, st, nzc); break;
+            default: rc = ff_adjoint<2048>(p, grid, T, U, planes, st, nzc); break;
         }
         if (rc) return rc;
         NufftDims dc = dims_of(p);          // the cropped result is a dense [n0][n1] "grid"
