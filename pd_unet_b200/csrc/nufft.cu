@@ -467,20 +467,22 @@ __global__ void __launch_bounds__(SEQ* FastFft<K>::TPS)
     ff_transform<K, 4, true, false, true, false, false, true>(buf + s * F::template pitch<4>(), tw, t, ld, st);
 }
 
-// The row pass on the COMPACT gridded samples (interp_adj_csrT_kernel<.., true>): a thread finds each of its eight inputs
-// through the occupancy word of the cell and the compact index at the word's start (two cached loads + a population
-// count) and loads the value only where the cell is non-empty.  Against the dense form the gather writes and this pass
-// reads one value per non-empty cell instead of K per row.  (First version: non-empty cells spread over a zeroed
-// shared-memory row and the transform started from there -- three more CTA barriers and the extra shared-memory round
-// trip made the pass slower than the dense one, 86 against 72 us at 64 planes of 640^2 in spite of 94 instead of 210 MB.)
-// (six CTAs per SM -- 32 registers, maximum shared-memory carve-out -- instead of four: 238.6 against 234.5 us for the call)
+// The row pass on the COMPACT gridded samples (interp_adj_csrT_kernel<.., true>): a thread looks up the compact index of
+// each of its eight inputs (nz_idx, 4 bytes per cell, coalesced and L2 resident) and loads the value only where the cell
+// is non-empty.  Against the dense form the gather writes and this pass reads one value per non-empty cell instead of K
+// per row.  Branch-free: an empty cell reads the plane's first value (one shared sector) and discards it, so that the
+// eight indices and then the eight values are in flight together -- with a branch per input the loads went out one at
+// a time (95 us for this pass at 64 planes of 640^2).  Other forms measured there: the non-empty cells spread over a
+// zeroed shared-memory row and the transform started from it (three more CTA barriers: 86 us against 72 for the dense
+// pass in spite of 94 instead of 210 MB); occupancy words + population count instead of the index array (two loads and
+// ~6 more instructions per input: 4 us more for the call; as two separate arrays 12 us more); six CTAs per SM (32
+// registers, maximum shared-memory carve-out) instead of four: 4 us more.
 template <int K, int SEQ>
 __global__ void __launch_bounds__(SEQ* FastFft<K>::TPS)
     ff_rows_adj_compact_kernel(const float2* __restrict__ gridc, float2* __restrict__ T, const float2* __restrict__ tw_g,
-                               const uint2* __restrict__ nz_mw, NufftDims d) {
+                               const int* __restrict__ nz_idx, NufftDims d) {
     using F = FastFft<K>;
     constexpr int N = K / 2, TPS = F::TPS, NS3 = F::NS3;
-    static_assert(K % 32 == 0, "a row is whole occupancy words");
     float2* buf = pf_smem<float2>();
     float2* tw = buf + SEQ * F::template pitch<4>();
     const int tid = threadIdx.x, s = tid / TPS, t = tid - s * TPS;
@@ -489,27 +491,17 @@ __global__ void __launch_bounds__(SEQ* FastFft<K>::TPS)
     for (int i = tid; i < K; i += SEQ * TPS) tw[i] = __ldg(tw_g + i);
     const bool live = row < K;
     const float2* src = gridc + (long)p * K * K;
-    const uint2* mwrow = nz_mw + row * (K / 32);
     float2* dst = T + ((long)p * K + row) * N;
-    // branch-free: an empty cell reads the row's first value (one shared sector) and discards it, so that the eight index
-    // pairs and then the eight values are in flight together (with a branch per input the loads went out one at a time)
     float2 val[8];
     {
-        unsigned m[8];
-        int wr[8];
+        const int* irow = nz_idx + (long)row * K + t;
+        int ix[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) ix[r] = live ? __ldg(irow + r * TPS) : -1;
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
-            const uint2 mw = live ? __ldg(mwrow + ((t + r * TPS) >> 5)) : make_uint2(0u, 0u);
-            m[r] = mw.x;
-            wr[r] = (int)mw.y;
-        }
-        const int first = live ? (int)__ldg(mwrow).y : 0;
-#pragma unroll
-        for (int r = 0; r < 8; ++r) {
-            const unsigned bit = 1u << ((t + r * TPS) & 31);
-            const bool on = (m[r] & bit) != 0;
-            const float2 x = __ldcs(src + (on ? wr[r] + __popc(m[r] & (bit - 1)) : first));
-            val[r] = on ? x : make_float2(0.f, 0.f);
+            const float2 x = __ldcs(src + (ix[r] >= 0 ? ix[r] : 0));
+            val[r] = ix[r] >= 0 ? x : make_float2(0.f, 0.f);
         }
     }
     auto ld = [&](int r) { return val[r]; };
@@ -568,10 +560,10 @@ static int ff_forward(pdu_nufft_plan* p, const float2* image, const float2* smap
     return PDU_OK;
 }
 
-// nz_mw: the compact form of the gridded samples (CsrView), nullptr for dense K x K planes
+// nz_idx: the compact form of the gridded samples (CsrView), nullptr for dense K x K planes
 template <int K>
 static int ff_adjoint(pdu_nufft_plan* p, const float2* grid, float2* T, float2* U, int planes, cudaStream_t st,
-                      const uint2* nz_mw = nullptr) {
+                      const int* nz_idx = nullptr) {
     const NufftDims d = dims_of(p);
     constexpr int FF_SEQ_COLS = ff_seq_cols<K>();
     auto rows = ff_rows_adj_kernel<K, FF_SEQ_ROWS>;
@@ -581,7 +573,7 @@ static int ff_adjoint(pdu_nufft_plan* p, const float2* grid, float2* T, float2* 
     PDU_CUDA((ensure_dyn_smem<ff_rows_adj_compact_kernel<K, FF_SEQ_ROWS>>((int)ff_smem_bytes<K>(FF_SEQ_ROWS))));
     PDU_CUDA((ensure_dyn_smem<ff_cols_adj_kernel<K, FF_SEQ_COLS>>((int)ff_smem_bytes<K>(FF_SEQ_COLS))));
     const dim3 gr((unsigned)cdiv(p->k0, FF_SEQ_ROWS), (unsigned)planes);
-    if (nz_mw) rows_c<<<gr, FF_SEQ_ROWS * FastFft<K>::TPS, ff_smem_bytes<K>(FF_SEQ_ROWS), st>>>(grid, T, p->d_w1, nz_mw, d);
+    if (nz_idx) rows_c<<<gr, FF_SEQ_ROWS * FastFft<K>::TPS, ff_smem_bytes<K>(FF_SEQ_ROWS), st>>>(grid, T, p->d_w1, nz_idx, d);
     else rows<<<gr, FF_SEQ_ROWS * FastFft<K>::TPS, ff_smem_bytes<K>(FF_SEQ_ROWS), st>>>(grid, T, p->d_w1, d);
     PDU_LAUNCHED();
     cols<<<dim3((unsigned)cdiv(p->n1, FF_SEQ_COLS), (unsigned)planes), FF_SEQ_COLS * FastFft<K>::TPS, ff_smem_bytes<K>(FF_SEQ_COLS), st>>>(
@@ -621,8 +613,7 @@ struct CsrView {
     int* long_rows;    // [cells] their indices in nz_cell (first n_long valid)
     int* nz_cell;      // [cells] the non-empty cells in increasing order (first nz_ptr[k0] valid)
     int* nz_ptr;       // [k0 + 1] grid row r owns nz_cell[nz_ptr[r] .. nz_ptr[r + 1])
-    uint2* nz_mw;      // [ceil(cells / 32)] .x: bit c % 32 of word c / 32 = cell c is non-empty; .y: compact index of the
-                       //                     first non-empty cell at or after cell 32 w
+    int* nz_idx;       // [cells] compact index of a non-empty cell, -1 for an empty one
     int* samp;
     float2* w;
     // build scratch
@@ -647,7 +638,7 @@ static CsrView csr_layout(const pdu_nufft_plan* p, long M, void* base, bool with
     v.long_rows = (int*)take(cells * 4);
     v.nz_cell = (int*)take(cells * 4);
     v.nz_ptr = (int*)take(((size_t)p->k0 + 1) * 4);
-    v.nz_mw = (uint2*)take((cells + 31) / 32 * 8);
+    v.nz_idx = (int*)take(cells * 4);
     v.samp = (int*)take(n * 4);
     v.w = (float2*)take(n * 8);
     v.key_in = (unsigned*)take(n * 4);
@@ -731,27 +722,17 @@ __global__ void __launch_bounds__(256) csr_flag_kernel(const int* __restrict__ r
 }
 // the compact list itself, the first compact index of every grid row, and the rows too long for one thread (the k-space
 // centre of a radial trajectory collects every spoke) by their compact index
-// 32 cells per word: the occupancy bits and the compact index at the word's start -- the row pass finds a cell's value
-// with two cached loads and a population count
-__global__ void __launch_bounds__(256)
-    csr_mask_kernel(const int* __restrict__ row_ptr, const int* __restrict__ rank, uint2* __restrict__ mw, long cells) {
-    const long wd = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (wd * 32 >= cells) return;
-    unsigned m = 0;
-    for (int b = 0; b < 32 && wd * 32 + b < cells; ++b)
-        if (row_ptr[wd * 32 + b + 1] > row_ptr[wd * 32 + b]) m |= 1u << b;
-    mw[wd] = make_uint2(m, (unsigned)rank[wd * 32]);
-}
 __global__ void __launch_bounds__(256)
     csr_compact_kernel(const int* __restrict__ row_ptr, const int* __restrict__ rank, int* __restrict__ nz_cell,
-                       int* __restrict__ nz_ptr, int* __restrict__ n_long, int* __restrict__ long_rows, long cells, int k0, int k1,
-                       int long_thresh) {
+                       int* __restrict__ nz_ptr, int* __restrict__ nz_idx, int* __restrict__ n_long, int* __restrict__ long_rows,
+                       long cells, int k0, int k1, int long_thresh) {
     const long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (c > cells) return;
     if (c % k1 == 0) nz_ptr[c / k1] = rank[c];          // c == cells: nz_ptr[k0] = the number of non-empty cells
     if (c == cells) return;
     const int len = row_ptr[c + 1] - row_ptr[c];
     if (len > 0) nz_cell[rank[c]] = (int)c;
+    nz_idx[c] = len > 0 ? rank[c] : -1;
     if (len > long_thresh) long_rows[atomicAdd(n_long, 1)] = rank[c];
 }
 
@@ -974,10 +955,8 @@ static int csr_build(pdu_nufft_plan* p, const float* omega, long M, void* buf, s
     PDU_LAUNCHED();
     PDU_CUDA(cub::DeviceScan::ExclusiveSum(v.cub_tmp, v.cub_bytes, flag_buf, v.rank, (int)(cells + 1), st));
     count_launch(2);
-    csr_compact_kernel<<<(unsigned)cdiv(cells + 1, 256), 256, 0, st>>>(v.row_ptr, v.rank, v.nz_cell, v.nz_ptr, v.n_long, v.long_rows,
+    csr_compact_kernel<<<(unsigned)cdiv(cells + 1, 256), 256, 0, st>>>(v.row_ptr, v.rank, v.nz_cell, v.nz_ptr, v.nz_idx, v.n_long, v.long_rows,
                                                                       cells, p->k0, p->k1, csr_long_threshold(p, M));
-    PDU_LAUNCHED();
-    csr_mask_kernel<<<(unsigned)cdiv(cdiv(cells, 32), 256), 256, 0, st>>>(v.row_ptr, v.rank, v.nz_mw, cells);
     PDU_LAUNCHED();
     return PDU_OK;
 }
@@ -1270,13 +1249,13 @@ static int nufft_adj_chunk(pdu_nufft_plan_t* p, const float2* kdata, float2* ima
         float2* T = grid + (long)planes * p->k0 * p->k1;
         float2* U = T + (long)planes * std::max((long)p->n0 * p->k1, (long)p->k0 * p->n1);
         const CsrView cv = compact ? csr_layout(p, m, const_cast<void*>(csr), false) : CsrView{};
-        const uint2* nzc = compact ? cv.nz_mw : nullptr;
+        const int* nzi = compact ? cv.nz_idx : nullptr;
         switch (p->k0) {
-            case 256: rc = ff_adjoint<256>(p, grid, T, U, planes, st, nzc); break;
-            case 512: rc = ff_adjoint<512>(p, grid, T, U, planes, st, nzc); break;
-            case 640: rc = ff_adjoint<640>(p, grid, T, U, planes, st, nzc); break;
-            case 1024: rc = ff_adjoint<1024>(p, grid, T, U, planes, st, nzc); break;
-            default: rc = ff_adjoint<2048>(p, grid, T, U, planes, st, nzc); break;
+            case 256: rc = ff_adjoint<256>(p, grid, T, U, planes, st, nzi); break;
+            case 512: rc = ff_adjoint<512>(p, grid, T, U, planes, st, nzi); break;
+            case 640: rc = ff_adjoint<640>(p, grid, T, U, planes, st, nzi); break;
+            case 1024: rc = ff_adjoint<1024>(p, grid, T, U, planes, st, nzi); break;
+            default: rc = ff_adjoint<2048>(p, grid, T, U, planes, st, nzi); break;
         }
         if (rc) return rc;
         NufftDims dc = dims_of(p);          // the cropped result is a dense [n0][n1] "grid"
