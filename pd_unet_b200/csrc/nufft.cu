@@ -614,6 +614,7 @@ struct CsrView {
     int* nz_cell;      // [cells] the non-empty cells in increasing order (first nz_ptr[k0] valid)
     int* nz_ptr;       // [k0 + 1] grid row r owns nz_cell[nz_ptr[r] .. nz_ptr[r + 1])
     int* nz_idx;       // [cells] compact index of a non-empty cell, -1 for an empty one
+    int* nz_rptr;      // [cells + 1] row_ptr of the non-empty cells: entries of compact cell i are [nz_rptr[i], nz_rptr[i + 1])
     int* samp;
     float2* w;
     // build scratch
@@ -639,6 +640,7 @@ static CsrView csr_layout(const pdu_nufft_plan* p, long M, void* base, bool with
     v.nz_cell = (int*)take(cells * 4);
     v.nz_ptr = (int*)take(((size_t)p->k0 + 1) * 4);
     v.nz_idx = (int*)take(cells * 4);
+    v.nz_rptr = (int*)take((cells + 1) * 4);
     v.samp = (int*)take(n * 4);
     v.w = (float2*)take(n * 8);
     v.key_in = (unsigned*)take(n * 4);
@@ -724,14 +726,20 @@ __global__ void __launch_bounds__(256) csr_flag_kernel(const int* __restrict__ r
 // centre of a radial trajectory collects every spoke) by their compact index
 __global__ void __launch_bounds__(256)
     csr_compact_kernel(const int* __restrict__ row_ptr, const int* __restrict__ rank, int* __restrict__ nz_cell,
-                       int* __restrict__ nz_ptr, int* __restrict__ nz_idx, int* __restrict__ n_long, int* __restrict__ long_rows,
-                       long cells, int k0, int k1, int long_thresh) {
+                       int* __restrict__ nz_ptr, int* __restrict__ nz_idx, int* __restrict__ nz_rptr, int* __restrict__ n_long,
+                       int* __restrict__ long_rows, long cells, int k0, int k1, int long_thresh) {
     const long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (c > cells) return;
     if (c % k1 == 0) nz_ptr[c / k1] = rank[c];          // c == cells: nz_ptr[k0] = the number of non-empty cells
-    if (c == cells) return;
+    if (c == cells) {
+        nz_rptr[rank[c]] = row_ptr[c];                  // closes the last non-empty cell
+        return;
+    }
     const int len = row_ptr[c + 1] - row_ptr[c];
-    if (len > 0) nz_cell[rank[c]] = (int)c;
+    if (len > 0) {
+        nz_cell[rank[c]] = (int)c;
+        nz_rptr[rank[c]] = row_ptr[c];
+    }
     nz_idx[c] = len > 0 ? rank[c] : -1;
     if (len > long_thresh) long_rows[atomicAdd(n_long, 1)] = rank[c];
 }
@@ -808,8 +816,8 @@ template <int LPC, int G, bool COMPACT>
 __global__ void __launch_bounds__(256)
     interp_adj_csrT_kernel(const float2* __restrict__ kT, float2* __restrict__ grid, const int* __restrict__ row_ptr,
                            const int* __restrict__ samp, const float2* __restrict__ w, const int* __restrict__ n_long,
-                           const int* __restrict__ long_rows, const int* __restrict__ nz_cell, const int* __restrict__ n_nz,
-                           long cells, int planes, int planes4, int long_blocks, int long_thresh) {
+                           const int* __restrict__ long_rows, const int* __restrict__ nz_cell, const int* __restrict__ nz_rptr,
+                           const int* __restrict__ n_nz, long cells, int planes, int planes4, int long_blocks, int long_thresh) {
     constexpr int CPB = 256 / LPC;
     if ((int)blockIdx.x < long_blocks) {
         constexpr int PG = 2 * LPC * G;                   // planes of this plane group
@@ -817,9 +825,8 @@ __global__ void __launch_bounds__(256)
         const int nl = __ldg(n_long);
         for (int r = blockIdx.x * 8 + (threadIdx.x >> 5); r < nl; r += long_blocks * 8) {
             const int ci = __ldg(long_rows + r);
-            const long c = __ldg(nz_cell + ci);
-            const long slot = COMPACT ? (long)ci : c;     // where the cell's value goes inside a plane
-            const int beg = __ldg(row_ptr + c), end = __ldg(row_ptr + c + 1);
+            const long slot = COMPACT ? (long)ci : (long)__ldg(nz_cell + ci);     // where the cell's value goes inside a plane
+            const int beg = __ldg(nz_rptr + ci), end = __ldg(nz_rptr + ci + 1);
             // four planes at a time: eight accumulators, so that this rare path does not set the kernel's register count
 #pragma unroll 1
             for (int h = 0; h < PG && p0 + h < planes4; h += 4) {
@@ -857,8 +864,9 @@ __global__ void __launch_bounds__(256)
     const long o = (long)(blockIdx.x - long_blocks) * CPB + threadIdx.x / LPC;
     const int p = blockIdx.y * (2 * LPC * G) + 2 * sub;   // first of this lane's planes; the others follow 2 LPC apart
     if (o >= (COMPACT ? (long)__ldg(n_nz) : cells) || p >= planes4) return;
-    const long c = COMPACT ? (long)__ldg(nz_cell + o) : o;
-    const int beg = __ldg(row_ptr + c), end = __ldg(row_ptr + c + 1);
+    // compact: the row pointer of the non-empty cells (one load level less than nz_cell -> row_ptr)
+    const int* rp = COMPACT ? nz_rptr + o : row_ptr + o;
+    const int beg = __ldg(rp), end = __ldg(rp + 1);
     if (end - beg > long_thresh) return;                  // the long-row CTAs own this cell
     float2 a0[G], a1[G];
 #pragma unroll
@@ -955,7 +963,7 @@ static int csr_build(pdu_nufft_plan* p, const float* omega, long M, void* buf, s
     PDU_LAUNCHED();
     PDU_CUDA(cub::DeviceScan::ExclusiveSum(v.cub_tmp, v.cub_bytes, flag_buf, v.rank, (int)(cells + 1), st));
     count_launch(2);
-    csr_compact_kernel<<<(unsigned)cdiv(cells + 1, 256), 256, 0, st>>>(v.row_ptr, v.rank, v.nz_cell, v.nz_ptr, v.nz_idx, v.n_long, v.long_rows,
+    csr_compact_kernel<<<(unsigned)cdiv(cells + 1, 256), 256, 0, st>>>(v.row_ptr, v.rank, v.nz_cell, v.nz_ptr, v.nz_idx, v.nz_rptr, v.n_long, v.long_rows,
                                                                       cells, p->k0, p->k1, csr_long_threshold(p, M));
     PDU_LAUNCHED();
     return PDU_OK;
@@ -985,12 +993,12 @@ static int launch_interp_adj_csr(pdu_nufft_plan* p, const float2* kdata, float2*
         dim3 gt_((unsigned)(long_blocks + cdiv(slots, 256 / L)), (unsigned)cdiv(planes4, 2 * L * G_));                       \
         if (cpt)                                                                                                            \
             interp_adj_csrT_kernel<L, G_, true><<<gt_, 256, 0, st>>>(kT_scratch, grid, v.row_ptr, v.samp, v.w, v.n_long,      \
-                                                                    v.long_rows, v.nz_cell, v.nz_ptr + p->k0, cells, planes, \
-                                                                    planes4, long_blocks, lt_);                             \
+                                                                    v.long_rows, v.nz_cell, v.nz_rptr, v.nz_ptr + p->k0, cells, \
+                                                                    planes, planes4, long_blocks, lt_);                     \
         else                                                                                                                \
             interp_adj_csrT_kernel<L, G_, false><<<gt_, 256, 0, st>>>(kT_scratch, grid, v.row_ptr, v.samp, v.w, v.n_long,     \
-                                                                     v.long_rows, v.nz_cell, v.nz_ptr + p->k0, cells, planes,\
-                                                                     planes4, long_blocks, lt_);                            \
+                                                                     v.long_rows, v.nz_cell, v.nz_rptr, v.nz_ptr + p->k0, cells,\
+                                                                     planes, planes4, long_blocks, lt_);                    \
     } while (0)
         // 16 planes per plane group for sparse trajectories (few entries per cell: the index loads are a large part of the
         // loop) and from 64 planes on; 8 otherwise (measured, 16 / 32 planes: 320^2 x 48 spokes 91 / 151 against 97 / 165 us,
