@@ -142,13 +142,13 @@ class _Plan:
             # 48 / 60, 48 / 61; 256^2 91 / 110, 118 / 118; 512^2 294 / 253, 339 / 521.)
             rho = omega.shape[1] / float(self.grid_size[0] * self.grid_size[1])
             sparse = rho <= 0.15
-            # adjoint with many planes: the sorted gather (4 lanes per cell x 16 planes since r02) + FFT passes overtake the
-            # row-binned kernel -- from 64 planes everywhere, from 32 on the 512 and 1024 grids
-            # (tools/prof_nufft_adj_policy.py, generic / fused us: 256^2 x 32 / 48 / 64 planes 105 / 149 / 185 against
-            # 114 / 161 / 208; 512^2 413 / 609 / 794 against 484 / 689 / 949; 320^2 151 / 212 / 269 against 147 / 210 / 273;
-            # with coil maps at the configs[3] share, 64 planes of 640^2: 253 against 294)
-            g0 = self.grid_size[0]
-            many = adjoint and (planes >= 64 or (planes >= 32 and (g0 == 512 or g0 >= 1024)))
+            # adjoint: from a grid-dependent plane count on, the sorted gather (4 lanes per cell x 16 planes, non-empty cells
+            # only, since r02) + FFT passes beat the row-binned kernel (tools/prof_nufft_adj_policy.py, REPS=21, generic /
+            # fused us: 128^2 x 32 spokes 16 / 48 / 64 planes 44 / 65 / 71 against 38 / 63 / 77; 256^2 x 48 16 / 24 / 32 / 64
+            # 71 / 85 / 101 / 173 against 65 / 91 / 114 / 208; 320^2 x 48 16 / 24 / 32 / 64 89 / 114 / 138 / 245 against
+            # 85 / 116 / 146 / 273; 512^2 x 96 8 / 16 / 32 124 / 208 / 392 against 124 / 226 / 484; 1024^2 x 128 8 / 16
+            # 419 / 744 against 484 / 1111)
+            many = adjoint and planes >= {256: 64, 512: 24, 640: 32, 1024: 16}.get(self.grid_size[0], 8)
             if planes < 8 or not sparse or many:
                 return None
         ent = self._entry(omega)

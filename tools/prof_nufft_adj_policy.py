@@ -10,8 +10,8 @@ def traj(spokes, readout):
     phi = np.arange(spokes) * (111.246117975 * np.pi / 180.0)
     r = (np.arange(readout) - readout / 2) * (2 * np.pi / readout)
     return torch.from_numpy(np.stack([(r[None] * np.sin(phi)[:, None]).reshape(-1), (r[None] * np.cos(phi)[:, None]).reshape(-1)]).astype(np.float32)).to(dev)
-def timed(fn, reps=7):
-    fn(); fn(); torch.cuda.synchronize(); ts = []
+def timed(fn, reps=int(os.environ.get("REPS", "7"))):
+    [fn() for _ in range(5)]; torch.cuda.synchronize(); ts = []
     for _ in range(reps):
         flush.zero_()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
