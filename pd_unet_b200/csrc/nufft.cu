@@ -1004,6 +1004,7 @@ static int launch_interp_adj_csr(pdu_nufft_plan* p, const float2* kdata, float2*
         // loop) and from 64 planes on; 8 otherwise (measured, 16 / 32 planes: 320^2 x 48 spokes 91 / 151 against 97 / 165 us,
         // 512^2 x 96 226 / 425 against 253 / 485; but 320^2 x 160 spokes 228 / 325 against 184 / 312)
         const double per_cell = (double)M * p->J * p->J / (double)cells;
+        // (re-measured in the compact form at 64 planes: (4, 1) 251, (4, 2) 228, (4, 4) 226, (8, 1) 249, (8, 2) 234 us)
         if (planes4 >= 16 && (per_cell <= 5.0 || planes4 >= 64)) PDU_CSRT(4, 2);
         else if (planes4 >= 8) PDU_CSRT(4, 1);
         else PDU_CSRT(2, 1);
