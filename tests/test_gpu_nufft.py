@@ -162,6 +162,41 @@ def test_sorted_gather_shapes_over_plane_counts(planes, dense):
     assert rel_l2(adj(k.to(DEV), omd), a1) <= 2e-6    # every plane agrees with the scatter
 
 
+@pytest.mark.parametrize("traj", ["radial", "few", "cluster", "uniform"])
+@pytest.mark.parametrize("planes", [(1, 8), (3, 4), (1, 17), (3, 11)])
+def test_compact_gridded_samples_between_gather_and_row_pass(planes, traj):
+    """On the grids with the register FFT a sparse trajectory's gridded samples stay compact (one value per non-empty
+    cell) between the sorted gather and the row pass: radial spokes, a handful of samples (most grid rows entirely
+    empty), a tight cluster (long rows only, a few cells) and uniform random samples, plane counts around the group
+    sizes -- against the oracle on three planes, against the atomic scatter on all, and bit-reproducible."""
+    from pd_unet_b200 import _lib
+    B, Cc = planes
+    im = (128, 128)
+    spec = oracle.NufftSpec(im)
+    rng = np.random.default_rng(7)
+    if traj == "radial":
+        om = _traj(12, 256)
+    elif traj == "few":
+        om = rng.uniform(-np.pi, np.pi, (2, 23))
+    elif traj == "cluster":
+        om = np.clip(rng.normal(0.3, 0.01, (2, 900)), -np.pi, np.pi)
+    else:
+        om = rng.uniform(-np.pi, np.pi, (2, 5000))
+    om = om.astype(np.float32).astype(np.float64)
+    omd = torch.from_numpy(om).to(DEV).float()
+    k = seeded((B, Cc, om.shape[1]), 300 + B * Cc, complex_=True)
+    adj = pdu.KbNufftAdjoint(im)
+    adj._plan.use_csr, adj._plan.use_fused = True, False
+    a1 = adj(k.to(DEV), omd)
+    name = _lib.last_kernel("nufft_adj")
+    assert "non-empty cells only" in name and "ff_rows_adj_compact_kernel" in name, name
+    assert torch.equal(a1, adj(k.to(DEV), omd))
+    for b, c in [(0, 0), (B - 1, Cc - 1), (B // 2, Cc // 2)]:
+        assert rel_l2(a1[b:b + 1, c:c + 1], oracle.nufft_adjoint(k[b:b + 1, c:c + 1], om, spec)) <= TOL
+    adj._plan.use_csr = False
+    assert rel_l2(adj(k.to(DEV), omd), a1) <= 2e-6
+
+
 @pytest.mark.parametrize("im", [(32, 32), (48, 40), (320, 320), (256, 256), (250, 250)])
 def test_pruned_fft_and_cufft_paths_agree(im):
     """variant 1: the own pruned shared-memory FFT; variant 0 (default, currently faster): pad + cuFFT.  Same
